@@ -1,0 +1,139 @@
+// common.cuh -- context, workspace and small device helpers shared by libcia's
+// translation units.  sm_100a only.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/cia.h"
+
+#define CIA_NUM_SMS_DEFAULT 148
+
+// CAE topology of CAE_improved_modeltrain.py:188-216
+#define CAE_NCONV 7
+static const int kCaeCin[CAE_NCONV]  = {1, 32, 64, 32, 32, 64, 32};
+static const int kCaeCout[CAE_NCONV] = {32, 64, 32, 32, 64, 32, 1};
+
+struct CaeWeights {
+    bool loaded = false;
+    int n_conv = 0;
+    float* kernel[CAE_NCONV] = {};   // HWIO fp32 (tap, ci, co)
+    float* bias[CAE_NCONV] = {};
+    float* bn_scale[CAE_NCONV] = {}; // gamma / sqrt(var + eps)            (fp32, folded like tf.nn.batch_normalization)
+    float* bn_shift[CAE_NCONV] = {}; // beta - mean * scale
+    // tensor-core operand images (built at load time, see cae_tc.cu)
+    void* tc_blob = nullptr;
+};
+
+struct SvmModel {
+    bool loaded = false;
+    int n_sv = 0, dim = 0;
+    double* sv_t = nullptr;   // [dim, n_sv_pad] transposed for coalesced reads
+    double* coef = nullptr;   // [n_sv_pad] (zero padded)
+    int n_sv_pad = 0;
+    double gamma = 0, rho = 0;
+};
+
+struct ScalerPca {
+    bool loaded = false;
+    int F = 0, C = 0;
+    int center_is_f32 = 1, f32_flow = 1, has_center = 0, has_scale = 0;
+    double* center = nullptr;   // [F]
+    double* scale = nullptr;    // [F]
+    double* comp_t = nullptr;   // [F, C] transposed components
+    double* offset = nullptr;   // [C]
+};
+
+struct Workspace {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct cia_ctx {
+    int device = 0;
+    int num_sms = CIA_NUM_SMS_DEFAULT;
+    std::string err;
+    CaeWeights cae[2];
+    ScalerPca sp;
+    SvmModel svm[2];
+    int32_t* status_dev = nullptr;        // device status word (CIA_E_* raised by kernels)
+    int32_t* status_host = nullptr;       // pinned
+    int64_t launches = 0;
+    // grow-only workspaces
+    Workspace ws_flags, ws_act, ws_crop_scratch, ws_pipe, ws_feat, ws_misc, ws_stage;
+    cudaEvent_t ev = nullptr;
+};
+
+#define CIA_CUDA(call)                                                              \
+    do {                                                                            \
+        cudaError_t e_ = (call);                                                    \
+        if (e_ != cudaSuccess) {                                                    \
+            h->err = std::string(#call) + ": " + cudaGetErrorString(e_);            \
+            return CIA_E_CUDA;                                                      \
+        }                                                                           \
+    } while (0)
+
+#define CIA_LAUNCH_CHECK()                                                          \
+    do {                                                                            \
+        h->launches++;                                                              \
+        cudaError_t e_ = cudaGetLastError();                                        \
+        if (e_ != cudaSuccess) {                                                    \
+            h->err = std::string("kernel launch: ") + cudaGetErrorString(e_);       \
+            return CIA_E_CUDA;                                                      \
+        }                                                                           \
+    } while (0)
+
+static inline int ws_reserve(cia_ctx* h, Workspace& w, size_t bytes) {
+    if (bytes <= w.cap) return CIA_OK;
+    if (w.p) {
+        CIA_CUDA(cudaDeviceSynchronize());
+        CIA_CUDA(cudaFree(w.p));
+        w.p = nullptr; w.cap = 0;
+    }
+    size_t want = bytes + bytes / 4 + 256;
+    CIA_CUDA(cudaMalloc(&w.p, want));
+    w.cap = want;
+    return CIA_OK;
+}
+
+// ---- device helpers -------------------------------------------------------
+__device__ __forceinline__ int dev_count(int n, const int32_t* n_dev) {
+    if (n_dev == nullptr) return n;
+    int m = *n_dev;
+    return m < n ? m : n;
+}
+
+__device__ __forceinline__ void raise_status(int32_t* status, int code) {
+    if (status) atomicMin(status, code);   // codes are negative; keep the first/lowest
+}
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// stage-level forward declarations (one per .cu)
+int k_label_scan(cia_ctx* h, const int32_t* labels, int n_fields, int H, int W, int max_label,
+                 cia_region* regions, cudaStream_t s);
+int k_filter(cia_ctx* h, const uint16_t* images, int n_fields, int H, int W, int max_label,
+             cia_region* regions, const cia_params* p, cia_cell* cells, int cells_cap,
+             int32_t* n_cells_dev, int32_t* field_counts_dev, cudaStream_t s);
+int k_crop_resize(cia_ctx* h, const uint16_t* images, int H, int W, const cia_cell* cells,
+                  int n_cells, const int32_t* n_cells_dev, const cia_params* p, float* crops32,
+                  double* crops64, cudaStream_t s, uint16_t* levels_out = nullptr,
+                  const int64_t* level_offsets = nullptr);
+int k_cae_forward_fp32(cia_ctx* h, const float* crops, int n, const int32_t* n_dev, float* mse,
+                       float* mae, float* features, cudaStream_t s);
+int k_cae_forward_tc(cia_ctx* h, const float* crops, int n, const int32_t* n_dev, float* mse,
+                     float* mae, float* features, cudaStream_t s);
+int k_cae_tc_prepare(cia_ctx* h, int which);
+int k_svm_decision(cia_ctx* h, const float* features, int n, const int32_t* n_dev,
+                   double* dec_cons, double* dec_mod, int8_t* pred_cons, int8_t* pred_mod,
+                   double* pca_out, cudaStream_t s);
+int k_strain_accumulate(cia_ctx* h, const cia_cell* cells, int n, const int32_t* n_dev,
+                        const cia_scores* sc, const int32_t* field_strain, double* acc,
+                        int n_strains, cudaStream_t s);

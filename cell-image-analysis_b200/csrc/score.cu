@@ -1,0 +1,207 @@
+// score.cu -- K4 RobustScaler -> PCA projection, K5 RBF one-class SVM decision for
+// both detectors (exact fp64 direct-difference path), K6 per-strain accumulators.
+//
+// Replaces improved_detection.py:134-135 (scaler.transform, pca.transform), :138-142
+// (predict + decision_function of the two OneClassSVMs; libsvm k_function RBF,
+// sklearn/svm/src/libsvm/svm.cpp:461-472, decision sum - rho, sign rule sum > 0) and
+// the reductions behind :151-152 and :202-211.
+#include "common.cuh"
+
+namespace {
+
+constexpr int PT = 256;        // threads
+constexpr int PCELLS = 8;      // cells per block in the projection kernel
+
+// z[c] = sum_f x2[f] * Wt[f][c] - offset[c], fp64 accumulation over fp32-rounded inputs.
+// x2 mirrors sklearn's in-place float32 flow: x1 = f32(x - center), x2 = f32(f64(x1)/scale).
+__global__ void __launch_bounds__(PT)
+scaler_pca_kernel(const float* __restrict__ feat, int n_cells, const int32_t* __restrict__ n_dev,
+                  int F, int C, const double* __restrict__ center, const double* __restrict__ scale,
+                  int center_is_f32, const double* __restrict__ comp_t,
+                  const double* __restrict__ offset, int f32_flow, double* __restrict__ z_out) {
+    extern __shared__ float xs[];   // [PCELLS][F]
+    const int n = dev_count(n_cells, n_dev);
+    const int cell0 = blockIdx.x * PCELLS;
+    if (cell0 >= n) return;
+    const int nc = min(PCELLS, n - cell0);
+    for (int i = threadIdx.x; i < PCELLS * F; i += PT) {
+        const int k = i / F, f = i - k * F;
+        float v = 0.f;
+        if (k < nc) {
+            v = __ldg(feat + (size_t)(cell0 + k) * F + f);
+            if (center) {
+                if (center_is_f32) v = __fsub_rn(v, (float)center[f]);
+                else v = (float)__dsub_rn((double)v, center[f]);
+            }
+            if (scale) v = (float)__ddiv_rn((double)v, scale[f]);
+        }
+        xs[i] = v;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += PT) {
+        double acc[PCELLS];
+#pragma unroll
+        for (int k = 0; k < PCELLS; ++k) acc[k] = 0.0;
+        for (int f = 0; f < F; ++f) {
+            const double w = __ldg(comp_t + (size_t)f * C + c);
+#pragma unroll
+            for (int k = 0; k < PCELLS; ++k) acc[k] = fma((double)xs[k * F + f], w, acc[k]);
+        }
+        const double off = offset[c];
+#pragma unroll
+        for (int k = 0; k < PCELLS; ++k) {
+            if (k < nc) {
+                double z;
+                if (f32_flow) z = (double)__fsub_rn((float)acc[k], (float)off);
+                else z = __dsub_rn(acc[k], off);
+                z_out[(size_t)(cell0 + k) * C + c] = z;
+            }
+        }
+    }
+}
+
+constexpr int SCELLS = 8;   // cells per block in the SVM kernel
+
+// dec = sum_i coef_i * exp(-gamma * ||z - sv_i||^2) - rho  (fp64, direct difference).
+__global__ void __launch_bounds__(PT)
+svm_rbf_kernel(const double* __restrict__ z, int n_cells, const int32_t* __restrict__ n_dev, int D,
+               const double* __restrict__ sv_t, const double* __restrict__ coef, int n_sv,
+               int n_sv_pad, double gamma, double rho, double* __restrict__ dec,
+               int8_t* __restrict__ pred) {
+    extern __shared__ double zs[];  // [SCELLS][D]
+    __shared__ double red[SCELLS][PT / 32];
+    const int n = dev_count(n_cells, n_dev);
+    const int cell0 = blockIdx.x * SCELLS;
+    if (cell0 >= n) return;
+    const int nc = min(SCELLS, n - cell0);
+    for (int i = threadIdx.x; i < SCELLS * D; i += PT) {
+        const int k = i / D;
+        zs[i] = k < nc ? z[(size_t)cell0 * D + i] : 0.0;
+    }
+    __syncthreads();
+    double part[SCELLS];
+#pragma unroll
+    for (int k = 0; k < SCELLS; ++k) part[k] = 0.0;
+    for (int i = threadIdx.x; i < n_sv; i += PT) {
+        double d2[SCELLS];
+#pragma unroll
+        for (int k = 0; k < SCELLS; ++k) d2[k] = 0.0;
+        for (int d = 0; d < D; ++d) {
+            const double s = __ldg(sv_t + (size_t)d * n_sv_pad + i);
+#pragma unroll
+            for (int k = 0; k < SCELLS; ++k) {
+                const double df = zs[k * D + d] - s;
+                d2[k] = fma(df, df, d2[k]);
+            }
+        }
+        const double a = coef[i];
+#pragma unroll
+        for (int k = 0; k < SCELLS; ++k) part[k] = fma(a, exp(-gamma * d2[k]), part[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < SCELLS; ++k) {
+        const double v = warp_sum(part[k]);
+        if ((threadIdx.x & 31) == 0) red[k][threadIdx.x >> 5] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < nc) {
+        double s = 0.0;
+        for (int w = 0; w < PT / 32; ++w) s += red[threadIdx.x][w];
+        s -= rho;
+        dec[cell0 + threadIdx.x] = s;
+        pred[cell0 + threadIdx.x] = s > 0.0 ? 1 : -1;     // svm.cpp:2841
+    }
+}
+
+// K6: acc[strain] += {1, cons anomalous, mod anomalous, mse, mse^2, mae, mae^2, 0}
+__global__ void __launch_bounds__(256)
+strain_accumulate_kernel(const cia_cell* __restrict__ cells, int n_cells,
+                         const int32_t* __restrict__ n_dev, const float* __restrict__ mse,
+                         const float* __restrict__ mae, const int8_t* __restrict__ pc,
+                         const int8_t* __restrict__ pm, const int32_t* __restrict__ field_strain,
+                         double* __restrict__ acc, int n_strains) {
+    const int n = dev_count(n_cells, n_dev);
+    const int lane = threadIdx.x & 31;
+    for (int base = (blockIdx.x * blockDim.x + threadIdx.x) - lane; base < n; base += gridDim.x * blockDim.x) {
+        const int i = base + lane;
+        const bool valid = i < n;
+        int strain = -1;
+        double v[7] = {0, 0, 0, 0, 0, 0, 0};
+        if (valid) {
+            strain = field_strain ? field_strain[cells[i].field] : 0;
+            if (strain < 0 || strain >= n_strains) strain = -1;
+            const double a = (double)mse[i], b = (double)mae[i];
+            v[0] = 1.0; v[1] = pc[i] == -1 ? 1.0 : 0.0; v[2] = pm[i] == -1 ? 1.0 : 0.0;
+            v[3] = a; v[4] = a * a; v[5] = b; v[6] = b * b;
+        }
+        const unsigned act = __ballot_sync(0xffffffffu, strain >= 0);
+        if (strain >= 0) {
+            const unsigned m = __match_any_sync(act, strain);
+            const int leader = __ffs(m) - 1;
+#pragma unroll
+            for (int k = 0; k < 7; ++k) {
+                // fixed-order reduction over the group's lanes
+                double s = 0.0;
+                for (unsigned mm = m; mm; mm &= mm - 1) {
+                    const int src = __ffs(mm) - 1;
+                    s += __shfl_sync(m, v[k], src);
+                }
+                if (lane == leader) atomicAdd(&acc[(size_t)strain * 8 + k], s);
+            }
+        }
+    }
+}
+
+}  // namespace
+
+int k_svm_decision(cia_ctx* h, const float* features, int n, const int32_t* n_dev,
+                   double* dec_cons, double* dec_mod, int8_t* pred_cons, int8_t* pred_mod,
+                   double* pca_out, cudaStream_t s) {
+    if (n <= 0) return CIA_OK;
+    if (!h->sp.loaded || !h->svm[0].loaded || !h->svm[1].loaded) {
+        h->err = "cia_svm_decision: scaler/pca/svm artifacts not loaded";
+        return CIA_E_STATE;
+    }
+    const ScalerPca& sp = h->sp;
+    double* z = pca_out;
+    if (!z) {
+        int rc = ws_reserve(h, h->ws_feat, (size_t)n * sp.C * sizeof(double));
+        if (rc) return rc;
+        z = (double*)h->ws_feat.p;
+    }
+    static bool attr = false;
+    const size_t sm1 = (size_t)PCELLS * sp.F * sizeof(float);
+    if (sm1 > 200 * 1024) { h->err = "feature dimension too large"; return CIA_E_ARG; }
+    if (!attr) {
+        CIA_CUDA(cudaFuncSetAttribute(scaler_pca_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CIA_CUDA(cudaFuncSetAttribute(svm_rbf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr = true;
+    }
+    scaler_pca_kernel<<<(n + PCELLS - 1) / PCELLS, PT, sm1, s>>>(
+        features, n, n_dev, sp.F, sp.C, sp.has_center ? sp.center : nullptr,
+        sp.has_scale ? sp.scale : nullptr, sp.center_is_f32, sp.comp_t, sp.offset, sp.f32_flow, z);
+    CIA_LAUNCH_CHECK();
+    for (int which = 0; which < 2; ++which) {
+        const SvmModel& m = h->svm[which];
+        if (m.dim != sp.C) { h->err = "svm dimension != pca components"; return CIA_E_STATE; }
+        const size_t sm2 = (size_t)SCELLS * m.dim * sizeof(double);
+        svm_rbf_kernel<<<(n + SCELLS - 1) / SCELLS, PT, sm2, s>>>(
+            z, n, n_dev, m.dim, m.sv_t, m.coef, m.n_sv, m.n_sv_pad, m.gamma, m.rho,
+            which == 0 ? dec_cons : dec_mod, which == 0 ? pred_cons : pred_mod);
+        CIA_LAUNCH_CHECK();
+    }
+    return CIA_OK;
+}
+
+int k_strain_accumulate(cia_ctx* h, const cia_cell* cells, int n, const int32_t* n_dev,
+                        const cia_scores* sc, const int32_t* field_strain, double* acc,
+                        int n_strains, cudaStream_t s) {
+    if (n <= 0 || !acc) return CIA_OK;
+    int blocks = (n + 255) / 256;
+    if (blocks > h->num_sms * 8) blocks = h->num_sms * 8;
+    strain_accumulate_kernel<<<blocks, 256, 0, s>>>(cells, n, n_dev, sc->mse, sc->mae,
+                                                    sc->pred_conservative, sc->pred_moderate,
+                                                    field_strain, acc, n_strains);
+    CIA_LAUNCH_CHECK();
+    return CIA_OK;
+}

@@ -1,0 +1,86 @@
+"""Seeded synthetic microscopy fields (SURVEY.md §8d "synthetic field generator").
+
+Pure NumPy, shared by the CUDA path, the tests and the CPU baseline so that both
+sides score the *same* bytes.  A field is the pair the reference holds at
+improved_detection.py:63-66: ``green`` uint16[H, W] (single-channel case of
+det:57-59) and ``labels`` int32[H, W] as StarDist would return them.
+
+* labels: filled ellipses on a jittered grid; a later ellipse never overwrites an
+  earlier one (so labels never overlap, but a crowded field clips shapes);
+  ids 1..n with ~1 % deleted (absent ids), ~5 % pushed against the 10-px margin.
+* image: Poisson(100) background + per-cell amplitude * exp(-r^2), Poisson noise
+  again, clipped to 65535.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+__all__ = ["make_field", "make_fields", "FIELD_CONFIGS"]
+
+# name -> (H, W, n_cells, a_lo, a_hi, log_uniform)
+FIELD_CONFIGS = {
+    "config1": (2048, 2048, 520, 9.0, 30.0, False),   # BASELINE.json configs[0]/[1]
+    "config3": (4096, 4096, 5000, 8.0, 50.0, True),   # dense, wide bbox distribution
+    "tiny": (256, 256, 16, 9.0, 20.0, False),          # unit tests
+}
+
+
+def make_field(seed: int, H: int = 2048, W: int = 2048, n_cells: int = 520,
+               a_lo: float = 9.0, a_hi: float = 30.0, log_uniform: bool = False):
+    """Return (green uint16[H,W], labels int32[H,W]) for ``seed``."""
+    rng = np.random.default_rng(seed)
+    g = int(np.ceil(np.sqrt(n_cells)))
+    pitch_r, pitch_c = H / g, W / g
+    labels = np.zeros((H, W), np.int32)
+    signal = np.zeros((H, W), np.float32)
+
+    if log_uniform:
+        a = np.exp(rng.uniform(np.log(a_lo), np.log(a_hi), n_cells))
+    else:
+        a = rng.uniform(a_lo, a_hi, n_cells)
+    b = a * rng.uniform(0.5, 1.0, n_cells)
+    theta = rng.uniform(0.0, np.pi, n_cells)
+    amp = rng.uniform(500.0, 4000.0, n_cells)
+    jit = rng.uniform(-3.0, 3.0, (n_cells, 2))
+    deleted = rng.random(n_cells) < 0.01
+    to_margin = rng.random(n_cells) < 0.05
+    slots = rng.permutation(g * g)[:n_cells]
+
+    for i in range(n_cells):
+        gr, gc = divmod(int(slots[i]), g)
+        cr = (gr + 0.5) * pitch_r + jit[i, 0]
+        cc = (gc + 0.5) * pitch_c + jit[i, 1]
+        ct, st = np.cos(theta[i]), np.sin(theta[i])
+        # half extents of the rotated ellipse's bbox
+        er = np.sqrt((a[i] * st) ** 2 + (b[i] * ct) ** 2)
+        ec = np.sqrt((a[i] * ct) ** 2 + (b[i] * st) ** 2)
+        if to_margin[i]:
+            # slide towards the nearest image edge so the bbox enters the 10-px margin
+            if gr < g // 2:
+                cr = er + rng.uniform(1.0, 9.0)
+            else:
+                cr = H - 1 - er - rng.uniform(1.0, 9.0)
+        if cr - er < 0 or cc - ec < 0 or cr + er > H - 1 or cc + ec > W - 1:
+            continue  # bbox would leave the image: rejected (id stays absent)
+        ext_r, ext_c = 2.5 * er, 2.5 * ec
+        r0, r1 = max(int(cr - ext_r), 0), min(int(cr + ext_r) + 2, H)
+        c0, c1 = max(int(cc - ext_c), 0), min(int(cc + ext_c) + 2, W)
+        rr = np.arange(r0, r1, dtype=np.float64)[:, None] - cr
+        cx = np.arange(c0, c1, dtype=np.float64)[None, :] - cc
+        u = (cx * ct + rr * st) / a[i]
+        v = (-cx * st + rr * ct) / b[i]
+        r2 = u * u + v * v
+        signal[r0:r1, c0:c1] += (amp[i] * np.exp(-r2)).astype(np.float32)
+        if not deleted[i]:
+            win = labels[r0:r1, c0:c1]
+            win[(r2 <= 1.0) & (win == 0)] = i + 1
+
+    lam = rng.poisson(100.0, (H, W)).astype(np.float32) + signal
+    img = rng.poisson(lam)
+    green = np.minimum(img, 65535).astype(np.uint16)
+    return green, labels
+
+
+def make_fields(seeds, config: str = "config1"):
+    H, W, n, lo, hi, lu = FIELD_CONFIGS[config]
+    return [make_field(int(s), H, W, n, lo, hi, lu) for s in seeds]

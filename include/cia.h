@@ -1,0 +1,197 @@
+/* cia.h -- C-ABI of libcia.so, the sm_100a implementation of the per-cell
+ * screening hot path of Kmatsuo57/cell-image-analysis.
+ *
+ * The reference has no FFI: its seams are the Python methods
+ *   ProductionMutantScreening.extract_quality_cells   improved_detection.py:48-115
+ *   ProductionMutantScreening.compute_anomaly_scores  improved_detection.py:117-153
+ * (training twins CAE_improved_modeltrain.py:39-111, 328-339, 398-402).  Each entry
+ * point below names the reference lines it replaces.  INTEGRATION.md shows the
+ * ctypes stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative CIA_E_* code on failure and
+ *     never throws or prints; cia_last_error() gives the message for the handle;
+ *   - image / label / crop / score buffers are raw DEVICE pointers unless the name
+ *     ends in _host; artifact tensors passed to cia_load_* are HOST pointers and
+ *     are copied -- the library keeps no reference to caller memory;
+ *   - `stream` is a cudaStream_t passed as void*; calls only enqueue work unless
+ *     stated otherwise ("synchronises");
+ *   - counts that are data dependent live in device memory (`*_dev`); a host
+ *     capacity bounds every output buffer and overflow is reported through
+ *     cia_check_status(), never by writing out of bounds.
+ */
+#ifndef CIA_H
+#define CIA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CIA_OK            0
+#define CIA_E_CUDA       -1   /* a CUDA runtime call failed                         */
+#define CIA_E_ARG        -2   /* bad argument                                       */
+#define CIA_E_STATE      -3   /* artifacts not loaded / wrong topology              */
+#define CIA_E_CAPACITY   -4   /* an output capacity was exceeded on the device      */
+#define CIA_E_LABEL      -5   /* a label outside [0, max_label] was seen            */
+#define CIA_E_UNSUPPORTED -6  /* bbox too large for the crop kernel's scratch, etc. */
+
+#define CIA_CROP 64                 /* det:99  resize target                         */
+#define CIA_FEATURES 2048           /* 8*8*32, det:131 HWC flatten                   */
+
+typedef struct cia_ctx* cia_handle;
+
+/* One labelled region, as skimage.measure.regionprops exposes it (det:67, 73, 80):
+ * half-open bbox and pixel count, plus the exact integer raw moments (image
+ * coordinates) the eccentricity of det:84 is derived from.  A zeroed record is an
+ * absent label.  Slot i of a field's table is label i+1. */
+typedef struct cia_region {
+    uint32_t area;                  /* prop.area                                     */
+    int32_t  minr, minc, maxr, maxc;/* prop.bbox (half open)                         */
+    int32_t  flags;                 /* bit0: passed all gates of det:76-95           */
+    uint64_t m10, m01, m20, m02, m11; /* sum r, sum c, sum r^2, sum c^2, sum r*c     */
+} cia_region;                        /* 64 bytes                                      */
+
+/* One cell that passed the gates, in reference order: fields in call order, labels
+ * ascending (det:72).  The stats are the cell_stats dict of det:103-109 (solidity is
+ * out of scope: dead in the screening path). */
+typedef struct cia_cell {
+    int32_t field;                  /* index of the field inside the call            */
+    int32_t label;
+    int32_t minr, minc, maxr, maxc;
+    int32_t area;
+    int32_t pad_;
+    double  eccentricity;
+    double  mean_intensity;
+    double  std_intensity;
+} cia_cell;                          /* 56 bytes                                      */
+
+/* Literals of det:76-99 / train:66-93 (defaults via cia_default_params). */
+typedef struct cia_params {
+    int32_t border_margin;          /* 10                                            */
+    int32_t area_min, area_max;     /* 200, 8000                                     */
+    double  ecc_max;                /* 0.95                                          */
+    double  mean_min, std_min;      /* 0.5, 0.1                                      */
+    double  clip_limit;             /* 0.02                                          */
+} cia_params;
+
+/* Per-cell scores, the arrays of the dict at det:144-153 (signs as libsvm returns
+ * them: decision > 0 <=> inlier; the Python layer negates like det:149-150). */
+typedef struct cia_scores {
+    float*  mse;                    /* [n]  det:126                                  */
+    float*  mae;                    /* [n]  det:127                                  */
+    double* dec_conservative;       /* [n]  det:141                                  */
+    double* dec_moderate;           /* [n]  det:142                                  */
+    int8_t* pred_conservative;      /* [n]  det:138  (+1 / -1)                       */
+    int8_t* pred_moderate;          /* [n]  det:139                                  */
+} cia_scores;
+
+/* ---- lifecycle ---------------------------------------------------------- */
+int  cia_version(void);
+int  cia_create(int device, cia_handle* out);
+int  cia_destroy(cia_handle h);
+const char* cia_last_error(cia_handle h);
+void cia_default_params(cia_params* p);
+/* Reads back the device status word (synchronises `stream`): 0 or a CIA_E_* code
+ * raised by a kernel since the last check (capacity / label / unsupported). */
+int  cia_check_status(cia_handle h, void* stream);
+
+/* ---- artifacts (replaces load_trained_models, det:23-41) ----------------- */
+/* which = 0: best_autoencoder.keras (7 Conv2D, 6 BatchNormalization);
+ * which = 1: encoder.keras (3 + 3) when its weights differ from the autoencoder's
+ *            encoder half (det:29-30, 130); never loading it makes the feature tap of
+ *            the autoencoder pass serve det:130.
+ * kernels[i]: float32 HWIO (3,3,Cin,Cout) as Keras stores them; bn[4*i+{0,1,2,3}] =
+ * gamma, beta, moving_mean, moving_variance of BatchNormalization i. */
+int cia_load_cae(cia_handle h, int which, int n_conv,
+                 const float* const* kernels, const float* const* biases,
+                 const float* const* bn, float bn_eps);
+/* RobustScaler (det:134) + PCA (det:135).  All vectors as float64; f32_flow=1 mirrors
+ * scikit-learn's dtype flow for float32-fitted artifacts (every intermediate rounded
+ * to float32), 0 the float64-components flow.  pca_offset = mean_ @ components_.T
+ * evaluated by the caller exactly as sklearn does. */
+int cia_load_scaler_pca(cia_handle h, int n_features, int n_components,
+                        const double* center /* or NULL */, const double* scale /* or NULL */,
+                        int center_is_f32, const double* components /* [C,F] */,
+                        const double* pca_offset /* [C] */, int f32_flow);
+/* OneClassSVM, RBF kernel (det:138-142).  which: 0 conservative, 1 moderate.
+ * rho = -intercept_[0]. */
+int cia_load_svm(cia_handle h, int which, int n_sv, int dim,
+                 const double* support_vectors /* [n_sv, dim] */,
+                 const double* dual_coef /* [n_sv] */, double gamma, double rho);
+
+/* ---- stage entry points -------------------------------------------------- */
+/* regionprops bbox/area/moments (det:67).  labels: int32 [n_fields, H, W];
+ * regions: [n_fields, max_label], zeroed by the call. */
+int cia_label_scan(cia_handle h, const int32_t* labels, int n_fields, int H, int W,
+                   int max_label, cia_region* regions, void* stream);
+/* Quality gates of det:76-95 and compaction in reference order.
+ * images: uint16 [n_fields, H, W].  cells: capacity cells_cap; n_cells_dev: int32
+ * total; field_counts_dev: int32 [n_fields] or NULL. */
+int cia_filter(cia_handle h, const uint16_t* images, int n_fields, int H, int W,
+               int max_label, cia_region* regions, const cia_params* params,
+               cia_cell* cells, int cells_cap, int32_t* n_cells_dev,
+               int32_t* field_counts_dev, void* stream);
+/* det:88 crop + det:98 equalize_adapthist + det:99 resize + det:122 float32 cast.
+ * n_cells: host upper bound; n_cells_dev (may be NULL) the device count.
+ * crops32: float32 [n,64,64]; crops64 (may be NULL): float64 [n,64,64]. */
+int cia_crop_resize(cia_handle h, const uint16_t* images, int H, int W,
+                    const cia_cell* cells, int n_cells, const int32_t* n_cells_dev,
+                    const cia_params* params, float* crops32, double* crops64,
+                    void* stream);
+/* Test tap: same as cia_crop_resize, additionally writing the uint16 CLAHE levels (the
+ * bit-exact integer core of det:98, before the final [0,1] rescale) of cell i as h*w
+ * values at levels_out + level_offsets[i] (device pointers). */
+int cia_debug_clahe_levels(cia_handle h, const uint16_t* images, int H, int W,
+                           const cia_cell* cells, int n_cells, const cia_params* params,
+                           float* crops32, uint16_t* levels_out,
+                           const int64_t* level_offsets, void* stream);
+/* autoencoder.predict + MSE/MAE (det:125-127) and encoder.predict + flatten
+ * (det:130-131).  features (may be NULL): float32 [n, 2048] HWC order.
+ * precision: 0 = fp32 CUDA-core path, 1 = tcgen05 tensor-core path. */
+int cia_cae_forward(cia_handle h, const float* crops32, int n_cells,
+                    const int32_t* n_cells_dev, float* mse, float* mae,
+                    float* features, int precision, void* stream);
+/* scaler.transform -> pca.transform -> both detectors' decision_function / predict
+ * (det:134-142).  pca_out (may be NULL): float64 [n, n_components]. */
+int cia_svm_decision(cia_handle h, const float* features, int n_cells,
+                     const int32_t* n_cells_dev, double* dec_cons, double* dec_mod,
+                     int8_t* pred_cons, int8_t* pred_mod, double* pca_out, void* stream);
+/* Per-strain accumulators behind det:151-152, 202-211: acc[s] = {n, n_cons_anom,
+ * n_mod_anom, sum mse, sum mse^2, sum mae, sum mae^2, 0} (float64 [S,8], added to).
+ * field_strain: int32 [n_fields] strain id of each field of the call. */
+int cia_strain_accumulate(cia_handle h, const cia_cell* cells, int n_cells,
+                          const int32_t* n_cells_dev, const cia_scores* scores,
+                          const int32_t* field_strain, double* acc, int n_strains,
+                          void* stream);
+
+/* ---- fused path ----------------------------------------------------------- */
+/* The whole hot path for a batch of device-resident fields, with no host
+ * synchronisation: scan -> gates -> crop/CLAHE/resize -> CAE -> scaler/PCA/SVM ->
+ * strain accumulate.  Optional outputs may be NULL (crops32, features, acc). */
+int cia_screen_fields(cia_handle h, const uint16_t* images, const int32_t* labels,
+                      int n_fields, int H, int W, int max_label,
+                      const cia_params* params, int precision,
+                      cia_cell* cells, int cells_cap, int32_t* n_cells_dev,
+                      int32_t* field_counts_dev, const cia_scores* scores,
+                      float* crops32, float* features,
+                      const int32_t* field_strain, double* acc, int n_strains,
+                      void* stream);
+/* Same, from HOST buffers (pinned or pageable): copies the fields in, runs the
+ * path, copies cells + scores out and synchronises.  All outputs are host
+ * pointers; returns the number of cells through *n_cells_host. */
+int cia_screen_fields_host(cia_handle h, const uint16_t* images_host,
+                           const int32_t* labels_host, int n_fields, int H, int W,
+                           int max_label, const cia_params* params, int precision,
+                           cia_cell* cells_host, int cells_cap, int32_t* n_cells_host,
+                           int32_t* field_counts_host, const cia_scores* scores_host,
+                           void* stream);
+
+/* Number of kernels this library has launched on the handle (bench's gpu_launches). */
+int64_t cia_launch_count(cia_handle h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CIA_H */

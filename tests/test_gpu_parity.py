@@ -1,0 +1,331 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the CPU oracle and the
+committed golden vectors.  Tolerances are BASELINE.json's north_star gates:
+  label / bbox / area .......... bit-exact
+  resized crops ................ |d| <= 1e-5 * max(|ref|, 1e-3)
+  reconstruction MSE ........... <= 1e-3 relative
+  SVM decision ................. identical signs, |d| <= 1e-4
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cae as ocae
+from oracle import clahe as oclahe
+from oracle import extraction as oext
+from oracle import regions as oreg
+from oracle import scoring as oscoring
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev_field(eng, green, labels):
+    g = torch.from_numpy(np.ascontiguousarray(green).view(np.int16)).to(eng.tdev)[None]
+    l = torch.from_numpy(np.ascontiguousarray(labels, dtype=np.int32)).to(eng.tdev)[None]
+    return g, l
+
+
+def _regions_np(regions_t):
+    from cell_image_analysis_b200 import _lib
+    return regions_t.cpu().numpy().view(_lib.REGION_DTYPE).reshape(regions_t.shape[0], -1)
+
+
+def _check_table(reg, tab, labels):
+    present = np.nonzero(reg["area"])[0] + 1
+    assert np.array_equal(present, tab[:, 0])
+    r = reg[tab[:, 0] - 1]
+    assert np.array_equal(r["minr"], tab[:, 1]) and np.array_equal(r["minc"], tab[:, 2])
+    assert np.array_equal(r["maxr"], tab[:, 3]) and np.array_equal(r["maxc"], tab[:, 4])
+    assert np.array_equal(r["area"], tab[:, 5])
+    # raw moments of a few regions, exact integers
+    for row in tab[:: max(1, len(tab) // 12)]:
+        lab = int(row[0])
+        n, m10, m01, m20, m02, m11 = oreg.raw_moments(labels, lab, tuple(row[1:5]))
+        q = reg[lab - 1]
+        assert (int(q["area"]), int(q["m10"]), int(q["m01"]), int(q["m20"]), int(q["m02"]),
+                int(q["m11"])) == (n, m10, m01, m20, m02, m11)
+
+
+def test_label_scan_bit_exact_tiny(screener, golden_tiny):
+    eng = screener.engine
+    g, l = _dev_field(eng, golden_tiny["green"], golden_tiny["labels"])
+    reg = _regions_np(eng.label_scan(l, int(golden_tiny["labels"].max())))[0]
+    eng.check_status()
+    _check_table(reg, golden_tiny["table"], golden_tiny["labels"])
+
+
+def test_label_scan_bit_exact_config1(screener, field_config1, golden_config1):
+    eng = screener.engine
+    green, labels = field_config1
+    g, l = _dev_field(eng, green, labels)
+    reg = _regions_np(eng.label_scan(l, int(labels.max())))[0]
+    eng.check_status()
+    _check_table(reg, golden_config1["table"], labels)
+    # and against the live oracle (scipy find_objects)
+    assert np.array_equal(oreg.region_table(labels), golden_config1["table"])
+
+
+@pytest.mark.parametrize("W", [250, 253, 131])
+def test_label_scan_odd_widths(screener, W):
+    """Widths that are not multiples of 4 / 128 take the scalar tail path."""
+    from cell_image_analysis_b200 import synth
+    eng = screener.engine
+    green, labels = synth.make_field(11, 200, 256, 12, 9.0, 20.0)
+    labels = np.ascontiguousarray(labels[:, :W])
+    l = torch.from_numpy(labels).to(eng.tdev)[None]
+    reg = _regions_np(eng.label_scan(l, max(int(labels.max()), 1)))[0]
+    eng.check_status()
+    _check_table(reg, oreg.region_table(labels), labels)
+
+
+def test_filter_and_stats_config1(screener, field_config1, golden_config1):
+    green, labels = field_config1
+    cells, stats, rec = screener.extract_quality_cells_from_labels(green, labels, return_regions=True)
+    assert np.array_equal(rec["label"], golden_config1["kept_labels"])
+    assert len(cells) == len(stats) == len(golden_config1["kept_labels"])
+    np.testing.assert_allclose(rec["eccentricity"], golden_config1["ecc"], rtol=0, atol=1e-9)
+    np.testing.assert_array_equal(rec["mean_intensity"], golden_config1["mean"])
+    np.testing.assert_allclose(rec["std_intensity"], golden_config1["std"], rtol=1e-12)
+
+
+def test_clahe_levels_bit_exact(screener, golden_tiny):
+    """The integer core of equalize_adapthist: uint16 levels identical to the oracle."""
+    eng = screener.engine
+    green, labels = golden_tiny["green"], golden_tiny["labels"]
+    g, l = _dev_field(eng, green, labels)
+    regions = eng.label_scan(l, int(labels.max()))
+    cells, counts = eng.filter(g, regions, int(labels.max()))
+    n = int(counts[0].item())
+    assert n == len(golden_tiny["kept_labels"])
+    bb = golden_tiny["kept_bbox"]
+    sizes = (bb[:, 2] - bb[:, 0]) * (bb[:, 3] - bb[:, 1])
+    lv, offs = eng.debug_clahe_levels(g, cells, n, sizes)
+    assert np.array_equal(lv, golden_tiny["levels"])
+
+
+def test_clahe_levels_bit_exact_config1(screener, field_config1):
+    eng = screener.engine
+    green, labels = field_config1
+    g, l = _dev_field(eng, green, labels)
+    regions = eng.label_scan(l, int(labels.max()))
+    cells, counts = eng.filter(g, regions, int(labels.max()))
+    n = int(counts[0].item())
+    from cell_image_analysis_b200 import _lib
+    rec = cells[:n].cpu().numpy().view(_lib.CELL_DTYPE).reshape(-1)
+    sizes = (rec["maxr"] - rec["minr"]) * (rec["maxc"] - rec["minc"])
+    lv, offs = eng.debug_clahe_levels(g, cells, n, sizes)
+    bad = 0
+    for i in range(0, n, 7):
+        r = rec[i]
+        ref = oclahe.clahe_levels(green[r["minr"]:r["maxr"], r["minc"]:r["maxc"]])
+        bad += int(not np.array_equal(lv[offs[i]:offs[i + 1]], ref.ravel()))
+    assert bad == 0
+
+
+def _crop_close(got, ref):
+    tol = 1e-5 * np.maximum(np.abs(ref), 1e-3)
+    d = np.abs(got - ref)
+    return d, tol
+
+
+def test_crops_match_golden_tiny(screener, golden_tiny):
+    cells, stats = screener.extract_quality_cells_from_labels(golden_tiny["green"], golden_tiny["labels"])
+    got = np.array(cells)
+    assert got.dtype == np.float64 and got.shape == golden_tiny["crops"].shape
+    d, tol = _crop_close(got, golden_tiny["crops"])
+    assert (d <= tol).all(), f"max |d| {d.max():.3e}"
+
+
+def test_crops_match_golden_config1(screener, field_config1, golden_config1):
+    green, labels = field_config1
+    cells, _ = screener.extract_quality_cells_from_labels(green, labels)
+    got = np.array(cells)[golden_config1["crop_subset_idx"]]
+    d, tol = _crop_close(got, golden_config1["crop_subset"])
+    assert (d <= tol).all(), f"max |d| {d.max():.3e}"
+
+
+def test_cae_fp32_matches_oracle(screener, golden_tiny):
+    r = screener.compute_anomaly_scores(list(golden_tiny["crops"]))
+    np.testing.assert_allclose(r["reconstruction_mse"], golden_tiny["mse"], rtol=1e-3)
+    np.testing.assert_allclose(r["reconstruction_mae"], golden_tiny["mae"], rtol=1e-3)
+    assert r["reconstruction_mse"].dtype == np.float32
+    assert r["conservative_predictions"].dtype == np.intp
+    assert r["conservative_scores"].dtype == np.float64
+
+
+def test_features_and_pca(screener, golden_tiny):
+    eng = screener.engine
+    X = golden_tiny["crops"].astype(np.float32)
+    n = len(X)
+    mse, mae, feat = eng.cae_forward(torch.from_numpy(X).to(eng.tdev), n)
+    f = feat[:n].cpu().numpy()
+    ref = golden_tiny["features"]
+    assert np.abs(f - ref).max() <= 1e-4 * max(1.0, np.abs(ref).max())
+    dc, dm, pc, pm, z = eng.svm_decision(feat, n, want_pca=True)
+    z = z[:n].cpu().numpy()
+    assert np.abs(z - golden_tiny["pca"]).max() <= 1e-3 * max(1.0, np.abs(golden_tiny["pca"]).max())
+    # the SVM kernel itself: real libsvm on the GPU's own PCA output must agree to fp64 noise
+    for det, d_gpu, p_gpu in ((screener.detector_conservative, dc, pc), (screener.detector_moderate, dm, pm)):
+        ref_dec = det.decision_function(z)
+        np.testing.assert_allclose(d_gpu[:n].cpu().numpy(), ref_dec, rtol=0, atol=1e-9)
+        assert np.array_equal(p_gpu[:n].cpu().numpy().astype(np.intp), det.predict(z))
+
+
+def test_svm_scores_within_gate(screener, golden_tiny):
+    r = screener.compute_anomaly_scores(list(golden_tiny["crops"]))
+    for key, dec, pred in (("conservative", "dec_cons", "pred_cons"), ("moderate", "dec_mod", "pred_mod")):
+        d = np.abs(-r[f"{key}_scores"] - golden_tiny[dec])
+        assert d.max() <= 1e-4, f"{key}: max |d dec| {d.max():.3e}"
+        assert np.array_equal(r[f"{key}_predictions"], golden_tiny[pred])
+
+
+def test_end_to_end_config1(screener, field_config1, golden_config1):
+    """B2' -> B3 on the 2048x2048 config-1 field: same kept cells, scores inside the gates."""
+    green, labels = field_config1
+    cells, stats = screener.extract_quality_cells_from_labels(green, labels)
+    r = screener.compute_anomaly_scores(cells)
+    g = golden_config1
+    assert len(cells) == len(g["kept_labels"])
+    np.testing.assert_allclose(r["reconstruction_mse"], g["mse"], rtol=1e-3)
+    np.testing.assert_allclose(r["reconstruction_mae"], g["mae"], rtol=1e-3)
+    for key, dec, pred in (("conservative", "dec_cons", "pred_cons"), ("moderate", "dec_mod", "pred_mod")):
+        d = np.abs(-r[f"{key}_scores"] - g[dec])
+        near = np.abs(g[dec]) < 1e-4          # reported separately
+        assert d.max() <= 1e-4, f"{key}: max |d dec| {d.max():.3e}"
+        assert np.array_equal(r[f"{key}_predictions"][~near], g[pred][~near])
+    assert abs(r["conservative_anomaly_rate"] - np.mean(g["pred_cons"] == -1)) < 1e-12
+
+
+def test_fused_equals_staged_and_host(screener, field_config1):
+    """cia_screen_fields (device) and cia_screen_fields_host give the staged results."""
+    from cell_image_analysis_b200 import _lib, synth
+    eng = screener.engine
+    fields = [field_config1, synth.make_field(1)]
+    greens = np.stack([f[0] for f in fields])
+    labs = np.stack([f[1] for f in fields])
+    max_label = int(labs.max())
+    gi = torch.from_numpy(greens.view(np.int16)).to(eng.tdev)
+    li = torch.from_numpy(labs).to(eng.tdev)
+    cap = 2 * max_label
+    out = eng.alloc_outputs(cap, 2, keep_crops=True)
+    strain = torch.tensor([0, 1], dtype=torch.int32, device=eng.tdev)
+    acc = torch.zeros((2, 8), dtype=torch.float64, device=eng.tdev)
+    eng.screen_fields(gi, li, max_label, out, field_strain=strain, acc=acc)
+    eng.check_status()
+    cnt = out["counts"].cpu().numpy()
+    n = int(cnt[0])
+    rec = out["cells"][:n].cpu().numpy().view(_lib.CELL_DTYPE).reshape(-1)
+    mse_all = out["mse"][:n].cpu().numpy()
+    dec_all = out["dec_cons"][:n].cpu().numpy()
+    start = 0
+    for fi, (green, labels) in enumerate(fields):
+        cells, stats, r2 = screener.extract_quality_cells_from_labels(green, labels, return_regions=True)
+        k = len(cells)
+        assert cnt[1 + fi] == k
+        sl = slice(start, start + k)
+        assert np.array_equal(rec["label"][sl], r2["label"]) and (rec["field"][sl] == fi).all()
+        s = screener.compute_anomaly_scores(cells)
+        np.testing.assert_array_equal(mse_all[sl], s["reconstruction_mse"])
+        np.testing.assert_array_equal(dec_all[sl], -s["conservative_scores"])
+        # accumulator row
+        a = acc[fi].cpu().numpy()
+        assert a[0] == k and a[1] == np.sum(s["conservative_predictions"] == -1)
+        assert a[2] == np.sum(s["moderate_predictions"] == -1)
+        np.testing.assert_allclose(a[3], s["reconstruction_mse"].astype(np.float64).sum(), rtol=1e-12)
+        start += k
+    assert start == n
+    # host-buffer entry point
+    h = eng.screen_fields_host(greens, labs, max_label, cap)
+    assert h["n_cells"] == n and np.array_equal(h["field_counts"], cnt[1:])
+    np.testing.assert_array_equal(h["mse"], mse_all)
+    np.testing.assert_array_equal(h["dec_cons"], dec_all)
+    assert np.array_equal(h["cells"]["label"], rec["label"])
+
+
+def test_empty_and_degenerate_inputs(screener):
+    z = np.zeros((128, 128), np.int32)
+    g = np.full((128, 128), 100, np.uint16)
+    assert screener.extract_quality_cells_from_labels(g, z) == ([], [])
+    assert screener.compute_anomaly_scores([]) == {}
+    # one label, constant image -> std gate drops it (det:94)
+    z2 = z.copy()
+    z2[40:70, 40:70] = 1
+    assert screener.extract_quality_cells_from_labels(g, z2) == ([], [])
+    # label touching the margin -> border gate (det:76)
+    rng = np.random.default_rng(0)
+    g2 = rng.integers(50, 4000, (128, 128)).astype(np.uint16)
+    z3 = z.copy()
+    z3[5:40, 40:70] = 3
+    assert screener.extract_quality_cells_from_labels(g2, z3) == ([], [])
+    z3[50:80, 50:80] = 7
+    cells, stats = screener.extract_quality_cells_from_labels(g2, z3)
+    assert len(cells) == 1 and stats[0]["area"] == 900.0
+
+
+def _blob_field(side, seed=5):
+    """One label made of four discs at the corners of a square: small area, large bbox,
+    near-isotropic moments (passes the eccentricity gate) -> exercises the big-bbox classes."""
+    H = W = side + 80
+    rng = np.random.default_rng(seed)
+    labels = np.zeros((H, W), np.int32)
+    yy, xx = np.mgrid[0:H, 0:W]
+    rad = 20
+    for cy, cx in ((40 + rad, 40 + rad), (40 + rad, 40 + side - rad), (40 + side - rad, 40 + rad),
+                   (40 + side - rad, 40 + side - rad)):
+        labels[(yy - cy) ** 2 + (xx - cx) ** 2 <= rad * rad] = 2
+    green = rng.poisson(300, (H, W)).astype(np.uint16)
+    green[labels > 0] += 2000
+    return green, labels
+
+
+@pytest.mark.parametrize("side", [120, 200, 330])
+def test_large_bbox_classes(screener, side):
+    green, labels = _blob_field(side)
+    ref_cells, ref_stats, kept, tab = oext.extract_quality_cells_from_labels(green, labels)
+    cells, stats = screener.extract_quality_cells_from_labels(green, labels)
+    assert len(cells) == len(ref_cells) == 1
+    d, tol = _crop_close(np.array(cells), np.array(ref_cells))
+    assert (d <= tol).all(), f"side {side}: max |d| {d.max():.3e}"
+
+
+def test_error_codes(screener):
+    from cell_image_analysis_b200 import _lib
+    eng = screener.engine
+    labels = np.zeros((64, 64), np.int32)
+    labels[10:20, 10:20] = 9
+    l = torch.from_numpy(labels).to(eng.tdev)[None]
+    eng.label_scan(l, 4)                      # label 9 > max_label 4
+    with pytest.raises(_lib.CiaError) as e:
+        eng.check_status()
+    assert e.value.code == -5
+    # capacity overflow in the fused path
+    from cell_image_analysis_b200 import synth
+    green, lab = synth.make_field(2, 512, 512, 40, 9.0, 14.0)
+    gi = torch.from_numpy(green.view(np.int16)).to(eng.tdev)[None]
+    li = torch.from_numpy(lab).to(eng.tdev)[None]
+    out = eng.alloc_outputs(2, 1)
+    eng.screen_fields(gi, li, int(lab.max()), out)
+    with pytest.raises(_lib.CiaError) as e:
+        eng.check_status()
+    assert e.value.code == -4
+
+
+def test_separate_encoder_weights(tmp_path, model_dir, golden_tiny, oracle_weights):
+    """D8: encoder.keras with weights that differ from the autoencoder's encoder half."""
+    import shutil
+    from oracle import h5write
+    from cell_image_analysis_b200.screening import ProductionMutantScreening
+    d = tmp_path / "models"
+    shutil.copytree(model_dir, d)
+    w2 = {"kernels": [k.copy() for k in oracle_weights["kernels"]],
+          "biases": [b.copy() for b in oracle_weights["biases"]],
+          "bns": [tuple(a.copy() for a in t) for t in oracle_weights["bns"]]}
+    w2["kernels"][1] = (w2["kernels"][1] * 1.01).astype(np.float32)
+    h5write.write_keras(str(d / "encoder.keras"), w2, encoder_only=True, name_offset=7)
+    s = ProductionMutantScreening(str(d), segmenter=lambda ch: None)
+    assert s.engine.encoder_separate
+    r = s.compute_anomaly_scores(list(golden_tiny["crops"]))
+    ref = oscoring.compute_anomaly_scores(list(golden_tiny["crops"]), oracle_weights, w2, s.scaler, s.pca,
+                                          s.detector_conservative, s.detector_moderate)
+    np.testing.assert_allclose(r["reconstruction_mse"], ref["reconstruction_mse"], rtol=1e-3)
+    assert np.abs(r["conservative_scores"] - ref["conservative_scores"]).max() <= 1e-4
+    s.engine.close()
