@@ -1,0 +1,374 @@
+#!/usr/bin/env python
+"""bench.py -- cells scored/sec through the per-cell screening hot path
+(label scan -> gates -> crop + CLAHE + resize -> CAE recon error -> scaler/PCA -> 2x RBF
+one-class SVM -> per-strain accumulators), BASELINE.json's metric.
+
+  python bench.py --gpus N --steps K --warmup W           # CUDA path (this repo)
+  python bench.py --impl reference --gpus N --steps K ...  # reference CPU path (oracle port)
+
+A step is one pass over ``--fields`` synthetic 2048x2048 fields (config 2 of
+BASELINE.json: 1000 fields, ~500k cells) per GPU, visiting a resident pool of
+``--pool`` distinct seeded fields chunk by chunk (the pool, 25 MB per field, is far
+larger than the 126 MB L2).  ``value`` is timed with the pool resident in HBM; ``e2e``
+runs the same pass from pinned HOST memory with the H2D copies and the D2H read of the
+per-cell results inside the timed region.  Multi-GPU: one process per GPU, fields
+sharded (each rank its own 1000 visits, weak scaling), one NCCL all-reduce of the
+per-strain accumulator per step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "cells scored/sec (crop+resize+CAE+SVM)"
+UNIT = "cells/s"
+MODEL_DIR = os.path.join(ROOT, "tests", "golden", "model_dir")
+FLOP_PER_CELL = 100.27e6          # L1..L7 conv MACs*2
+H = W = 2048
+N_CELLS_PER_FIELD = 520
+
+
+def _gen_field(seed):
+    from cell_image_analysis_b200 import synth
+    return synth.make_field(int(seed))
+
+
+def make_pool(seeds):
+    import multiprocessing as mp
+    with mp.get_context("fork").Pool(min(len(seeds), os.cpu_count() or 1)) as pool:
+        fields = pool.map(_gen_field, list(seeds))
+    greens = np.stack([f[0] for f in fields])
+    labels = np.stack([f[1] for f in fields])
+    return greens, labels
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d["bf16_tflops_sustained"],
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.gpu, self.proc, self.lines = gpu, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------
+# reference CPU path (oracle port), used by cpu_baseline and --impl reference
+# ---------------------------------------------------------------------------
+_REF = {}
+
+
+def _ref_init(threads):
+    import pickle
+    import torch
+    torch.set_num_threads(threads)
+    from cell_image_analysis_b200.artifacts import load_model_dir
+    a = load_model_dir(MODEL_DIR)
+    ae = a["autoencoder"]
+    _REF["w"] = {"kernels": ae["kernels"], "biases": ae["biases"], "bns": ae["bns"]}
+    _REF["sk"] = a["sklearn"]
+
+
+def _ref_field(idx):
+    """One field through the restated reference path: per-cell Python loop
+    (improved_detection.py:72-111) then one compute_anomaly_scores call (det:117-153)."""
+    from oracle import extraction, scoring
+    green, labels = _REF["fields"][idx]
+    t0 = time.perf_counter()
+    cells, stats, kept, tab = extraction.extract_quality_cells_from_labels(green, labels)
+    t1 = time.perf_counter()
+    sk = _REF["sk"]
+    s = scoring.compute_anomaly_scores(cells, _REF["w"], _REF["w"], sk["scaler"], sk["pca"],
+                                       sk["detector_conservative"], sk["detector_moderate"], exact=False)
+    t2 = time.perf_counter()
+    return len(cells), t1 - t0, t2 - t1
+
+
+def cpu_baseline_inline(n_fields=2):
+    """Single process, as the reference runs: Python per-cell loop, BLAS/conv threads =
+    all cores, libsvm serial.  Bounded sample; field synthesis is outside the timing."""
+    cores = os.cpu_count() or 1
+    _ref_init(cores)
+    _REF["fields"] = [_gen_field(s) for s in range(n_fields)]
+    n, te, ts = 0, 0.0, 0.0
+    for i in range(n_fields):
+        k, a, b = _ref_field(i)
+        n += k; te += a; ts += b
+    return {"value": n / (te + ts), "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n_fields} config-1 fields (seeds 0..{n_fields - 1}, {n} cells), restated reference "
+                      f"CPU path (oracle; scipy/sklearn real, skimage/Keras restated), single process, "
+                      f"{cores} BLAS/conv threads; extraction {te:.1f}s, scoring {ts:.1f}s"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (the oracle port;
+    the reference itself is two Python scripts whose skimage/TensorFlow imports are not
+    installable here) on all host cores: one worker process per core, each running the
+    reference's single-threaded per-cell loop on its own field."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    per_step = cores
+    _REF["fields"] = [_gen_field(s) for s in range(per_step)]      # inherited by the forked workers
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores, initializer=_ref_init, initargs=(1,)) as pool:
+        for _ in range(args.warmup):
+            pool.map(_ref_field, range(per_step), chunksize=1)
+        n, dt = 0, 0.0
+        for _ in range(args.steps):
+            t_s = time.perf_counter()
+            res = pool.map(_ref_field, range(per_step), chunksize=1)
+            dt += time.perf_counter() - t_s
+            n += sum(r[0] for r in res)
+    val = n / dt
+    sample = (f"{per_step} config-1 fields per step ({n // max(args.steps, 1)} cells), one worker process per "
+              f"core ({cores}) running the reference's per-cell Python loop + one scoring call per field")
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64/f32 (CPU)",
+            "data": "synthetic",
+            "config": {"workload": "config 2 sample: 2048x2048 uint16 fields + int32 labels, ~475 scored cells/field",
+                       "fields_per_step": per_step},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from cell_image_analysis_b200.artifacts import load_model_dir
+    from cell_image_analysis_b200.batch import BatchScreen
+    from cell_image_analysis_b200.distributed import allreduce_strain_acc
+    from cell_image_analysis_b200.screening import Engine
+
+    eng = Engine(device=local, precision=args.precision)
+    eng.load_artifacts(load_model_dir(MODEL_DIR))
+    dev = eng.tdev
+
+    Fc, P, NF = args.chunk, args.pool, args.fields
+    assert P % Fc == 0 and NF % Fc == 0
+    greens, labels = make_pool([rank * 100003 + i for i in range(P)])
+    max_label = int(labels.max())
+    g_pin = torch.from_numpy(greens.view(np.int16)).pin_memory()
+    l_pin = torch.from_numpy(labels).pin_memory()
+    g_dev, l_dev = g_pin.to(dev), l_pin.to(dev)
+    n_strains = args.strains
+    visit_strain = (torch.arange(NF, dtype=torch.int32) * n_strains // NF).to(dev)   # contiguous blocks
+    bs = BatchScreen(eng, H, W, max_label, chunk_fields=Fc, n_strains=n_strains)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        with torch.cuda.stream(bs.compute):
+            bs.acc.zero_()
+        bs.run_device(g_dev, l_dev, NF, visit_strain)
+        if world > 1:
+            with torch.cuda.stream(bs.compute):
+                allreduce_strain_acc(bs.acc)        # the path's only collective
+
+    def step_host():
+        with torch.cuda.stream(bs.compute):
+            bs.acc.zero_()
+        bs.run_host(g_pin, l_pin, NF, visit_strain)
+        if world > 1:
+            with torch.cuda.stream(bs.compute):
+                allreduce_strain_acc(bs.acc)
+
+    # ---- device-resident: warmup, then K timed steps ----
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    eng.check_status()
+    chunks_per_step = NF // Fc
+    bs.profile_begin(args.steps * chunks_per_step)
+    l0 = eng.launch_count
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(bs.compute)
+    for _ in range(args.steps):
+        step_device()
+    e1.record(bs.compute)
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    clocks = sampler.stop()
+    launches = eng.launch_count - l0
+    stage_ms, nrec = bs.profile_end()
+    eng.check_status()
+    # cells per step on this rank: one extra untimed pass without the all-reduce
+    cells_local = torch.tensor([0.0], dtype=torch.float64, device=dev)
+    bs.sync(); bs.acc.zero_(); bs.run_device(g_dev, l_dev, NF, visit_strain); bs.sync()
+    cells_local[0] = bs.acc[:, 0].sum()
+    cells_per_step_local = float(cells_local.item())
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cells_local, op=dist.ReduceOp.SUM)
+    cells_per_step = float(cells_local.item())
+    t_ms = float(ms.item())
+    value = cells_per_step * args.steps / (t_ms * 1e-3)
+
+    # ---- end to end from pinned host memory ----
+    step_host(); bs.sync()
+    res = bs.collect_host()
+    assert res["n_cells"] == int(round(cells_per_step_local)), (res["n_cells"], cells_per_step_local)
+    sum_hw = int(((res["cells"]["maxr"] - res["cells"]["minr"]).astype(np.int64) *
+                  (res["cells"]["maxc"] - res["cells"]["minc"])).sum())
+    barrier()
+    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    h0.record(bs.compute)
+    t_wall = time.perf_counter()
+    for _ in range(args.steps):
+        step_host()
+    h1.record(bs.compute)
+    bs.sync()
+    t_wall = time.perf_counter() - t_wall
+    barrier()
+    ems = torch.tensor([max(h0.elapsed_time(h1), 0.0)], dtype=torch.float64, device=dev)
+    ems[0] = max(float(ems.item()), t_wall * 1e3)       # copy-stream time before the first compute
+    if world > 1:
+        dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+    e2e_value = cells_per_step * args.steps / (float(ems.item()) * 1e-3)
+    h2d, d2h = bs.host_bytes_per_pass(NF)
+    eng.check_status()
+
+    if rank == 0:
+        pk = peaks()
+        cae_ms = stage_ms["cae"] / args.steps
+        crop_ms = stage_ms["crop"] / args.steps
+        scan_ms = stage_ms["scan"] / args.steps
+        svm_ms = stage_ms["svm"] / args.steps
+        tf = FLOP_PER_CELL * cells_per_step_local / (cae_ms * 1e-3) / 1e12
+        crop_gbs = (2.0 * sum_hw + 16384.0 * cells_per_step_local) / (crop_ms * 1e-3) / 1e9
+        scan_gbs = 4.0 * H * W * NF / (scan_ms * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get("cae_stage_dram_bytes_per_cell")
+            traffic = None if traffic is None else traffic * cells_per_step_local
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": t_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 (CAE fp32 FMA, fp64 flush) / f64 (CLAHE+resize, PCA, SVM) / int (scan)"
+                     if args.precision == 0 else "f16 tensor core CAE / f64 SVM",
+            "data": "synthetic",
+            "config": {"workload": f"config 2: {NF} visits/GPU/step of 2048x2048 uint16 fields + int32 labels "
+                                   f"(~{cells_per_step_local / NF:.0f} scored cells/field), resident pool of {P} "
+                                   f"distinct seeded fields ({P * 25.2:.0f} MB > 126 MB L2) cycled in chunks of {Fc}",
+                       "fields_per_step_per_gpu": NF, "cells_per_step": cells_per_step,
+                       "artifacts": "tests/golden/model_dir (synthetic CAE weights; scaler/PCA(100)/2 SVMs fit with sklearn)",
+                       "precision": args.precision, "l2_policy": "inputs larger than L2"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": float(ems.item()) / args.steps,
+                    "api": "BatchScreen.run_host -> cia_screen_fields (pinned host pool, double-buffered H2D)"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"kernel": "CAE forward stage (7 conv layers + error reduction)", "bound": "tensor",
+                         "achieved": tf, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": tf / pk["tf_sust"],
+                         "traffic": traffic, "peak_source": pk["source"] + ", bf16 dense sustained",
+                         "share_of_step": cae_ms / (t_ms / args.steps)},
+            "stages_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
+            "stage_rooflines": {
+                "label_scan": {"bound": "hbm", "achieved": scan_gbs, "peak": pk["hbm"], "unit": "GB/s",
+                               "frac": scan_gbs / pk["hbm"]},
+                "crop_clahe_resize": {"bound": "hbm", "achieved": crop_gbs, "peak": pk["hbm"], "unit": "GB/s",
+                                      "frac": crop_gbs / pk["hbm"]},
+                "svm_ms": svm_ms},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_inline(args.cpu_fields)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--fields", type=int, default=1008, help="field visits per GPU per step (config 2: ~1000)")
+    ap.add_argument("--pool", type=int, default=48, help="distinct resident fields per GPU")
+    ap.add_argument("--chunk", type=int, default=16, help="fields per fused call")
+    ap.add_argument("--strains", type=int, default=4)
+    ap.add_argument("--precision", type=int, default=0)
+    ap.add_argument("--cpu-fields", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

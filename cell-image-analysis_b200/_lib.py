@@ -76,6 +76,8 @@ SIGNATURES = {
                                C.POINTER(Scores), _P, _P, _P, _P, _I, _P]),
     "cia_screen_fields_host": (_I, [_P, _P, _P, _I, _I, _I, _I, C.POINTER(Params), _I, _P, _I, _P,
                                     _P, C.POINTER(Scores), _P]),
+    "cia_profile_begin": (_I, [_P, _I]),
+    "cia_profile_end": (_I, [_P, C.POINTER(C.c_double), C.POINTER(_I)]),
     "cia_launch_count": (C.c_int64, [_P]),
 }
 

@@ -1,0 +1,145 @@
+"""Chunked, stream-pipelined screening of many equally sized fields -- the
+throughput form of the ``screen_mutant_samples`` loop (improved_detection.py:164-199):
+fields -> cells -> scores -> per-strain accumulators, with no host synchronisation
+inside a pass.
+
+Two entry points:
+  * ``run_device``: fields already resident in HBM (a pool tensor indexed by chunk);
+  * ``run_host``: fields in pinned host memory; H2D copies run on a copy stream into
+    double-buffered device chunks while the previous chunk is being scored, and the
+    per-cell results are copied back D2H inside the pass.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+STAGES = ("scan", "gates", "crop", "cae", "svm", "accumulate")
+
+
+class BatchScreen:
+    def __init__(self, engine, H: int, W: int, max_label: int, chunk_fields: int = 16,
+                 n_strains: int = 1, cells_per_field_cap: int | None = None):
+        self.eng = engine
+        self.H, self.W, self.max_label = H, W, max_label
+        self.Fc = chunk_fields
+        self.cap = chunk_fields * (cells_per_field_cap or max_label)
+        self.n_strains = n_strains
+        d = engine.tdev
+        self.out = [engine.alloc_outputs(self.cap, chunk_fields) for _ in range(2)]
+        self.acc = torch.zeros((n_strains, 8), dtype=torch.float64, device=d)
+        self.compute = torch.cuda.Stream(device=d)
+        self.copy = torch.cuda.Stream(device=d)
+        self._stage = None
+
+    # ---- profiling ----
+    def profile_begin(self, n_calls: int):
+        self.eng._check(self.eng.lib.cia_profile_begin(self.eng.h, n_calls))
+
+    def profile_end(self):
+        ms = (C.c_double * 6)()
+        n = C.c_int(0)
+        self.eng._check(self.eng.lib.cia_profile_end(self.eng.h, ms, C.byref(n)))
+        return dict(zip(STAGES, [float(v) for v in ms])), int(n.value)
+
+    # ---- device-resident pass ----
+    def run_device(self, images: torch.Tensor, labels: torch.Tensor, n_fields: int,
+                   strain_of_visit: torch.Tensor | None = None):
+        """One pass over ``n_fields`` field visits, cycling the resident pool
+        ``images``/``labels`` [P,H,W] chunk by chunk.  Enqueues only; returns nothing.
+        Per-strain accumulators (column 0 = cell count) land in ``self.acc``."""
+        P = images.shape[0]
+        assert P % self.Fc == 0 and n_fields % self.Fc == 0
+        eng = self.eng
+        with torch.cuda.stream(self.compute):
+            for i in range(n_fields // self.Fc):
+                p0 = (i * self.Fc) % P
+                o = self.out[i & 1]
+                st = None if strain_of_visit is None else strain_of_visit[i * self.Fc:(i + 1) * self.Fc]
+                eng.screen_fields(images[p0:p0 + self.Fc], labels[p0:p0 + self.Fc], self.max_label, o,
+                                  field_strain=st, acc=self.acc)
+
+    # ---- host-resident pass (H2D + D2H inside) ----
+    def _ensure_stage(self, n_chunks):
+        d = self.eng.tdev
+        if self._stage is None:
+            self._stage = dict(
+                img=[torch.empty((self.Fc, self.H, self.W), dtype=torch.int16, device=d) for _ in range(2)],
+                lab=[torch.empty((self.Fc, self.H, self.W), dtype=torch.int32, device=d) for _ in range(2)],
+                ready=[torch.cuda.Event() for _ in range(2)],
+                done=[torch.cuda.Event() for _ in range(2)])
+        if getattr(self, "_host_chunks", 0) < n_chunks:
+            cap = self.cap
+            pin = dict(pin_memory=True)
+            self.h_cells = torch.empty((n_chunks, cap, 56), dtype=torch.uint8, **pin)
+            self.h_counts = torch.empty((n_chunks, 1 + self.Fc), dtype=torch.int32, **pin)
+            self.h_mse = torch.empty((n_chunks, cap), dtype=torch.float32, **pin)
+            self.h_mae = torch.empty((n_chunks, cap), dtype=torch.float32, **pin)
+            self.h_dc = torch.empty((n_chunks, cap), dtype=torch.float64, **pin)
+            self.h_dm = torch.empty((n_chunks, cap), dtype=torch.float64, **pin)
+            self.h_pc = torch.empty((n_chunks, cap), dtype=torch.int8, **pin)
+            self.h_pm = torch.empty((n_chunks, cap), dtype=torch.int8, **pin)
+            self._host_chunks = n_chunks
+
+    def host_bytes_per_pass(self, n_fields):
+        n_chunks = n_fields // self.Fc
+        h2d = n_fields * self.H * self.W * 6
+        per_chunk = self.cap * (56 + 4 + 4 + 8 + 8 + 1 + 1) + 4 * (1 + self.Fc)
+        return h2d, n_chunks * per_chunk + self.n_strains * 64
+
+    def run_host(self, images_pinned: torch.Tensor, labels_pinned: torch.Tensor, n_fields: int,
+                 strain_of_visit: torch.Tensor | None = None):
+        """One pass over ``n_fields`` field visits read from pinned host pools [P,H,W]
+        (int16-viewed uint16 image, int32 labels).  Enqueues copies + compute; call
+        ``collect_host`` (after a stream sync) for the results."""
+        P = images_pinned.shape[0]
+        assert P % self.Fc == 0 and n_fields % self.Fc == 0
+        n_chunks = n_fields // self.Fc
+        self._ensure_stage(n_chunks)
+        S, eng = self._stage, self.eng
+        for i in range(n_chunks):
+            b = i & 1
+            p0 = (i * self.Fc) % P
+            with torch.cuda.stream(self.copy):
+                self.copy.wait_event(S["done"][b])
+                S["img"][b].copy_(images_pinned[p0:p0 + self.Fc], non_blocking=True)
+                S["lab"][b].copy_(labels_pinned[p0:p0 + self.Fc], non_blocking=True)
+                S["ready"][b].record(self.copy)
+            with torch.cuda.stream(self.compute):
+                self.compute.wait_event(S["ready"][b])
+                o = self.out[b]
+                st = None if strain_of_visit is None else strain_of_visit[i * self.Fc:(i + 1) * self.Fc]
+                eng.screen_fields(S["img"][b], S["lab"][b], self.max_label, o, field_strain=st, acc=self.acc)
+                S["done"][b].record(self.compute)
+                self.h_counts[i].copy_(o["counts"], non_blocking=True)
+                self.h_cells[i].copy_(o["cells"], non_blocking=True)
+                self.h_mse[i].copy_(o["mse"], non_blocking=True)
+                self.h_mae[i].copy_(o["mae"], non_blocking=True)
+                self.h_dc[i].copy_(o["dec_cons"], non_blocking=True)
+                self.h_dm[i].copy_(o["dec_mod"], non_blocking=True)
+                self.h_pc[i].copy_(o["pred_cons"], non_blocking=True)
+                self.h_pm[i].copy_(o["pred_mod"], non_blocking=True)
+        self._last_chunks = n_chunks
+
+    def collect_host(self):
+        """Compact the per-chunk host buffers of the last ``run_host`` into flat arrays."""
+        n_chunks = self._last_chunks
+        counts = self.h_counts[:n_chunks].numpy()
+        ks = np.minimum(counts[:, 0], self.cap)
+        cat = lambda t: np.concatenate([t[i, :ks[i]].numpy() for i in range(n_chunks)])
+        cells = np.concatenate([self.h_cells[i, :ks[i]].numpy().view(_lib.CELL_DTYPE).reshape(-1)
+                                for i in range(n_chunks)])
+        chunk_of = np.repeat(np.arange(n_chunks), ks)
+        cells = cells.copy()
+        cells["field"] += chunk_of.astype(np.int32) * self.Fc      # visit index within the pass
+        return dict(n_cells=int(ks.sum()), field_counts=counts[:, 1:].reshape(-1), cells=cells,
+                    mse=cat(self.h_mse), mae=cat(self.h_mae), dec_cons=cat(self.h_dc),
+                    dec_mod=cat(self.h_dm), pred_cons=cat(self.h_pc), pred_mod=cat(self.h_pm))
+
+    def sync(self):
+        self.compute.synchronize()
+        self.copy.synchronize()

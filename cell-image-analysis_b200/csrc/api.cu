@@ -76,6 +76,7 @@ int cia_destroy(cia_handle h) {
     cudaFree(h->status_dev);
     cudaFreeHost(h->status_host);
     if (h->ev) cudaEventDestroy(h->ev);
+    for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
     delete h;
     return CIA_OK;
 }
@@ -270,19 +271,65 @@ int cia_screen_fields(cia_handle h, const uint16_t* images, const int32_t* label
     float* crops = crops32 ? crops32 : (float*)p; p += (crop_bytes + 255) & ~(size_t)255;
     float* feats = features ? features : (float*)p;
 
+    cudaEvent_t* pe = nullptr;
+    if (h->prof_records > 0 && h->prof_used < h->prof_records)
+        pe = &h->prof_ev[(size_t)(h->prof_used++) * CIA_PROF_MARKS];
+#define CIA_MARK(i) do { if (pe) CIA_CUDA(cudaEventRecord(pe[i], s)); } while (0)
+    CIA_MARK(0);
     if ((rc = k_label_scan(h, labels, n_fields, H, W, max_label, regions, s))) return rc;
+    CIA_MARK(1);
     if ((rc = k_filter(h, images, n_fields, H, W, max_label, regions, params, cells, cells_cap,
                        n_cells_dev, field_counts_dev, s))) return rc;
+    CIA_MARK(2);
     if ((rc = k_crop_resize(h, images, H, W, cells, cells_cap, n_cells_dev, params, crops, nullptr, s))) return rc;
+    CIA_MARK(3);
     if (precision == 0) rc = k_cae_forward_fp32(h, crops, cells_cap, n_cells_dev, scores->mse, scores->mae, feats, s);
     else rc = k_cae_forward_tc(h, crops, cells_cap, n_cells_dev, scores->mse, scores->mae, feats, s);
     if (rc) return rc;
+    CIA_MARK(4);
     if ((rc = k_svm_decision(h, feats, cells_cap, n_cells_dev, scores->dec_conservative,
                              scores->dec_moderate, scores->pred_conservative, scores->pred_moderate,
                              nullptr, s))) return rc;
+    CIA_MARK(5);
     if (acc) {
         if ((rc = k_strain_accumulate(h, cells, cells_cap, n_cells_dev, scores, field_strain, acc, n_strains, s))) return rc;
     }
+    CIA_MARK(6);
+#undef CIA_MARK
+    return CIA_OK;
+}
+
+int cia_profile_begin(cia_handle h, int max_records) {
+    if (!h) return bad_handle();
+    if (max_records < 0) { h->err = "cia_profile_begin: bad argument"; return CIA_E_ARG; }
+    CIA_CUDA(cudaSetDevice(h->device));
+    const size_t want = (size_t)max_records * CIA_PROF_MARKS;
+    while (h->prof_ev.size() < want) {
+        cudaEvent_t e;
+        CIA_CUDA(cudaEventCreate(&e));
+        h->prof_ev.push_back(e);
+    }
+    h->prof_records = max_records;
+    h->prof_used = 0;
+    return CIA_OK;
+}
+
+int cia_profile_end(cia_handle h, double* stage_ms /* [6] */, int* n_records) {
+    if (!h) return bad_handle();
+    if (!stage_ms || !n_records) { h->err = "cia_profile_end: null pointer"; return CIA_E_ARG; }
+    for (int k = 0; k < CIA_PROF_MARKS - 1; ++k) stage_ms[k] = 0.0;
+    for (int r = 0; r < h->prof_used; ++r) {
+        cudaEvent_t* pe = &h->prof_ev[(size_t)r * CIA_PROF_MARKS];
+        CIA_CUDA(cudaEventSynchronize(pe[CIA_PROF_MARKS - 1]));
+        for (int k = 0; k < CIA_PROF_MARKS - 1; ++k) {
+            float ms = 0.f;
+            CIA_CUDA(cudaEventElapsedTime(&ms, pe[k], pe[k + 1]));
+            stage_ms[k] += ms;
+        }
+    }
+    *n_records = h->prof_used;
+    h->prof_records = 0;
+    h->prof_used = 0;
     return CIA_OK;
 }
 

@@ -13,8 +13,12 @@ namespace {
 
 constexpr int CT = 256;   // threads per block
 
-// One block: a TS x TS tile of conv pixels (TS = min(16, R)) x all COUT channels of one cell.
-// thread -> (channel group cg = tid / 64, 2x2 pixel unit = tid % 64).
+// One block: an 8 x TSX tile of conv pixels (TSX = min(16, R)) x all COUT channels of one
+// cell.  thread -> (channel group cg = warp id, 2x2 pixel unit = lane).  Products are
+// accumulated in fp32 over FLUSH input channels (9*FLUSH FMAs), then flushed into an
+// fp64 accumulator, so a layer output is within ~2e-7 relative of the correctly rounded
+// fp32 sum regardless of K -- the one-class SVM downstream amplifies feature noise
+// (1e-6 relative -> 7e-5 in the decision value), see DESIGN.md "precision".
 template <int CIN, int COUT, int R, bool POOL, bool UPS>
 __global__ void __launch_bounds__(CT)
 conv3x3_kernel(const float* __restrict__ in, float* __restrict__ out,
@@ -22,41 +26,46 @@ conv3x3_kernel(const float* __restrict__ in, float* __restrict__ out,
                const float* __restrict__ bias, const float* __restrict__ bn_s,
                const float* __restrict__ bn_t, int n_cells, const int32_t* __restrict__ n_dev,
                int cell0) {
-    constexpr int TS = R < 16 ? R : 16;
-    constexpr int TILES = (R / TS) * (R / TS);
+    constexpr int TSX = R < 16 ? R : 16;
+    constexpr int TSY = 8;
+    constexpr int TX = R / TSX, TY = R / TSY;
+    constexpr int TILES = TX * TY;
     constexpr int CK = CIN < 8 ? CIN : 8;
-    constexpr int CPT = COUT / 4;
-    constexpr int PP = TS + 2;
+    constexpr int FLUSH = CK < 2 ? CK : 2;
+    constexpr int CPT = COUT / 8;
+    constexpr int PPX = TSX + 2, PPY = TSY + 2;
     constexpr int RIN = UPS ? R / 2 : R;
-    constexpr int UNITS = (TS / 2) * (TS / 2);
+    constexpr int UX = TSX / 2;
+    constexpr int UNITS = UX * (TSY / 2);
 
-    __shared__ __align__(16) float in_s[CK][PP][PP + 1];
+    __shared__ __align__(16) float in_s[CK][PPY][PPX + 1];
     __shared__ __align__(16) float w_s[9][CK][COUT];
 
     const int n = dev_count(n_cells, n_dev);
     const int cell = cell0 + blockIdx.x / TILES;
     if (cell >= n) return;
     const int tile = blockIdx.x % TILES;
-    const int ty0 = (tile / (R / TS)) * TS, tx0 = (tile % (R / TS)) * TS;
+    const int ty0 = (tile / TX) * TSY, tx0 = (tile % TX) * TSX;
     const int tid = threadIdx.x;
-    const int cg = tid >> 6, unit = tid & 63;
+    const int cg = tid >> 5, unit = tid & 31;
     const bool active = unit < UNITS;
-    const int uy = unit / (TS / 2), ux = unit % (TS / 2);
+    const int uy = unit / UX, ux = unit % UX;
 
     float acc[4][CPT];
+    double dacc[4][CPT];
 #pragma unroll
     for (int p = 0; p < 4; ++p)
 #pragma unroll
-        for (int k = 0; k < CPT; ++k) acc[p][k] = 0.f;
+        for (int k = 0; k < CPT; ++k) { acc[p][k] = 0.f; dacc[p][k] = 0.0; }
 
     const float* src = in + (size_t)cell * RIN * RIN * CIN;
 
     for (int c0 = 0; c0 < CIN; c0 += CK) {
         __syncthreads();
         // stage the input patch (zero padded; nearest up-sampling folded in)
-        for (int i = tid; i < PP * PP * CK; i += CT) {
+        for (int i = tid; i < PPY * PPX * CK; i += CT) {
             const int c = i % CK, pix = i / CK;
-            const int py = pix / PP, px = pix % PP;
+            const int py = pix / PPX, px = pix % PPX;
             const int y = ty0 + py - 1, x = tx0 + px - 1;
             float v = 0.f;
             if (y >= 0 && y < R && x >= 0 && x < R) {
@@ -73,32 +82,39 @@ conv3x3_kernel(const float* __restrict__ in, float* __restrict__ out,
         __syncthreads();
         if (active) {
 #pragma unroll 1
-            for (int c = 0; c < CK; ++c) {
-                float win[4][4];
+            for (int cc = 0; cc < CK; cc += FLUSH) {
 #pragma unroll
-                for (int a = 0; a < 4; ++a)
+                for (int c = cc; c < cc + FLUSH; ++c) {
+                    float win[4][4];
 #pragma unroll
-                    for (int b = 0; b < 4; ++b) win[a][b] = in_s[c][2 * uy + a][2 * ux + b];
+                    for (int a = 0; a < 4; ++a)
 #pragma unroll
-                for (int dy = 0; dy < 3; ++dy)
+                        for (int b = 0; b < 4; ++b) win[a][b] = in_s[c][2 * uy + a][2 * ux + b];
 #pragma unroll
-                    for (int dx = 0; dx < 3; ++dx) {
-                        const float* wp = &w_s[dy * 3 + dx][c][cg * CPT];
+                    for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
-                        for (int k = 0; k < CPT; ++k) {
-                            const float w = wp[k];
-                            acc[0][k] = fmaf(win[dy][dx], w, acc[0][k]);
-                            acc[1][k] = fmaf(win[dy][dx + 1], w, acc[1][k]);
-                            acc[2][k] = fmaf(win[dy + 1][dx], w, acc[2][k]);
-                            acc[3][k] = fmaf(win[dy + 1][dx + 1], w, acc[3][k]);
+                        for (int dx = 0; dx < 3; ++dx) {
+                            const float* wp = &w_s[dy * 3 + dx][c][cg * CPT];
+#pragma unroll
+                            for (int k = 0; k < CPT; ++k) {
+                                const float w = wp[k];
+                                acc[0][k] = fmaf(win[dy][dx], w, acc[0][k]);
+                                acc[1][k] = fmaf(win[dy][dx + 1], w, acc[1][k]);
+                                acc[2][k] = fmaf(win[dy + 1][dx], w, acc[2][k]);
+                                acc[3][k] = fmaf(win[dy + 1][dx + 1], w, acc[3][k]);
+                            }
                         }
-                    }
+                }
+#pragma unroll
+                for (int p = 0; p < 4; ++p)
+#pragma unroll
+                    for (int k = 0; k < CPT; ++k) { dacc[p][k] += (double)acc[p][k]; acc[p][k] = 0.f; }
             }
         }
     }
     if (!active) return;
 
-    // epilogue: bias -> ReLU -> BN affine -> (2x2 max | store)
+    // epilogue: round to fp32 -> bias -> ReLU -> BN affine -> (2x2 max | store)
     const int cbase = cg * CPT;
     if (POOL) {
         constexpr int RO = R / 2;
@@ -109,7 +125,7 @@ conv3x3_kernel(const float* __restrict__ in, float* __restrict__ out,
             float m = -INFINITY;
 #pragma unroll
             for (int p = 0; p < 4; ++p) {
-                float v = acc[p][k] + b;
+                float v = __fadd_rn((float)dacc[p][k], b);
                 v = v > 0.f ? v : 0.f;
                 v = __fadd_rn(__fmul_rn(v, s), t);
                 m = fmaxf(m, v);
@@ -123,7 +139,7 @@ conv3x3_kernel(const float* __restrict__ in, float* __restrict__ out,
             float* dst = out + (((size_t)cell * R + y) * R + x) * COUT + cbase;
 #pragma unroll
             for (int k = 0; k < CPT; ++k) {
-                float v = acc[p][k] + bias[cbase + k];
+                float v = __fadd_rn((float)dacc[p][k], bias[cbase + k]);
                 v = v > 0.f ? v : 0.f;
                 dst[k] = __fadd_rn(__fmul_rn(v, bn_s[cbase + k]), bn_t[cbase + k]);
             }
@@ -199,8 +215,8 @@ final_layer_kernel(const float* __restrict__ a6, const float* __restrict__ crops
 template <int CIN, int COUT, int R, bool POOL, bool UPS>
 int launch_conv(cia_ctx* h, const CaeWeights& w, int layer, const float* in, float* out, int n,
                 const int32_t* n_dev, int cell0, int chunk, cudaStream_t s) {
-    constexpr int TS = R < 16 ? R : 16;
-    constexpr int TILES = (R / TS) * (R / TS);
+    constexpr int TSX = R < 16 ? R : 16;
+    constexpr int TILES = (R / TSX) * (R / 8);
     conv3x3_kernel<CIN, COUT, R, POOL, UPS><<<chunk * TILES, CT, 0, s>>>(
         in, out, w.kernel[layer], w.bias[layer], w.bn_scale[layer], w.bn_shift[layer], n, n_dev, cell0);
     CIA_LAUNCH_CHECK();

@@ -64,7 +64,11 @@ struct cia_ctx {
     // grow-only workspaces
     Workspace ws_flags, ws_act, ws_crop_scratch, ws_pipe, ws_feat, ws_misc, ws_stage;
     cudaEvent_t ev = nullptr;
+    // stage profiler: ring of CUDA events recorded in-stream by the fused path
+    std::vector<cudaEvent_t> prof_ev;     // [records][CIA_PROF_MARKS]
+    int prof_records = 0, prof_used = 0;
 };
+#define CIA_PROF_MARKS 7   // before scan, after scan, gates, crop, cae, svm, accumulate
 
 #define CIA_CUDA(call)                                                              \
     do {                                                                            \

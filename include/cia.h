@@ -188,6 +188,14 @@ int cia_screen_fields_host(cia_handle h, const uint16_t* images_host,
                            int32_t* field_counts_host, const cia_scores* scores_host,
                            void* stream);
 
+/* Stage timing of the fused path with CUDA events recorded in-stream (no host sync is
+ * added to the timed region): after cia_profile_begin(h, R) the next R calls of
+ * cia_screen_fields bracket scan / gates / crop / CAE / SVM / accumulate with events;
+ * cia_profile_end sums the elapsed milliseconds per stage over the recorded calls
+ * (synchronises on the last event of each). */
+int cia_profile_begin(cia_handle h, int max_records);
+int cia_profile_end(cia_handle h, double* stage_ms /* [6] */, int* n_records);
+
 /* Number of kernels this library has launched on the handle (bench's gpu_launches). */
 int64_t cia_launch_count(cia_handle h);
 

@@ -26,9 +26,23 @@ def bn_affine(gamma, beta, mean, var, eps=BN_EPS):
     return inv, (beta.astype(np.float32) - mean.astype(np.float32) * inv).astype(np.float32)
 
 
-def _conv(x, k, b):
+def _conv(x, k, b, exact=True):
+    """Conv2D 'same' cross-correlation + bias, float32.
+
+    ``exact=True`` (parity tests): every output is the CORRECTLY ROUNDED float32 of the
+    exact sum of products (float32 x float32 products are exact in float64; the float64
+    accumulation error is ~1e-16), then the bias is added in float32 like TF's separate
+    BiasAdd.  This is the order-independent centre of every float32 summation order a
+    real TensorFlow/Eigen/oneDNN build may use (each deviates from it by its own
+    ~sqrt(K)*2^-24 noise) -- which matters because the one-class SVM decision moves by
+    ~7e-5 per 1e-6 relative feature noise (measured), i.e. the 1e-4 gate sits at the
+    float32 noise floor of the reference itself.
+    ``exact=False`` (CPU-baseline timing): plain torch/oneDNN float32 convolution."""
     w = torch.from_numpy(np.ascontiguousarray(k.transpose(3, 2, 0, 1)))  # HWIO -> OIHW
-    return F.conv2d(x, w, torch.from_numpy(b), padding=1)                # cross-correlation, 'same'
+    if not exact:
+        return F.conv2d(x, w, torch.from_numpy(b), padding=1)
+    y = F.conv2d(x.double(), w.double(), None, padding=1).float()
+    return y + torch.from_numpy(b)[None, :, None, None]
 
 
 def _bn(x, bn):
@@ -37,7 +51,7 @@ def _bn(x, bn):
 
 
 @torch.no_grad()
-def forward(X: np.ndarray, w, batch: int = 256, n_layers: int = 7):
+def forward(X: np.ndarray, w, batch: int = 256, n_layers: int = 7, exact: bool = True):
     """X float32 [N,64,64,1] -> (recon float32 [N,64,64,1], encoded float32 [N,8,8,32]).
 
     ``w`` has attributes/keys ``kernels`` (7), ``biases`` (7), ``bns`` (6 x (gamma,
@@ -48,7 +62,7 @@ def forward(X: np.ndarray, w, batch: int = 256, n_layers: int = 7):
         x = torch.from_numpy(np.ascontiguousarray(X[s:s + batch, :, :, 0]))[:, None]
         enc = None
         for i in range(n_layers):
-            x = _conv(x, w["kernels"][i], w["biases"][i])
+            x = _conv(x, w["kernels"][i], w["biases"][i], exact)
             if i < 6:
                 x = _bn(torch.relu(x), w["bns"][i])
                 if i < 3:

@@ -201,8 +201,9 @@ def write_keras(path, w, encoder_only=False, name_offset=0, with_optimizer=True)
     meta = {"keras_version": "3.3.3", "date_saved": "2025-01-01@00:00:00"}
     bio = io.BytesIO()
     with zipfile.ZipFile(bio, "w", zipfile.ZIP_STORED) as z:
-        z.writestr("metadata.json", json.dumps(meta))
-        z.writestr("config.json", json.dumps(cae_config(encoder_only, name_offset)))
-        z.writestr("model.weights.h5", h5)
+        for name, data in (("metadata.json", json.dumps(meta)),
+                           ("config.json", json.dumps(cae_config(encoder_only, name_offset))),
+                           ("model.weights.h5", h5)):
+            z.writestr(zipfile.ZipInfo(name, date_time=(2025, 1, 1, 0, 0, 0)), data)  # reproducible bytes
     with open(path, "wb") as f:
         f.write(bio.getvalue())

@@ -11,16 +11,16 @@ import numpy as np
 from . import cae
 
 
-def compute_anomaly_scores(cell_images, ae_w, enc_w, scaler, pca, det_cons, det_mod):
+def compute_anomaly_scores(cell_images, ae_w, enc_w, scaler, pca, det_cons, det_mod, exact=True):
     if len(cell_images) == 0:                                                # det:119
         return {}
     X = np.expand_dims(np.array(cell_images), axis=-1).astype("float32")     # det:122
-    recon, enc_ae = cae.forward(X, ae_w)                                     # det:125
+    recon, enc_ae = cae.forward(X, ae_w, exact=exact)                                     # det:125
     mse, mae = cae.recon_errors(X, recon)                                    # det:126-127
     if enc_w is ae_w:
         enc = enc_ae
     else:
-        _, enc = cae.forward(X, enc_w, n_layers=3)                           # det:130
+        _, enc = cae.forward(X, enc_w, n_layers=3, exact=exact)                           # det:130
     flat = enc.reshape(len(enc), -1)                                         # det:131 (HWC)
     z = pca.transform(scaler.transform(flat))                                # det:134-135
     cp, mp = det_cons.predict(z), det_mod.predict(z)                         # det:138-139
