@@ -78,6 +78,7 @@ SIGNATURES = {
                                     _P, C.POINTER(Scores), _P]),
     "cia_profile_begin": (_I, [_P, _I]),
     "cia_profile_end": (_I, [_P, C.POINTER(C.c_double), C.POINTER(_I)]),
+    "cia_debug_copy_workspace": (_I, [_P, _I, C.c_size_t, _P, C.c_size_t]),
     "cia_launch_count": (C.c_int64, [_P]),
 }
 

@@ -59,7 +59,9 @@ static void free_cae(CaeWeights& w) {
         cudaFree(w.kernel[i]); cudaFree(w.bias[i]); cudaFree(w.bn_scale[i]); cudaFree(w.bn_shift[i]);
         w.kernel[i] = w.bias[i] = w.bn_scale[i] = w.bn_shift[i] = nullptr;
     }
-    cudaFree(w.tc_blob); w.tc_blob = nullptr;
+    for (int i = 0; i < CAE_NCONV; ++i)
+        for (int j = 0; j < 2; ++j) { cudaFree(w.tc_w[i][j]); w.tc_w[i][j] = nullptr; }
+    w.tc_ready = false;
     w.loaded = false;
 }
 
@@ -84,6 +86,19 @@ int cia_destroy(cia_handle h) {
 const char* cia_last_error(cia_handle h) { return h ? h->err.c_str() : "null handle"; }
 
 int64_t cia_launch_count(cia_handle h) { return h ? h->launches : 0; }
+
+int cia_debug_copy_workspace(cia_handle h, int ws_id, size_t offset, void* dst_host, size_t bytes) {
+    if (!h) return bad_handle();
+    Workspace* ws[] = {&h->ws_flags, &h->ws_act, &h->ws_crop_scratch, &h->ws_pipe, &h->ws_feat,
+                       &h->ws_misc, &h->ws_stage};
+    if (ws_id < 0 || ws_id >= 7 || !dst_host || offset + bytes > ws[ws_id]->cap) {
+        h->err = "cia_debug_copy_workspace: bad argument";
+        return CIA_E_ARG;
+    }
+    CIA_CUDA(cudaDeviceSynchronize());
+    CIA_CUDA(cudaMemcpy(dst_host, (const char*)ws[ws_id]->p + offset, bytes, cudaMemcpyDeviceToHost));
+    return CIA_OK;
+}
 
 int cia_check_status(cia_handle h, void* stream) {
     if (!h) return bad_handle();
@@ -221,9 +236,9 @@ int cia_cae_forward(cia_handle h, const float* crops32, int n_cells, const int32
     if (!crops32 || !mse || !mae) { h->err = "cia_cae_forward: null pointer"; return CIA_E_ARG; }
     if (precision == 0)
         return k_cae_forward_fp32(h, crops32, n_cells, n_cells_dev, mse, mae, features, (cudaStream_t)stream);
-    if (precision == 1)
-        return k_cae_forward_tc(h, crops32, n_cells, n_cells_dev, mse, mae, features, (cudaStream_t)stream);
-    h->err = "cia_cae_forward: precision must be 0 (fp32) or 1 (tensor core)";
+    if (precision == 1 || precision == 2)
+        return k_cae_forward_tc(h, crops32, n_cells, n_cells_dev, mse, mae, features, precision, (cudaStream_t)stream);
+    h->err = "cia_cae_forward: precision must be 0 (fp32), 1 (tensor core) or 2 (tensor core + fp32 encoder)";
     return CIA_E_ARG;
 }
 
@@ -284,7 +299,7 @@ int cia_screen_fields(cia_handle h, const uint16_t* images, const int32_t* label
     if ((rc = k_crop_resize(h, images, H, W, cells, cells_cap, n_cells_dev, params, crops, nullptr, s))) return rc;
     CIA_MARK(3);
     if (precision == 0) rc = k_cae_forward_fp32(h, crops, cells_cap, n_cells_dev, scores->mse, scores->mae, feats, s);
-    else rc = k_cae_forward_tc(h, crops, cells_cap, n_cells_dev, scores->mse, scores->mae, feats, s);
+    else rc = k_cae_forward_tc(h, crops, cells_cap, n_cells_dev, scores->mse, scores->mae, feats, precision, s);
     if (rc) return rc;
     CIA_MARK(4);
     if ((rc = k_svm_decision(h, feats, cells_cap, n_cells_dev, scores->dec_conservative,

@@ -225,6 +225,27 @@ int launch_conv(cia_ctx* h, const CaeWeights& w, int layer, const float* in, flo
 
 }  // namespace
 
+// encoder.predict + flatten (det:130-131) alone: the three encoder layers in exact fp32.
+int k_encoder_fp32(cia_ctx* h, const CaeWeights& w, const float* crops, int n, const int32_t* n_dev,
+                   float* features, cudaStream_t s) {
+    if (n <= 0) return CIA_OK;
+    if (!w.loaded || w.n_conv < 3) { h->err = "encoder weights not loaded"; return CIA_E_STATE; }
+    const int CH = 2048;
+    const size_t a1 = 32 * 32 * 32, a2 = 16 * 16 * 64;
+    int rc = ws_reserve(h, h->ws_act, (size_t)CH * (a1 + a2) * sizeof(float));
+    if (rc) return rc;
+    float* A1 = (float*)h->ws_act.p;
+    float* A2 = A1 + CH * a1;
+    for (int c0 = 0; c0 < n; c0 += CH) {
+        const int chunk = (n - c0) < CH ? (n - c0) : CH;
+        float* a1p = A1 - (size_t)c0 * a1; float* a2p = A2 - (size_t)c0 * a2;
+        if ((rc = launch_conv<1, 32, 64, true, false>(h, w, 0, crops, a1p, n, n_dev, c0, chunk, s))) return rc;
+        if ((rc = launch_conv<32, 64, 32, true, false>(h, w, 1, a1p, a2p, n, n_dev, c0, chunk, s))) return rc;
+        if ((rc = launch_conv<64, 32, 16, true, false>(h, w, 2, a2p, features, n, n_dev, c0, chunk, s))) return rc;
+    }
+    return CIA_OK;
+}
+
 // Activations per cell (fp32): A1 32x32x32, A2 16x16x64, A3 8x8x32, A4 8x8x32, A5 16x16x64,
 // A6 32x32x32.  Buffers are indexed by absolute cell so chunks never alias.
 int k_cae_forward_fp32(cia_ctx* h, const float* crops, int n, const int32_t* n_dev, float* mse,

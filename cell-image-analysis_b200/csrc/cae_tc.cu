@@ -1,10 +1,639 @@
-// cae_tc.cu -- K3 tensor-core path (tcgen05 implicit GEMM).  Placeholder until the
-// UMMA kernels land: refuses loudly instead of falling back.
+// cae_tc.cu -- K3 tensor-core path: the convolutional autoencoder as tcgen05 implicit
+// GEMMs (UMMA, accumulators in TMEM), one kernel per layer, activations as fp16 in
+// "chunk-planar" order [cell][C/8][y][x][8] so that every 16-byte unit is one pixel's 8
+// channels -- exactly one row of a K-major UMMA core matrix.
+//
+// Replaces autoencoder.predict + MSE/MAE (improved_detection.py:125-127) and, in
+// precision mode 1, encoder.predict (det:130); architecture CAE_improved_modeltrain.py:188-216.
+//
+// Implicit GEMM without im2col: a padded input block lives in shared memory; for filter
+// tap (dy,dx) the A operand of the MMA is the SAME block addressed with a shifted start
+// address (descriptor start += (dy*pitch+dx)*16 B).  An MMA tile is M=128 output pixels =
+// 16 rows x 8 columns: 8 consecutive pixels are the 8 rows of a core matrix (16 B apart),
+// the 16 image rows are the 16 core-matrix groups (stride-byte-offset = row pitch).
+// N = Cout, K = 16 input channels per instruction, 9 taps x Cin/16 instructions per tile.
+// Pooling layers use four "phase" tiles (py,px) over de-interleaved even/odd columns so
+// that the 2x2 max-pool partners of a pooled pixel sit in the SAME TMEM lane (no shuffles).
+// fp32-grade encoder features: operands are split x = hi + lo (two fp16), weights scaled by
+// a power of two; three MMAs (hi*hi, hi*lo, lo*hi) accumulate into one fp32 TMEM tile.
 #include "common.cuh"
 
-int k_cae_tc_prepare(cia_ctx* h, int which) { (void)h; (void)which; return CIA_OK; }
+#include <cuda_fp16.h>
 
-int k_cae_forward_tc(cia_ctx* h, const float*, int, const int32_t*, float*, float*, float*, cudaStream_t) {
-    h->err = "cia_cae_forward: tensor-core path not built in this library version";
-    return CIA_E_STATE;
+#include <cmath>
+
+namespace {
+
+constexpr int TCT = 256;   // 8 warps: warp&3 = TMEM lane quadrant, warp>>2 = column-slice parity
+enum { EPI_POOL = 0, EPI_UP = 1, EPI_PLAIN = 2, EPI_FINAL = 3 };
+
+// ---------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t a = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(a), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {   // one full warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {     // same warp
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], kind::f16 (fp16 operands, fp32 accumulate), issued by ONE thread
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x 8 consecutive fp32 columns -> 8 registers per thread (lane = TMEM lane of the warp's quadrant)
+#define TMEM_LD8(taddr, v)                                                                          \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"            \
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), \
+                   "=r"(v[7]) : "r"(taddr))
+// wait for the loads AND make every later use of the registers depend on the wait
+#define TMEM_WAIT8(v)                                                                               \
+    asm volatile("tcgen05.wait::ld.sync.aligned;"                                                   \
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), \
+                   "+r"(v[7]) :: "memory")
+
+// K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+// canonical layout ((8,m),2):((16 B, SBO), LBO) in 16-byte units.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;                 // descriptor version 1 (sm_100)
+    return d;                               // layout_type 0 = SWIZZLE_NONE, base_offset 0
+}
+// cute::UMMA::InstrDescriptor: c_format f32 (bit 4), a/b format f16 (0), K-major A and B,
+// n_dim = N >> 3 at [17,23), m_dim = M >> 4 at [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+constexpr int pow2_cols(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
+
+__device__ __forceinline__ void split_store8(const float (&o)[8], __half* hi_dst, __half* lo_dst) {
+    __align__(16) __half hh[8];
+    __align__(16) __half ll[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        hh[k] = __float2half_rn(o[k]);
+        ll[k] = __float2half_rn(o[k] - __half2float(hh[k]));
+    }
+    *reinterpret_cast<uint4*>(hi_dst) = *reinterpret_cast<const uint4*>(hh);
+    if (lo_dst) *reinterpret_cast<uint4*>(lo_dst) = *reinterpret_cast<const uint4*>(ll);
+}
+
+// ---------------------------------------------------------------------------------------
+// Layers 2..7 (Cin >= 32)
+// ---------------------------------------------------------------------------------------
+template <int CIN, int COUT, int R, int EPI, int NPASS>
+struct Cfg {
+    static constexpr bool POOL = EPI == EPI_POOL;
+    static constexpr int NCH = CIN / 8;
+    static constexpr int FILL_ROWS = POOL ? R + 2 : 18;              // rows actually staged
+    static constexpr int ROW_UNITS = POOL ? 9 : R + 2;                // 16-byte units per staged row
+    static constexpr int ROW_B = ROW_UNITS * 16;
+    static constexpr int PLANE_B = FILL_ROWS * ROW_B;
+    static constexpr int CHUNK_B = (POOL ? 2 : 1) * PLANE_B;          // = LBO of A
+    static constexpr int REGION_B = NCH * CHUNK_B;
+    static constexpr int SBO_A = POOL ? 2 * ROW_B : ROW_B;
+    static constexpr int TILES = POOL ? 4 : (R >= 32 ? 4 : (R == 16 ? 2 : 1));
+    static constexpr int UNITS_PER_CELL = POOL ? (R >= 32 ? 2 : 1) : (R >= 32 ? 2 : 1);
+    static constexpr int TMEM_COLS = pow2_cols(TILES * COUT);
+    static constexpr int W_B = 9 * NCH * COUT * 16;
+    static constexpr int PARTS = NPASS > 1 ? 2 : 1;
+    static constexpr int SMEM_B = PARTS * (REGION_B + W_B);
+};
+
+template <int CIN, int COUT, int R, int EPI, int NPASS>
+__global__ void __launch_bounds__(TCT, 1)
+conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo,
+               const uint4* __restrict__ w_hi, const uint4* __restrict__ w_lo, float inv_scale,
+               const float* __restrict__ bias, const float* __restrict__ bn_s,
+               const float* __restrict__ bn_t, __half* __restrict__ out_hi, __half* __restrict__ out_lo,
+               float* __restrict__ feat, const float* __restrict__ crops, float* __restrict__ mse,
+               float* __restrict__ mae, int n_cells, const int32_t* __restrict__ n_dev, int cell0,
+               int chunk_cells) {
+    using C = Cfg<CIN, COUT, R, EPI, NPASS>;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ float red_s[2][TCT / 32];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    unsigned char* a_part[2] = {smem, smem + C::REGION_B};
+    unsigned char* w_part[2] = {smem + C::PARTS * C::REGION_B, smem + C::PARTS * C::REGION_B + C::W_B};
+
+    int n = dev_count(n_cells, n_dev) - cell0;
+    if (n > chunk_cells) n = chunk_cells;
+    if (n <= 0) return;                       // uniform: nothing allocated yet
+    const int n_units = n * C::UNITS_PER_CELL;
+
+    if (warp == 0) tmem_alloc(&tmem_base_s, C::TMEM_COLS);
+    if (tid == 32) { mbar_init(&bar, 1); fence_barrier_init(); }
+    // weights: linear copy of the prepared UMMA images
+    for (int i = tid; i < C::W_B / 16; i += TCT) {
+        reinterpret_cast<uint4*>(w_part[0])[i] = __ldg(w_hi + i);
+        if (NPASS > 1) reinterpret_cast<uint4*>(w_part[1])[i] = __ldg(w_lo + i);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    constexpr uint32_t IDESC = make_idesc(128, COUT);
+    uint32_t parity = 0;
+
+    for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        const int cell = cell0 + unit / C::UNITS_PER_CELL;
+        const int sub = unit % C::UNITS_PER_CELL;   // POOL: pooled X half; else: 16-row band
+
+        // ---- stage the zero-padded input block ----
+        constexpr int N_UNITS16 = C::NCH * C::FILL_ROWS * (C::POOL ? 18 : C::ROW_UNITS);
+        for (int idx = tid; idx < N_UNITS16; idx += TCT) {
+            int c, ry, rc, y, x;
+            uint32_t dst;
+            if (C::POOL) {
+                c = idx / (C::FILL_ROWS * 18);
+                const int rem = idx - c * (C::FILL_ROWS * 18);
+                ry = rem / 18; rc = rem - ry * 18;
+                y = ry - 1; x = 16 * sub - 1 + rc;
+                dst = (uint32_t)(((c * 2 + (rc & 1)) * C::FILL_ROWS + ry) * 9 + (rc >> 1)) * 16u;
+            } else {
+                c = idx / (C::FILL_ROWS * C::ROW_UNITS);
+                const int rem = idx - c * (C::FILL_ROWS * C::ROW_UNITS);
+                ry = rem / C::ROW_UNITS; rc = rem - ry * C::ROW_UNITS;
+                y = 16 * sub + ry - 1; x = rc - 1;
+                dst = (uint32_t)((c * C::FILL_ROWS + ry) * C::ROW_UNITS + rc) * 16u;
+            }
+            uint4 vh = make_uint4(0, 0, 0, 0), vl = make_uint4(0, 0, 0, 0);
+            if (y >= 0 && y < R && x >= 0 && x < R) {
+                const size_t src = ((((size_t)cell * C::NCH + c) * R + y) * R + x);
+                vh = __ldg(reinterpret_cast<const uint4*>(in_hi) + src);
+                if (NPASS > 1) vl = __ldg(reinterpret_cast<const uint4*>(in_lo) + src);
+            }
+            *reinterpret_cast<uint4*>(a_part[0] + dst) = vh;
+            if (NPASS > 1) *reinterpret_cast<uint4*>(a_part[1] + dst) = vl;
+        }
+        fence_async_smem();
+        __syncthreads();
+
+        // ---- MMA issue: one thread ----
+        if (tid == 32) {
+            tc_fence_after();
+#pragma unroll 1
+            for (int t = 0; t < C::TILES; ++t) {
+                const uint32_t d_tmem = tmem_base + (uint32_t)(t * COUT);
+                uint32_t acc = 0;
+#pragma unroll 1
+                for (int pass = 0; pass < NPASS; ++pass) {
+                    const uint32_t abase = smem_u32(a_part[pass == 2 ? 1 : 0]);
+                    const uint32_t wbase = smem_u32(w_part[pass == 1 ? 1 : 0]);
+#pragma unroll 1
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const int dy = tap / 3, dx = tap - dy * 3;
+                        uint32_t aoff;
+                        if (C::POOL) {
+                            const int py = t >> 1, px = t & 1;
+                            aoff = (uint32_t)(((px + dx) & 1) * C::PLANE_B + ((py + dy) * 9 + ((px + dx) >> 1)) * 16);
+                        } else {
+                            aoff = (uint32_t)((dy * C::ROW_UNITS + t * 8 + dx) * 16);
+                        }
+#pragma unroll
+                        for (int s = 0; s < CIN / 16; ++s) {
+                            const uint64_t ad = make_smem_desc(abase + aoff + (uint32_t)(2 * s * C::CHUNK_B),
+                                                               C::CHUNK_B, C::SBO_A);
+                            const uint64_t bd = make_smem_desc(wbase + (uint32_t)((tap * C::NCH + 2 * s) * COUT * 16),
+                                                               COUT * 16, 128);
+                            umma_f16(d_tmem, ad, bd, IDESC, acc);
+                            acc = 1;
+                        }
+                    }
+                }
+            }
+            umma_commit(&bar);
+        }
+        mbar_wait(&bar, parity);
+        parity ^= 1;
+        tc_fence_after();
+
+        // ---- epilogue: TMEM -> registers -> bias/ReLU/BN (-> pool) -> global ----
+        const int q = warp & 3, half_sel = warp >> 2;
+        const int r = 32 * q + lane;                   // MMA row = TMEM lane
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * q) << 16);
+        float se = 0.f, ae = 0.f;
+        if (EPI == EPI_POOL) {
+            constexpr int RO = R / 2;
+            const int Y = r >> 3, X = 8 * sub + (r & 7);
+#pragma unroll 1
+            for (int sl = half_sel; sl < COUT / 8; sl += 2) {
+                const int c0 = sl * 8;
+                uint32_t v[4][8];
+#pragma unroll
+                for (int ph = 0; ph < 4; ++ph) TMEM_LD8(lane_addr + (uint32_t)(ph * COUT + c0), v[ph]);
+#pragma unroll
+                for (int ph = 0; ph < 4; ++ph) TMEM_WAIT8(v[ph]);
+                float o[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float b = __ldg(bias + c0 + k), s = __ldg(bn_s + c0 + k), t = __ldg(bn_t + c0 + k);
+                    float m = -INFINITY;
+#pragma unroll
+                    for (int ph = 0; ph < 4; ++ph) {
+                        float a = fmaf(__uint_as_float(v[ph][k]), inv_scale, b);
+                        a = fmaxf(a, 0.f);
+                        m = fmaxf(m, fmaf(a, s, t));
+                    }
+                    o[k] = m;
+                }
+                if (Y < RO) {
+                    const size_t off = ((((size_t)cell * (COUT / 8) + sl) * RO + Y) * RO + X) * 8;
+                    split_store8(o, out_hi + off, out_lo ? out_lo + off : nullptr);
+                    if (feat) {
+                        float4* f = reinterpret_cast<float4*>(feat + (size_t)cell * (RO * RO * COUT) +
+                                                             (size_t)(Y * RO + X) * COUT + c0);
+                        f[0] = make_float4(o[0], o[1], o[2], o[3]);
+                        f[1] = make_float4(o[4], o[5], o[6], o[7]);
+                    }
+                }
+            }
+        } else {
+            const int y = 16 * sub + (r >> 3);
+            constexpr int SL = EPI == EPI_FINAL ? 1 : COUT / 8;
+#pragma unroll 1
+            for (int p = half_sel; p < C::TILES * SL; p += 2) {
+                const int t = p / SL, sl = p - t * SL;
+                const int c0 = sl * 8;
+                const int x = 8 * t + (r & 7);
+                uint32_t v[8];
+                TMEM_LD8(lane_addr + (uint32_t)(t * COUT + c0), v);
+                TMEM_WAIT8(v);
+                if (EPI == EPI_FINAL) {
+                    // columns 0..3 = output phases (py,px) of the up-sampled 64x64 reconstruction
+                    if (y < R) {
+                        const float b = __ldg(bias);
+                        const float* xr = crops + (size_t)cell * 4096;
+#pragma unroll
+                        for (int ph = 0; ph < 4; ++ph) {
+                            const float a = fmaf(__uint_as_float(v[ph]), inv_scale, b);
+                            const float rec = 1.f / (1.f + expf(-a));
+                            const float d = __ldg(xr + (2 * y + (ph >> 1)) * 64 + 2 * x + (ph & 1)) - rec;
+                            se = fmaf(d, d, se);
+                            ae += fabsf(d);
+                        }
+                    }
+                } else {
+                    float o[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        float a = fmaf(__uint_as_float(v[k]), inv_scale, __ldg(bias + c0 + k));
+                        a = fmaxf(a, 0.f);
+                        o[k] = fmaf(a, __ldg(bn_s + c0 + k), __ldg(bn_t + c0 + k));
+                    }
+                    if (y < R) {
+                        if (EPI == EPI_UP) {
+                            constexpr int RO = 2 * R;
+                            const size_t base = (((size_t)cell * (COUT / 8) + sl) * RO + 2 * y) * RO + 2 * x;
+                            __align__(16) __half hh[8];
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) hh[k] = __float2half_rn(o[k]);
+                            const uint4 pk = *reinterpret_cast<const uint4*>(hh);
+                            uint4* dst = reinterpret_cast<uint4*>(out_hi);
+                            dst[base] = pk; dst[base + 1] = pk; dst[base + RO] = pk; dst[base + RO + 1] = pk;
+                        } else {
+                            const size_t off = ((((size_t)cell * (COUT / 8) + sl) * R + y) * R + x) * 8;
+                            split_store8(o, out_hi + off, nullptr);
+                        }
+                    }
+                }
+            }
+        }
+        if (EPI == EPI_FINAL) {
+            se = warp_sum(se); ae = warp_sum(ae);
+            if (lane == 0) { red_s[0][warp] = se; red_s[1][warp] = ae; }
+        }
+        tc_fence_before();
+        __syncthreads();
+        if (EPI == EPI_FINAL && tid == 0) {
+            float s = 0.f, a = 0.f;
+#pragma unroll
+            for (int w = 0; w < TCT / 32; ++w) { s += red_s[0][w]; a += red_s[1][w]; }
+            // two bands per cell: two commutative float adds onto a zeroed slot -> deterministic
+            atomicAdd(mse + cell, s * (1.f / 4096.f));
+            atomicAdd(mae + cell, a * (1.f / 4096.f));
+        }
+    }
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------
+// Layer 1 (Cin = 1): K = 9 taps padded to 16; the A operand is an explicit im2col of the
+// fp32 crop, built per pooling phase.  Unit = pooled 16x8 tile = conv 32x16 block.
+// ---------------------------------------------------------------------------------------
+template <int NPASS>
+__global__ void __launch_bounds__(TCT, 2)
+conv1_tc_kernel(const float* __restrict__ crops, const uint4* __restrict__ w_hi,
+                const uint4* __restrict__ w_lo, float inv_scale, const float* __restrict__ bias,
+                const float* __restrict__ bn_s, const float* __restrict__ bn_t,
+                __half* __restrict__ out_hi, __half* __restrict__ out_lo, int n_cells,
+                const int32_t* __restrict__ n_dev, int cell0, int chunk_cells) {
+    constexpr int COUT = 32, PARTS = NPASS > 1 ? 2 : 1;
+    constexpr int A_B = 4 * 2 * 128 * 16;           // [phase][k-chunk][row][8 halves]
+    constexpr int W_B = 2 * COUT * 16;
+    __shared__ __align__(1024) unsigned char a_s[PARTS][A_B];
+    __shared__ __align__(16) unsigned char w_s[PARTS][W_B];
+    __shared__ float xs[34][19];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    constexpr int TMEM_COLS = 128;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    int n = dev_count(n_cells, n_dev) - cell0;
+    if (n > chunk_cells) n = chunk_cells;
+    if (n <= 0) return;
+    const int n_units = n * 8;
+
+    if (warp == 0) tmem_alloc(&tmem_base_s, TMEM_COLS);
+    if (tid == 32) { mbar_init(&bar, 1); fence_barrier_init(); }
+    for (int i = tid; i < W_B / 16; i += TCT) {
+        reinterpret_cast<uint4*>(w_s[0])[i] = __ldg(w_hi + i);
+        if (NPASS > 1) reinterpret_cast<uint4*>(w_s[PARTS - 1])[i] = __ldg(w_lo + i);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    constexpr uint32_t IDESC = make_idesc(128, COUT);
+    uint32_t parity = 0;
+
+    for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        const int cell = cell0 + (unit >> 3);
+        const int by = (unit >> 2) & 1, bx = unit & 3;
+        const float* xr = crops + (size_t)cell * 4096;
+        for (int i = tid; i < 34 * 18; i += TCT) {
+            const int ry = i / 18, rc = i - ry * 18;
+            const int y = 32 * by + ry - 1, x = 16 * bx + rc - 1;
+            xs[ry][rc] = (y >= 0 && y < 64 && x >= 0 && x < 64) ? __ldg(xr + y * 64 + x) : 0.f;
+        }
+        __syncthreads();
+        // im2col: item = (phase, k-chunk, row)
+        for (int item = tid; item < 4 * 2 * 128; item += TCT) {
+            const int ph = item >> 8, ck = (item >> 7) & 1, r = item & 127;
+            const int Y = r >> 3, X = r & 7, py = ph >> 1, px = ph & 1;
+            __align__(16) __half hh[8];
+            __align__(16) __half ll[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int tap = ck * 8 + j;
+                float v = 0.f;
+                if (tap < 9) v = xs[2 * Y + py + tap / 3][2 * X + px + tap % 3];
+                hh[j] = __float2half_rn(v);
+                ll[j] = __float2half_rn(v - __half2float(hh[j]));
+            }
+            const int off = ((ph * 2 + ck) * 128 + r) * 16;
+            *reinterpret_cast<uint4*>(a_s[0] + off) = *reinterpret_cast<const uint4*>(hh);
+            if (NPASS > 1) *reinterpret_cast<uint4*>(a_s[PARTS - 1] + off) = *reinterpret_cast<const uint4*>(ll);
+        }
+        fence_async_smem();
+        __syncthreads();
+        if (tid == 32) {
+            tc_fence_after();
+#pragma unroll 1
+            for (int ph = 0; ph < 4; ++ph) {
+#pragma unroll 1
+                for (int pass = 0; pass < NPASS; ++pass) {
+                    const uint32_t abase = smem_u32(a_s[pass == 2 ? PARTS - 1 : 0]) + (uint32_t)(ph * 2 * 128 * 16);
+                    const uint32_t wbase = smem_u32(w_s[pass == 1 ? PARTS - 1 : 0]);
+                    umma_f16(tmem_base + (uint32_t)(ph * COUT), make_smem_desc(abase, 128 * 16, 128),
+                             make_smem_desc(wbase, COUT * 16, 128), IDESC, pass > 0 ? 1u : 0u);
+                }
+            }
+            umma_commit(&bar);
+        }
+        mbar_wait(&bar, parity);
+        parity ^= 1;
+        tc_fence_after();
+
+        const int q = warp & 3, half_sel = warp >> 2;
+        const int r = 32 * q + lane;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * q) << 16);
+        const int Y = 16 * by + (r >> 3), X = 8 * bx + (r & 7);
+#pragma unroll 1
+        for (int sl = half_sel; sl < COUT / 8; sl += 2) {
+            const int c0 = sl * 8;
+            uint32_t v[4][8];
+#pragma unroll
+            for (int ph = 0; ph < 4; ++ph) TMEM_LD8(lane_addr + (uint32_t)(ph * COUT + c0), v[ph]);
+#pragma unroll
+            for (int ph = 0; ph < 4; ++ph) TMEM_WAIT8(v[ph]);
+            float o[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float b = __ldg(bias + c0 + k), s = __ldg(bn_s + c0 + k), t = __ldg(bn_t + c0 + k);
+                float m = -INFINITY;
+#pragma unroll
+                for (int ph = 0; ph < 4; ++ph) {
+                    float a = fmaf(__uint_as_float(v[ph][k]), inv_scale, b);
+                    a = fmaxf(a, 0.f);
+                    m = fmaxf(m, fmaf(a, s, t));
+                }
+                o[k] = m;
+            }
+            const size_t off = ((((size_t)cell * (COUT / 8) + sl) * 32 + Y) * 32 + X) * 8;
+            split_store8(o, out_hi + off, out_lo ? out_lo + off : nullptr);
+        }
+        tc_fence_before();
+        __syncthreads();
+    }
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+template <int CIN, int COUT, int R, int EPI, int NPASS>
+int launch_tc(cia_ctx* h, const CaeWeights& w, int layer, const __half* in_hi, const __half* in_lo,
+              __half* out_hi, __half* out_lo, float* feat, const float* crops, float* mse, float* mae,
+              int n, const int32_t* n_dev, int cell0, int chunk, cudaStream_t s) {
+    using C = Cfg<CIN, COUT, R, EPI, NPASS>;
+    auto kern = conv_tc_kernel<CIN, COUT, R, EPI, NPASS>;
+    static bool attr = false;
+    if (!attr) {
+        CIA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_B));
+        attr = true;
+    }
+    int grid = chunk * C::UNITS_PER_CELL;
+    const int cap = h->num_sms * (C::SMEM_B > 100 * 1024 ? 1 : 2);
+    if (grid > cap) grid = cap;
+    kern<<<grid, TCT, C::SMEM_B, s>>>(in_hi, in_lo, (const uint4*)w.tc_w[layer][0], (const uint4*)w.tc_w[layer][1],
+                                      w.tc_inv_scale[layer], w.bias[layer], w.bn_scale[layer], w.bn_shift[layer],
+                                      out_hi, out_lo, feat, crops, mse, mae, n, n_dev, cell0, chunk);
+    CIA_LAUNCH_CHECK();
+    return CIA_OK;
+}
+
+// One B image: [(tap*NCH + chunk)*N + n][8] halves = w[tap][chunk*8 + j][n] * 2^sw, hi and lo parts.
+static void pack_image(const std::vector<float>& w /* [taps][cin][n] */, int taps, int cin, int N,
+                       int n_real, int sw, std::vector<__half>& hi, std::vector<__half>& lo) {
+    const int nch = cin / 8;
+    hi.assign((size_t)taps * nch * N * 8, __float2half_rn(0.f));
+    lo = hi;
+    const float sc = std::ldexp(1.f, sw);
+    for (int tap = 0; tap < taps; ++tap)
+        for (int c = 0; c < cin; ++c)
+            for (int nn = 0; nn < n_real; ++nn) {
+                const float v = w[((size_t)tap * cin + c) * n_real + nn] * sc;
+                const __half hv = __float2half_rn(v);
+                const size_t idx = (((size_t)tap * nch + c / 8) * N + nn) * 8 + (c % 8);
+                hi[idx] = hv;
+                lo[idx] = __float2half_rn(v - __half2float(hv));
+            }
+}
+
+static int scale_exp(const std::vector<float>& w) {
+    float m = 0.f;
+    for (float v : w) m = std::fmax(m, std::fabs(v));
+    if (!(m > 0.f)) return 0;
+    int e;
+    std::frexp(m, &e);          // m = f * 2^e, f in [0.5, 1)
+    return 2 - e;               // m * 2^sw in [2, 4)
+}
+
+}  // namespace
+
+int k_cae_tc_prepare(cia_ctx* h, int which) {
+    CaeWeights& w = h->cae[which];
+    w.tc_ready = false;
+    for (int L = 0; L < w.n_conv; ++L) {
+        const int cin = kCaeCin[L], cout = kCaeCout[L];
+        std::vector<float> k((size_t)9 * cin * cout);
+        CIA_CUDA(cudaMemcpy(k.data(), w.kernel[L], k.size() * sizeof(float), cudaMemcpyDeviceToHost));
+        std::vector<__half> hi, lo;
+        int sw;
+        if (L == 0) {
+            // K = tap index, padded 9 -> 16: treat as 1 "tap" with 16 "input channels"
+            std::vector<float> kk((size_t)16 * cout, 0.f);
+            for (int tap = 0; tap < 9; ++tap)
+                for (int nn = 0; nn < cout; ++nn) kk[(size_t)tap * cout + nn] = k[(size_t)tap * cout + nn];
+            sw = scale_exp(kk);
+            pack_image(kk, 1, 16, cout, cout, sw, hi, lo);
+        } else if (L == 6) {
+            // phase form: conv on the nearest-up-sampled input == 3x3 conv on the low-res input
+            // with 4 outputs (py,px); weights of hi-res taps that fall on the same low-res pixel add up
+            std::vector<float> kp((size_t)9 * cin * 4, 0.f);
+            for (int py = 0; py < 2; ++py)
+                for (int px = 0; px < 2; ++px)
+                    for (int dy = 0; dy < 3; ++dy)
+                        for (int dx = 0; dx < 3; ++dx) {
+                            const int oy = (int)std::floor((py + dy - 1) / 2.0), ox = (int)std::floor((px + dx - 1) / 2.0);
+                            const int tl = (oy + 1) * 3 + (ox + 1);
+                            for (int c = 0; c < cin; ++c)
+                                kp[((size_t)tl * cin + c) * 4 + py * 2 + px] += k[((size_t)(dy * 3 + dx) * cin + c)];
+                        }
+            sw = scale_exp(kp);
+            pack_image(kp, 9, cin, 16, 4, sw, hi, lo);
+        } else {
+            sw = scale_exp(k);
+            pack_image(k, 9, cin, cout, cout, sw, hi, lo);
+        }
+        w.tc_inv_scale[L] = std::ldexp(1.f, -sw);
+        for (int j = 0; j < 2; ++j) {
+            cudaFree(w.tc_w[L][j]); w.tc_w[L][j] = nullptr;
+            const std::vector<__half>& src = j == 0 ? hi : lo;
+            CIA_CUDA(cudaMalloc(&w.tc_w[L][j], src.size() * sizeof(__half)));
+            CIA_CUDA(cudaMemcpy(w.tc_w[L][j], src.data(), src.size() * sizeof(__half), cudaMemcpyHostToDevice));
+        }
+    }
+    w.tc_ready = true;
+    return CIA_OK;
+}
+
+// precision 1: split-precision (3 MMAs) encoder, features tapped from the tensor-core pass.
+// precision 2: single-pass tensor-core autoencoder for MSE/MAE; features from the exact fp32
+//              encoder (the reference itself runs encoder.predict as a second pass, det:130).
+int k_cae_forward_tc(cia_ctx* h, const float* crops, int n, const int32_t* n_dev, float* mse,
+                     float* mae, float* features, int mode, cudaStream_t s) {
+    if (n <= 0) return CIA_OK;
+    const CaeWeights& ae = h->cae[0];
+    if (!ae.loaded || ae.n_conv != 7 || !ae.tc_ready) { h->err = "cia_cae_forward: autoencoder not loaded"; return CIA_E_STATE; }
+    const bool sep = h->cae[1].loaded;
+    const bool tc_feat = mode == 1 && !sep;
+    const int CH = 512;
+    const size_t a1 = 4 * 32 * 32 * 8, a2 = 8 * 16 * 16 * 8, a3 = 4 * 8 * 8 * 8, a4u = 4 * 16 * 16 * 8,
+                 a5u = 8 * 32 * 32 * 8, a6 = 4 * 32 * 32 * 8;
+    const size_t per_cell = 2 * a1 + 2 * a2 + a3 + a4u + a5u + a6;     // halves
+    int rc = ws_reserve(h, h->ws_misc, (size_t)CH * per_cell * sizeof(__half));
+    if (rc) return rc;
+    __half* A1h = (__half*)h->ws_misc.p;
+    __half* A1l = A1h + CH * a1;
+    __half* A2h = A1l + CH * a1;
+    __half* A2l = A2h + CH * a2;
+    __half* A3h = A2l + CH * a2;
+    __half* A4u = A3h + CH * a3;
+    __half* A5u = A4u + CH * a4u;
+    __half* A6 = A5u + CH * a5u;
+    CIA_CUDA(cudaMemsetAsync(mse, 0, (size_t)n * sizeof(float), s));
+    CIA_CUDA(cudaMemsetAsync(mae, 0, (size_t)n * sizeof(float), s));
+    for (int c0 = 0; c0 < n; c0 += CH) {
+        const int chunk = (n - c0) < CH ? (n - c0) : CH;
+        // activation buffers are chunk-relative; kernels index by absolute cell
+        __half* a1h = A1h - (size_t)c0 * a1; __half* a1l = A1l - (size_t)c0 * a1;
+        __half* a2h = A2h - (size_t)c0 * a2; __half* a2l = A2l - (size_t)c0 * a2;
+        __half* a3h = A3h - (size_t)c0 * a3; __half* a4 = A4u - (size_t)c0 * a4u;
+        __half* a5 = A5u - (size_t)c0 * a5u; __half* a6p = A6 - (size_t)c0 * a6;
+        float* feat = tc_feat ? features : nullptr;
+        int grid1 = chunk * 8;
+        if (grid1 > h->num_sms * 2) grid1 = h->num_sms * 2;
+        if (tc_feat) {
+            conv1_tc_kernel<3><<<grid1, TCT, 0, s>>>(crops, (const uint4*)ae.tc_w[0][0], (const uint4*)ae.tc_w[0][1],
+                                                     ae.tc_inv_scale[0], ae.bias[0], ae.bn_scale[0], ae.bn_shift[0],
+                                                     a1h, a1l, n, n_dev, c0, chunk);
+            CIA_LAUNCH_CHECK();
+            if ((rc = launch_tc<32, 64, 32, EPI_POOL, 3>(h, ae, 1, a1h, a1l, a2h, a2l, nullptr, nullptr, nullptr, nullptr, n, n_dev, c0, chunk, s))) return rc;
+            if ((rc = launch_tc<64, 32, 16, EPI_POOL, 3>(h, ae, 2, a2h, a2l, a3h, nullptr, feat, nullptr, nullptr, nullptr, n, n_dev, c0, chunk, s))) return rc;
+        } else {
+            conv1_tc_kernel<1><<<grid1, TCT, 0, s>>>(crops, (const uint4*)ae.tc_w[0][0], (const uint4*)ae.tc_w[0][1],
+                                                     ae.tc_inv_scale[0], ae.bias[0], ae.bn_scale[0], ae.bn_shift[0],
+                                                     a1h, nullptr, n, n_dev, c0, chunk);
+            CIA_LAUNCH_CHECK();
+            if ((rc = launch_tc<32, 64, 32, EPI_POOL, 1>(h, ae, 1, a1h, nullptr, a2h, nullptr, nullptr, nullptr, nullptr, nullptr, n, n_dev, c0, chunk, s))) return rc;
+            if ((rc = launch_tc<64, 32, 16, EPI_POOL, 1>(h, ae, 2, a2h, nullptr, a3h, nullptr, nullptr, nullptr, nullptr, nullptr, n, n_dev, c0, chunk, s))) return rc;
+        }
+        if ((rc = launch_tc<32, 32, 8, EPI_UP, 1>(h, ae, 3, a3h, nullptr, a4, nullptr, nullptr, nullptr, nullptr, nullptr, n, n_dev, c0, chunk, s))) return rc;
+        if ((rc = launch_tc<32, 64, 16, EPI_UP, 1>(h, ae, 4, a4, nullptr, a5, nullptr, nullptr, nullptr, nullptr, nullptr, n, n_dev, c0, chunk, s))) return rc;
+        if ((rc = launch_tc<64, 32, 32, EPI_PLAIN, 1>(h, ae, 5, a5, nullptr, a6p, nullptr, nullptr, nullptr, nullptr, nullptr, n, n_dev, c0, chunk, s))) return rc;
+        if ((rc = launch_tc<32, 16, 32, EPI_FINAL, 1>(h, ae, 6, a6p, nullptr, nullptr, nullptr, nullptr, crops, mse, mae, n, n_dev, c0, chunk, s))) return rc;
+    }
+    if (features && !tc_feat) {
+        rc = k_encoder_fp32(h, sep ? h->cae[1] : h->cae[0], crops, n, n_dev, features, s);
+        if (rc) return rc;
+    }
+    return CIA_OK;
 }

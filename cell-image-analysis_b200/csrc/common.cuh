@@ -23,8 +23,11 @@ struct CaeWeights {
     float* bias[CAE_NCONV] = {};
     float* bn_scale[CAE_NCONV] = {}; // gamma / sqrt(var + eps)            (fp32, folded like tf.nn.batch_normalization)
     float* bn_shift[CAE_NCONV] = {}; // beta - mean * scale
-    // tensor-core operand images (built at load time, see cae_tc.cu)
-    void* tc_blob = nullptr;
+    // tensor-core operand images (built at load time, see cae_tc.cu): per layer the fp16
+    // hi / lo parts of the power-of-two scaled weights in UMMA K-major core-matrix order
+    void* tc_w[CAE_NCONV][2] = {};
+    float tc_inv_scale[CAE_NCONV] = {};
+    bool tc_ready = false;
 };
 
 struct SvmModel {
@@ -133,7 +136,9 @@ int k_crop_resize(cia_ctx* h, const uint16_t* images, int H, int W, const cia_ce
 int k_cae_forward_fp32(cia_ctx* h, const float* crops, int n, const int32_t* n_dev, float* mse,
                        float* mae, float* features, cudaStream_t s);
 int k_cae_forward_tc(cia_ctx* h, const float* crops, int n, const int32_t* n_dev, float* mse,
-                     float* mae, float* features, cudaStream_t s);
+                     float* mae, float* features, int mode, cudaStream_t s);
+int k_encoder_fp32(cia_ctx* h, const CaeWeights& w, const float* crops, int n, const int32_t* n_dev,
+                   float* features, cudaStream_t s);
 int k_cae_tc_prepare(cia_ctx* h, int which);
 int k_svm_decision(cia_ctx* h, const float* features, int n, const int32_t* n_dev,
                    double* dec_cons, double* dec_mod, int8_t* pred_cons, int8_t* pred_mod,

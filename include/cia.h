@@ -196,6 +196,10 @@ int cia_screen_fields_host(cia_handle h, const uint16_t* images_host,
 int cia_profile_begin(cia_handle h, int max_records);
 int cia_profile_end(cia_handle h, double* stage_ms /* [6] */, int* n_records);
 
+/* Test tap: copy `bytes` at `offset` of internal workspace `ws_id` to host (synchronises).
+ * ws_id 5 holds the tensor-core path's fp16 activations (layout in cae_tc.cu). */
+int cia_debug_copy_workspace(cia_handle h, int ws_id, size_t offset, void* dst_host, size_t bytes);
+
 /* Number of kernels this library has launched on the handle (bench's gpu_launches). */
 int64_t cia_launch_count(cia_handle h);
 
