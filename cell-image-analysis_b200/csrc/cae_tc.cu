@@ -206,32 +206,29 @@ conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_l
         // ---- MMA issue: one thread ----
         if (tid == 32) {
             tc_fence_after();
+            // The single issuing thread is the bottleneck unless the per-MMA work is ~a few
+            // instructions (profiles/umma_microbench.cu): descriptors are built once per pass and
+            // every tile/tap/k-step offset is a compile-time constant added to their low word.
 #pragma unroll 1
-            for (int t = 0; t < C::TILES; ++t) {
-                const uint32_t d_tmem = tmem_base + (uint32_t)(t * COUT);
-                uint32_t acc = 0;
-#pragma unroll 1
-                for (int pass = 0; pass < NPASS; ++pass) {
-                    const uint32_t abase = smem_u32(a_part[pass == 2 ? 1 : 0]);
-                    const uint32_t wbase = smem_u32(w_part[pass == 1 ? 1 : 0]);
-#pragma unroll 1
+            for (int pass = 0; pass < NPASS; ++pass) {
+                const uint64_t ad0 = make_smem_desc(smem_u32(a_part[pass == 2 ? 1 : 0]), C::CHUNK_B, C::SBO_A);
+                const uint64_t bd0 = make_smem_desc(smem_u32(w_part[pass == 1 ? 1 : 0]), COUT * 16, 128);
+                const uint32_t acc0 = pass > 0 ? 1u : 0u;
+#pragma unroll
+                for (int t = 0; t < C::TILES; ++t) {
+#pragma unroll
                     for (int tap = 0; tap < 9; ++tap) {
-                        const int dy = tap / 3, dx = tap - dy * 3;
-                        uint32_t aoff;
-                        if (C::POOL) {
-                            const int py = t >> 1, px = t & 1;
-                            aoff = (uint32_t)(((px + dx) & 1) * C::PLANE_B + ((py + dy) * 9 + ((px + dx) >> 1)) * 16);
-                        } else {
-                            aoff = (uint32_t)((dy * C::ROW_UNITS + t * 8 + dx) * 16);
-                        }
+                        const int dy = tap / 3, dx = tap % 3;
+                        const int py = t >> 1, px = t & 1;
+                        const int aoff = C::POOL
+                            ? ((px + dx) & 1) * C::PLANE_B + ((py + dy) * 9 + ((px + dx) >> 1)) * 16
+                            : (dy * C::ROW_UNITS + t * 8 + dx) * 16;
 #pragma unroll
                         for (int s = 0; s < CIN / 16; ++s) {
-                            const uint64_t ad = make_smem_desc(abase + aoff + (uint32_t)(2 * s * C::CHUNK_B),
-                                                               C::CHUNK_B, C::SBO_A);
-                            const uint64_t bd = make_smem_desc(wbase + (uint32_t)((tap * C::NCH + 2 * s) * COUT * 16),
-                                                               COUT * 16, 128);
-                            umma_f16(d_tmem, ad, bd, IDESC, acc);
-                            acc = 1;
+                            const uint64_t ad = ad0 + (uint64_t)((aoff + 2 * s * C::CHUNK_B) >> 4);
+                            const uint64_t bd = bd0 + (uint64_t)(((tap * C::NCH + 2 * s) * COUT * 16) >> 4);
+                            umma_f16(tmem_base + (uint32_t)(t * COUT), ad, bd, IDESC,
+                                     (tap == 0 && s == 0) ? acc0 : 1u);
                         }
                     }
                 }

@@ -10,51 +10,84 @@
 namespace {
 
 constexpr int PT = 256;        // threads
-constexpr int PCELLS = 8;      // cells per block in the projection kernel
+constexpr int PB = 64;         // cells per block
+constexpr int PFT = 32;        // features per shared-memory tile
+constexpr int PCT = 128;       // components per block tile
+constexpr int XPAD = PB + 2;   // padded row of the transposed x tile
 
-// z[c] = sum_f x2[f] * Wt[f][c] - offset[c], fp64 accumulation over fp32-rounded inputs.
+// z[c] = sum_f x2[f] * Wt[f][c] - offset[c]: a register-blocked fp64 GEMM tile (64 cells x 128
+// components per block, 8 x 4 accumulators per thread) over fp32-rounded inputs.
 // x2 mirrors sklearn's in-place float32 flow: x1 = f32(x - center), x2 = f32(f64(x1)/scale).
 __global__ void __launch_bounds__(PT)
 scaler_pca_kernel(const float* __restrict__ feat, int n_cells, const int32_t* __restrict__ n_dev,
                   int F, int C, const double* __restrict__ center, const double* __restrict__ scale,
                   int center_is_f32, const double* __restrict__ comp_t,
                   const double* __restrict__ offset, int f32_flow, double* __restrict__ z_out) {
-    extern __shared__ float xs[];   // [PCELLS][F]
+    extern __shared__ __align__(16) unsigned char pca_smem[];
+    double (*ws)[PCT] = reinterpret_cast<double (*)[PCT]>(pca_smem);
+    double (*xs)[XPAD] = reinterpret_cast<double (*)[XPAD]>(pca_smem + sizeof(double) * PFT * PCT);
     const int n = dev_count(n_cells, n_dev);
-    const int cell0 = blockIdx.x * PCELLS;
+    const int cell0 = blockIdx.x * PB;
     if (cell0 >= n) return;
-    const int nc = min(PCELLS, n - cell0);
-    for (int i = threadIdx.x; i < PCELLS * F; i += PT) {
-        const int k = i / F, f = i - k * F;
-        float v = 0.f;
-        if (k < nc) {
-            v = __ldg(feat + (size_t)(cell0 + k) * F + f);
-            if (center) {
-                if (center_is_f32) v = __fsub_rn(v, (float)center[f]);
-                else v = (float)__dsub_rn((double)v, center[f]);
+    const int c_tile0 = blockIdx.y * PCT;
+    const int tid = threadIdx.x, cx = tid & 31, cy = tid >> 5;
+    double acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+
+    for (int f0 = 0; f0 < F; f0 += PFT) {
+        __syncthreads();
+        for (int idx = tid; idx < PB * PFT; idx += PT) {
+            const int i = idx / PFT, ff = idx - i * PFT;
+            const int f = f0 + ff, cell = cell0 + i;
+            float v = 0.f;
+            if (cell < n && f < F) {
+                v = __ldg(feat + (size_t)cell * F + f);
+                if (center) {
+                    if (center_is_f32) v = __fsub_rn(v, (float)center[f]);
+                    else v = (float)__dsub_rn((double)v, center[f]);
+                }
+                if (scale) v = (float)__ddiv_rn((double)v, scale[f]);
             }
-            if (scale) v = (float)__ddiv_rn((double)v, scale[f]);
+            xs[ff][i] = (double)v;
         }
-        xs[i] = v;
+        for (int idx = tid; idx < PFT * PCT; idx += PT) {
+            const int ff = idx / PCT, c = idx - ff * PCT;
+            const int f = f0 + ff, cc = c_tile0 + c;
+            ws[ff][c] = (f < F && cc < C) ? __ldg(comp_t + (size_t)f * C + cc) : 0.0;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int ff = 0; ff < PFT; ++ff) {
+            double w[4], x[8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) w[j] = ws[ff][cx + 32 * j];
+#pragma unroll
+            for (int i = 0; i < 8; i += 2) {
+                const double2 t = *reinterpret_cast<const double2*>(&xs[ff][cy * 8 + i]);
+                x[i] = t.x; x[i + 1] = t.y;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fma(x[i], w[j], acc[i][j]);
+        }
     }
-    __syncthreads();
-    for (int c = threadIdx.x; c < C; c += PT) {
-        double acc[PCELLS];
 #pragma unroll
-        for (int k = 0; k < PCELLS; ++k) acc[k] = 0.0;
-        for (int f = 0; f < F; ++f) {
-            const double w = __ldg(comp_t + (size_t)f * C + c);
-#pragma unroll
-            for (int k = 0; k < PCELLS; ++k) acc[k] = fma((double)xs[k * F + f], w, acc[k]);
-        }
+    for (int j = 0; j < 4; ++j) {
+        const int c = c_tile0 + cx + 32 * j;
+        if (c >= C) continue;
         const double off = offset[c];
 #pragma unroll
-        for (int k = 0; k < PCELLS; ++k) {
-            if (k < nc) {
+        for (int i = 0; i < 8; ++i) {
+            const int cell = cell0 + cy * 8 + i;
+            if (cell < n) {
                 double z;
-                if (f32_flow) z = (double)__fsub_rn((float)acc[k], (float)off);
-                else z = __dsub_rn(acc[k], off);
-                z_out[(size_t)(cell0 + k) * C + c] = z;
+                if (f32_flow) z = (double)__fsub_rn((float)acc[i][j], (float)off);
+                else z = __dsub_rn(acc[i][j], off);
+                z_out[(size_t)cell * C + c] = z;
             }
         }
     }
@@ -170,14 +203,13 @@ int k_svm_decision(cia_ctx* h, const float* features, int n, const int32_t* n_de
         z = (double*)h->ws_feat.p;
     }
     static bool attr = false;
-    const size_t sm1 = (size_t)PCELLS * sp.F * sizeof(float);
-    if (sm1 > 200 * 1024) { h->err = "feature dimension too large"; return CIA_E_ARG; }
     if (!attr) {
-        CIA_CUDA(cudaFuncSetAttribute(scaler_pca_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CIA_CUDA(cudaFuncSetAttribute(svm_rbf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CIA_CUDA(cudaFuncSetAttribute(scaler_pca_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         attr = true;
     }
-    scaler_pca_kernel<<<(n + PCELLS - 1) / PCELLS, PT, sm1, s>>>(
+    const size_t sm1 = sizeof(double) * PFT * (PCT + XPAD);
+    scaler_pca_kernel<<<dim3((n + PB - 1) / PB, (sp.C + PCT - 1) / PCT), PT, sm1, s>>>(
         features, n, n_dev, sp.F, sp.C, sp.has_center ? sp.center : nullptr,
         sp.has_scale ? sp.scale : nullptr, sp.center_is_f32, sp.comp_t, sp.offset, sp.f32_flow, z);
     CIA_LAUNCH_CHECK();
