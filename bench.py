@@ -360,7 +360,8 @@ def main():
     ap.add_argument("--pool", type=int, default=48, help="distinct resident fields per GPU")
     ap.add_argument("--chunk", type=int, default=16, help="fields per fused call")
     ap.add_argument("--strains", type=int, default=4)
-    ap.add_argument("--precision", type=int, default=0)
+    ap.add_argument("--precision", type=int, default=1,
+                    help="CAE path: 0 exact fp32 CUDA cores, 1 tcgen05 (split-precision encoder), 2 tcgen05 + fp32 encoder")
     ap.add_argument("--cpu-fields", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -46,7 +46,10 @@ int cia_create(int device, cia_handle* out) {
     if (cudaMalloc(&h->status_dev, sizeof(int32_t)) != cudaSuccess ||
         cudaMemset(h->status_dev, 0, sizeof(int32_t)) != cudaSuccess ||
         cudaMallocHost(&h->status_host, sizeof(int32_t)) != cudaSuccess ||
-        cudaEventCreateWithFlags(&h->ev, cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventCreateWithFlags(&h->ev, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess) {
         delete h;
         return CIA_E_CUDA;
     }
@@ -78,6 +81,9 @@ int cia_destroy(cia_handle h) {
     cudaFree(h->status_dev);
     cudaFreeHost(h->status_host);
     if (h->ev) cudaEventDestroy(h->ev);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->side) cudaStreamDestroy(h->side);
     for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
     delete h;
     return CIA_OK;
@@ -236,9 +242,9 @@ int cia_cae_forward(cia_handle h, const float* crops32, int n_cells, const int32
     if (!crops32 || !mse || !mae) { h->err = "cia_cae_forward: null pointer"; return CIA_E_ARG; }
     if (precision == 0)
         return k_cae_forward_fp32(h, crops32, n_cells, n_cells_dev, mse, mae, features, (cudaStream_t)stream);
-    if (precision == 1 || precision == 2)
+    if (precision >= 1 && precision <= 3)
         return k_cae_forward_tc(h, crops32, n_cells, n_cells_dev, mse, mae, features, precision, (cudaStream_t)stream);
-    h->err = "cia_cae_forward: precision must be 0 (fp32), 1 (tensor core) or 2 (tensor core + fp32 encoder)";
+    h->err = "cia_cae_forward: precision must be 0 (fp32), 1 (tensor core), 2 (tensor core + fp32 encoder) or 3 (tensor core + fp32 third layer)";
     return CIA_E_ARG;
 }
 

@@ -225,6 +225,12 @@ int launch_conv(cia_ctx* h, const CaeWeights& w, int layer, const float* in, flo
 
 }  // namespace
 
+// Third encoder layer alone in exact fp32 (input: fp32 NHWC 16x16x64, output: features).
+int k_conv3_fp32(cia_ctx* h, const CaeWeights& w, const float* a2, int n, const int32_t* n_dev,
+                 float* features, int cell0, int chunk, cudaStream_t s) {
+    return launch_conv<64, 32, 16, true, false>(h, w, 2, a2, features, n, n_dev, cell0, chunk, s);
+}
+
 // encoder.predict + flatten (det:130-131) alone: the three encoder layers in exact fp32.
 int k_encoder_fp32(cia_ctx* h, const CaeWeights& w, const float* crops, int n, const int32_t* n_dev,
                    float* features, cudaStream_t s) {

@@ -95,7 +95,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
     return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
-constexpr int pow2_cols(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
+__host__ __device__ constexpr int pow2_cols(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
 
 __device__ __forceinline__ void split_store8(const float (&o)[8], __half* hi_dst, __half* lo_dst) {
     __align__(16) __half hh[8];
@@ -350,6 +350,217 @@ conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_l
 }
 
 // ---------------------------------------------------------------------------------------
+// Split-precision pooling layers with ACCURATE accumulation (encoder layers 2 and 3).
+//
+// tcgen05.mma adds every k-step into its fp32 TMEM accumulator with round-toward-zero
+// (profiles/umma_rounding_test.cu): a K = 288..576 chain picks up a ~1e-6 relative bias, too
+// much for the one-class SVM downstream.  Here a TMEM accumulator only ever holds ONE filter
+// tap: the cross terms (hi*lo, lo*hi; 2^-11 of the magnitude) are issued first into the fresh
+// accumulator, the hi*hi k-steps last, so only Cin/16 truncations happen at a third of the
+// final magnitude.  The nine per-tap partial sums are added in fp32 registers (round to
+// nearest) by the epilogue warps while the MMA warp already fills the other TMEM stage.
+//   warps 0..15: stage input block, per tap tcgen05.ld the partial and add, final epilogue
+//   warp 16    : one lane issues the MMAs (descriptors precomputed, offsets compile-time)
+// ---------------------------------------------------------------------------------------
+constexpr int ACC_EPI_WARPS = 16;
+constexpr int ACC_THREADS = (ACC_EPI_WARPS + 1) * 32;
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int CIN, int COUT, int R>
+__global__ void __launch_bounds__(ACC_THREADS, 1)
+conv_tc_acc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo,
+                   const uint4* __restrict__ w_hi, const uint4* __restrict__ w_lo, float inv_scale,
+                   const float* __restrict__ bias, const float* __restrict__ bn_s,
+                   const float* __restrict__ bn_t, __half* __restrict__ out_hi, __half* __restrict__ out_lo,
+                   float* __restrict__ feat, int n_cells, const int32_t* __restrict__ n_dev, int cell0,
+                   int chunk_cells) {
+    using C = Cfg<CIN, COUT, R, EPI_POOL, 3>;
+    constexpr int STAGE_COLS = 4 * COUT;
+    constexpr int TMEM_COLS = pow2_cols(2 * STAGE_COLS);
+    constexpr int CW = COUT / 4;                 // columns per epilogue warp
+    constexpr int EPT = ACC_EPI_WARPS * 32;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ __align__(8) uint64_t full_bar[2], empty_bar[2], ready_bar;
+    __shared__ uint32_t tmem_base_s;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    unsigned char* a_part[2] = {smem, smem + C::REGION_B};
+    unsigned char* w_part[2] = {smem + 2 * C::REGION_B, smem + 2 * C::REGION_B + C::W_B};
+
+    int n = dev_count(n_cells, n_dev) - cell0;
+    if (n > chunk_cells) n = chunk_cells;
+    if (n <= 0) return;
+    const int n_units = n * C::UNITS_PER_CELL;
+
+    if (warp == 0) tmem_alloc(&tmem_base_s, TMEM_COLS);
+    if (tid == 32) {
+        mbar_init(&full_bar[0], 1); mbar_init(&full_bar[1], 1);
+        mbar_init(&empty_bar[0], ACC_EPI_WARPS); mbar_init(&empty_bar[1], ACC_EPI_WARPS);
+        mbar_init(&ready_bar, ACC_EPI_WARPS);
+        fence_barrier_init();
+    }
+    for (int i = tid; i < C::W_B / 16; i += ACC_THREADS) {
+        reinterpret_cast<uint4*>(w_part[0])[i] = __ldg(w_hi + i);
+        reinterpret_cast<uint4*>(w_part[1])[i] = __ldg(w_lo + i);
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    constexpr uint32_t IDESC = make_idesc(128, COUT);
+
+    if (warp == ACC_EPI_WARPS) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            const uint64_t a_hi0 = make_smem_desc(smem_u32(a_part[0]), C::CHUNK_B, C::SBO_A);
+            const uint64_t a_lo0 = make_smem_desc(smem_u32(a_part[1]), C::CHUNK_B, C::SBO_A);
+            const uint64_t b_hi0 = make_smem_desc(smem_u32(w_part[0]), COUT * 16, 128);
+            const uint64_t b_lo0 = make_smem_desc(smem_u32(w_part[1]), COUT * 16, 128);
+            uint32_t it = 0, uphase = 0;
+            for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+                mbar_wait(&ready_bar, uphase);
+                uphase ^= 1;
+                tc_fence_after();
+#pragma unroll
+                for (int tap = 0; tap < 9; ++tap) {
+                    const uint32_t st = it & 1;
+                    mbar_wait(&empty_bar[st], ((it >> 1) & 1) ^ 1);
+                    tc_fence_after();
+                    const int dy = tap / 3, dx = tap % 3;
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const int py = t >> 1, px = t & 1;
+                        const int aoff = ((px + dx) & 1) * C::PLANE_B + ((py + dy) * 9 + ((px + dx) >> 1)) * 16;
+                        const uint32_t d = tmem_base + st * STAGE_COLS + (uint32_t)(t * COUT);
+                        // pass order: hi*lo, lo*hi (tiny), then hi*hi (see header comment)
+#pragma unroll
+                        for (int pass = 0; pass < 3; ++pass) {
+                            const uint64_t a0 = pass == 1 ? a_lo0 : a_hi0;
+                            const uint64_t b0 = pass == 0 ? b_lo0 : b_hi0;
+#pragma unroll
+                            for (int s = 0; s < CIN / 16; ++s) {
+                                const uint64_t ad = a0 + (uint64_t)((aoff + 2 * s * C::CHUNK_B) >> 4);
+                                const uint64_t bd = b0 + (uint64_t)(((tap * C::NCH + 2 * s) * COUT * 16) >> 4);
+                                umma_f16(d, ad, bd, IDESC, (pass == 0 && s == 0) ? 0u : 1u);
+                            }
+                        }
+                    }
+                    umma_commit(&full_bar[st]);
+                    ++it;
+                }
+            }
+        }
+    } else {
+        // ================= loaders / accumulating epilogue =================
+        const int q = warp & 3, cq = warp >> 2;
+        const int r = 32 * q + lane;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(cq * CW);
+        uint32_t it = 0;
+        for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+            const int cell = cell0 + unit / C::UNITS_PER_CELL;
+            const int sub = unit % C::UNITS_PER_CELL;
+            // stage the zero-padded, column-parity de-interleaved input block (hi and lo)
+            constexpr int N_UNITS16 = C::NCH * C::FILL_ROWS * 18;
+            for (int idx = tid; idx < N_UNITS16; idx += EPT) {
+                const int c = idx / (C::FILL_ROWS * 18);
+                const int rem = idx - c * (C::FILL_ROWS * 18);
+                const int ry = rem / 18, rc = rem - ry * 18;
+                const int y = ry - 1, x = 16 * sub - 1 + rc;
+                const uint32_t dst = (uint32_t)(((c * 2 + (rc & 1)) * C::FILL_ROWS + ry) * 9 + (rc >> 1)) * 16u;
+                uint4 vh = make_uint4(0, 0, 0, 0), vl = make_uint4(0, 0, 0, 0);
+                if (y >= 0 && y < R && x >= 0 && x < R) {
+                    const size_t src = ((((size_t)cell * C::NCH + c) * R + y) * R + x);
+                    vh = __ldg(reinterpret_cast<const uint4*>(in_hi) + src);
+                    vl = __ldg(reinterpret_cast<const uint4*>(in_lo) + src);
+                }
+                *reinterpret_cast<uint4*>(a_part[0] + dst) = vh;
+                *reinterpret_cast<uint4*>(a_part[1] + dst) = vl;
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ready_bar);
+
+            float acc[4][CW];
+#pragma unroll
+            for (int ph = 0; ph < 4; ++ph)
+#pragma unroll
+                for (int k = 0; k < CW; ++k) acc[ph][k] = 0.f;
+#pragma unroll 1
+            for (int tap = 0; tap < 9; ++tap) {
+                const uint32_t st = it & 1;
+                mbar_wait(&full_bar[st], (it >> 1) & 1);
+                tc_fence_after();
+                // two phases at a time keeps the live registers under the 120-per-thread budget
+#pragma unroll
+                for (int hp = 0; hp < 2; ++hp) {
+                    uint32_t v[2][CW / 8][8];
+#pragma unroll
+                    for (int p2 = 0; p2 < 2; ++p2)
+#pragma unroll
+                        for (int k8 = 0; k8 < CW / 8; ++k8)
+                            TMEM_LD8(lane_addr + st * STAGE_COLS + (uint32_t)((2 * hp + p2) * COUT + k8 * 8), v[p2][k8]);
+#pragma unroll
+                    for (int p2 = 0; p2 < 2; ++p2)
+#pragma unroll
+                        for (int k8 = 0; k8 < CW / 8; ++k8) TMEM_WAIT8(v[p2][k8]);
+                    if (hp == 1) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&empty_bar[st]);
+                    }
+#pragma unroll
+                    for (int p2 = 0; p2 < 2; ++p2)
+#pragma unroll
+                        for (int k8 = 0; k8 < CW / 8; ++k8)
+#pragma unroll
+                            for (int k = 0; k < 8; ++k)
+                                acc[2 * hp + p2][k8 * 8 + k] =
+                                    __fadd_rn(acc[2 * hp + p2][k8 * 8 + k], __uint_as_float(v[p2][k8][k]));
+                }
+                ++it;
+            }
+            // final epilogue from registers: bias -> ReLU -> BN -> 2x2 max -> hi/lo fp16 (+ fp32 tap)
+            constexpr int RO = R / 2;
+            const int Y = r >> 3, X = 8 * sub + (r & 7);
+            if (Y < RO) {
+#pragma unroll
+                for (int k8 = 0; k8 < CW / 8; ++k8) {
+                    const int c0 = cq * CW + k8 * 8;
+                    float o[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const float b = __ldg(bias + c0 + k), s = __ldg(bn_s + c0 + k), t = __ldg(bn_t + c0 + k);
+                        float m = -INFINITY;
+#pragma unroll
+                        for (int ph = 0; ph < 4; ++ph) {
+                            float a = fmaf(acc[ph][k8 * 8 + k], inv_scale, b);
+                            a = fmaxf(a, 0.f);
+                            m = fmaxf(m, fmaf(a, s, t));
+                        }
+                        o[k] = m;
+                    }
+                    const size_t off = ((((size_t)cell * (COUT / 8) + c0 / 8) * RO + Y) * RO + X) * 8;
+                    split_store8(o, out_hi + off, out_lo ? out_lo + off : nullptr);
+                    if (feat) {
+                        float4* f = reinterpret_cast<float4*>(feat + (size_t)cell * (RO * RO * COUT) +
+                                                             (size_t)(Y * RO + X) * COUT + c0);
+                        f[0] = make_float4(o[0], o[1], o[2], o[3]);
+                        f[1] = make_float4(o[4], o[5], o[6], o[7]);
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------
 // Layer 1 (Cin = 1): K = 9 taps padded to 16; the A operand is an explicit im2col of the
 // fp32 crop, built per pooling phase.  Unit = pooled 16x8 tile = conv 32x16 block.
 // ---------------------------------------------------------------------------------------
@@ -496,6 +707,27 @@ int launch_tc(cia_ctx* h, const CaeWeights& w, int layer, const __half* in_hi, c
     return CIA_OK;
 }
 
+template <int CIN, int COUT, int R>
+int launch_tc_acc(cia_ctx* h, const CaeWeights& w, int layer, const __half* in_hi, const __half* in_lo,
+                  __half* out_hi, __half* out_lo, float* feat, int n, const int32_t* n_dev, int cell0,
+                  int chunk, cudaStream_t s) {
+    using C = Cfg<CIN, COUT, R, EPI_POOL, 3>;
+    auto kern = conv_tc_acc_kernel<CIN, COUT, R>;
+    static bool attr = false;
+    if (!attr) {
+        CIA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_B));
+        attr = true;
+    }
+    int grid = chunk * C::UNITS_PER_CELL;
+    if (grid > h->num_sms) grid = h->num_sms;
+    kern<<<grid, ACC_THREADS, C::SMEM_B, s>>>(in_hi, in_lo, (const uint4*)w.tc_w[layer][0],
+                                              (const uint4*)w.tc_w[layer][1], w.tc_inv_scale[layer], w.bias[layer],
+                                              w.bn_scale[layer], w.bn_shift[layer], out_hi, out_lo, feat, n, n_dev,
+                                              cell0, chunk);
+    CIA_LAUNCH_CHECK();
+    return CIA_OK;
+}
+
 // One B image: [(tap*NCH + chunk)*N + n][8] halves = w[tap][chunk*8 + j][n] * 2^sw, hi and lo parts.
 static void pack_image(const std::vector<float>& w /* [taps][cin][n] */, int taps, int cin, int N,
                        int n_real, int sw, std::vector<__half>& hi, std::vector<__half>& lo) {
@@ -582,12 +814,20 @@ int k_cae_forward_tc(cia_ctx* h, const float* crops, int n, const int32_t* n_dev
     if (!ae.loaded || ae.n_conv != 7 || !ae.tc_ready) { h->err = "cia_cae_forward: autoencoder not loaded"; return CIA_E_STATE; }
     const bool sep = h->cae[1].loaded;
     const bool tc_feat = mode == 1 && !sep;
+    // mode 3: L1 + L2 on tensor cores with split operands, fp32 tap of the 16x16x64 activation,
+    // L3 (the layer whose long RZ-accumulated K=576 chains dominate the feature error) in exact fp32
+    const bool l3_exact = mode == 3 && !sep;
     const int CH = 512;
     const size_t a1 = 4 * 32 * 32 * 8, a2 = 8 * 16 * 16 * 8, a3 = 4 * 8 * 8 * 8, a4u = 4 * 16 * 16 * 8,
                  a5u = 8 * 32 * 32 * 8, a6 = 4 * 32 * 32 * 8;
     const size_t per_cell = 2 * a1 + 2 * a2 + a3 + a4u + a5u + a6;     // halves
     int rc = ws_reserve(h, h->ws_misc, (size_t)CH * per_cell * sizeof(__half));
     if (rc) return rc;
+    float* A2f = nullptr;
+    if (l3_exact) {
+        if ((rc = ws_reserve(h, h->ws_act, (size_t)CH * 16 * 16 * 64 * sizeof(float)))) return rc;
+        A2f = (float*)h->ws_act.p;
+    }
     __half* A1h = (__half*)h->ws_misc.p;
     __half* A1l = A1h + CH * a1;
     __half* A2h = A1l + CH * a1;
@@ -598,6 +838,16 @@ int k_cae_forward_tc(cia_ctx* h, const float* crops, int n, const int32_t* n_dev
     __half* A6 = A5u + CH * a5u;
     CIA_CUDA(cudaMemsetAsync(mse, 0, (size_t)n * sizeof(float), s));
     CIA_CUDA(cudaMemsetAsync(mae, 0, (size_t)n * sizeof(float), s));
+    const bool side_encoder = features && !tc_feat && !l3_exact;
+    if (side_encoder) {
+        // fork: encoder.predict (det:130) in exact fp32 on the side stream, concurrently with
+        // autoencoder.predict (det:125) on the tensor cores
+        CIA_CUDA(cudaEventRecord(h->ev_fork, s));
+        CIA_CUDA(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+        rc = k_encoder_fp32(h, sep ? h->cae[1] : h->cae[0], crops, n, n_dev, features, h->side);
+        if (rc) return rc;
+        CIA_CUDA(cudaEventRecord(h->ev_join, h->side));
+    }
     for (int c0 = 0; c0 < n; c0 += CH) {
         const int chunk = (n - c0) < CH ? (n - c0) : CH;
         // activation buffers are chunk-relative; kernels index by absolute cell
@@ -608,13 +858,19 @@ int k_cae_forward_tc(cia_ctx* h, const float* crops, int n, const int32_t* n_dev
         float* feat = tc_feat ? features : nullptr;
         int grid1 = chunk * 8;
         if (grid1 > h->num_sms * 2) grid1 = h->num_sms * 2;
-        if (tc_feat) {
+        if (tc_feat || l3_exact) {
             conv1_tc_kernel<3><<<grid1, TCT, 0, s>>>(crops, (const uint4*)ae.tc_w[0][0], (const uint4*)ae.tc_w[0][1],
                                                      ae.tc_inv_scale[0], ae.bias[0], ae.bn_scale[0], ae.bn_shift[0],
                                                      a1h, a1l, n, n_dev, c0, chunk);
             CIA_LAUNCH_CHECK();
-            if ((rc = launch_tc<32, 64, 32, EPI_POOL, 3>(h, ae, 1, a1h, a1l, a2h, a2l, nullptr, nullptr, nullptr, nullptr, n, n_dev, c0, chunk, s))) return rc;
-            if ((rc = launch_tc<64, 32, 16, EPI_POOL, 3>(h, ae, 2, a2h, a2l, a3h, nullptr, feat, nullptr, nullptr, nullptr, n, n_dev, c0, chunk, s))) return rc;
+            float* a2f = l3_exact ? A2f - (size_t)c0 * (16 * 16 * 64) : nullptr;
+            if ((rc = launch_tc_acc<32, 64, 32>(h, ae, 1, a1h, a1l, a2h, a2l, a2f, n, n_dev, c0, chunk, s))) return rc;
+            if (l3_exact) {
+                if ((rc = launch_tc<64, 32, 16, EPI_POOL, 1>(h, ae, 2, a2h, nullptr, a3h, nullptr, nullptr, nullptr, nullptr, nullptr, n, n_dev, c0, chunk, s))) return rc;
+                if (features && (rc = k_conv3_fp32(h, ae, a2f, n, n_dev, features, c0, chunk, s))) return rc;
+            } else {
+                if ((rc = launch_tc_acc<64, 32, 16>(h, ae, 2, a2h, a2l, a3h, nullptr, feat, n, n_dev, c0, chunk, s))) return rc;
+            }
         } else {
             conv1_tc_kernel<1><<<grid1, TCT, 0, s>>>(crops, (const uint4*)ae.tc_w[0][0], (const uint4*)ae.tc_w[0][1],
                                                      ae.tc_inv_scale[0], ae.bias[0], ae.bn_scale[0], ae.bn_shift[0],
@@ -628,9 +884,6 @@ int k_cae_forward_tc(cia_ctx* h, const float* crops, int n, const int32_t* n_dev
         if ((rc = launch_tc<64, 32, 32, EPI_PLAIN, 1>(h, ae, 5, a5, nullptr, a6p, nullptr, nullptr, nullptr, nullptr, nullptr, n, n_dev, c0, chunk, s))) return rc;
         if ((rc = launch_tc<32, 16, 32, EPI_FINAL, 1>(h, ae, 6, a6p, nullptr, nullptr, nullptr, nullptr, crops, mse, mae, n, n_dev, c0, chunk, s))) return rc;
     }
-    if (features && !tc_feat) {
-        rc = k_encoder_fp32(h, sep ? h->cae[1] : h->cae[0], crops, n, n_dev, features, s);
-        if (rc) return rc;
-    }
+    if (side_encoder) CIA_CUDA(cudaStreamWaitEvent(s, h->ev_join, 0));
     return CIA_OK;
 }

@@ -67,6 +67,9 @@ struct cia_ctx {
     // grow-only workspaces
     Workspace ws_flags, ws_act, ws_crop_scratch, ws_pipe, ws_feat, ws_misc, ws_stage;
     cudaEvent_t ev = nullptr;
+    // side stream: the exact-fp32 encoder pass (FMA pipe) overlaps the tensor-core autoencoder
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // stage profiler: ring of CUDA events recorded in-stream by the fused path
     std::vector<cudaEvent_t> prof_ev;     // [records][CIA_PROF_MARKS]
     int prof_records = 0, prof_used = 0;
@@ -139,6 +142,8 @@ int k_cae_forward_tc(cia_ctx* h, const float* crops, int n, const int32_t* n_dev
                      float* mae, float* features, int mode, cudaStream_t s);
 int k_encoder_fp32(cia_ctx* h, const CaeWeights& w, const float* crops, int n, const int32_t* n_dev,
                    float* features, cudaStream_t s);
+int k_conv3_fp32(cia_ctx* h, const CaeWeights& w, const float* a2, int n, const int32_t* n_dev,
+                 float* features, int cell0, int chunk, cudaStream_t s);
 int k_cae_tc_prepare(cia_ctx* h, int which);
 int k_svm_decision(cia_ctx* h, const float* features, int n, const int32_t* n_dev,
                    double* dec_cons, double* dec_mod, int8_t* pred_cons, int8_t* pred_mod,

@@ -33,7 +33,7 @@ def _np_ptr(a):
 class Engine:
     """Owns a libcia handle on one GPU and the uploaded artifacts."""
 
-    def __init__(self, device: int = 0, precision: int = PRECISION_FP32):
+    def __init__(self, device: int = 0, precision: int = PRECISION_TC):
         if not torch.cuda.is_available():
             raise RuntimeError("cell_image_analysis_b200 needs a CUDA device (sm_100a); no CPU fallback")
         self.lib = _lib.load()
@@ -253,7 +253,7 @@ class ProductionMutantScreening:
     """
 
     def __init__(self, model_dir, segmenter=None, imread=None, device: int = 0,
-                 precision: int = PRECISION_FP32):
+                 precision: int = PRECISION_TC):
         self.model_dir = model_dir
         self.segmenter = segmenter
         self.imread = imread or _default_imread

@@ -47,7 +47,7 @@ def oracle_weights(artifacts):
 def screener(model_dir):
     """The drop-in class on cuda:0 (fp32 CAE path)."""
     from cell_image_analysis_b200.screening import ProductionMutantScreening
-    return ProductionMutantScreening(model_dir, segmenter=lambda ch: None, device=0)
+    return ProductionMutantScreening(model_dir, segmenter=lambda ch: None, device=0, precision=0)
 
 
 @pytest.fixture(scope="session")
