@@ -131,8 +131,55 @@ struct Cfg {
     static constexpr int SMEM_B = PARTS * (REGION_B + W_B);
 };
 
+// Stage the zero-padded input block of one unit into shared memory (pool layers: columns
+// de-interleaved by parity).  Loads are issued in batches of BATCH independent 16-byte
+// requests per thread before any store, so a unit pays ~one L2 latency instead of one per element.
+template <class C, int R, int NPASS, int NT, int BATCH>
+__device__ __forceinline__ void stage_block(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo,
+                                            unsigned char* a0, unsigned char* a1, int cell, int sub, int tid) {
+    constexpr int COLS = C::POOL ? 18 : C::ROW_UNITS;
+    constexpr int N_UNITS16 = C::NCH * C::FILL_ROWS * COLS;
+    constexpr int ITERS = (N_UNITS16 + NT - 1) / NT;
+#pragma unroll 1
+    for (int i0 = 0; i0 < ITERS; i0 += BATCH) {
+        uint4 vh[BATCH], vl[BATCH];
+        uint32_t dst[BATCH];
+#pragma unroll
+        for (int j = 0; j < BATCH; ++j) {
+            const int idx = tid + (i0 + j) * NT;
+            vh[j] = make_uint4(0, 0, 0, 0); vl[j] = make_uint4(0, 0, 0, 0);
+            dst[j] = 0xFFFFFFFFu;
+            if (i0 + j < ITERS && idx < N_UNITS16) {
+                const int c = idx / (C::FILL_ROWS * COLS);
+                const int rem = idx - c * (C::FILL_ROWS * COLS);
+                const int ry = rem / COLS, rc = rem - ry * COLS;
+                int y, x;
+                if (C::POOL) {
+                    y = ry - 1; x = 16 * sub - 1 + rc;
+                    dst[j] = (uint32_t)(((c * 2 + (rc & 1)) * C::FILL_ROWS + ry) * 9 + (rc >> 1)) * 16u;
+                } else {
+                    y = 16 * sub + ry - 1; x = rc - 1;
+                    dst[j] = (uint32_t)((c * C::FILL_ROWS + ry) * C::ROW_UNITS + rc) * 16u;
+                }
+                if (y >= 0 && y < R && x >= 0 && x < R) {
+                    const size_t src = ((((size_t)cell * C::NCH + c) * R + y) * R + x);
+                    vh[j] = __ldg(reinterpret_cast<const uint4*>(in_hi) + src);
+                    if (NPASS > 1) vl[j] = __ldg(reinterpret_cast<const uint4*>(in_lo) + src);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < BATCH; ++j) {
+            if (dst[j] != 0xFFFFFFFFu) {
+                *reinterpret_cast<uint4*>(a0 + dst[j]) = vh[j];
+                if (NPASS > 1) *reinterpret_cast<uint4*>(a1 + dst[j]) = vl[j];
+            }
+        }
+    }
+}
+
 template <int CIN, int COUT, int R, int EPI, int NPASS>
-__global__ void __launch_bounds__(TCT, 1)
+__global__ void __launch_bounds__(TCT, (Cfg<CIN, COUT, R, EPI, NPASS>::SMEM_B > 100 * 1024) ? 1 : 2)
 conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo,
                const uint4* __restrict__ w_hi, const uint4* __restrict__ w_lo, float inv_scale,
                const float* __restrict__ bias, const float* __restrict__ bn_s,
@@ -174,32 +221,7 @@ conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_l
         const int sub = unit % C::UNITS_PER_CELL;   // POOL: pooled X half; else: 16-row band
 
         // ---- stage the zero-padded input block ----
-        constexpr int N_UNITS16 = C::NCH * C::FILL_ROWS * (C::POOL ? 18 : C::ROW_UNITS);
-        for (int idx = tid; idx < N_UNITS16; idx += TCT) {
-            int c, ry, rc, y, x;
-            uint32_t dst;
-            if (C::POOL) {
-                c = idx / (C::FILL_ROWS * 18);
-                const int rem = idx - c * (C::FILL_ROWS * 18);
-                ry = rem / 18; rc = rem - ry * 18;
-                y = ry - 1; x = 16 * sub - 1 + rc;
-                dst = (uint32_t)(((c * 2 + (rc & 1)) * C::FILL_ROWS + ry) * 9 + (rc >> 1)) * 16u;
-            } else {
-                c = idx / (C::FILL_ROWS * C::ROW_UNITS);
-                const int rem = idx - c * (C::FILL_ROWS * C::ROW_UNITS);
-                ry = rem / C::ROW_UNITS; rc = rem - ry * C::ROW_UNITS;
-                y = 16 * sub + ry - 1; x = rc - 1;
-                dst = (uint32_t)((c * C::FILL_ROWS + ry) * C::ROW_UNITS + rc) * 16u;
-            }
-            uint4 vh = make_uint4(0, 0, 0, 0), vl = make_uint4(0, 0, 0, 0);
-            if (y >= 0 && y < R && x >= 0 && x < R) {
-                const size_t src = ((((size_t)cell * C::NCH + c) * R + y) * R + x);
-                vh = __ldg(reinterpret_cast<const uint4*>(in_hi) + src);
-                if (NPASS > 1) vl = __ldg(reinterpret_cast<const uint4*>(in_lo) + src);
-            }
-            *reinterpret_cast<uint4*>(a_part[0] + dst) = vh;
-            if (NPASS > 1) *reinterpret_cast<uint4*>(a_part[1] + dst) = vl;
-        }
+        stage_block<C, R, NPASS, TCT, 8>(in_hi, in_lo, a_part[0], a_part[1], cell, sub, tid);
         fence_async_smem();
         __syncthreads();
 
@@ -464,22 +486,7 @@ conv_tc_acc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
             const int cell = cell0 + unit / C::UNITS_PER_CELL;
             const int sub = unit % C::UNITS_PER_CELL;
             // stage the zero-padded, column-parity de-interleaved input block (hi and lo)
-            constexpr int N_UNITS16 = C::NCH * C::FILL_ROWS * 18;
-            for (int idx = tid; idx < N_UNITS16; idx += EPT) {
-                const int c = idx / (C::FILL_ROWS * 18);
-                const int rem = idx - c * (C::FILL_ROWS * 18);
-                const int ry = rem / 18, rc = rem - ry * 18;
-                const int y = ry - 1, x = 16 * sub - 1 + rc;
-                const uint32_t dst = (uint32_t)(((c * 2 + (rc & 1)) * C::FILL_ROWS + ry) * 9 + (rc >> 1)) * 16u;
-                uint4 vh = make_uint4(0, 0, 0, 0), vl = make_uint4(0, 0, 0, 0);
-                if (y >= 0 && y < R && x >= 0 && x < R) {
-                    const size_t src = ((((size_t)cell * C::NCH + c) * R + y) * R + x);
-                    vh = __ldg(reinterpret_cast<const uint4*>(in_hi) + src);
-                    vl = __ldg(reinterpret_cast<const uint4*>(in_lo) + src);
-                }
-                *reinterpret_cast<uint4*>(a_part[0] + dst) = vh;
-                *reinterpret_cast<uint4*>(a_part[1] + dst) = vl;
-            }
+            stage_block<C, R, 3, EPT, 6>(in_hi, in_lo, a_part[0], a_part[1], cell, sub, tid);
             fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&ready_bar);
