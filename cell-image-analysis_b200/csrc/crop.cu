@@ -49,69 +49,87 @@ __host__ __device__ inline size_t cell_bytes(int h, int w, int ntr, int ntc) {
     return align16(hw) + align16(2 * hw) + align16(maps > t ? maps : t);
 }
 
-// One warp: clip + redistribute a 256-bin histogram held 8 bins per lane
-// (bin = lane + 32*m), then cumulative mapping.  skimage clip_histogram / map_histogram.
-__device__ __forceinline__ void clip_and_map(int (&hv)[8], int clim, int npix, int lane,
+// One warp: clip + redistribute a 256-bin histogram held 8 CONSECUTIVE bins per lane
+// (bin = 8*lane + m), then cumulative mapping.  skimage clip_histogram / map_histogram.
+// Instruction diet (the kernel is issue-bound): the strided selection `(b - index) % step`
+// uses one reciprocal per iteration (exact for b < 256), the prefix sum is 7 local adds + one
+// warp scan, the 8 uint16 map entries of a lane leave as one 16-byte store.
+__device__ __forceinline__ void clip_and_map(int (&hv)[8], int clim, double scale, int lane,
                                              uint16_t* __restrict__ map_out) {
     int ex = 0;
 #pragma unroll
     for (int m = 0; m < 8; ++m)
         if (hv[m] > clim) { ex += hv[m] - clim; hv[m] = clim; }
     ex = warp_sum(ex);
-    const int incr = ex / NBINS;
-    const int upper = clim - incr;
-    int nlow = 0;
+    if (ex > 0) {
+        const int incr = ex / NBINS;
+        const int upper = clim - incr;
+        int nlow = 0;
 #pragma unroll
-    for (int m = 0; m < 8; ++m)
-        if (hv[m] < upper) { hv[m] += incr; ++nlow; }
-    ex -= warp_sum(nlow) * incr;
-    int midsum = 0, nmid = 0;
+        for (int m = 0; m < 8; ++m)
+            if (hv[m] < upper) { hv[m] += incr; ++nlow; }
+        int midsum = 0, nmid = 0;
 #pragma unroll
-    for (int m = 0; m < 8; ++m)
-        if (hv[m] >= upper && hv[m] < clim) { midsum += hv[m]; ++nmid; hv[m] = clim; }
-    ex += warp_sum(midsum) - warp_sum(nmid) * clim;
+        for (int m = 0; m < 8; ++m)
+            if (hv[m] >= upper && hv[m] < clim) { midsum += hv[m]; ++nmid; hv[m] = clim; }
+        // one packed reduction: nlow, nmid <= 256 each, midsum <= 256 * clim < 2^22
+        const unsigned long long packed =
+            warp_sum((unsigned long long)nlow | ((unsigned long long)nmid << 10) | ((unsigned long long)midsum << 20));
+        ex -= (int)(packed & 1023u) * incr;
+        ex += (int)(packed >> 20) - (int)((packed >> 10) & 1023u) * clim;
 
-    while (ex > 0) {
-        const int prev = ex;
-        bool stuck = false;
-        for (int index = 0; index < NBINS; ++index) {
-            int cnt = 0;
+        while (ex > 0) {
+            const int prev = ex;
+            bool stuck = false;
+            for (int index = 0; index < NBINS; ++index) {
+                unsigned under = 0;
 #pragma unroll
-            for (int m = 0; m < 8; ++m) cnt += __popc(__ballot_sync(0xffffffffu, hv[m] < clim));
-            if (cnt == 0) { stuck = true; break; }   // nothing can move any more
-            int step = cnt / ex;
-            if (step < 1) step = 1;
-            int moved = 0;
+                for (int m = 0; m < 8; ++m) under |= (hv[m] < clim ? 1u : 0u) << m;
+                // count of under-limit bins over the warp
+                int cnt = __popc(under);
+                cnt = warp_sum(cnt);
+                if (cnt == 0) { stuck = true; break; }   // nothing can move any more
+                int step = cnt / ex;
+                if (step < 1) step = 1;
+                const unsigned magic = 0xFFFFFFFFu / (unsigned)step + 1u;   // ceil(2^32 / step)
+                int moved = 0;
 #pragma unroll
-            for (int m = 0; m < 8; ++m) {
-                const int b = lane + 32 * m;
-                const bool sel = b >= index && hv[m] < clim && ((b - index) % step) == 0;
-                if (sel) ++hv[m];
-                moved += __popc(__ballot_sync(0xffffffffu, sel));
+                for (int m = 0; m < 8; ++m) {
+                    const int d = 8 * lane + m - index;
+                    bool sel = d >= 0 && ((under >> m) & 1u);
+                    if (sel && step > 1) {
+                        const unsigned qd = __umulhi((unsigned)d, magic);    // floor(d / step), exact for d < 2^16
+                        sel = (unsigned)d - qd * (unsigned)step == 0u;
+                    }
+                    if (sel) { ++hv[m]; ++moved; }
+                }
+                ex -= warp_sum(moved);
+                if (ex <= 0) break;
             }
-            ex -= moved;
-            if (ex <= 0) break;
+            if (stuck || prev == ex) break;
         }
-        if (stuck || prev == ex) break;
     }
 
     // cumulative sum in bin order, scale, clip, truncate
-    const double scale = __ddiv_rn(16383.0, (double)npix);
-    int carry = 0;
+    int pre[8];
+    pre[0] = hv[0];
+#pragma unroll
+    for (int m = 1; m < 8; ++m) pre[m] = pre[m - 1] + hv[m];
+    int run = pre[7];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, run, o);
+        if (lane >= o) run += t;
+    }
+    const int base = run - pre[7];
+    __align__(16) uint16_t mv16[8];
 #pragma unroll
     for (int m = 0; m < 8; ++m) {
-        int v = hv[m];
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, v, o);
-            if (lane >= o) v += t;
-        }
-        const int incl = v + carry;
-        carry += __shfl_sync(0xffffffffu, v, 31);
-        double mv = __dmul_rn((double)incl, scale);
+        double mv = __dmul_rn((double)(base + pre[m]), scale);
         if (mv > 16383.0) mv = 16383.0;
-        map_out[lane + 32 * m] = (uint16_t)(int)mv;
+        mv16[m] = (uint16_t)(int)mv;
     }
+    *reinterpret_cast<uint4*>(map_out + 8 * lane) = *reinterpret_cast<const uint4*>(mv16);
 }
 
 __device__ __forceinline__ void block_minmax(int& mn, int& mx, int* sh) {
@@ -140,7 +158,8 @@ crop_clahe_resize_kernel(const uint16_t* __restrict__ images, int H, int W,
                          int32_t* status, uint16_t* __restrict__ levels_out,
                          const int64_t* __restrict__ level_offsets) {
     extern __shared__ __align__(16) unsigned char dyn[];
-    __shared__ uint32_t hist_s[K2_WARPS][NBINS];
+    __shared__ __align__(16) uint32_t hist_s[K2_WARPS][NBINS];
+    __shared__ double ctab_s[2][MAX_SIDE / 8];      // a/kh and b/kw interpolation coefficients
     __shared__ int red_s[2 * K2_WARPS];
     __shared__ double gw_s[2][2 * MAX_RADIUS + 2];
 
@@ -215,24 +234,30 @@ crop_clahe_resize_kernel(const uint16_t* __restrict__ images, int H, int W,
 
         // ---- C: per-tile histogram -> clipped mapping ----
         const int ntiles = g.ntr * g.ntc;
+        const double map_scale = __ddiv_rn(16383.0, (double)g.npix);
+        const unsigned kw_magic = 0xFFFFFFFFu / (unsigned)g.kw + 1u;       // p / kw for p < 2^16 (npix <= 128*128)
         for (int t = wid; t < ntiles; t += K2_WARPS) {
             const int ti = t / g.ntc, tj = t - ti * g.ntc;
             uint32_t* hs = hist_s[wid];
-#pragma unroll
-            for (int m = 0; m < 8; ++m) hs[lane + 32 * m] = 0;
+            reinterpret_cast<uint4*>(hs)[2 * lane] = make_uint4(0, 0, 0, 0);
+            reinterpret_cast<uint4*>(hs)[2 * lane + 1] = make_uint4(0, 0, 0, 0);
             __syncwarp();
             for (int p = lane; p < g.npix; p += 32) {
-                const int a = p / g.kw, b = p - a * g.kw;
+                const int a = (g.kw == 1) ? p : (int)__umulhi((unsigned)p, kw_magic), b = p - a * g.kw;
                 const int y = reflect_idx(ti * g.kh + a, g.h);
                 const int x = reflect_idx(tj * g.kw + b, g.w);
                 atomicAdd(&hs[bins[y * g.w + x]], 1u);
             }
             __syncwarp();
             int hv[8];
-#pragma unroll
-            for (int m = 0; m < 8; ++m) hv[m] = (int)hs[lane + 32 * m];
+            {
+                const uint4 h0 = reinterpret_cast<const uint4*>(hs)[2 * lane];
+                const uint4 h1 = reinterpret_cast<const uint4*>(hs)[2 * lane + 1];
+                hv[0] = (int)h0.x; hv[1] = (int)h0.y; hv[2] = (int)h0.z; hv[3] = (int)h0.w;
+                hv[4] = (int)h1.x; hv[5] = (int)h1.y; hv[6] = (int)h1.z; hv[7] = (int)h1.w;
+            }
             __syncwarp();
-            clip_and_map(hv, g.clim, g.npix, lane, maps + (size_t)t * NBINS);
+            clip_and_map(hv, g.clim, map_scale, lane, maps + (size_t)t * NBINS);
         }
         __syncthreads();
 
@@ -240,13 +265,19 @@ crop_clahe_resize_kernel(const uint16_t* __restrict__ images, int H, int W,
         int rmn = 65535, rmx = 0;
         {
             const int pr = g.kh / 2, pc = g.kw / 2;
+            // np.arange(k) / k tables (fp64 divisions once per cell instead of twice per pixel)
+            for (int a = tid; a < g.kh; a += K2_THREADS) ctab_s[0][a] = __ddiv_rn((double)a, (double)g.kh);
+            for (int b = tid; b < g.kw; b += K2_THREADS) ctab_s[1][b] = __ddiv_rn((double)b, (double)g.kw);
+            __syncthreads();
+            const unsigned w_magic = 0xFFFFFFFFu / (unsigned)g.w + 1u;      // exact for i < 2^16 * ... (hw <= 2^20, w <= 2^10)
+            const unsigned kh_magic = 0xFFFFFFFFu / (unsigned)g.kh + 1u;
             for (int i = tid; i < hw; i += K2_THREADS) {
-                const int y = i / g.w, x = i - y * g.w;
+                const int y = (g.w == 1) ? i : (int)__umulhi((unsigned)i, w_magic), x = i - y * g.w;
                 const int Y = y + pr, X = x + pc;
-                const int I = Y / g.kh, a = Y - I * g.kh;
-                const int J = X / g.kw, b = X - J * g.kw;
-                const double cr = __ddiv_rn((double)a, (double)g.kh);
-                const double cc = __ddiv_rn((double)b, (double)g.kw);
+                const int I = (g.kh == 1) ? Y : (int)__umulhi((unsigned)Y, kh_magic), a = Y - I * g.kh;
+                const int J = (g.kw == 1) ? X : (int)__umulhi((unsigned)X, kw_magic), b = X - J * g.kw;
+                const double cr = ctab_s[0][a];
+                const double cc = ctab_s[1][b];
                 const double icr = __dsub_rn(1.0, cr), icc = __dsub_rn(1.0, cc);
                 const int t0 = min(max(I - 1, 0), g.ntr - 1), t1 = min(max(I, 0), g.ntr - 1);
                 const int u0 = min(max(J - 1, 0), g.ntc - 1), u1 = min(max(J, 0), g.ntc - 1);
@@ -370,7 +401,7 @@ int k_crop_resize(cia_ctx* h, const uint16_t* images, int H, int W, const cia_ce
                   const int64_t* level_offsets) {
     if (n_cells <= 0) return CIA_OK;
     static bool attr_set = false;
-    const size_t lo_bytes = 94 * 1024, hi_bytes = 208 * 1024;   // 2 CTAs/SM and 1 CTA/SM with the 17 KB static part
+    const size_t lo_bytes = 92 * 1024, hi_bytes = 206 * 1024;   // 2 CTAs/SM and 1 CTA/SM with the 19.5 KB static part
     if (!attr_set) {
         CIA_CUDA(cudaFuncSetAttribute(crop_clahe_resize_kernel,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hi_bytes));
