@@ -21,22 +21,24 @@ label_scan_kernel(const int32_t* __restrict__ labels, int n_fields, int H, int W
     const int lane = threadIdx.x & 31;
     const int warps_per_block = SCAN_THREADS / 32;
     const int segs = (W + 127) >> 7;
-    const long long units_per_field = (long long)H * segs;
-    const long long total_units = units_per_field * n_fields;
-    long long unit = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
-    const long long stride = (long long)gridDim.x * warps_per_block;
+    const int f = blockIdx.y;                         // one field per grid row: no 64-bit divisions
+    const int row_stride = gridDim.x * warps_per_block;
+    cia_region* tab = regions + (size_t)f * max_label;
 
-    for (; unit < total_units; unit += stride) {
-        const int f = (int)(unit / units_per_field);
-        const long long u = unit - (long long)f * units_per_field;
-        const int r = (int)(u / segs);
-        const int seg = (int)(u - (long long)r * segs);
+    for (int r = blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < H; r += row_stride) {
+      const int32_t* row = labels + ((size_t)f * H + r) * (size_t)W;
+      // software pipeline: the next segment's 16-byte load is in flight while this one is reduced
+      int4 nxt = make_int4(0, 0, 0, 0);
+      if (vec_ok && (lane << 2) + 3 < W) nxt = __ldg(reinterpret_cast<const int4*>(row + (lane << 2)));
+      for (int seg = 0; seg < segs; ++seg) {
         const int c0 = (seg << 7) + (lane << 2);
-        const int32_t* row = labels + ((size_t)f * H + r) * (size_t)W;
         int lab[4];
-        if (vec_ok && c0 + 3 < W) {
-            int4 v = __ldg(reinterpret_cast<const int4*>(row + c0));
-            lab[0] = v.x; lab[1] = v.y; lab[2] = v.z; lab[3] = v.w;
+        if (vec_ok) {
+            lab[0] = nxt.x; lab[1] = nxt.y; lab[2] = nxt.z; lab[3] = nxt.w;
+            const int cn = c0 + 128;
+            nxt = make_int4(0, 0, 0, 0);
+            if (seg + 1 < segs && cn + 3 < W) nxt = __ldg(reinterpret_cast<const int4*>(row + cn));
+            if (c0 + 3 >= W) { lab[0] = lab[1] = lab[2] = lab[3] = 0; }
         } else {
 #pragma unroll
             for (int k = 0; k < 4; ++k) lab[k] = (c0 + k < W) ? __ldg(row + c0 + k) : 0;
@@ -50,7 +52,6 @@ label_scan_kernel(const int32_t* __restrict__ labels, int n_fields, int H, int W
         const unsigned any = __ballot_sync(0xffffffffu, (lab[0] | lab[1] | lab[2] | lab[3]) != 0);
         if (any == 0) continue;
 
-        cia_region* tab = regions + (size_t)f * max_label;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const bool start = lab[j] != 0 && (j == 0 || lab[j] != lab[j - 1]);
@@ -97,6 +98,7 @@ label_scan_kernel(const int32_t* __restrict__ labels, int n_fields, int H, int W
                 }
             }
         }
+      }
     }
 }
 
@@ -269,12 +271,13 @@ int k_label_scan(cia_ctx* h, const int32_t* labels, int n_fields, int H, int W, 
     const size_t n_slots = (size_t)n_fields * max_label;
     CIA_CUDA(cudaMemsetAsync(regions, 0, n_slots * sizeof(cia_region), s));
     const int vec_ok = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(labels) & 15) == 0);
-    const long long units = (long long)n_fields * H * ((W + 127) / 128);
-    long long blocks = (units + 7) / 8;
-    const long long cap = (long long)h->num_sms * 16;
-    if (blocks > cap) blocks = cap;
-    label_scan_kernel<<<(int)blocks, SCAN_THREADS, 0, s>>>(labels, n_fields, H, W, max_label,
-                                                          regions, h->status_dev, vec_ok);
+    if (n_fields > 65535) { h->err = "cia_label_scan: at most 65535 fields per call"; return CIA_E_ARG; }
+    int bx = (H + 7) / 8;
+    const int want = (h->num_sms * 16 + n_fields - 1) / n_fields;      // ~16 resident blocks per SM overall
+    if (bx > want) bx = want;
+    if (bx < 1) bx = 1;
+    label_scan_kernel<<<dim3(bx, n_fields), SCAN_THREADS, 0, s>>>(labels, n_fields, H, W, max_label,
+                                                                 regions, h->status_dev, vec_ok);
     CIA_LAUNCH_CHECK();
     finalize_regions_kernel<<<(int)((n_slots + 255) / 256), 256, 0, s>>>(regions, (long long)n_slots, H, W);
     CIA_LAUNCH_CHECK();
