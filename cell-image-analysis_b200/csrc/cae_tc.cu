@@ -117,14 +117,18 @@ struct Cfg {
     static constexpr bool POOL = EPI == EPI_POOL;
     static constexpr int NCH = CIN / 8;
     static constexpr int FILL_ROWS = POOL ? R + 2 : 18;              // rows actually staged
-    static constexpr int ROW_UNITS = POOL ? 9 : R + 2;                // 16-byte units per staged row
+    // non-pool units: a 16-row band x UNIT_COLS columns (16 instead of 32 for the 64-channel 32x32
+    // layer, so that two CTAs fit per SM and one's staging/epilogue overlaps the other's MMAs)
+    static constexpr int UNIT_COLS = (R >= 32 && CIN >= 64) ? 16 : R;
+    static constexpr int COL_BLOCKS = R / UNIT_COLS;
+    static constexpr int ROW_UNITS = POOL ? 9 : UNIT_COLS + 2;        // 16-byte units per staged row
     static constexpr int ROW_B = ROW_UNITS * 16;
     static constexpr int PLANE_B = FILL_ROWS * ROW_B;
     static constexpr int CHUNK_B = (POOL ? 2 : 1) * PLANE_B;          // = LBO of A
     static constexpr int REGION_B = NCH * CHUNK_B;
     static constexpr int SBO_A = POOL ? 2 * ROW_B : ROW_B;
-    static constexpr int TILES = POOL ? 4 : (R >= 32 ? 4 : (R == 16 ? 2 : 1));
-    static constexpr int UNITS_PER_CELL = POOL ? (R >= 32 ? 2 : 1) : (R >= 32 ? 2 : 1);
+    static constexpr int TILES = POOL ? 4 : (UNIT_COLS >= 8 ? UNIT_COLS / 8 : 1);
+    static constexpr int UNITS_PER_CELL = POOL ? (R >= 32 ? 2 : 1) : (R >= 32 ? 2 : 1) * COL_BLOCKS;
     static constexpr int TMEM_COLS = pow2_cols(TILES * COUT);
     static constexpr int W_B = 9 * NCH * COUT * 16;
     static constexpr int PARTS = NPASS > 1 ? 2 : 1;
@@ -134,7 +138,7 @@ struct Cfg {
 // Stage the zero-padded input block of one unit into shared memory (pool layers: columns
 // de-interleaved by parity).  Loads are issued in batches of BATCH independent 16-byte
 // requests per thread before any store, so a unit pays ~one L2 latency instead of one per element.
-template <class C, int R, int NPASS, int NT, int BATCH>
+template <class C, int R, int NPASS, int NT, int BATCH, bool UPSIN = false>
 __device__ __forceinline__ void stage_block(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo,
                                             unsigned char* a0, unsigned char* a1, int cell, int sub, int tid) {
     constexpr int COLS = C::POOL ? 18 : C::ROW_UNITS;
@@ -158,11 +162,15 @@ __device__ __forceinline__ void stage_block(const __half* __restrict__ in_hi, co
                     y = ry - 1; x = 16 * sub - 1 + rc;
                     dst[j] = (uint32_t)(((c * 2 + (rc & 1)) * C::FILL_ROWS + ry) * 9 + (rc >> 1)) * 16u;
                 } else {
-                    y = 16 * sub + ry - 1; x = rc - 1;
+                    y = 16 * (sub / C::COL_BLOCKS) + ry - 1;
+                    x = C::UNIT_COLS * (sub % C::COL_BLOCKS) + rc - 1;
                     dst[j] = (uint32_t)((c * C::FILL_ROWS + ry) * C::ROW_UNITS + rc) * 16u;
                 }
                 if (y >= 0 && y < R && x >= 0 && x < R) {
-                    const size_t src = ((((size_t)cell * C::NCH + c) * R + y) * R + x);
+                    // UPSIN: the producer stored the low-res activation; nearest up-sampling happens here
+                    constexpr int RS = UPSIN ? R / 2 : R;
+                    const int ys = UPSIN ? (y >> 1) : y, xs = UPSIN ? (x >> 1) : x;
+                    const size_t src = ((((size_t)cell * C::NCH + c) * RS + ys) * RS + xs);
                     vh[j] = __ldg(reinterpret_cast<const uint4*>(in_hi) + src);
                     if (NPASS > 1) vl[j] = __ldg(reinterpret_cast<const uint4*>(in_lo) + src);
                 }
@@ -178,7 +186,7 @@ __device__ __forceinline__ void stage_block(const __half* __restrict__ in_hi, co
     }
 }
 
-template <int CIN, int COUT, int R, int EPI, int NPASS>
+template <int CIN, int COUT, int R, int EPI, int NPASS, bool UPSIN>
 __global__ void __launch_bounds__(TCT, (Cfg<CIN, COUT, R, EPI, NPASS>::SMEM_B > 100 * 1024) ? 1 : 2)
 conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo,
                const uint4* __restrict__ w_hi, const uint4* __restrict__ w_lo, float inv_scale,
@@ -221,7 +229,7 @@ conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_l
         const int sub = unit % C::UNITS_PER_CELL;   // POOL: pooled X half; else: 16-row band
 
         // ---- stage the zero-padded input block ----
-        stage_block<C, R, NPASS, TCT, 8>(in_hi, in_lo, a_part[0], a_part[1], cell, sub, tid);
+        stage_block<C, R, NPASS, TCT, 8, UPSIN>(in_hi, in_lo, a_part[0], a_part[1], cell, sub, tid);
         fence_async_smem();
         __syncthreads();
 
@@ -302,13 +310,14 @@ conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_l
                 }
             }
         } else {
-            const int y = 16 * sub + (r >> 3);
+            const int y = 16 * (sub / C::COL_BLOCKS) + (r >> 3);
+            const int xblk = C::UNIT_COLS * (sub % C::COL_BLOCKS);
             constexpr int SL = EPI == EPI_FINAL ? 1 : COUT / 8;
 #pragma unroll 1
             for (int p = half_sel; p < C::TILES * SL; p += 2) {
                 const int t = p / SL, sl = p - t * SL;
                 const int c0 = sl * 8;
-                const int x = 8 * t + (r & 7);
+                const int x = xblk + 8 * t + (r & 7);
                 uint32_t v[8];
                 TMEM_LD8(lane_addr + (uint32_t)(t * COUT + c0), v);
                 TMEM_WAIT8(v);
@@ -320,7 +329,7 @@ conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_l
 #pragma unroll
                         for (int ph = 0; ph < 4; ++ph) {
                             const float a = fmaf(__uint_as_float(v[ph]), inv_scale, b);
-                            const float rec = 1.f / (1.f + expf(-a));
+                            const float rec = __fdividef(1.f, 1.f + __expf(-a));   // |err| ~1e-6, MSE gate is 1e-3
                             const float d = __ldg(xr + (2 * y + (ph >> 1)) * 64 + 2 * x + (ph & 1)) - rec;
                             se = fmaf(d, d, se);
                             ae += fabsf(d);
@@ -693,12 +702,12 @@ conv1_tc_kernel(const float* __restrict__ crops, const uint4* __restrict__ w_hi,
 // ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
-template <int CIN, int COUT, int R, int EPI, int NPASS>
+template <int CIN, int COUT, int R, int EPI, int NPASS, bool UPSIN = false>
 int launch_tc(cia_ctx* h, const CaeWeights& w, int layer, const __half* in_hi, const __half* in_lo,
               __half* out_hi, __half* out_lo, float* feat, const float* crops, float* mse, float* mae,
               int n, const int32_t* n_dev, int cell0, int chunk, cudaStream_t s) {
     using C = Cfg<CIN, COUT, R, EPI, NPASS>;
-    auto kern = conv_tc_kernel<CIN, COUT, R, EPI, NPASS>;
+    auto kern = conv_tc_kernel<CIN, COUT, R, EPI, NPASS, UPSIN>;
     static bool attr = false;
     if (!attr) {
         CIA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_B));
@@ -825,8 +834,9 @@ int k_cae_forward_tc(cia_ctx* h, const float* crops, int n, const int32_t* n_dev
     // L3 (the layer whose long RZ-accumulated K=576 chains dominate the feature error) in exact fp32
     const bool l3_exact = mode == 3 && !sep;
     const int CH = 512;
-    const size_t a1 = 4 * 32 * 32 * 8, a2 = 8 * 16 * 16 * 8, a3 = 4 * 8 * 8 * 8, a4u = 4 * 16 * 16 * 8,
-                 a5u = 8 * 32 * 32 * 8, a6 = 4 * 32 * 32 * 8;
+    // halves per cell; A4 / A5 are stored at their own (pre-upsampling) resolution
+    const size_t a1 = 4 * 32 * 32 * 8, a2 = 8 * 16 * 16 * 8, a3 = 4 * 8 * 8 * 8, a4u = 4 * 8 * 8 * 8,
+                 a5u = 8 * 16 * 16 * 8, a6 = 4 * 32 * 32 * 8;
     const size_t per_cell = 2 * a1 + 2 * a2 + a3 + a4u + a5u + a6;     // halves
     int rc = ws_reserve(h, h->ws_misc, (size_t)CH * per_cell * sizeof(__half));
     if (rc) return rc;
@@ -886,9 +896,9 @@ int k_cae_forward_tc(cia_ctx* h, const float* crops, int n, const int32_t* n_dev
             if ((rc = launch_tc<32, 64, 32, EPI_POOL, 1>(h, ae, 1, a1h, nullptr, a2h, nullptr, nullptr, nullptr, nullptr, nullptr, n, n_dev, c0, chunk, s))) return rc;
             if ((rc = launch_tc<64, 32, 16, EPI_POOL, 1>(h, ae, 2, a2h, nullptr, a3h, nullptr, nullptr, nullptr, nullptr, nullptr, n, n_dev, c0, chunk, s))) return rc;
         }
-        if ((rc = launch_tc<32, 32, 8, EPI_UP, 1>(h, ae, 3, a3h, nullptr, a4, nullptr, nullptr, nullptr, nullptr, nullptr, n, n_dev, c0, chunk, s))) return rc;
-        if ((rc = launch_tc<32, 64, 16, EPI_UP, 1>(h, ae, 4, a4, nullptr, a5, nullptr, nullptr, nullptr, nullptr, nullptr, n, n_dev, c0, chunk, s))) return rc;
-        if ((rc = launch_tc<64, 32, 32, EPI_PLAIN, 1>(h, ae, 5, a5, nullptr, a6p, nullptr, nullptr, nullptr, nullptr, nullptr, n, n_dev, c0, chunk, s))) return rc;
+        if ((rc = launch_tc<32, 32, 8, EPI_PLAIN, 1>(h, ae, 3, a3h, nullptr, a4, nullptr, nullptr, nullptr, nullptr, nullptr, n, n_dev, c0, chunk, s))) return rc;
+        if ((rc = launch_tc<32, 64, 16, EPI_PLAIN, 1, true>(h, ae, 4, a4, nullptr, a5, nullptr, nullptr, nullptr, nullptr, nullptr, n, n_dev, c0, chunk, s))) return rc;
+        if ((rc = launch_tc<64, 32, 32, EPI_PLAIN, 1, true>(h, ae, 5, a5, nullptr, a6p, nullptr, nullptr, nullptr, nullptr, nullptr, n, n_dev, c0, chunk, s))) return rc;
         if ((rc = launch_tc<32, 16, 32, EPI_FINAL, 1>(h, ae, 6, a6p, nullptr, nullptr, nullptr, nullptr, crops, mse, mae, n, n_dev, c0, chunk, s))) return rc;
     }
     if (side_encoder) CIA_CUDA(cudaStreamWaitEvent(s, h->ev_join, 0));
