@@ -577,126 +577,85 @@ conv_tc_acc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------
-// Layer 1 (Cin = 1): K = 9 taps padded to 16; the A operand is an explicit im2col of the
-// fp32 crop, built per pooling phase.  Unit = pooled 16x8 tile = conv 32x16 block.
+// Layer 1 (Cin = 1, K = 9)
 // ---------------------------------------------------------------------------------------
-template <int NPASS>
-__global__ void __launch_bounds__(TCT, 2)
-conv1_tc_kernel(const float* __restrict__ crops, const uint4* __restrict__ w_hi,
-                const uint4* __restrict__ w_lo, float inv_scale, const float* __restrict__ bias,
-                const float* __restrict__ bn_s, const float* __restrict__ bn_t,
-                __half* __restrict__ out_hi, __half* __restrict__ out_lo, int n_cells,
-                const int32_t* __restrict__ n_dev, int cell0, int chunk_cells) {
-    constexpr int COUT = 32, PARTS = NPASS > 1 ? 2 : 1;
-    constexpr int A_B = 4 * 2 * 128 * 16;           // [phase][k-chunk][row][8 halves]
-    constexpr int W_B = 2 * COUT * 16;
-    __shared__ __align__(1024) unsigned char a_s[PARTS][A_B];
-    __shared__ __align__(16) unsigned char w_s[PARTS][W_B];
-    __shared__ float xs[34][19];
-    __shared__ __align__(8) uint64_t bar;
-    __shared__ uint32_t tmem_base_s;
-    constexpr int TMEM_COLS = 128;
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+// Layer 1 on the CUDA cores: with K = 9 the layer is epilogue-bound, not MMA-bound, and plain
+// fp32 FMAs are both faster than the im2col + tcgen05 route below and exact.  One block = one
+// quadrant of a cell (pooled 16x16 = conv 32x32); thread = (channel group of 8, pooled pixel),
+// 4 conv pixels x 8 channels in registers; output = the chunk-planar hi/lo fp16 planes.
+__global__ void __launch_bounds__(256, 2)
+conv1_fp32_planar_kernel(const float* __restrict__ crops, const float* __restrict__ wgt /* [9][32] */,
+                         const float* __restrict__ bias, const float* __restrict__ bn_s,
+                         const float* __restrict__ bn_t, __half* __restrict__ out_hi,
+                         __half* __restrict__ out_lo, int n_cells, const int32_t* __restrict__ n_dev,
+                         int cell0, int chunk_cells) {
+    __shared__ __align__(16) float xs[34][36];
+    __shared__ __align__(16) float ws[9][32];
     int n = dev_count(n_cells, n_dev) - cell0;
     if (n > chunk_cells) n = chunk_cells;
-    if (n <= 0) return;
-    const int n_units = n * 8;
-
-    if (warp == 0) tmem_alloc(&tmem_base_s, TMEM_COLS);
-    if (tid == 32) { mbar_init(&bar, 1); fence_barrier_init(); }
-    for (int i = tid; i < W_B / 16; i += TCT) {
-        reinterpret_cast<uint4*>(w_s[0])[i] = __ldg(w_hi + i);
-        if (NPASS > 1) reinterpret_cast<uint4*>(w_s[PARTS - 1])[i] = __ldg(w_lo + i);
+    const int tid = threadIdx.x, cg = tid >> 6, p = tid & 63;
+    for (int i = tid; i < 9 * 32; i += 256) ws[i >> 5][i & 31] = __ldg(wgt + i);
+    float b8[8], s8[8], t8[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        b8[k] = __ldg(bias + cg * 8 + k); s8[k] = __ldg(bn_s + cg * 8 + k); t8[k] = __ldg(bn_t + cg * 8 + k);
     }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = tmem_base_s;
-    constexpr uint32_t IDESC = make_idesc(128, COUT);
-    uint32_t parity = 0;
-
-    for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-        const int cell = cell0 + (unit >> 3);
-        const int by = (unit >> 2) & 1, bx = unit & 3;
+    for (int unit = blockIdx.x; unit < n * 4; unit += gridDim.x) {
+        const int cell = cell0 + (unit >> 2), qy = (unit >> 1) & 1, qx = unit & 1;
         const float* xr = crops + (size_t)cell * 4096;
-        for (int i = tid; i < 34 * 18; i += TCT) {
-            const int ry = i / 18, rc = i - ry * 18;
-            const int y = 32 * by + ry - 1, x = 16 * bx + rc - 1;
+        __syncthreads();
+        for (int i = tid; i < 34 * 34; i += 256) {
+            const int ry = i / 34, rc = i - ry * 34;
+            const int y = 32 * qy + ry - 1, x = 32 * qx + rc - 1;
             xs[ry][rc] = (y >= 0 && y < 64 && x >= 0 && x < 64) ? __ldg(xr + y * 64 + x) : 0.f;
         }
         __syncthreads();
-        // im2col: item = (phase, k-chunk, row)
-        for (int item = tid; item < 4 * 2 * 128; item += TCT) {
-            const int ph = item >> 8, ck = (item >> 7) & 1, r = item & 127;
-            const int Y = r >> 3, X = r & 7, py = ph >> 1, px = ph & 1;
-            __align__(16) __half hh[8];
-            __align__(16) __half ll[8];
+#pragma unroll 1
+        for (int it = 0; it < 4; ++it) {
+            const int P = it * 64 + p, Y = P >> 4, X = P & 15;
+            float win[4][4];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int tap = ck * 8 + j;
-                float v = 0.f;
-                if (tap < 9) v = xs[2 * Y + py + tap / 3][2 * X + px + tap % 3];
-                hh[j] = __float2half_rn(v);
-                ll[j] = __float2half_rn(v - __half2float(hh[j]));
+            for (int a = 0; a < 4; ++a) {
+                const float2 v0 = *reinterpret_cast<const float2*>(&xs[2 * Y + a][2 * X]);
+                const float2 v1 = *reinterpret_cast<const float2*>(&xs[2 * Y + a][2 * X + 2]);
+                win[a][0] = v0.x; win[a][1] = v0.y; win[a][2] = v1.x; win[a][3] = v1.y;
             }
-            const int off = ((ph * 2 + ck) * 128 + r) * 16;
-            *reinterpret_cast<uint4*>(a_s[0] + off) = *reinterpret_cast<const uint4*>(hh);
-            if (NPASS > 1) *reinterpret_cast<uint4*>(a_s[PARTS - 1] + off) = *reinterpret_cast<const uint4*>(ll);
-        }
-        fence_async_smem();
-        __syncthreads();
-        if (tid == 32) {
-            tc_fence_after();
-#pragma unroll 1
-            for (int ph = 0; ph < 4; ++ph) {
-#pragma unroll 1
-                for (int pass = 0; pass < NPASS; ++pass) {
-                    const uint32_t abase = smem_u32(a_s[pass == 2 ? PARTS - 1 : 0]) + (uint32_t)(ph * 2 * 128 * 16);
-                    const uint32_t wbase = smem_u32(w_s[pass == 1 ? PARTS - 1 : 0]);
-                    umma_f16(tmem_base + (uint32_t)(ph * COUT), make_smem_desc(abase, 128 * 16, 128),
-                             make_smem_desc(wbase, COUT * 16, 128), IDESC, pass > 0 ? 1u : 0u);
+            float acc[4][8];
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[q][k] = 0.f;
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx) {
+                    const float4 w0 = *reinterpret_cast<const float4*>(&ws[dy * 3 + dx][cg * 8]);
+                    const float4 w1 = *reinterpret_cast<const float4*>(&ws[dy * 3 + dx][cg * 8 + 4]);
+                    const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        acc[0][k] = fmaf(win[dy][dx], w[k], acc[0][k]);
+                        acc[1][k] = fmaf(win[dy][dx + 1], w[k], acc[1][k]);
+                        acc[2][k] = fmaf(win[dy + 1][dx], w[k], acc[2][k]);
+                        acc[3][k] = fmaf(win[dy + 1][dx + 1], w[k], acc[3][k]);
+                    }
                 }
-            }
-            umma_commit(&bar);
-        }
-        mbar_wait(&bar, parity);
-        parity ^= 1;
-        tc_fence_after();
-
-        const int q = warp & 3, half_sel = warp >> 2;
-        const int r = 32 * q + lane;
-        const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * q) << 16);
-        const int Y = 16 * by + (r >> 3), X = 8 * bx + (r & 7);
-#pragma unroll 1
-        for (int sl = half_sel; sl < COUT / 8; sl += 2) {
-            const int c0 = sl * 8;
-            uint32_t v[4][8];
-#pragma unroll
-            for (int ph = 0; ph < 4; ++ph) TMEM_LD8(lane_addr + (uint32_t)(ph * COUT + c0), v[ph]);
-#pragma unroll
-            for (int ph = 0; ph < 4; ++ph) TMEM_WAIT8(v[ph]);
             float o[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                const float b = __ldg(bias + c0 + k), s = __ldg(bn_s + c0 + k), t = __ldg(bn_t + c0 + k);
                 float m = -INFINITY;
 #pragma unroll
-                for (int ph = 0; ph < 4; ++ph) {
-                    float a = fmaf(__uint_as_float(v[ph][k]), inv_scale, b);
+                for (int q = 0; q < 4; ++q) {
+                    float a = __fadd_rn(acc[q][k], b8[k]);
                     a = fmaxf(a, 0.f);
-                    m = fmaxf(m, fmaf(a, s, t));
+                    m = fmaxf(m, __fadd_rn(__fmul_rn(a, s8[k]), t8[k]));
                 }
                 o[k] = m;
             }
-            const size_t off = ((((size_t)cell * (COUT / 8) + sl) * 32 + Y) * 32 + X) * 8;
+            const size_t off = ((((size_t)cell * 4 + cg) * 32 + (16 * qy + Y)) * 32 + (16 * qx + X)) * 8;
             split_store8(o, out_hi + off, out_lo ? out_lo + off : nullptr);
         }
-        tc_fence_before();
-        __syncthreads();
     }
-    __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -833,7 +792,7 @@ int k_cae_forward_tc(cia_ctx* h, const float* crops, int n, const int32_t* n_dev
     // mode 3: L1 + L2 on tensor cores with split operands, fp32 tap of the 16x16x64 activation,
     // L3 (the layer whose long RZ-accumulated K=576 chains dominate the feature error) in exact fp32
     const bool l3_exact = mode == 3 && !sep;
-    const int CH = 512;
+    const int CH = 1024;
     // halves per cell; A4 / A5 are stored at their own (pre-upsampling) resolution
     const size_t a1 = 4 * 32 * 32 * 8, a2 = 8 * 16 * 16 * 8, a3 = 4 * 8 * 8 * 8, a4u = 4 * 8 * 8 * 8,
                  a5u = 8 * 16 * 16 * 8, a6 = 4 * 32 * 32 * 8;
@@ -873,12 +832,11 @@ int k_cae_forward_tc(cia_ctx* h, const float* crops, int n, const int32_t* n_dev
         __half* a3h = A3h - (size_t)c0 * a3; __half* a4 = A4u - (size_t)c0 * a4u;
         __half* a5 = A5u - (size_t)c0 * a5u; __half* a6p = A6 - (size_t)c0 * a6;
         float* feat = tc_feat ? features : nullptr;
-        int grid1 = chunk * 8;
-        if (grid1 > h->num_sms * 2) grid1 = h->num_sms * 2;
+        int grid1 = chunk * 4;
+        if (grid1 > h->num_sms * 8) grid1 = h->num_sms * 8;
         if (tc_feat || l3_exact) {
-            conv1_tc_kernel<3><<<grid1, TCT, 0, s>>>(crops, (const uint4*)ae.tc_w[0][0], (const uint4*)ae.tc_w[0][1],
-                                                     ae.tc_inv_scale[0], ae.bias[0], ae.bn_scale[0], ae.bn_shift[0],
-                                                     a1h, a1l, n, n_dev, c0, chunk);
+            conv1_fp32_planar_kernel<<<grid1, 256, 0, s>>>(crops, ae.kernel[0], ae.bias[0], ae.bn_scale[0],
+                                                           ae.bn_shift[0], a1h, a1l, n, n_dev, c0, chunk);
             CIA_LAUNCH_CHECK();
             float* a2f = l3_exact ? A2f - (size_t)c0 * (16 * 16 * 64) : nullptr;
             if ((rc = launch_tc_acc<32, 64, 32>(h, ae, 1, a1h, a1l, a2h, a2l, a2f, n, n_dev, c0, chunk, s))) return rc;
@@ -889,9 +847,8 @@ int k_cae_forward_tc(cia_ctx* h, const float* crops, int n, const int32_t* n_dev
                 if ((rc = launch_tc_acc<64, 32, 16>(h, ae, 2, a2h, a2l, a3h, nullptr, feat, n, n_dev, c0, chunk, s))) return rc;
             }
         } else {
-            conv1_tc_kernel<1><<<grid1, TCT, 0, s>>>(crops, (const uint4*)ae.tc_w[0][0], (const uint4*)ae.tc_w[0][1],
-                                                     ae.tc_inv_scale[0], ae.bias[0], ae.bn_scale[0], ae.bn_shift[0],
-                                                     a1h, nullptr, n, n_dev, c0, chunk);
+            conv1_fp32_planar_kernel<<<grid1, 256, 0, s>>>(crops, ae.kernel[0], ae.bias[0], ae.bn_scale[0],
+                                                           ae.bn_shift[0], a1h, nullptr, n, n_dev, c0, chunk);
             CIA_LAUNCH_CHECK();
             if ((rc = launch_tc<32, 64, 32, EPI_POOL, 1>(h, ae, 1, a1h, nullptr, a2h, nullptr, nullptr, nullptr, nullptr, nullptr, n, n_dev, c0, chunk, s))) return rc;
             if ((rc = launch_tc<64, 32, 16, EPI_POOL, 1>(h, ae, 2, a2h, nullptr, a3h, nullptr, nullptr, nullptr, nullptr, nullptr, n, n_dev, c0, chunk, s))) return rc;
