@@ -667,11 +667,8 @@ int launch_tc(cia_ctx* h, const CaeWeights& w, int layer, const __half* in_hi, c
               int n, const int32_t* n_dev, int cell0, int chunk, cudaStream_t s) {
     using C = Cfg<CIN, COUT, R, EPI, NPASS>;
     auto kern = conv_tc_kernel<CIN, COUT, R, EPI, NPASS, UPSIN>;
-    static bool attr = false;
-    if (!attr) {
+    if (first_use(h, (const void*)kern))
         CIA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_B));
-        attr = true;
-    }
     int grid = chunk * C::UNITS_PER_CELL;
     const int cap = h->num_sms * (C::SMEM_B > 100 * 1024 ? 1 : 2);
     if (grid > cap) grid = cap;
@@ -688,11 +685,8 @@ int launch_tc_acc(cia_ctx* h, const CaeWeights& w, int layer, const __half* in_h
                   int chunk, cudaStream_t s) {
     using C = Cfg<CIN, COUT, R, EPI_POOL, 3>;
     auto kern = conv_tc_acc_kernel<CIN, COUT, R>;
-    static bool attr = false;
-    if (!attr) {
+    if (first_use(h, (const void*)kern))
         CIA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_B));
-        attr = true;
-    }
     int grid = chunk * C::UNITS_PER_CELL;
     if (grid > h->num_sms) grid = h->num_sms;
     kern<<<grid, ACC_THREADS, C::SMEM_B, s>>>(in_hi, in_lo, (const uint4*)w.tc_w[layer][0],

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -64,6 +65,7 @@ struct cia_ctx {
     int32_t* status_dev = nullptr;        // device status word (CIA_E_* raised by kernels)
     int32_t* status_host = nullptr;       // pinned
     int64_t launches = 0;
+    std::set<const void*> attr_done;       // kernels whose opt-in smem attribute is set on THIS device
     // grow-only workspaces
     Workspace ws_flags, ws_act, ws_crop_scratch, ws_pipe, ws_feat, ws_misc, ws_stage;
     cudaEvent_t ev = nullptr;
@@ -107,6 +109,9 @@ static inline int ws_reserve(cia_ctx* h, Workspace& w, size_t bytes) {
     w.cap = want;
     return CIA_OK;
 }
+
+// function attributes are per device: remember them per handle, not in a process-wide static
+static inline bool first_use(cia_ctx* h, const void* fn) { return h->attr_done.insert(fn).second; }
 
 // ---- device helpers -------------------------------------------------------
 __device__ __forceinline__ int dev_count(int n, const int32_t* n_dev) {

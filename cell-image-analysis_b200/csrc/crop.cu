@@ -400,13 +400,10 @@ int k_crop_resize(cia_ctx* h, const uint16_t* images, int H, int W, const cia_ce
                   double* crops64, cudaStream_t s, uint16_t* levels_out,
                   const int64_t* level_offsets) {
     if (n_cells <= 0) return CIA_OK;
-    static bool attr_set = false;
     const size_t lo_bytes = 92 * 1024, hi_bytes = 206 * 1024;   // 2 CTAs/SM and 1 CTA/SM with the 19.5 KB static part
-    if (!attr_set) {
+    if (first_use(h, (const void*)crop_clahe_resize_kernel))
         CIA_CUDA(cudaFuncSetAttribute(crop_clahe_resize_kernel,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hi_bytes));
-        attr_set = true;
-    }
     const int huge_ctas = 32;
     const size_t per_cta = cell_bytes(MAX_SIDE, MAX_SIDE, 15, 15);
     int rc = ws_reserve(h, h->ws_crop_scratch, per_cta * huge_ctas);

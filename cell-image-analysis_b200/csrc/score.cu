@@ -202,11 +202,9 @@ int k_svm_decision(cia_ctx* h, const float* features, int n, const int32_t* n_de
         if (rc) return rc;
         z = (double*)h->ws_feat.p;
     }
-    static bool attr = false;
-    if (!attr) {
+    if (first_use(h, (const void*)svm_rbf_kernel)) {
         CIA_CUDA(cudaFuncSetAttribute(svm_rbf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CIA_CUDA(cudaFuncSetAttribute(scaler_pca_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        attr = true;
     }
     const size_t sm1 = sizeof(double) * PFT * (PCT + XPAD);
     scaler_pca_kernel<<<dim3((n + PB - 1) / PB, (sp.C + PCT - 1) / PCT), PT, sm1, s>>>(
