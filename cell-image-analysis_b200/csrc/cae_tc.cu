@@ -211,7 +211,8 @@ conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_l
     const int n_units = n * C::UNITS_PER_CELL;
 
     if (warp == 0) tmem_alloc(&tmem_base_s, C::TMEM_COLS);
-    if (tid == 32) { mbar_init(&bar, 1); fence_barrier_init(); }
+    constexpr int NISS = C::TILES;           // issuing warps (TILES <= 4 <= warps)
+    if (tid == 32) { mbar_init(&bar, NISS); fence_barrier_init(); }
     // weights: linear copy of the prepared UMMA images
     for (int i = tid; i < C::W_B / 16; i += TCT) {
         reinterpret_cast<uint4*>(w_part[0])[i] = __ldg(w_hi + i);
@@ -233,33 +234,30 @@ conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_l
         fence_async_smem();
         __syncthreads();
 
-        // ---- MMA issue: one thread ----
-        if (tid == 32) {
+        // ---- MMA issue: one lane of one warp PER TILE (a single thread sustains only ~one
+        // tcgen05.mma per 60 cycles; the tiles' accumulators are independent) ----
+        if (lane == 0 && warp < NISS) {
             tc_fence_after();
-            // The single issuing thread is the bottleneck unless the per-MMA work is ~a few
-            // instructions (profiles/umma_microbench.cu): descriptors are built once per pass and
-            // every tile/tap/k-step offset is a compile-time constant added to their low word.
+            const int t = warp, py = t >> 1, px = t & 1;
+            uint64_t dxo[3];          // tap-column offset in 16-byte units (pool: parity plane + half-column)
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx)
+                dxo[dx] = C::POOL ? (uint64_t)((((px + dx) & 1) * C::PLANE_B + ((px + dx) >> 1) * 16) >> 4)
+                                  : (uint64_t)dx;
+            const uint32_t tile_off = C::POOL ? (uint32_t)(py * C::ROW_B) : (uint32_t)(t * 8 * 16);
 #pragma unroll 1
             for (int pass = 0; pass < NPASS; ++pass) {
-                const uint64_t ad0 = make_smem_desc(smem_u32(a_part[pass == 2 ? 1 : 0]), C::CHUNK_B, C::SBO_A);
+                const uint64_t ad0 = make_smem_desc(smem_u32(a_part[pass == 2 ? 1 : 0]) + tile_off, C::CHUNK_B, C::SBO_A);
                 const uint64_t bd0 = make_smem_desc(smem_u32(w_part[pass == 1 ? 1 : 0]), COUT * 16, 128);
                 const uint32_t acc0 = pass > 0 ? 1u : 0u;
 #pragma unroll
-                for (int t = 0; t < C::TILES; ++t) {
+                for (int tap = 0; tap < 9; ++tap) {
+                    const int dy = tap / 3, dx = tap % 3;
 #pragma unroll
-                    for (int tap = 0; tap < 9; ++tap) {
-                        const int dy = tap / 3, dx = tap % 3;
-                        const int py = t >> 1, px = t & 1;
-                        const int aoff = C::POOL
-                            ? ((px + dx) & 1) * C::PLANE_B + ((py + dy) * 9 + ((px + dx) >> 1)) * 16
-                            : (dy * C::ROW_UNITS + t * 8 + dx) * 16;
-#pragma unroll
-                        for (int s = 0; s < CIN / 16; ++s) {
-                            const uint64_t ad = ad0 + (uint64_t)((aoff + 2 * s * C::CHUNK_B) >> 4);
-                            const uint64_t bd = bd0 + (uint64_t)(((tap * C::NCH + 2 * s) * COUT * 16) >> 4);
-                            umma_f16(tmem_base + (uint32_t)(t * COUT), ad, bd, IDESC,
-                                     (tap == 0 && s == 0) ? acc0 : 1u);
-                        }
+                    for (int s = 0; s < CIN / 16; ++s) {
+                        const uint64_t ad = ad0 + dxo[dx] + (uint64_t)((dy * C::ROW_B + 2 * s * C::CHUNK_B) >> 4);
+                        const uint64_t bd = bd0 + (uint64_t)(((tap * C::NCH + 2 * s) * COUT * 16) >> 4);
+                        umma_f16(tmem_base + (uint32_t)(t * COUT), ad, bd, IDESC, (tap == 0 && s == 0) ? acc0 : 1u);
                     }
                 }
             }
@@ -391,13 +389,71 @@ conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_l
 // final magnitude.  The nine per-tap partial sums are added in fp32 registers (round to
 // nearest) by the epilogue warps while the MMA warp already fills the other TMEM stage.
 //   warps 0..15: stage input block, per tap tcgen05.ld the partial and add, final epilogue
-//   warp 16    : one lane issues the MMAs (descriptors precomputed, offsets compile-time)
+//   warps 16-19: one lane each issues the MMAs of one pooling-phase tile (a single thread
+//                cannot issue faster than ~60 cycles per tcgen05.mma)
 // ---------------------------------------------------------------------------------------
 constexpr int ACC_EPI_WARPS = 16;
-constexpr int ACC_THREADS = (ACC_EPI_WARPS + 1) * 32;
+constexpr int ACC_MMA_WARPS = 4;
+constexpr int ACC_THREADS = (ACC_EPI_WARPS + ACC_MMA_WARPS) * 32;
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Geometry of the accurate-accumulation kernel: ONE unit = one whole cell.  The zero-padded
+// (R+2) x (R+2) input is staged once, column-parity de-interleaved, and serves both pooled
+// X-halves (R = 32) -- half as many unit boundaries (staging, pipeline fill/drain) per MMA.
+template <int CIN, int COUT, int R>
+struct AccCfg {
+    static constexpr int NCH = CIN / 8;
+    static constexpr int FILL_ROWS = R + 2;
+    static constexpr int COLS = R + 2;                    // staged columns
+    static constexpr int ROW_UNITS = COLS / 2;            // 16-byte units per parity-plane row
+    static constexpr int ROW_B = ROW_UNITS * 16;
+    static constexpr int PLANE_B = FILL_ROWS * ROW_B;
+    static constexpr int CHUNK_B = 2 * PLANE_B;           // = LBO of A
+    static constexpr int REGION_B = NCH * CHUNK_B;
+    static constexpr int SBO_A = 2 * ROW_B;
+    static constexpr int HALVES = R >= 32 ? 2 : 1;        // pooled 16x8 tiles per cell
+    static constexpr int W_B = 9 * NCH * COUT * 16;
+    static constexpr int SMEM_B = 2 * (REGION_B + W_B);
+};
+
+template <class A, int R, int NT, int BATCH>
+__device__ __forceinline__ void stage_pool_cell(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo,
+                                                unsigned char* a0, unsigned char* a1, int cell, int tid) {
+    constexpr int N_UNITS16 = A::NCH * A::FILL_ROWS * A::COLS;
+    constexpr int ITERS = (N_UNITS16 + NT - 1) / NT;
+#pragma unroll 1
+    for (int i0 = 0; i0 < ITERS; i0 += BATCH) {
+        uint4 vh[BATCH], vl[BATCH];
+        uint32_t dst[BATCH];
+#pragma unroll
+        for (int j = 0; j < BATCH; ++j) {
+            const int idx = tid + (i0 + j) * NT;
+            vh[j] = make_uint4(0, 0, 0, 0); vl[j] = make_uint4(0, 0, 0, 0);
+            dst[j] = 0xFFFFFFFFu;
+            if (i0 + j < ITERS && idx < N_UNITS16) {
+                const int c = idx / (A::FILL_ROWS * A::COLS);
+                const int rem = idx - c * (A::FILL_ROWS * A::COLS);
+                const int ry = rem / A::COLS, rc = rem - ry * A::COLS;
+                const int y = ry - 1, x = rc - 1;
+                dst[j] = (uint32_t)(((c * 2 + (rc & 1)) * A::FILL_ROWS + ry) * A::ROW_UNITS + (rc >> 1)) * 16u;
+                if (y >= 0 && y < R && x >= 0 && x < R) {
+                    const size_t src = ((((size_t)cell * A::NCH + c) * R + y) * R + x);
+                    vh[j] = __ldg(reinterpret_cast<const uint4*>(in_hi) + src);
+                    vl[j] = __ldg(reinterpret_cast<const uint4*>(in_lo) + src);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < BATCH; ++j) {
+            if (dst[j] != 0xFFFFFFFFu) {
+                *reinterpret_cast<uint4*>(a0 + dst[j]) = vh[j];
+                *reinterpret_cast<uint4*>(a1 + dst[j]) = vl[j];
+            }
+        }
+    }
 }
 
 template <int CIN, int COUT, int R>
@@ -408,7 +464,7 @@ conv_tc_acc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
                    const float* __restrict__ bn_t, __half* __restrict__ out_hi, __half* __restrict__ out_lo,
                    float* __restrict__ feat, int n_cells, const int32_t* __restrict__ n_dev, int cell0,
                    int chunk_cells) {
-    using C = Cfg<CIN, COUT, R, EPI_POOL, 3>;
+    using C = AccCfg<CIN, COUT, R>;
     constexpr int STAGE_COLS = 4 * COUT;
     constexpr int TMEM_COLS = pow2_cols(2 * STAGE_COLS);
     constexpr int CW = COUT / 4;                 // columns per epilogue warp
@@ -424,11 +480,11 @@ conv_tc_acc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
     int n = dev_count(n_cells, n_dev) - cell0;
     if (n > chunk_cells) n = chunk_cells;
     if (n <= 0) return;
-    const int n_units = n * C::UNITS_PER_CELL;
+    const int n_units = n;                       // one unit = one cell (C::HALVES pooled tiles)
 
     if (warp == 0) tmem_alloc(&tmem_base_s, TMEM_COLS);
     if (tid == 32) {
-        mbar_init(&full_bar[0], 1); mbar_init(&full_bar[1], 1);
+        mbar_init(&full_bar[0], ACC_MMA_WARPS); mbar_init(&full_bar[1], ACC_MMA_WARPS);
         mbar_init(&empty_bar[0], ACC_EPI_WARPS); mbar_init(&empty_bar[1], ACC_EPI_WARPS);
         mbar_init(&ready_bar, ACC_EPI_WARPS);
         fence_barrier_init();
@@ -444,40 +500,45 @@ conv_tc_acc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
     const uint32_t tmem_base = tmem_base_s;
     constexpr uint32_t IDESC = make_idesc(128, COUT);
 
-    if (warp == ACC_EPI_WARPS) {
-        // ================= MMA issuer =================
+    if (warp >= ACC_EPI_WARPS) {
+        // ================= MMA issuers: one warp per phase tile =================
+        // A single thread sustains only one tcgen05.mma per ~60 cycles (elect loop, R2UR moves,
+        // dependent uniform-register adds), more than the 45-48 cycles an M128 x N<=64 MMA takes;
+        // four issuing warps, each owning the accumulator tile of one pooling phase, keep the
+        // tensor pipe fed.  Each commits to the stage's full barrier (count 4).
         if (lane == 0) {
-            const uint64_t a_hi0 = make_smem_desc(smem_u32(a_part[0]), C::CHUNK_B, C::SBO_A);
-            const uint64_t a_lo0 = make_smem_desc(smem_u32(a_part[1]), C::CHUNK_B, C::SBO_A);
+            const int t = warp - ACC_EPI_WARPS, py = t >> 1, px = t & 1;
+            const uint64_t a_hi0 = make_smem_desc(smem_u32(a_part[0]) + py * C::ROW_B, C::CHUNK_B, C::SBO_A);
+            const uint64_t a_lo0 = make_smem_desc(smem_u32(a_part[1]) + py * C::ROW_B, C::CHUNK_B, C::SBO_A);
             const uint64_t b_hi0 = make_smem_desc(smem_u32(w_part[0]), COUT * 16, 128);
             const uint64_t b_lo0 = make_smem_desc(smem_u32(w_part[1]), COUT * 16, 128);
+            uint64_t dxo[3];                   // (parity plane, half-column shift) of tap column dx, in 16-byte units
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) dxo[dx] = (uint64_t)((((px + dx) & 1) * C::PLANE_B + ((px + dx) >> 1) * 16) >> 4);
             uint32_t it = 0, uphase = 0;
             for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
                 mbar_wait(&ready_bar, uphase);
                 uphase ^= 1;
                 tc_fence_after();
 #pragma unroll
+                for (int half = 0; half < C::HALVES; ++half)
+#pragma unroll
                 for (int tap = 0; tap < 9; ++tap) {
                     const uint32_t st = it & 1;
                     mbar_wait(&empty_bar[st], ((it >> 1) & 1) ^ 1);
                     tc_fence_after();
                     const int dy = tap / 3, dx = tap % 3;
+                    const uint32_t d = tmem_base + st * STAGE_COLS + (uint32_t)(t * COUT);
+                    // pass order: hi*lo, lo*hi (tiny), then hi*hi (see header comment)
 #pragma unroll
-                    for (int t = 0; t < 4; ++t) {
-                        const int py = t >> 1, px = t & 1;
-                        const int aoff = ((px + dx) & 1) * C::PLANE_B + ((py + dy) * 9 + ((px + dx) >> 1)) * 16;
-                        const uint32_t d = tmem_base + st * STAGE_COLS + (uint32_t)(t * COUT);
-                        // pass order: hi*lo, lo*hi (tiny), then hi*hi (see header comment)
+                    for (int pass = 0; pass < 3; ++pass) {
+                        const uint64_t a0 = (pass == 1 ? a_lo0 : a_hi0) + dxo[dx];
+                        const uint64_t b0 = pass == 0 ? b_lo0 : b_hi0;
 #pragma unroll
-                        for (int pass = 0; pass < 3; ++pass) {
-                            const uint64_t a0 = pass == 1 ? a_lo0 : a_hi0;
-                            const uint64_t b0 = pass == 0 ? b_lo0 : b_hi0;
-#pragma unroll
-                            for (int s = 0; s < CIN / 16; ++s) {
-                                const uint64_t ad = a0 + (uint64_t)((aoff + 2 * s * C::CHUNK_B) >> 4);
-                                const uint64_t bd = b0 + (uint64_t)(((tap * C::NCH + 2 * s) * COUT * 16) >> 4);
-                                umma_f16(d, ad, bd, IDESC, (pass == 0 && s == 0) ? 0u : 1u);
-                            }
+                        for (int s = 0; s < CIN / 16; ++s) {
+                            const uint64_t ad = a0 + (uint64_t)(((dy * C::ROW_UNITS + 8 * half) * 16 + 2 * s * C::CHUNK_B) >> 4);
+                            const uint64_t bd = b0 + (uint64_t)(((tap * C::NCH + 2 * s) * COUT * 16) >> 4);
+                            umma_f16(d, ad, bd, IDESC, (pass == 0 && s == 0) ? 0u : 1u);
                         }
                     }
                     umma_commit(&full_bar[st]);
@@ -492,14 +553,15 @@ conv_tc_acc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
         const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(cq * CW);
         uint32_t it = 0;
         for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-            const int cell = cell0 + unit / C::UNITS_PER_CELL;
-            const int sub = unit % C::UNITS_PER_CELL;
+            const int cell = cell0 + unit;
             // stage the zero-padded, column-parity de-interleaved input block (hi and lo)
-            stage_block<C, R, 3, EPT, 6>(in_hi, in_lo, a_part[0], a_part[1], cell, sub, tid);
+            stage_pool_cell<C, R, EPT, 6>(in_hi, in_lo, a_part[0], a_part[1], cell, tid);
             fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&ready_bar);
 
+#pragma unroll 1
+            for (int sub = 0; sub < C::HALVES; ++sub) {
             float acc[4][CW];
 #pragma unroll
             for (int ph = 0; ph < 4; ++ph)
@@ -569,6 +631,7 @@ conv_tc_acc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
                     }
                 }
             }
+            }   // sub (pooled X half)
         }
     }
     tc_fence_before();
@@ -683,11 +746,11 @@ template <int CIN, int COUT, int R>
 int launch_tc_acc(cia_ctx* h, const CaeWeights& w, int layer, const __half* in_hi, const __half* in_lo,
                   __half* out_hi, __half* out_lo, float* feat, int n, const int32_t* n_dev, int cell0,
                   int chunk, cudaStream_t s) {
-    using C = Cfg<CIN, COUT, R, EPI_POOL, 3>;
+    using C = AccCfg<CIN, COUT, R>;
     auto kern = conv_tc_acc_kernel<CIN, COUT, R>;
     if (first_use(h, (const void*)kern))
         CIA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_B));
-    int grid = chunk * C::UNITS_PER_CELL;
+    int grid = chunk;
     if (grid > h->num_sms) grid = h->num_sms;
     kern<<<grid, ACC_THREADS, C::SMEM_B, s>>>(in_hi, in_lo, (const uint4*)w.tc_w[layer][0],
                                               (const uint4*)w.tc_w[layer][1], w.tc_inv_scale[layer], w.bias[layer],
