@@ -396,6 +396,13 @@ constexpr int ACC_EPI_WARPS = 16;
 constexpr int ACC_MMA_WARPS = 4;
 constexpr int ACC_THREADS = (ACC_EPI_WARPS + ACC_MMA_WARPS) * 32;
 
+// (a0, a1) += (b0, b1): one FADD2 (sm_100 packed fp32x2, IEEE round-to-nearest per lane)
+__device__ __forceinline__ void fadd2(float& a0, float& a1, uint32_t b0, uint32_t b1) {
+    asm("{\n\t.reg .b64 ra, rb;\n\tmov.b64 ra, {%0,%1};\n\tmov.b64 rb, {%2,%3};\n\t"
+        "add.rn.f32x2 ra, ra, rb;\n\tmov.b64 {%0,%1}, ra;\n\t}"
+        : "+f"(a0), "+f"(a1) : "r"(b0), "r"(b1));
+}
+
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -595,9 +602,9 @@ conv_tc_acc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
 #pragma unroll
                         for (int k8 = 0; k8 < CW / 8; ++k8)
 #pragma unroll
-                            for (int k = 0; k < 8; ++k)
-                                acc[2 * hp + p2][k8 * 8 + k] =
-                                    __fadd_rn(acc[2 * hp + p2][k8 * 8 + k], __uint_as_float(v[p2][k8][k]));
+                            for (int k = 0; k < 8; k += 2)   // packed fp32x2 add (FADD2), round to nearest
+                                fadd2(acc[2 * hp + p2][k8 * 8 + k], acc[2 * hp + p2][k8 * 8 + k + 1],
+                                      v[p2][k8][k], v[p2][k8][k + 1]);
                 }
                 ++it;
             }
@@ -683,11 +690,11 @@ conv1_fp32_planar_kernel(const float* __restrict__ crops, const float* __restric
                 const float2 v1 = *reinterpret_cast<const float2*>(&xs[2 * Y + a][2 * X + 2]);
                 win[a][0] = v0.x; win[a][1] = v0.y; win[a][2] = v1.x; win[a][3] = v1.y;
             }
-            float acc[4][8];
+            float acc[4][8];               // start from the bias: (bias + sum) in one FMA chain
 #pragma unroll
             for (int q = 0; q < 4; ++q)
 #pragma unroll
-                for (int k = 0; k < 8; ++k) acc[q][k] = 0.f;
+                for (int k = 0; k < 8; ++k) acc[q][k] = b8[k];
 #pragma unroll
             for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
@@ -708,11 +715,7 @@ conv1_fp32_planar_kernel(const float* __restrict__ crops, const float* __restric
             for (int k = 0; k < 8; ++k) {
                 float m = -INFINITY;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    float a = __fadd_rn(acc[q][k], b8[k]);
-                    a = fmaxf(a, 0.f);
-                    m = fmaxf(m, __fadd_rn(__fmul_rn(a, s8[k]), t8[k]));
-                }
+                for (int q = 0; q < 4; ++q) m = fmaxf(m, fmaf(fmaxf(acc[q][k], 0.f), s8[k], t8[k]));
                 o[k] = m;
             }
             const size_t off = ((((size_t)cell * 4 + cg) * 32 + (16 * qy + Y)) * 32 + (16 * qx + X)) * 8;

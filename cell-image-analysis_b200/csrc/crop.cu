@@ -60,7 +60,7 @@ __device__ __forceinline__ void clip_and_map(int (&hv)[8], int clim, double scal
 #pragma unroll
     for (int m = 0; m < 8; ++m)
         if (hv[m] > clim) { ex += hv[m] - clim; hv[m] = clim; }
-    ex = warp_sum(ex);
+    ex = __reduce_add_sync(0xffffffffu, ex);          // REDUX: one instruction instead of a 5-step shuffle tree
     if (ex > 0) {
         const int incr = ex / NBINS;
         const int upper = clim - incr;
@@ -72,11 +72,11 @@ __device__ __forceinline__ void clip_and_map(int (&hv)[8], int clim, double scal
 #pragma unroll
         for (int m = 0; m < 8; ++m)
             if (hv[m] >= upper && hv[m] < clim) { midsum += hv[m]; ++nmid; hv[m] = clim; }
-        // one packed reduction: nlow, nmid <= 256 each, midsum <= 256 * clim < 2^22
-        const unsigned long long packed =
-            warp_sum((unsigned long long)nlow | ((unsigned long long)nmid << 10) | ((unsigned long long)midsum << 20));
-        ex -= (int)(packed & 1023u) * incr;
-        ex += (int)(packed >> 20) - (int)((packed >> 10) & 1023u) * clim;
+        // nlow, nmid <= 256 each and midsum <= 256 * clim < 2^17 fit one 32-bit REDUX each way
+        const unsigned cnts = __reduce_add_sync(0xffffffffu, (unsigned)nlow | ((unsigned)nmid << 16));
+        const int msum = __reduce_add_sync(0xffffffffu, midsum);
+        ex -= (int)(cnts & 0xFFFFu) * incr;
+        ex += msum - (int)(cnts >> 16) * clim;
 
         while (ex > 0) {
             const int prev = ex;
@@ -86,8 +86,7 @@ __device__ __forceinline__ void clip_and_map(int (&hv)[8], int clim, double scal
 #pragma unroll
                 for (int m = 0; m < 8; ++m) under |= (hv[m] < clim ? 1u : 0u) << m;
                 // count of under-limit bins over the warp
-                int cnt = __popc(under);
-                cnt = warp_sum(cnt);
+                const int cnt = __reduce_add_sync(0xffffffffu, __popc(under));
                 if (cnt == 0) { stuck = true; break; }   // nothing can move any more
                 int step = cnt / ex;
                 if (step < 1) step = 1;
@@ -103,7 +102,7 @@ __device__ __forceinline__ void clip_and_map(int (&hv)[8], int clim, double scal
                     }
                     if (sel) { ++hv[m]; ++moved; }
                 }
-                ex -= warp_sum(moved);
+                ex -= __reduce_add_sync(0xffffffffu, moved);
                 if (ex <= 0) break;
             }
             if (stuck || prev == ex) break;
