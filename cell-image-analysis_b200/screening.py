@@ -225,12 +225,18 @@ class Engine:
 
 
 def _default_imread(path):
-    """tiff.imread (det:51).  tifffile when present; otherwise OpenCV's TIFF decoder
-    (channel order restored to the file's).  Upstream of the hot path."""
+    """tiff.imread (det:51): tifffile when installed, else the in-tree baseline-TIFF reader
+    (uncompressed strips), else OpenCV's decoder with the file's channel order restored.
+    Upstream of the hot path."""
     try:
         import tifffile
         return tifffile.imread(path)
     except ImportError:
+        pass
+    from .tiff_min import TiffError, read_tiff
+    try:
+        return read_tiff(path)
+    except TiffError:
         import cv2
         img = cv2.imread(path, cv2.IMREAD_UNCHANGED)
         if img is None:
@@ -356,7 +362,23 @@ class ProductionMutantScreening:
         r = self.compute_anomaly_scores(cell_images)
         return r["reconstruction_mse"], r["reconstruction_mae"]
 
-    # det:155-244 minus save_and_visualize_results (C11, out of scope)
+    # train:398-402: encoder.predict + flatten, the features create_anomaly_detector fits on
+    def encode_features(self, cell_images):
+        if len(cell_images) == 0:
+            return np.zeros((0, 2048), np.float32)
+        eng = self.engine
+        X = np.expand_dims(np.array(cell_images), axis=-1).astype("float32")
+        x = torch.from_numpy(np.ascontiguousarray(X[..., 0])).to(eng.tdev)
+        _mse, _mae, feat = eng.cae_forward(x, X.shape[0])
+        eng.check_status()
+        return feat[:X.shape[0]].cpu().numpy()
+
+    # det:246-261: CSV files + text report (figures are presentation only and not produced)
+    def save_and_visualize_results(self, results, detailed_results, output_dir):
+        from .reporting import save_and_report
+        return save_and_report(results, detailed_results, output_dir)
+
+    # det:155-244
     def screen_mutant_samples(self, test_folders_dict, output_dir=None):
         if output_dir:
             os.makedirs(output_dir, exist_ok=True)
@@ -380,6 +402,8 @@ class ProductionMutantScreening:
             s = self.compute_anomaly_scores(sample_cells)
             results[sample_name] = summarize_sample(sample_name, len(tif_files), s)
             detailed_results.extend(detail_rows(sample_name, s))
+        if output_dir:
+            self.save_and_visualize_results(results, detailed_results, output_dir)      # det:242
         return results, detailed_results
 
 
