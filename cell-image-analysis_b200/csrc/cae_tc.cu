@@ -225,12 +225,61 @@ conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_l
     constexpr uint32_t IDESC = make_idesc(128, COUT);
     uint32_t parity = 0;
 
+    // ---- input staging as a software pipeline (single-pass layers): the 16-byte loads of unit
+    // u+1 are issued into registers right after the MMAs of unit u and parked in shared memory
+    // once the block has been consumed; element -> (chunk, row, col, smem offset) is unit-invariant.
+    constexpr int S_COLS = C::POOL ? 18 : C::ROW_UNITS;
+    constexpr int S_N = C::NCH * C::FILL_ROWS * S_COLS;
+    constexpr int S_IT = (S_N + TCT - 1) / TCT;
+    constexpr bool PIPE = NPASS == 1;
+    uint32_t s_dst[S_IT], s_crc[S_IT];
+    uint4 s_val[S_IT];
+    if (PIPE) {
+#pragma unroll
+        for (int j = 0; j < S_IT; ++j) {
+            const int idx = tid + j * TCT;
+            s_dst[j] = 0xFFFFFFFFu; s_crc[j] = 0;
+            if (idx < S_N) {
+                const int c = idx / (C::FILL_ROWS * S_COLS);
+                const int rem = idx - c * (C::FILL_ROWS * S_COLS);
+                const int ry = rem / S_COLS, rc = rem - ry * S_COLS;
+                s_crc[j] = (uint32_t)((c << 16) | (ry << 8) | rc);
+                s_dst[j] = C::POOL ? (uint32_t)(((c * 2 + (rc & 1)) * C::FILL_ROWS + ry) * 9 + (rc >> 1)) * 16u
+                                   : (uint32_t)((c * C::FILL_ROWS + ry) * C::ROW_UNITS + rc) * 16u;
+            }
+        }
+    }
+    auto prefetch = [&](int unit) {
+        const int cell = cell0 + unit / C::UNITS_PER_CELL;
+        const int sub = unit % C::UNITS_PER_CELL;
+        const int y0 = C::POOL ? -1 : 16 * (sub / C::COL_BLOCKS) - 1;
+        const int x0 = C::POOL ? 16 * sub - 1 : C::UNIT_COLS * (sub % C::COL_BLOCKS) - 1;
+        constexpr int RS = UPSIN ? R / 2 : R;
+        const uint4* base = reinterpret_cast<const uint4*>(in_hi) + (size_t)cell * C::NCH * RS * RS;
+#pragma unroll
+        for (int j = 0; j < S_IT; ++j) {
+            const int c = (int)(s_crc[j] >> 16), y = y0 + (int)((s_crc[j] >> 8) & 255u), x = x0 + (int)(s_crc[j] & 255u);
+            s_val[j] = make_uint4(0, 0, 0, 0);
+            if (s_dst[j] != 0xFFFFFFFFu && y >= 0 && y < R && x >= 0 && x < R) {
+                const int ys = UPSIN ? (y >> 1) : y, xs = UPSIN ? (x >> 1) : x;
+                s_val[j] = __ldg(base + ((size_t)c * RS + ys) * RS + xs);
+            }
+        }
+    };
+    if (PIPE && (int)blockIdx.x < n_units) prefetch(blockIdx.x);
+
     for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
         const int cell = cell0 + unit / C::UNITS_PER_CELL;
         const int sub = unit % C::UNITS_PER_CELL;   // POOL: pooled X half; else: 16-row band
 
         // ---- stage the zero-padded input block ----
-        stage_block<C, R, NPASS, TCT, 8, UPSIN>(in_hi, in_lo, a_part[0], a_part[1], cell, sub, tid);
+        if (PIPE) {
+#pragma unroll
+            for (int j = 0; j < S_IT; ++j)
+                if (s_dst[j] != 0xFFFFFFFFu) *reinterpret_cast<uint4*>(a_part[0] + s_dst[j]) = s_val[j];
+        } else {
+            stage_block<C, R, NPASS, TCT, 8, UPSIN>(in_hi, in_lo, a_part[0], a_part[1], cell, sub, tid);
+        }
         fence_async_smem();
         __syncthreads();
 
@@ -263,6 +312,7 @@ conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_l
             }
             umma_commit(&bar);
         }
+        if (PIPE && unit + (int)gridDim.x < n_units) prefetch(unit + gridDim.x);   // overlaps the MMAs + epilogue
         mbar_wait(&bar, parity);
         parity ^= 1;
         tc_fence_after();
@@ -674,10 +724,20 @@ conv1_fp32_planar_kernel(const float* __restrict__ crops, const float* __restric
         const int cell = cell0 + (unit >> 2), qy = (unit >> 1) & 1, qx = unit & 1;
         const float* xr = crops + (size_t)cell * 4096;
         __syncthreads();
-        for (int i = tid; i < 34 * 34; i += 256) {
-            const int ry = i / 34, rc = i - ry * 34;
-            const int y = 32 * qy + ry - 1, x = 32 * qx + rc - 1;
-            xs[ry][rc] = (y >= 0 && y < 64 && x >= 0 && x < 64) ? __ldg(xr + y * 64 + x) : 0.f;
+        {   // all five loads of a thread in flight before the first store (one latency, not five)
+            float v[5];
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+                const int i = tid + j * 256;
+                const int ry = i / 34, rc = i - ry * 34;
+                const int y = 32 * qy + ry - 1, x = 32 * qx + rc - 1;
+                v[j] = (i < 34 * 34 && y >= 0 && y < 64 && x >= 0 && x < 64) ? __ldg(xr + y * 64 + x) : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+                const int i = tid + j * 256;
+                if (i < 34 * 34) xs[i / 34][i % 34] = v[j];
+            }
         }
         __syncthreads();
 #pragma unroll 1
