@@ -446,6 +446,20 @@ constexpr int ACC_EPI_WARPS = 16;
 constexpr int ACC_MMA_WARPS = 4;
 constexpr int ACC_THREADS = (ACC_EPI_WARPS + ACC_MMA_WARPS) * 32;
 
+// packed fp32x2 helpers (sm_100): two IEEE fp32 lanes in one 64-bit register
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float& lo, float& hi) {
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
 // (a0, a1) += (b0, b1): one FADD2 (sm_100 packed fp32x2, IEEE round-to-nearest per lane)
 __device__ __forceinline__ void fadd2(float& a0, float& a1, uint32_t b0, uint32_t b1) {
     asm("{\n\t.reg .b64 ra, rb;\n\tmov.b64 ra, {%0,%1};\n\tmov.b64 rb, {%2,%3};\n\t"
@@ -750,26 +764,37 @@ conv1_fp32_planar_kernel(const float* __restrict__ crops, const float* __restric
                 const float2 v1 = *reinterpret_cast<const float2*>(&xs[2 * Y + a][2 * X + 2]);
                 win[a][0] = v0.x; win[a][1] = v0.y; win[a][2] = v1.x; win[a][3] = v1.y;
             }
-            float acc[4][8];               // start from the bias: (bias + sum) in one FMA chain
+            // packed fp32x2 FMAs (FFMA2): two output channels per instruction, IEEE RN per lane;
+            // accumulators start from the bias so that (bias + sum) is one FMA chain
+            unsigned long long acc2[4][4], win2[4][4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) win2[a][b] = pack2(win[a][b], win[a][b]);
 #pragma unroll
             for (int q = 0; q < 4; ++q)
 #pragma unroll
-                for (int k = 0; k < 8; ++k) acc[q][k] = b8[k];
+                for (int kk = 0; kk < 4; ++kk) acc2[q][kk] = pack2(b8[2 * kk], b8[2 * kk + 1]);
 #pragma unroll
             for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
                 for (int dx = 0; dx < 3; ++dx) {
-                    const float4 w0 = *reinterpret_cast<const float4*>(&ws[dy * 3 + dx][cg * 8]);
-                    const float4 w1 = *reinterpret_cast<const float4*>(&ws[dy * 3 + dx][cg * 8 + 4]);
-                    const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+                    const ulonglong2 w0 = *reinterpret_cast<const ulonglong2*>(&ws[dy * 3 + dx][cg * 8]);
+                    const ulonglong2 w1 = *reinterpret_cast<const ulonglong2*>(&ws[dy * 3 + dx][cg * 8 + 4]);
+                    const unsigned long long wp[4] = {w0.x, w0.y, w1.x, w1.y};
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        acc[0][k] = fmaf(win[dy][dx], w[k], acc[0][k]);
-                        acc[1][k] = fmaf(win[dy][dx + 1], w[k], acc[1][k]);
-                        acc[2][k] = fmaf(win[dy + 1][dx], w[k], acc[2][k]);
-                        acc[3][k] = fmaf(win[dy + 1][dx + 1], w[k], acc[3][k]);
+                    for (int kk = 0; kk < 4; ++kk) {
+                        acc2[0][kk] = fma2(win2[dy][dx], wp[kk], acc2[0][kk]);
+                        acc2[1][kk] = fma2(win2[dy][dx + 1], wp[kk], acc2[1][kk]);
+                        acc2[2][kk] = fma2(win2[dy + 1][dx], wp[kk], acc2[2][kk]);
+                        acc2[3][kk] = fma2(win2[dy + 1][dx + 1], wp[kk], acc2[3][kk]);
                     }
                 }
+            float acc[4][8];
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) unpack2(acc2[q][kk], acc[q][2 * kk], acc[q][2 * kk + 1]);
             float o[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
