@@ -527,7 +527,7 @@ __device__ __forceinline__ void stage_pool_cell(const __half* __restrict__ in_hi
     }
 }
 
-template <int CIN, int COUT, int R>
+template <int CIN, int COUT, int R, int G>
 __global__ void __launch_bounds__(ACC_THREADS, 1)
 conv_tc_acc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo,
                    const uint4* __restrict__ w_hi, const uint4* __restrict__ w_lo, float inv_scale,
@@ -539,6 +539,7 @@ conv_tc_acc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
     constexpr int STAGE_COLS = 4 * COUT;
     constexpr int TMEM_COLS = pow2_cols(2 * STAGE_COLS);
     constexpr int CW = COUT / 4;                 // columns per epilogue warp
+    constexpr int NGRP = (9 + G - 1) / G;        // TMEM flushes per pooled tile (G filter taps each)
     constexpr int EPT = ACC_EPI_WARPS * 32;
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ __align__(8) uint64_t full_bar[2], empty_bar[2], ready_bar;
@@ -594,22 +595,28 @@ conv_tc_acc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
 #pragma unroll
                 for (int half = 0; half < C::HALVES; ++half)
 #pragma unroll
-                for (int tap = 0; tap < 9; ++tap) {
+                for (int grp = 0; grp < NGRP; ++grp) {
                     const uint32_t st = it & 1;
                     mbar_wait(&empty_bar[st], ((it >> 1) & 1) ^ 1);
                     tc_fence_after();
-                    const int dy = tap / 3, dx = tap % 3;
                     const uint32_t d = tmem_base + st * STAGE_COLS + (uint32_t)(t * COUT);
-                    // pass order: hi*lo, lo*hi (tiny), then hi*hi (see header comment)
+                    // within a flush group: all cross terms (hi*lo, lo*hi; tiny) first, hi*hi last
 #pragma unroll
                     for (int pass = 0; pass < 3; ++pass) {
-                        const uint64_t a0 = (pass == 1 ? a_lo0 : a_hi0) + dxo[dx];
-                        const uint64_t b0 = pass == 0 ? b_lo0 : b_hi0;
 #pragma unroll
-                        for (int s = 0; s < CIN / 16; ++s) {
-                            const uint64_t ad = a0 + (uint64_t)(((dy * C::ROW_UNITS + 8 * half) * 16 + 2 * s * C::CHUNK_B) >> 4);
-                            const uint64_t bd = b0 + (uint64_t)(((tap * C::NCH + 2 * s) * COUT * 16) >> 4);
-                            umma_f16(d, ad, bd, IDESC, (pass == 0 && s == 0) ? 0u : 1u);
+                        for (int tg = 0; tg < G; ++tg) {
+                            const int tap = grp * G + tg;
+                            if (tap < 9) {
+                                const int dy = tap / 3, dx = tap % 3;
+                                const uint64_t a0 = (pass == 1 ? a_lo0 : a_hi0) + dxo[dx];
+                                const uint64_t b0 = pass == 0 ? b_lo0 : b_hi0;
+#pragma unroll
+                                for (int s = 0; s < CIN / 16; ++s) {
+                                    const uint64_t ad = a0 + (uint64_t)(((dy * C::ROW_UNITS + 8 * half) * 16 + 2 * s * C::CHUNK_B) >> 4);
+                                    const uint64_t bd = b0 + (uint64_t)(((tap * C::NCH + 2 * s) * COUT * 16) >> 4);
+                                    umma_f16(d, ad, bd, IDESC, (pass == 0 && tg == 0 && s == 0) ? 0u : 1u);
+                                }
+                            }
                         }
                     }
                     umma_commit(&full_bar[st]);
@@ -639,7 +646,7 @@ conv_tc_acc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
 #pragma unroll
                 for (int k = 0; k < CW; ++k) acc[ph][k] = 0.f;
 #pragma unroll 1
-            for (int tap = 0; tap < 9; ++tap) {
+            for (int grp = 0; grp < NGRP; ++grp) {
                 const uint32_t st = it & 1;
                 mbar_wait(&full_bar[st], (it >> 1) & 1);
                 tc_fence_after();
@@ -830,12 +837,12 @@ int launch_tc(cia_ctx* h, const CaeWeights& w, int layer, const __half* in_hi, c
     return CIA_OK;
 }
 
-template <int CIN, int COUT, int R>
+template <int CIN, int COUT, int R, int G = 1>
 int launch_tc_acc(cia_ctx* h, const CaeWeights& w, int layer, const __half* in_hi, const __half* in_lo,
                   __half* out_hi, __half* out_lo, float* feat, int n, const int32_t* n_dev, int cell0,
                   int chunk, cudaStream_t s) {
     using C = AccCfg<CIN, COUT, R>;
-    auto kern = conv_tc_acc_kernel<CIN, COUT, R>;
+    auto kern = conv_tc_acc_kernel<CIN, COUT, R, G>;
     if (first_use(h, (const void*)kern))
         CIA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_B));
     int grid = chunk;
@@ -984,7 +991,13 @@ int k_cae_forward_tc(cia_ctx* h, const float* crops, int n, const int32_t* n_dev
                                                            ae.bn_shift[0], a1h, a1l, n, n_dev, c0, chunk);
             CIA_LAUNCH_CHECK();
             float* a2f = l3_exact ? A2f - (size_t)c0 * (16 * 16 * 64) : nullptr;
-            if ((rc = launch_tc_acc<32, 64, 32>(h, ae, 1, a1h, a1l, a2h, a2l, a2f, n, n_dev, c0, chunk, s))) return rc;
+            // layer 2 is bound by the TMEM reads of its per-tap partials (131 KB per tap at ~64 B/clk);
+            // CIA_L2_TAPS_PER_FLUSH=2|3 trades accuracy for fewer flushes (default 1: see DESIGN.md)
+            static const int l2_g = [] { const char* e = getenv("CIA_L2_TAPS_PER_FLUSH"); return e ? atoi(e) : 1; }();
+            if (l2_g == 3) rc = launch_tc_acc<32, 64, 32, 3>(h, ae, 1, a1h, a1l, a2h, a2l, a2f, n, n_dev, c0, chunk, s);
+            else if (l2_g == 2) rc = launch_tc_acc<32, 64, 32, 2>(h, ae, 1, a1h, a1l, a2h, a2l, a2f, n, n_dev, c0, chunk, s);
+            else rc = launch_tc_acc<32, 64, 32, 1>(h, ae, 1, a1h, a1l, a2h, a2l, a2f, n, n_dev, c0, chunk, s);
+            if (rc) return rc;
             if (l3_exact) {
                 if ((rc = launch_tc<64, 32, 16, EPI_POOL, 1>(h, ae, 2, a2h, nullptr, a3h, nullptr, nullptr, nullptr, nullptr, nullptr, n, n_dev, c0, chunk, s))) return rc;
                 if (features && (rc = k_conv3_fp32(h, ae, a2f, n, n_dev, features, c0, chunk, s))) return rc;
