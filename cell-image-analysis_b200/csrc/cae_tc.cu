@@ -18,6 +18,7 @@
 // a power of two; three MMAs (hi*hi, hi*lo, lo*hi) accumulate into one fp32 TMEM tile.
 #include "common.cuh"
 
+#include <cuda.h>          // CUtensorMap (types only; the encoder is fetched through the runtime)
 #include <cuda_fp16.h>
 
 #include <cmath>
@@ -527,6 +528,15 @@ __device__ __forceinline__ void stage_pool_cell(const __half* __restrict__ in_hi
     }
 }
 
+#ifdef CIA_ACC_TIMING
+__device__ unsigned long long g_acc_dbg[16];
+#define DBG_T(var) const long long var = clock64()
+#define DBG_ADD(acc, a, b) acc += (b) - (a)
+#else
+#define DBG_T(var)
+#define DBG_ADD(acc, a, b)
+#endif
+
 template <int CIN, int COUT, int R, int G>
 __global__ void __launch_bounds__(ACC_THREADS, 1)
 conv_tc_acc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo,
@@ -588,8 +598,14 @@ conv_tc_acc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
 #pragma unroll
             for (int dx = 0; dx < 3; ++dx) dxo[dx] = (uint64_t)((((px + dx) & 1) * C::PLANE_B + ((px + dx) >> 1) * 16) >> 4);
             uint32_t it = 0, uphase = 0;
+#ifdef CIA_ACC_TIMING
+            long long m_ready = 0, m_empty = 0, m_issue = 0;
+#endif
             for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+                DBG_T(m0);
                 mbar_wait(&ready_bar, uphase);
+                DBG_T(m1);
+                DBG_ADD(m_ready, m0, m1);
                 uphase ^= 1;
                 tc_fence_after();
 #pragma unroll
@@ -597,7 +613,10 @@ conv_tc_acc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
 #pragma unroll
                 for (int grp = 0; grp < NGRP; ++grp) {
                     const uint32_t st = it & 1;
+                    DBG_T(m2);
                     mbar_wait(&empty_bar[st], ((it >> 1) & 1) ^ 1);
+                    DBG_T(m3);
+                    DBG_ADD(m_empty, m2, m3);
                     tc_fence_after();
                     const uint32_t d = tmem_base + st * STAGE_COLS + (uint32_t)(t * COUT);
                     // within a flush group: all cross terms (hi*lo, lo*hi; tiny) first, hi*hi last
@@ -620,9 +639,18 @@ conv_tc_acc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
                         }
                     }
                     umma_commit(&full_bar[st]);
+                    DBG_T(m4);
+                    DBG_ADD(m_issue, m3, m4);
                     ++it;
                 }
             }
+#ifdef CIA_ACC_TIMING
+            if (warp == ACC_EPI_WARPS) {
+                atomicAdd(&g_acc_dbg[8], (unsigned long long)m_ready);
+                atomicAdd(&g_acc_dbg[9], (unsigned long long)m_empty);
+                atomicAdd(&g_acc_dbg[10], (unsigned long long)m_issue);
+            }
+#endif
         }
     } else {
         // ================= loaders / accumulating epilogue =================
@@ -630,13 +658,22 @@ conv_tc_acc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
         const int r = 32 * q + lane;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(cq * CW);
         uint32_t it = 0;
+#ifdef CIA_ACC_TIMING
+        long long e_stage = 0, e_full = 0, e_ld = 0, e_add = 0, e_final = 0, e_units = 0;
+#endif
         for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
             const int cell = cell0 + unit;
+            DBG_T(e0);
             // stage the zero-padded, column-parity de-interleaved input block (hi and lo)
             stage_pool_cell<C, R, EPT, 6>(in_hi, in_lo, a_part[0], a_part[1], cell, tid);
             fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&ready_bar);
+            DBG_T(e1);
+            DBG_ADD(e_stage, e0, e1);
+#ifdef CIA_ACC_TIMING
+            ++e_units;
+#endif
 
 #pragma unroll 1
             for (int sub = 0; sub < C::HALVES; ++sub) {
@@ -648,7 +685,10 @@ conv_tc_acc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
 #pragma unroll 1
             for (int grp = 0; grp < NGRP; ++grp) {
                 const uint32_t st = it & 1;
+                DBG_T(e2);
                 mbar_wait(&full_bar[st], (it >> 1) & 1);
+                DBG_T(e3);
+                DBG_ADD(e_full, e2, e3);
                 tc_fence_after();
                 // two phases at a time keeps the live registers under the 120-per-thread budget
 #pragma unroll
@@ -667,6 +707,8 @@ conv_tc_acc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&empty_bar[st]);
+                        DBG_T(e4);
+                        DBG_ADD(e_ld, e3, e4);
                     }
 #pragma unroll
                     for (int p2 = 0; p2 < 2; ++p2)
@@ -677,8 +719,11 @@ conv_tc_acc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
                                 fadd2(acc[2 * hp + p2][k8 * 8 + k], acc[2 * hp + p2][k8 * 8 + k + 1],
                                       v[p2][k8][k], v[p2][k8][k + 1]);
                 }
+                DBG_T(e5);
+                DBG_ADD(e_add, e3, e5);
                 ++it;
             }
+            DBG_T(e6);
             // final epilogue from registers: bias -> ReLU -> BN -> 2x2 max -> hi/lo fp16 (+ fp32 tap)
             constexpr int RO = R / 2;
             const int Y = r >> 3, X = 8 * sub + (r & 7);
@@ -709,8 +754,305 @@ conv_tc_acc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
                     }
                 }
             }
+            DBG_T(e7);
+            DBG_ADD(e_final, e6, e7);
             }   // sub (pooled X half)
         }
+#ifdef CIA_ACC_TIMING
+        if (tid == 0) {
+            atomicAdd(&g_acc_dbg[0], (unsigned long long)e_stage);
+            atomicAdd(&g_acc_dbg[1], (unsigned long long)e_full);
+            atomicAdd(&g_acc_dbg[2], (unsigned long long)e_ld);
+            atomicAdd(&g_acc_dbg[3], (unsigned long long)e_add);
+            atomicAdd(&g_acc_dbg[4], (unsigned long long)e_final);
+            atomicAdd(&g_acc_dbg[5], (unsigned long long)e_units);
+        }
+#endif
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------
+// Accurate accumulation for the R = 32 pooling layer (L2): TMA-fed, double-buffered blocks.
+// In-kernel clocks on the whole-cell kernel above (profiles/r1_acc_phase_cycles.txt) show its
+// phases running back to back per cell: staging 7.7k cycles -> MMAs 22k (issue-bound at ~51
+// cycles per M128xN64xK16 instruction) -> final epilogue 3.7k, with per-tap flushes keeping
+// the epilogue warps busier (27k) than the tensor pipe.  Here one unit = one pooled X-half
+// (16 input columns + halo, 2 x 39 KB hi/lo) and the two halves of a cell alternate between
+// two shared-memory buffers.  A block is four TMA boxes (hi/lo x column parity): the tensor
+// map walks x with element stride 2, which de-interleaves the columns by parity on the fly,
+// and out-of-bounds coordinates (x = -1 / 32, y = -1 / 32) zero-fill the halo.  The copy of
+// half-unit k+2 is issued by one thread the moment the last MMAs of half-unit k (same buffer)
+// have completed, i.e. a whole half-unit ahead of its use; no warp stages anything.
+// ---------------------------------------------------------------------------------------
+template <int CIN, int COUT>
+struct Acc2Cfg {
+    static constexpr int R = 32;
+    static constexpr int NCH = CIN / 8;
+    static constexpr int FILL_ROWS = R + 2;
+    static constexpr int BOX_X = R / 2 + 2;               // columns a box spans (every second one is read)
+    static constexpr int ROW_UNITS = BOX_X / 2;           // 16-byte units per parity-plane row
+    static constexpr int ROW_B = ROW_UNITS * 16;
+    static constexpr int PLANE_B = FILL_ROWS * ROW_B;     // one (parity, chunk) plane = LBO of A
+    static constexpr int PAR_B = NCH * PLANE_B;           // one TMA box: all chunks of one column parity
+    static constexpr int REGION_B = 2 * PAR_B;            // hi or lo part of a block
+    static constexpr int SBO_A = 2 * ROW_B;
+    static constexpr int BUF_B = 2 * REGION_B;            // hi + lo of one half block
+    static constexpr int W_B = 9 * NCH * COUT * 16;
+    static constexpr int SMEM_B = 2 * BUF_B + 2 * W_B;
+    static_assert(PAR_B % 128 == 0, "TMA destinations must be 128-byte aligned");
+};
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3,
+                                            int c4, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2,%3,%4,%5,%6}], [%7];"
+        ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(smem_u32(bar)) : "memory");
+}
+// one half block = 4 boxes over the [cell][chunk][y][x][8] fp16 activations (tensor-map dims 8, x, y, chunk, cell)
+template <class A>
+__device__ __forceinline__ void tma_load_half_block(const CUtensorMap* tm_hi, const CUtensorMap* tm_lo, uint32_t buf,
+                                                    int cell_rel, int half, uint64_t* bar) {
+    mbar_expect_tx(bar, A::BUF_B);
+#pragma unroll
+    for (int par = 0; par < 2; ++par) {
+        const int x0 = half * (A::R / 2) - 1 + par;
+        tma_load_5d(buf + par * A::PAR_B, tm_hi, 0, x0, -1, 0, cell_rel, bar);
+        tma_load_5d(buf + A::REGION_B + par * A::PAR_B, tm_lo, 0, x0, -1, 0, cell_rel, bar);
+    }
+}
+
+template <int CIN, int COUT, int G>
+__global__ void __launch_bounds__(ACC_THREADS, 1)
+conv_tc_acc2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
+                    const uint4* __restrict__ w_hi, const uint4* __restrict__ w_lo, float inv_scale,
+                    const float* __restrict__ bias, const float* __restrict__ bn_s,
+                    const float* __restrict__ bn_t, __half* __restrict__ out_hi, __half* __restrict__ out_lo,
+                    float* __restrict__ feat, int n_cells, const int32_t* __restrict__ n_dev, int cell0,
+                    int chunk_cells) {
+    using C = Acc2Cfg<CIN, COUT>;
+    constexpr int R = C::R;
+    constexpr int STAGE_COLS = 4 * COUT;
+    constexpr int TMEM_COLS = pow2_cols(2 * STAGE_COLS);
+    constexpr int CW = COUT / 4;                 // columns per epilogue warp
+    constexpr int NGRP = (9 + G - 1) / G;        // TMEM flushes per pooled tile (G filter taps each)
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ __align__(8) uint64_t full_bar[2], empty_bar[2], ready_bar[2];
+    __shared__ uint32_t tmem_base_s;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    unsigned char* w_part[2] = {smem + 2 * C::BUF_B, smem + 2 * C::BUF_B + C::W_B};
+
+    int n = dev_count(n_cells, n_dev) - cell0;
+    if (n > chunk_cells) n = chunk_cells;
+    if (n <= 0) return;
+    const int n_units = n;                       // CTA-level unit = one cell = two half blocks
+
+    if (warp == 0) tmem_alloc(&tmem_base_s, TMEM_COLS);
+    if (tid == 32) {
+        mbar_init(&full_bar[0], ACC_MMA_WARPS); mbar_init(&full_bar[1], ACC_MMA_WARPS);
+        mbar_init(&empty_bar[0], ACC_EPI_WARPS); mbar_init(&empty_bar[1], ACC_EPI_WARPS);
+        mbar_init(&ready_bar[0], 1); mbar_init(&ready_bar[1], 1);
+        fence_barrier_init();
+    }
+    for (int i = tid; i < C::W_B / 16; i += ACC_THREADS) {
+        reinterpret_cast<uint4*>(w_part[0])[i] = __ldg(w_hi + i);
+        reinterpret_cast<uint4*>(w_part[1])[i] = __ldg(w_lo + i);
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    const uint32_t sbase = smem_u32(smem);
+    constexpr uint32_t IDESC = make_idesc(128, COUT);
+
+    if (warp >= ACC_EPI_WARPS) {
+        // ================= MMA issuers: one warp per phase tile =================
+        if (lane == 0) {
+            const int t = warp - ACC_EPI_WARPS, py = t >> 1, px = t & 1;
+            const uint64_t b_hi0 = make_smem_desc(smem_u32(w_part[0]), COUT * 16, 128);
+            const uint64_t b_lo0 = make_smem_desc(smem_u32(w_part[1]), COUT * 16, 128);
+            uint64_t dxo[3];                   // (parity plane, half-column shift) of tap column dx, in 16-byte units
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) dxo[dx] = (uint64_t)((((px + dx) & 1) * C::PAR_B + ((px + dx) >> 1) * 16) >> 4);
+            uint32_t it = 0, cphase = 0;
+#ifdef CIA_ACC_TIMING
+            long long m_ready = 0, m_empty = 0, m_issue = 0;
+#endif
+            for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const uint32_t abase = sbase + half * C::BUF_B + py * C::ROW_B;
+                    const uint64_t a_hi0 = make_smem_desc(abase, C::PLANE_B, C::SBO_A);
+                    const uint64_t a_lo0 = make_smem_desc(abase + C::REGION_B, C::PLANE_B, C::SBO_A);
+                    DBG_T(m0);
+                    mbar_wait(&ready_bar[half], cphase);
+                    DBG_T(m1);
+                    DBG_ADD(m_ready, m0, m1);
+                    tc_fence_after();
+#pragma unroll
+                    for (int grp = 0; grp < NGRP; ++grp) {
+                        const uint32_t st = it & 1;
+                        DBG_T(m2);
+                        mbar_wait(&empty_bar[st], ((it >> 1) & 1) ^ 1);
+                        DBG_T(m3);
+                        DBG_ADD(m_empty, m2, m3);
+                        tc_fence_after();
+                        const uint32_t d = tmem_base + st * STAGE_COLS + (uint32_t)(t * COUT);
+                        // within a flush group: all cross terms (hi*lo, lo*hi; tiny) first, hi*hi last
+#pragma unroll
+                        for (int pass = 0; pass < 3; ++pass) {
+#pragma unroll
+                            for (int tg = 0; tg < G; ++tg) {
+                                const int tap = grp * G + tg;
+                                if (tap < 9) {
+                                    const int dy = tap / 3, dx = tap % 3;
+                                    const uint64_t a0 = (pass == 1 ? a_lo0 : a_hi0) + dxo[dx];
+                                    const uint64_t b0 = pass == 0 ? b_lo0 : b_hi0;
+#pragma unroll
+                                    for (int s = 0; s < CIN / 16; ++s) {
+                                        const uint64_t ad = a0 + (uint64_t)((dy * C::ROW_B + 2 * s * C::PLANE_B) >> 4);
+                                        const uint64_t bd = b0 + (uint64_t)(((tap * C::NCH + 2 * s) * COUT * 16) >> 4);
+                                        umma_f16(d, ad, bd, IDESC, (pass == 0 && tg == 0 && s == 0) ? 0u : 1u);
+                                    }
+                                }
+                            }
+                        }
+                        umma_commit(&full_bar[st]);
+                        DBG_T(m4);
+                        DBG_ADD(m_issue, m3, m4);
+                        ++it;
+                    }
+                }
+                cphase ^= 1;
+            }
+#ifdef CIA_ACC_TIMING
+            if (warp == ACC_EPI_WARPS) {
+                atomicAdd(&g_acc_dbg[8], (unsigned long long)m_ready);
+                atomicAdd(&g_acc_dbg[9], (unsigned long long)m_empty);
+                atomicAdd(&g_acc_dbg[10], (unsigned long long)m_issue);
+            }
+#endif
+        }
+    } else {
+        // ================= copy issuers / accumulating epilogue =================
+        const int q = warp & 3, cq = warp >> 2;
+        const int r = 32 * q + lane;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(cq * CW);
+        uint32_t it = 0;
+#ifdef CIA_ACC_TIMING
+        long long e_stage = 0, e_full = 0, e_ld = 0, e_add = 0, e_final = 0, e_units = 0;
+#endif
+        if (tid == 0 && (int)blockIdx.x < n_units) {          // prologue: both half blocks of the first cell
+            tma_load_half_block<C>(&tm_hi, &tm_lo, sbase, blockIdx.x, 0, &ready_bar[0]);
+            tma_load_half_block<C>(&tm_hi, &tm_lo, sbase + C::BUF_B, blockIdx.x, 1, &ready_bar[1]);
+        }
+        for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+            const int cell = cell0 + unit;
+#ifdef CIA_ACC_TIMING
+            ++e_units;
+#endif
+#pragma unroll 1
+            for (int sub = 0; sub < 2; ++sub) {
+                float acc[4][CW];
+#pragma unroll
+                for (int ph = 0; ph < 4; ++ph)
+#pragma unroll
+                    for (int k = 0; k < CW; ++k) acc[ph][k] = 0.f;
+#pragma unroll 1
+                for (int grp = 0; grp < NGRP; ++grp) {
+                    const uint32_t st = it & 1;
+                    DBG_T(e2);
+                    mbar_wait(&full_bar[st], (it >> 1) & 1);
+                    DBG_T(e3);
+                    DBG_ADD(e_full, e2, e3);
+                    tc_fence_after();
+                    // the last MMAs reading this buffer are done: refill it with the same half of the next cell
+                    if (grp == NGRP - 1 && tid == 0 && unit + (int)gridDim.x < n_units)
+                        tma_load_half_block<C>(&tm_hi, &tm_lo, sbase + sub * C::BUF_B, unit + (int)gridDim.x, sub,
+                                               &ready_bar[sub]);
+                    // two phases at a time keeps the live registers under the 102-per-thread budget
+#pragma unroll
+                    for (int hp = 0; hp < 2; ++hp) {
+                        uint32_t v[2][CW / 8][8];
+#pragma unroll
+                        for (int p2 = 0; p2 < 2; ++p2)
+#pragma unroll
+                            for (int k8 = 0; k8 < CW / 8; ++k8)
+                                TMEM_LD8(lane_addr + st * STAGE_COLS + (uint32_t)((2 * hp + p2) * COUT + k8 * 8), v[p2][k8]);
+#pragma unroll
+                        for (int p2 = 0; p2 < 2; ++p2)
+#pragma unroll
+                            for (int k8 = 0; k8 < CW / 8; ++k8) TMEM_WAIT8(v[p2][k8]);
+                        if (hp == 1) {
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&empty_bar[st]);
+                            DBG_T(e4);
+                            DBG_ADD(e_ld, e3, e4);
+                        }
+#pragma unroll
+                        for (int p2 = 0; p2 < 2; ++p2)
+#pragma unroll
+                            for (int k8 = 0; k8 < CW / 8; ++k8)
+#pragma unroll
+                                for (int k = 0; k < 8; k += 2)   // packed fp32x2 add (FADD2), round to nearest
+                                    fadd2(acc[2 * hp + p2][k8 * 8 + k], acc[2 * hp + p2][k8 * 8 + k + 1],
+                                          v[p2][k8][k], v[p2][k8][k + 1]);
+                    }
+                    DBG_T(e5);
+                    DBG_ADD(e_add, e3, e5);
+                    ++it;
+                }
+                DBG_T(e6);
+                // final epilogue from registers: bias -> ReLU -> BN -> 2x2 max -> hi/lo fp16 (+ fp32 tap)
+                constexpr int RO = R / 2;
+                const int Y = r >> 3, X = 8 * sub + (r & 7);
+#pragma unroll
+                for (int k8 = 0; k8 < CW / 8; ++k8) {
+                    const int c0 = cq * CW + k8 * 8;
+                    float o[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const float b = __ldg(bias + c0 + k), sc = __ldg(bn_s + c0 + k), sh = __ldg(bn_t + c0 + k);
+                        float m = -INFINITY;
+#pragma unroll
+                        for (int ph = 0; ph < 4; ++ph) {
+                            float a = fmaf(acc[ph][k8 * 8 + k], inv_scale, b);
+                            a = fmaxf(a, 0.f);
+                            m = fmaxf(m, fmaf(a, sc, sh));
+                        }
+                        o[k] = m;
+                    }
+                    const size_t off = ((((size_t)cell * (COUT / 8) + c0 / 8) * RO + Y) * RO + X) * 8;
+                    split_store8(o, out_hi + off, out_lo ? out_lo + off : nullptr);
+                    if (feat) {
+                        float4* f = reinterpret_cast<float4*>(feat + (size_t)cell * (RO * RO * COUT) +
+                                                             (size_t)(Y * RO + X) * COUT + c0);
+                        f[0] = make_float4(o[0], o[1], o[2], o[3]);
+                        f[1] = make_float4(o[4], o[5], o[6], o[7]);
+                    }
+                }
+                DBG_T(e7);
+                DBG_ADD(e_final, e6, e7);
+            }   // sub (pooled X half)
+        }
+#ifdef CIA_ACC_TIMING
+        if (tid == 0) {
+            atomicAdd(&g_acc_dbg[0], (unsigned long long)e_stage);
+            atomicAdd(&g_acc_dbg[1], (unsigned long long)e_full);
+            atomicAdd(&g_acc_dbg[2], (unsigned long long)e_ld);
+            atomicAdd(&g_acc_dbg[3], (unsigned long long)e_add);
+            atomicAdd(&g_acc_dbg[4], (unsigned long long)e_final);
+            atomicAdd(&g_acc_dbg[5], (unsigned long long)e_units);
+        }
+#endif
     }
     tc_fence_before();
     __syncthreads();
@@ -837,6 +1179,24 @@ int launch_tc(cia_ctx* h, const CaeWeights& w, int layer, const __half* in_hi, c
     return CIA_OK;
 }
 
+#ifdef CIA_ACC_TIMING
+// per-phase cycle sums of one launch (thread 0 / first MMA warp of every CTA), averaged per cell
+static void acc_timing_dump(const char* name, int cin, int cout, int r, int g, cudaStream_t s) {
+    if (!getenv("CIA_ACC_DUMP")) return;
+    unsigned long long d[16];
+    cudaStreamSynchronize(s);
+    cudaMemcpyFromSymbol(d, g_acc_dbg, sizeof(d));
+    const double u = d[5] ? (double)d[5] : 1.0;
+    fprintf(stderr, "%s<%d,%d,%d,G%d> cells %llu per-cell cycles: stage %.0f wait_full %.0f ld %.0f ld+add %.0f "
+                    "final %.0f | mma: wait_ready %.0f wait_empty %.0f issue %.0f\n", name, cin, cout, r, g, d[5],
+            d[0] / u, d[1] / u, d[2] / u, d[3] / u, d[4] / u, d[8] / u, d[9] / u, d[10] / u);
+    memset(d, 0, sizeof(d));
+    cudaMemcpyToSymbol(g_acc_dbg, d, sizeof(d));
+}
+#else
+static inline void acc_timing_dump(const char*, int, int, int, int, cudaStream_t) {}
+#endif
+
 template <int CIN, int COUT, int R, int G = 1>
 int launch_tc_acc(cia_ctx* h, const CaeWeights& w, int layer, const __half* in_hi, const __half* in_lo,
                   __half* out_hi, __half* out_lo, float* feat, int n, const int32_t* n_dev, int cell0,
@@ -852,6 +1212,59 @@ int launch_tc_acc(cia_ctx* h, const CaeWeights& w, int layer, const __half* in_h
                                               w.bn_scale[layer], w.bn_shift[layer], out_hi, out_lo, feat, n, n_dev,
                                               cell0, chunk);
     CIA_LAUNCH_CHECK();
+    acc_timing_dump("acc", CIN, COUT, R, G, s);
+    return CIA_OK;
+}
+
+// Tensor map over one chunk buffer of chunk-planar fp16 activations [cells][C/8][R][R][8]:
+// dims (8, x, y, chunk, cell); the box reads every second column (element stride 2 along x).
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                      const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int encode_act_map(cia_ctx* h, CUtensorMap* tm, const __half* base, int nch, int r, int cells, int box_x,
+                          int box_y) {
+    static TensorMapEncodeFn encode = [] {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess) fn = nullptr;
+        return (TensorMapEncodeFn)fn;
+    }();
+    if (!encode) { h->err = "cuTensorMapEncodeTiled is not available from this driver"; return CIA_E_UNSUPPORTED; }
+    const cuuint64_t dims[5] = {8, (cuuint64_t)r, (cuuint64_t)r, (cuuint64_t)nch, (cuuint64_t)cells};
+    const cuuint64_t strides[4] = {16, (cuuint64_t)16 * r, (cuuint64_t)16 * r * r, (cuuint64_t)16 * r * r * nch};
+    const cuuint32_t box[5] = {8, (cuuint32_t)box_x, (cuuint32_t)box_y, (cuuint32_t)nch, 1};
+    const cuuint32_t estr[5] = {1, 2, 1, 1, 1};
+    const CUresult rc = encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, (void*)base, dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) { h->err = "cuTensorMapEncodeTiled failed"; return CIA_E_CUDA; }
+    return CIA_OK;
+}
+
+// R = 32 pooling layer with TMA-fed double-buffered half-cell blocks (conv_tc_acc2_kernel).
+// in_hi / in_lo are the chunk buffers' own base addresses (cell 0 of the chunk).
+template <int CIN, int COUT, int G>
+int launch_tc_acc2(cia_ctx* h, const CaeWeights& w, int layer, const __half* in_hi, const __half* in_lo,
+                   int buf_cells, __half* out_hi, __half* out_lo, float* feat, int n, const int32_t* n_dev,
+                   int cell0, int chunk, cudaStream_t s) {
+    using C = Acc2Cfg<CIN, COUT>;
+    static_assert(C::SMEM_B + 1280 <= 227 * 1024, "double-buffered blocks do not fit in shared memory");
+    auto kern = conv_tc_acc2_kernel<CIN, COUT, G>;
+    if (first_use(h, (const void*)kern))
+        CIA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_B));
+    CUtensorMap tm_hi, tm_lo;
+    int rc;
+    if ((rc = encode_act_map(h, &tm_hi, in_hi, C::NCH, C::R, buf_cells, C::BOX_X, C::FILL_ROWS))) return rc;
+    if ((rc = encode_act_map(h, &tm_lo, in_lo, C::NCH, C::R, buf_cells, C::BOX_X, C::FILL_ROWS))) return rc;
+    int grid = chunk;
+    if (grid > h->num_sms) grid = h->num_sms;
+    kern<<<grid, ACC_THREADS, C::SMEM_B, s>>>(tm_hi, tm_lo, (const uint4*)w.tc_w[layer][0],
+                                              (const uint4*)w.tc_w[layer][1], w.tc_inv_scale[layer], w.bias[layer],
+                                              w.bn_scale[layer], w.bn_shift[layer], out_hi, out_lo, feat, n, n_dev,
+                                              cell0, chunk);
+    CIA_LAUNCH_CHECK();
+    acc_timing_dump("acc2", CIN, COUT, 32, G, s);
     return CIA_OK;
 }
 
@@ -991,12 +1404,13 @@ int k_cae_forward_tc(cia_ctx* h, const float* crops, int n, const int32_t* n_dev
                                                            ae.bn_shift[0], a1h, a1l, n, n_dev, c0, chunk);
             CIA_LAUNCH_CHECK();
             float* a2f = l3_exact ? A2f - (size_t)c0 * (16 * 16 * 64) : nullptr;
-            // layer 2 is bound by the TMEM reads of its per-tap partials (131 KB per tap at ~64 B/clk);
-            // CIA_L2_TAPS_PER_FLUSH=2|3 trades accuracy for fewer flushes (default 1: see DESIGN.md)
-            static const int l2_g = [] { const char* e = getenv("CIA_L2_TAPS_PER_FLUSH"); return e ? atoi(e) : 1; }();
-            if (l2_g == 3) rc = launch_tc_acc<32, 64, 32, 3>(h, ae, 1, a1h, a1l, a2h, a2l, a2f, n, n_dev, c0, chunk, s);
-            else if (l2_g == 2) rc = launch_tc_acc<32, 64, 32, 2>(h, ae, 1, a1h, a1l, a2h, a2l, a2f, n, n_dev, c0, chunk, s);
-            else rc = launch_tc_acc<32, 64, 32, 1>(h, ae, 1, a1h, a1l, a2h, a2l, a2f, n, n_dev, c0, chunk, s);
+            // taps per TMEM flush of layer 2 (CIA_L2_TAPS_PER_FLUSH=1|2|3; 0 = the single-buffered
+            // whole-cell kernel): 3 keeps the epilogue warps below the tensor pipe's time, see DESIGN.md
+            static const int l2_g = [] { const char* e = getenv("CIA_L2_TAPS_PER_FLUSH"); return e ? atoi(e) : 3; }();
+            if (l2_g == 0) rc = launch_tc_acc<32, 64, 32, 1>(h, ae, 1, a1h, a1l, a2h, a2l, a2f, n, n_dev, c0, chunk, s);
+            else if (l2_g == 1) rc = launch_tc_acc2<32, 64, 1>(h, ae, 1, A1h, A1l, CH, a2h, a2l, a2f, n, n_dev, c0, chunk, s);
+            else if (l2_g == 2) rc = launch_tc_acc2<32, 64, 2>(h, ae, 1, A1h, A1l, CH, a2h, a2l, a2f, n, n_dev, c0, chunk, s);
+            else rc = launch_tc_acc2<32, 64, 3>(h, ae, 1, A1h, A1l, CH, a2h, a2l, a2f, n, n_dev, c0, chunk, s);
             if (rc) return rc;
             if (l3_exact) {
                 if ((rc = launch_tc<64, 32, 16, EPI_POOL, 1>(h, ae, 2, a2h, nullptr, a3h, nullptr, nullptr, nullptr, nullptr, nullptr, n, n_dev, c0, chunk, s))) return rc;
