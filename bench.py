@@ -217,7 +217,12 @@ def run_native(args):
     g_dev, l_dev = g_pin.to(dev), l_pin.to(dev)
     n_strains = args.strains
     visit_strain = (torch.arange(NF, dtype=torch.int32) * n_strains // NF).to(dev)   # contiguous blocks
-    bs = BatchScreen(eng, H, W, max_label, chunk_fields=Fc, n_strains=n_strains)
+    if args.label_transport == "auto":
+        # the encoder needs ~all 16 host cores to keep pace with one GPU; with several ranks per
+        # host the per-GPU PCIe links (raw copies) outrun the shared cores
+        args.label_transport = "rle" if world == 1 else "raw"
+    bs = BatchScreen(eng, H, W, max_label, chunk_fields=Fc, n_strains=n_strains,
+                     label_transport=args.label_transport, host_threads=args.host_threads)
 
     def barrier():
         if world > 1:
@@ -327,7 +332,10 @@ def run_native(args):
                        "precision": args.precision, "l2_policy": "inputs larger than L2"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": float(ems.item()) / args.steps,
-                    "api": "BatchScreen.run_host -> cia_screen_fields (pinned host pool, double-buffered H2D)"},
+                    "label_transport": args.label_transport,
+                    "api": "BatchScreen.run_host -> cia_screen_fields (pinned host pool of uint16 images + int32 "
+                           "labels; labels run-length encoded by the host cores inside the timed region when "
+                           "label_transport=rle; double-buffered H2D)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"kernel": "CAE forward stage (7 conv layers + error reduction)", "bound": "tensor",
@@ -362,6 +370,10 @@ def main():
     ap.add_argument("--strains", type=int, default=4)
     ap.add_argument("--precision", type=int, default=1,
                     help="CAE path: 0 exact fp32 CUDA cores, 1 tcgen05 (split-precision encoder), 2 tcgen05 + fp32 encoder")
+    ap.add_argument("--label-transport", default="auto", choices=["auto", "rle", "raw"],
+                    help="e2e arm: how the int32 label fields cross PCIe (rle = lossless host run-length encode; "
+                         "auto = rle on one GPU, raw when several ranks share the host cores)")
+    ap.add_argument("--host-threads", type=int, default=0, help="host threads of the RLE encoder (0 = all cores)")
     ap.add_argument("--cpu-fields", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -11,6 +11,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libcia.so")
 
 
+CIA_E_CUDA, CIA_E_ARG, CIA_E_STATE, CIA_E_CAPACITY, CIA_E_LABEL, CIA_E_UNSUPPORTED = -1, -2, -3, -4, -5, -6
+
+
 class CiaError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"libcia error {code}: {msg}")
@@ -76,6 +79,10 @@ SIGNATURES = {
                                C.POINTER(Scores), _P, _P, _P, _P, _I, _P]),
     "cia_screen_fields_host": (_I, [_P, _P, _P, _I, _I, _I, _I, C.POINTER(Params), _I, _P, _I, _P,
                                     _P, C.POINTER(Scores), _P]),
+    "cia_rle_slot_words": (C.c_size_t, [_I, _I]),
+    "cia_rle_encode_fields": (_I, [_P, _I, _I, _I, _P, C.c_size_t, _P, _P, _I]),
+    "cia_rle_upload": (_I, [_P, _P, _I, C.c_size_t, _P, _P, _P]),
+    "cia_rle_expand": (_I, [_P, _P, _I, C.c_size_t, _I, _I, _P, _P]),
     "cia_profile_begin": (_I, [_P, _I]),
     "cia_profile_end": (_I, [_P, C.POINTER(C.c_double), C.POINTER(_I)]),
     "cia_debug_copy_workspace": (_I, [_P, _I, C.c_size_t, _P, C.c_size_t]),

@@ -23,7 +23,12 @@ STAGES = ("scan", "gates", "crop", "cae", "svm", "accumulate")
 
 class BatchScreen:
     def __init__(self, engine, H: int, W: int, max_label: int, chunk_fields: int = 16,
-                 n_strains: int = 1, cells_per_field_cap: int | None = None):
+                 n_strains: int = 1, cells_per_field_cap: int | None = None,
+                 label_transport: str = "rle", host_threads: int = 0):
+        """``label_transport``: "rle" run-length encodes the int32 label fields on the host
+        cores (csrc/transport.cu) so that only the runs cross PCIe; "raw" copies them as is."""
+        assert label_transport in ("rle", "raw")
+        self.label_transport, self.host_threads = label_transport, host_threads
         self.eng = engine
         self.H, self.W, self.max_label = H, W, max_label
         self.Fc = chunk_fields
@@ -72,6 +77,12 @@ class BatchScreen:
                 lab=[torch.empty((self.Fc, self.H, self.W), dtype=torch.int32, device=d) for _ in range(2)],
                 ready=[torch.cuda.Event() for _ in range(2)],
                 done=[torch.cuda.Event() for _ in range(2)])
+            if self.label_transport == "rle":
+                sw = self.eng.rle_slot_words(self.H, self.W)
+                self._stage.update(
+                    h_rle=[torch.empty((self.Fc, sw), dtype=torch.int32, pin_memory=True) for _ in range(2)],
+                    d_rle=[torch.empty((self.Fc, sw), dtype=torch.int32, device=d) for _ in range(2)],
+                    words=[np.zeros(self.Fc, np.uint32) for _ in range(2)])
         if getattr(self, "_host_chunks", 0) < n_chunks:
             cap = self.cap
             pin = dict(pin_memory=True)
@@ -86,8 +97,9 @@ class BatchScreen:
             self._host_chunks = n_chunks
 
     def host_bytes_per_pass(self, n_fields):
+        """(H2D, D2H) bytes of one ``run_host`` pass; H2D is what the last pass actually sent."""
         n_chunks = n_fields // self.Fc
-        h2d = n_fields * self.H * self.W * 6
+        h2d = getattr(self, "h2d_bytes", 0) or n_fields * self.H * self.W * 6
         per_chunk = self.cap * (56 + 4 + 4 + 8 + 8 + 1 + 1) + 4 * (1 + self.Fc)
         return h2d, n_chunks * per_chunk + self.n_strains * 64
 
@@ -101,13 +113,27 @@ class BatchScreen:
         n_chunks = n_fields // self.Fc
         self._ensure_stage(n_chunks)
         S, eng = self._stage, self.eng
+        px = self.Fc * self.H * self.W
+        self.h2d_bytes = 0
         for i in range(n_chunks):
             b = i & 1
             p0 = (i * self.Fc) % P
+            rle = self.label_transport == "rle"
+            if rle:
+                # the host encodes chunk i while the device still works on chunk i-1; the slot
+                # buffer is reused only after its previous upload (chunk i-2) has finished
+                S["ready"][b].synchronize()
+                rle = eng.rle_encode(labels_pinned[p0:p0 + self.Fc], S["h_rle"][b], S["words"][b],
+                                     self.host_threads)
             with torch.cuda.stream(self.copy):
                 self.copy.wait_event(S["done"][b])
                 S["img"][b].copy_(images_pinned[p0:p0 + self.Fc], non_blocking=True)
-                S["lab"][b].copy_(labels_pinned[p0:p0 + self.Fc], non_blocking=True)
+                if rle:
+                    eng.rle_upload_expand(S["h_rle"][b], S["words"][b], S["d_rle"][b], S["lab"][b])
+                    self.h2d_bytes += 2 * px + 4 * int(S["words"][b].sum())
+                else:
+                    S["lab"][b].copy_(labels_pinned[p0:p0 + self.Fc], non_blocking=True)
+                    self.h2d_bytes += 6 * px
                 S["ready"][b].record(self.copy)
             with torch.cuda.stream(self.compute):
                 self.compute.wait_event(S["ready"][b])

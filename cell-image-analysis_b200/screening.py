@@ -163,6 +163,33 @@ class Engine:
                                               _ptr(pc), _ptr(pm), _ptr(z), self._stream()))
         return dc, dm, pc, pm, z
 
+    # ---- run-length label transport (csrc/transport.cu) ----
+    def rle_slot_words(self, H: int, W: int) -> int:
+        return int(self.lib.cia_rle_slot_words(H, W))
+
+    def rle_encode(self, labels_host: torch.Tensor, slots_host: torch.Tensor, field_words: np.ndarray,
+                   threads: int = 0) -> bool:
+        """Encode int32 host labels [F,H,W] into ``slots_host`` [F, slot_words] (int32-viewed
+        words).  Returns False if a field does not fit its slot (caller sends raw labels)."""
+        F, H, W = labels_host.shape
+        rc = self.lib.cia_rle_encode_fields(labels_host.data_ptr(), F, H, W, slots_host.data_ptr(),
+                                            slots_host.shape[1], field_words.ctypes.data, None, threads)
+        if rc == _lib.CIA_E_CAPACITY:
+            return False
+        if rc != 0:
+            raise _lib.CiaError(rc, "cia_rle_encode_fields failed")
+        return True
+
+    def rle_upload_expand(self, slots_host: torch.Tensor, field_words: np.ndarray, slots_dev: torch.Tensor,
+                          labels_dev: torch.Tensor):
+        """Async: copy the used words of every slot and expand to dense int32 labels [F,H,W]."""
+        F, H, W = labels_dev.shape
+        sw = slots_host.shape[1]
+        self._check(self.lib.cia_rle_upload(self.h, slots_host.data_ptr(), F, sw, field_words.ctypes.data,
+                                            slots_dev.data_ptr(), self._stream()))
+        self._check(self.lib.cia_rle_expand(self.h, slots_dev.data_ptr(), F, sw, H, W, labels_dev.data_ptr(),
+                                            self._stream()))
+
     # ---- fused path ----
     def alloc_outputs(self, cells_cap: int, n_fields: int, keep_crops=False, keep_features=False):
         d = self.tdev

@@ -23,6 +23,7 @@
 #ifndef CIA_H
 #define CIA_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -187,6 +188,28 @@ int cia_screen_fields_host(cia_handle h, const uint16_t* images_host,
                            cia_cell* cells_host, int cells_cap, int32_t* n_cells_host,
                            int32_t* field_counts_host, const cia_scores* scores_host,
                            void* stream);
+
+/* Run-length transport of label fields (host -> device).  The int32 label image the
+ * reference passes to regionprops (improved_detection.py:66-70) is 16.8 MB per 2048 x 2048
+ * field and its PCIe copy, not a kernel, bounds the end-to-end rate; label images are
+ * piecewise constant along rows, so the host encodes runs, only those cross the bus, and
+ * cia_rle_expand rebuilds the dense field in HBM bit for bit.
+ *   cia_rle_slot_words   words per field slot that always suffice for <= 1 run per 8 pixels
+ *   cia_rle_encode_fields host-only (no handle, no GPU): encodes n_fields fields with
+ *                        n_threads host threads (<= 0: CIA_HOST_THREADS or all cores) into
+ *                        slots_host + f * slot_words; field_words[f] = words used;
+ *                        *max_label = largest label seen (may be NULL).  CIA_E_CAPACITY if a
+ *                        field does not fit its slot (send that batch as raw int32 instead).
+ *   cia_rle_upload       one async copy per field of exactly the words used
+ *   cia_rle_expand       device slots -> dense int32 labels [n_fields, H, W] */
+size_t cia_rle_slot_words(int H, int W);
+int cia_rle_encode_fields(const int32_t* labels_host, int n_fields, int H, int W,
+                          uint32_t* slots_host, size_t slot_words, uint32_t* field_words,
+                          int32_t* max_label, int n_threads);
+int cia_rle_upload(cia_handle h, const uint32_t* slots_host, int n_fields, size_t slot_words,
+                   const uint32_t* field_words, uint32_t* slots_dev, void* stream);
+int cia_rle_expand(cia_handle h, const uint32_t* slots_dev, int n_fields, size_t slot_words,
+                   int H, int W, int32_t* labels_dev, void* stream);
 
 /* Stage timing of the fused path with CUDA events recorded in-stream (no host sync is
  * added to the timed region): after cia_profile_begin(h, R) the next R calls of

@@ -1,0 +1,114 @@
+"""Run-length label transport (csrc/transport.cu): the host encoder is CPU code in the C-ABI
+library and is checked here without a GPU; the device expansion is a GPU test."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from cell_image_analysis_b200 import _lib
+from cell_image_analysis_b200.synth import make_field
+
+
+def _decode(slot, H, W):
+    r0 = (H + 2) & ~1
+    out = np.empty((H, W), np.int32)
+    for y in range(H):
+        lo, hi = int(slot[y]), int(slot[y + 1])
+        runs = slot[r0 + 2 * lo: r0 + 2 * hi].reshape(-1, 2)
+        assert runs[0, 0] == 0
+        xs = list(runs[:, 0]) + [W]
+        for (x0, lab), x1 in zip(runs, xs[1:]):
+            out[y, x0:x1] = np.uint32(lab).astype(np.int32)
+    assert int(slot[H]) == hi
+    return out
+
+
+def _fields(H, W):
+    rng = np.random.default_rng(5)
+    cells = make_field(3, H, W, 30, 6.0, 14.0)[1]
+    stripes = (np.arange(H * W, dtype=np.int32).reshape(H, W) // 9) % 1000        # runs crossing the 8-wide skip
+    short = np.repeat(rng.integers(0, 70000, (H, W // 2 + 1), dtype=np.int32), 2, axis=1)[:, :W]
+    big = np.full((H, W), 2**31 - 1, np.int32)
+    return np.ascontiguousarray(np.stack([cells, np.zeros_like(cells), stripes, short, big]))
+
+
+@pytest.mark.parametrize("shape", [(64, 64), (37, 101), (5, 7), (128, 1030)])
+@pytest.mark.parametrize("threads", [1, 3])
+def test_rle_encode_roundtrip_cpu(shape, threads):
+    lib = _lib.load()
+    H, W = shape
+    labs = _fields(H, W)
+    F = labs.shape[0]
+    sw = 2 * H * W + H + 4            # generous slot: even one run per pixel fits
+    slots = np.zeros((F, sw), np.uint32)
+    words = np.zeros(F, np.uint32)
+    mx = C.c_int32(-1)
+    rc = lib.cia_rle_encode_fields(labs.ctypes.data, F, H, W, slots.ctypes.data, sw, words.ctypes.data,
+                                   C.byref(mx), threads)
+    assert rc == 0
+    assert mx.value == labs.max()
+    for f in range(F):
+        assert np.array_equal(_decode(slots[f], H, W), labs[f])
+        n_runs = int(slots[f][H])
+        assert words[f] == ((H + 2) & ~1) + 2 * n_runs
+        assert n_runs == int((np.diff(labs[f], axis=1) != 0).sum()) + H
+
+
+def test_rle_encode_capacity_cpu():
+    lib = _lib.load()
+    H, W = 32, 64
+    noise = np.random.default_rng(0).integers(0, 1000, (1, H, W), dtype=np.int32)
+    sw = lib.cia_rle_slot_words(H, W)
+    slots = np.zeros((1, sw), np.uint32)
+    words = np.zeros(1, np.uint32)
+    rc = lib.cia_rle_encode_fields(noise.ctypes.data, 1, H, W, slots.ctypes.data, sw, words.ctypes.data, None, 1)
+    assert rc == _lib.CIA_E_CAPACITY and words[0] == 0
+    assert lib.cia_rle_encode_fields(None, 1, H, W, slots.ctypes.data, sw, words.ctypes.data, None, 1) == _lib.CIA_E_ARG
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(64, 64), (37, 101), (128, 1030), (512, 2048)])
+def test_rle_expand_gpu(shape):
+    import torch
+    from cell_image_analysis_b200.screening import Engine
+    eng = Engine()
+    H, W = shape
+    labs = torch.from_numpy(_fields(H, W))
+    F = labs.shape[0]
+    sw = 2 * H * W + H + 4
+    h_slots = torch.zeros((F, sw), dtype=torch.int32).pin_memory()
+    d_slots = torch.zeros((F, sw), dtype=torch.int32, device="cuda")
+    words = np.zeros(F, np.uint32)
+    assert eng.rle_encode(labs, h_slots, words, 2)
+    out = torch.full((F, H, W), -7, dtype=torch.int32, device="cuda")
+    eng.rle_upload_expand(h_slots, words, d_slots, out)
+    torch.cuda.synchronize()
+    assert torch.equal(out.cpu(), labs)
+
+
+@pytest.mark.gpu
+def test_run_host_rle_equals_raw(golden_config1, model_dir):
+    """The whole host pass gives identical cells and scores with either label transport."""
+    import torch
+    from cell_image_analysis_b200.artifacts import load_model_dir
+    from cell_image_analysis_b200.batch import BatchScreen
+    from cell_image_analysis_b200.screening import Engine
+    from cell_image_analysis_b200.synth import make_fields
+    eng = Engine()
+    eng.load_artifacts(load_model_dir(model_dir))
+    fields = make_fields(range(4), "config1")
+    g = torch.from_numpy(np.stack([f[0] for f in fields]).view(np.int16)).pin_memory()
+    lab = torch.from_numpy(np.stack([f[1] for f in fields])).pin_memory()
+    H, W = lab.shape[1:]
+    res = {}
+    for mode in ("raw", "rle"):
+        bs = BatchScreen(eng, H, W, int(lab.max()), chunk_fields=2, label_transport=mode)
+        bs.run_host(g, lab, 4)
+        bs.sync()
+        res[mode] = bs.collect_host()
+        h2d = bs.host_bytes_per_pass(4)[0]
+        assert (h2d < 4 * H * W * 3) == (mode == "rle")
+    a, b = res["raw"], res["rle"]
+    assert a["n_cells"] == b["n_cells"] > 0
+    for k in ("cells", "mse", "mae", "dec_cons", "dec_mod", "pred_cons", "pred_mod", "field_counts"):
+        assert np.array_equal(a[k], b[k]), k
