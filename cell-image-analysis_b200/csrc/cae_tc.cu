@@ -546,7 +546,12 @@ conv_tc_acc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
                    float* __restrict__ feat, int n_cells, const int32_t* __restrict__ n_dev, int cell0,
                    int chunk_cells) {
     using C = AccCfg<CIN, COUT, R>;
-    constexpr int STAGE_COLS = 4 * COUT;
+    // R = 16: the pooled output is only 8 x 8, so a 16-row-group tile takes BOTH row phases
+    // (row group g = conv row g, stride one staged row) and there are two tiles (px = 0, 1) instead
+    // of four half-empty ones; the 2x2 pool then pairs lanes r and r^8 with one shuffle per value.
+    constexpr bool ROWPAIR = R == 16;
+    constexpr int NT = ROWPAIR ? 2 : 4;          // accumulator tiles per stage = issuing warps
+    constexpr int STAGE_COLS = NT * COUT;
     constexpr int TMEM_COLS = pow2_cols(2 * STAGE_COLS);
     constexpr int CW = COUT / 4;                 // columns per epilogue warp
     constexpr int NGRP = (9 + G - 1) / G;        // TMEM flushes per pooled tile (G filter taps each)
@@ -566,7 +571,7 @@ conv_tc_acc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
 
     if (warp == 0) tmem_alloc(&tmem_base_s, TMEM_COLS);
     if (tid == 32) {
-        mbar_init(&full_bar[0], ACC_MMA_WARPS); mbar_init(&full_bar[1], ACC_MMA_WARPS);
+        mbar_init(&full_bar[0], NT); mbar_init(&full_bar[1], NT);
         mbar_init(&empty_bar[0], ACC_EPI_WARPS); mbar_init(&empty_bar[1], ACC_EPI_WARPS);
         mbar_init(&ready_bar, ACC_EPI_WARPS);
         fence_barrier_init();
@@ -588,10 +593,11 @@ conv_tc_acc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
         // dependent uniform-register adds), more than the 45-48 cycles an M128 x N<=64 MMA takes;
         // four issuing warps, each owning the accumulator tile of one pooling phase, keep the
         // tensor pipe fed.  Each commits to the stage's full barrier (count 4).
-        if (lane == 0) {
-            const int t = warp - ACC_EPI_WARPS, py = t >> 1, px = t & 1;
-            const uint64_t a_hi0 = make_smem_desc(smem_u32(a_part[0]) + py * C::ROW_B, C::CHUNK_B, C::SBO_A);
-            const uint64_t a_lo0 = make_smem_desc(smem_u32(a_part[1]) + py * C::ROW_B, C::CHUNK_B, C::SBO_A);
+        if (lane == 0 && warp - ACC_EPI_WARPS < NT) {
+            const int t = warp - ACC_EPI_WARPS, py = ROWPAIR ? 0 : t >> 1, px = t & 1;
+            constexpr uint32_t SBO = ROWPAIR ? C::ROW_B : C::SBO_A;
+            const uint64_t a_hi0 = make_smem_desc(smem_u32(a_part[0]) + py * C::ROW_B, C::CHUNK_B, SBO);
+            const uint64_t a_lo0 = make_smem_desc(smem_u32(a_part[1]) + py * C::ROW_B, C::CHUNK_B, SBO);
             const uint64_t b_hi0 = make_smem_desc(smem_u32(w_part[0]), COUT * 16, 128);
             const uint64_t b_lo0 = make_smem_desc(smem_u32(w_part[1]), COUT * 16, 128);
             uint64_t dxo[3];                   // (parity plane, half-column shift) of tap column dx, in 16-byte units
@@ -677,9 +683,9 @@ conv_tc_acc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
 
 #pragma unroll 1
             for (int sub = 0; sub < C::HALVES; ++sub) {
-            float acc[4][CW];
+            float acc[NT][CW];
 #pragma unroll
-            for (int ph = 0; ph < 4; ++ph)
+            for (int ph = 0; ph < NT; ++ph)
 #pragma unroll
                 for (int k = 0; k < CW; ++k) acc[ph][k] = 0.f;
 #pragma unroll 1
@@ -692,7 +698,7 @@ conv_tc_acc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
                 tc_fence_after();
                 // two phases at a time keeps the live registers under the 120-per-thread budget
 #pragma unroll
-                for (int hp = 0; hp < 2; ++hp) {
+                for (int hp = 0; hp < NT / 2; ++hp) {
                     uint32_t v[2][CW / 8][8];
 #pragma unroll
                     for (int p2 = 0; p2 < 2; ++p2)
@@ -703,7 +709,7 @@ conv_tc_acc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
                     for (int p2 = 0; p2 < 2; ++p2)
 #pragma unroll
                         for (int k8 = 0; k8 < CW / 8; ++k8) TMEM_WAIT8(v[p2][k8]);
-                    if (hp == 1) {
+                    if (hp == NT / 2 - 1) {
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&empty_bar[st]);
@@ -726,8 +732,8 @@ conv_tc_acc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
             DBG_T(e6);
             // final epilogue from registers: bias -> ReLU -> BN -> 2x2 max -> hi/lo fp16 (+ fp32 tap)
             constexpr int RO = R / 2;
-            const int Y = r >> 3, X = 8 * sub + (r & 7);
-            if (Y < RO) {
+            const int Y = ROWPAIR ? r >> 4 : r >> 3, X = 8 * sub + (r & 7);
+            if (ROWPAIR || Y < RO) {
 #pragma unroll
                 for (int k8 = 0; k8 < CW / 8; ++k8) {
                     const int c0 = cq * CW + k8 * 8;
@@ -737,13 +743,15 @@ conv_tc_acc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
                         const float b = __ldg(bias + c0 + k), s = __ldg(bn_s + c0 + k), t = __ldg(bn_t + c0 + k);
                         float m = -INFINITY;
 #pragma unroll
-                        for (int ph = 0; ph < 4; ++ph) {
+                        for (int ph = 0; ph < NT; ++ph) {
                             float a = fmaf(acc[ph][k8 * 8 + k], inv_scale, b);
                             a = fmaxf(a, 0.f);
                             m = fmaxf(m, fmaf(a, s, t));
                         }
+                        if (ROWPAIR) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));   // conv rows 2Y, 2Y+1
                         o[k] = m;
                     }
+                    if (ROWPAIR && (r & 8)) continue;      // the even conv row's lane stores the pooled pixel
                     const size_t off = ((((size_t)cell * (COUT / 8) + c0 / 8) * RO + Y) * RO + X) * 8;
                     split_store8(o, out_hi + off, out_lo ? out_lo + off : nullptr);
                     if (feat) {
