@@ -73,7 +73,7 @@ int cia_destroy(cia_handle h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     free_cae(h->cae[0]); free_cae(h->cae[1]);
-    cudaFree(h->sp.center); cudaFree(h->sp.scale); cudaFree(h->sp.comp_t); cudaFree(h->sp.offset);
+    cudaFree(h->sp.center); cudaFree(h->sp.scale); cudaFree(h->sp.comp_t); cudaFree(h->sp.comp_pad); cudaFree(h->sp.offset);
     for (int i = 0; i < 2; ++i) { cudaFree(h->svm[i].sv_t); cudaFree(h->svm[i].coef); }
     Workspace* ws[] = {&h->ws_flags, &h->ws_act, &h->ws_crop_scratch, &h->ws_pipe, &h->ws_feat,
                        &h->ws_misc, &h->ws_stage};
@@ -174,6 +174,14 @@ int cia_load_scaler_pca(cia_handle h, int F, int C, const double* center, const 
     for (int c = 0; c < C; ++c)
         for (int f = 0; f < F; ++f) t[(size_t)f * C + c] = components[(size_t)c * F + f];
     if ((rc = upload(h, &sp.comp_t, t.data(), t.size()))) return rc;
+    {
+        const int FP = (F + 31) / 32 * 32, CP = (C + 103) / 104 * 104;
+        std::vector<double> tp((size_t)FP * CP, 0.0);
+        for (int f = 0; f < F; ++f)
+            for (int c = 0; c < C; ++c) tp[(size_t)f * CP + c] = t[(size_t)f * C + c];
+        if ((rc = upload(h, &sp.comp_pad, tp.data(), tp.size()))) return rc;
+        sp.CP = CP;
+    }
     if ((rc = upload(h, &sp.offset, pca_offset, (size_t)C))) return rc;
     sp.F = F; sp.C = C; sp.center_is_f32 = center_is_f32; sp.f32_flow = f32_flow;
     sp.loaded = true;

@@ -47,6 +47,8 @@ struct ScalerPca {
     double* center = nullptr;   // [F]
     double* scale = nullptr;    // [F]
     double* comp_t = nullptr;   // [F, C] transposed components
+    double* comp_pad = nullptr; // [F rounded up to 32, CP] zero-padded copy for the cp.async-fed DMMA kernel
+    int CP = 0;                 // C rounded up to a multiple of 104
     double* offset = nullptr;   // [C]
 };
 

@@ -93,6 +93,140 @@ scaler_pca_kernel(const float* __restrict__ feat, int n_cells, const int32_t* __
     }
 }
 
+// ---- fp64 tensor-core form of the projection (mma.sync m8n8k4 f64), software pipelined ----
+// Measured on this B200 (profiles/fp64_peak_test.cu): DFMA 36 TFLOP/s, DMMA 37 TFLOP/s; the
+// register-tiled kernel above reaches ~9 because every 32-feature stage first waits for its
+// global loads.  Here the components come through cp.async into a second buffer and the raw
+// features of the next stage are prefetched into registers while the current stage computes.
+// Block = 4 warps = 64 cells x 104 components (13 n8 tiles; blockIdx.y tiles wider PCAs);
+// warp = 16 cells x 104 components = 26 accumulator tiles.  Shared-memory pitches put the 64-bit
+// fragment loads of a half-warp on 16 distinct bank pairs (x: 36 doubles per cell row, w: 108
+// per feature row).  comp_pad is the [F rounded to 32][C rounded to 104] zero-padded copy.
+constexpr int DT = 128;          // threads
+constexpr int DM = 64;           // cells per block
+constexpr int DK = 32;           // features per stage
+constexpr int DN = 104;          // components per block tile
+constexpr int DXP = DK + 4;      // x pitch (doubles)
+constexpr int DWP = DN + 4;      // w pitch (doubles)
+constexpr int DXR = DM / (DT / 32);   // cell rows per warp in the x tile
+
+__device__ __forceinline__ void dmma884(double (&d)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d[0]), "+d"(d[1]) : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(DT)
+scaler_pca_dmma_kernel(const float* __restrict__ feat, int n_cells, const int32_t* __restrict__ n_dev,
+                       int F, int C, int CP, const double* __restrict__ center, const double* __restrict__ scale,
+                       int center_is_f32, const double* __restrict__ comp_pad,
+                       const double* __restrict__ offset, int f32_flow, double* __restrict__ z_out) {
+    extern __shared__ __align__(16) unsigned char pca_smem[];
+    double* xs = reinterpret_cast<double*>(pca_smem);                 // [2][DM][DXP]
+    double* ws = xs + 2 * DM * DXP;                                   // [2][DK][DWP]
+    const int n = dev_count(n_cells, n_dev);
+    const int cell0 = blockIdx.x * DM;
+    if (cell0 >= n) return;
+    const int c_tile0 = blockIdx.y * DN;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int gid = lane >> 2, tig = lane & 3;
+    const int n_stages = (F + DK - 1) / DK;
+    double acc[2][DN / 8][2];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < DN / 8; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+
+    auto issue_w = [&](int stage, int buf) {          // DK x DN doubles as 16-byte chunks
+        const double* src = comp_pad + (size_t)stage * DK * CP + c_tile0;
+        double* dst = ws + buf * DK * DWP;
+        for (int idx = tid; idx < DK * (DN / 2); idx += DT) {
+            const int ff = idx / (DN / 2), c2 = idx - ff * (DN / 2);
+            const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst + ff * DWP + 2 * c2);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src + (size_t)ff * CP + 2 * c2) : "memory");
+        }
+    };
+    float xr[DXR];
+    auto load_x = [&](int stage) {                    // raw features: one cell row per warp iteration
+        const int f = stage * DK + lane;
+#pragma unroll
+        for (int j = 0; j < DXR; ++j) {
+            const int cell = cell0 + warp + j * (DT / 32);
+            xr[j] = (cell < n && f < F) ? __ldg(feat + (size_t)cell * F + f) : 0.f;
+        }
+    };
+    auto store_x = [&](int stage, int buf) {          // scaler applied on the way (sklearn's float32 flow)
+        const int f = stage * DK + lane;
+        double cen = 0.0, sc = 1.0;
+        if (f < F) {
+            if (center) cen = center[f];
+            if (scale) sc = scale[f];
+        }
+        double* dst = xs + buf * DM * DXP;
+#pragma unroll
+        for (int j = 0; j < DXR; ++j) {
+            float v = xr[j];
+            if (f < F) {
+                if (center) {
+                    if (center_is_f32) v = __fsub_rn(v, (float)cen);
+                    else v = (float)__dsub_rn((double)v, cen);
+                }
+                if (scale) v = (float)__ddiv_rn((double)v, sc);
+            }
+            dst[(warp + j * (DT / 32)) * DXP + lane] = (double)v;
+        }
+    };
+
+    issue_w(0, 0);
+    load_x(0);
+    store_x(0, 0);
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+    for (int st = 0; st < n_stages; ++st) {
+        const int buf = st & 1;
+        const bool more = st + 1 < n_stages;
+        if (more) {
+            issue_w(st + 1, buf ^ 1);
+            load_x(st + 1);
+        }
+        const double* xb = xs + buf * DM * DXP;
+        const double* wb = ws + buf * DK * DWP;
+#pragma unroll
+        for (int k4 = 0; k4 < DK / 4; ++k4) {
+            const double a0 = xb[(warp * 16 + gid) * DXP + k4 * 4 + tig];
+            const double a1 = xb[(warp * 16 + 8 + gid) * DXP + k4 * 4 + tig];
+            const double* wrow = wb + (k4 * 4 + tig) * DWP + gid;
+#pragma unroll
+            for (int nt = 0; nt < DN / 8; ++nt) {
+                const double b = wrow[nt * 8];
+                dmma884(acc[0][nt], a0, b);
+                dmma884(acc[1][nt], a1, b);
+            }
+        }
+        if (more) {
+            store_x(st + 1, buf ^ 1);
+            asm volatile("cp.async.wait_all;" ::: "memory");
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+        const int cell = cell0 + warp * 16 + mt * 8 + gid;
+        if (cell >= n) continue;
+#pragma unroll
+        for (int nt = 0; nt < DN / 8; ++nt)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int c = c_tile0 + nt * 8 + 2 * tig + j;
+                if (c >= C) continue;
+                const double off = offset[c];
+                double z;
+                if (f32_flow) z = (double)__fsub_rn((float)acc[mt][nt][j], (float)off);
+                else z = __dsub_rn(acc[mt][nt][j], off);
+                z_out[(size_t)cell * C + c] = z;
+            }
+    }
+}
+
 constexpr int SCELLS = 8;   // cells per block in the SVM kernel
 
 // dec = sum_i coef_i * exp(-gamma * ||z - sv_i||^2) - rho  (fp64, direct difference).
@@ -205,11 +339,20 @@ int k_svm_decision(cia_ctx* h, const float* features, int n, const int32_t* n_de
     if (first_use(h, (const void*)svm_rbf_kernel)) {
         CIA_CUDA(cudaFuncSetAttribute(svm_rbf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CIA_CUDA(cudaFuncSetAttribute(scaler_pca_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        CIA_CUDA(cudaFuncSetAttribute(scaler_pca_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     }
-    const size_t sm1 = sizeof(double) * PFT * (PCT + XPAD);
-    scaler_pca_kernel<<<dim3((n + PB - 1) / PB, (sp.C + PCT - 1) / PCT), PT, sm1, s>>>(
-        features, n, n_dev, sp.F, sp.C, sp.has_center ? sp.center : nullptr,
-        sp.has_scale ? sp.scale : nullptr, sp.center_is_f32, sp.comp_t, sp.offset, sp.f32_flow, z);
+    static const bool vector_pca = getenv("CIA_PCA_VECTOR") != nullptr;   // A/B switch: CUDA-core fp64 tile
+    if (vector_pca) {
+        const size_t sm1 = sizeof(double) * PFT * (PCT + XPAD);
+        scaler_pca_kernel<<<dim3((n + PB - 1) / PB, (sp.C + PCT - 1) / PCT), PT, sm1, s>>>(
+            features, n, n_dev, sp.F, sp.C, sp.has_center ? sp.center : nullptr,
+            sp.has_scale ? sp.scale : nullptr, sp.center_is_f32, sp.comp_t, sp.offset, sp.f32_flow, z);
+    } else {
+        const size_t sm1 = sizeof(double) * 2 * (DM * DXP + DK * DWP);
+        scaler_pca_dmma_kernel<<<dim3((n + DM - 1) / DM, sp.CP / DN), DT, sm1, s>>>(
+            features, n, n_dev, sp.F, sp.C, sp.CP, sp.has_center ? sp.center : nullptr,
+            sp.has_scale ? sp.scale : nullptr, sp.center_is_f32, sp.comp_pad, sp.offset, sp.f32_flow, z);
+    }
     CIA_LAUNCH_CHECK();
     for (int which = 0; which < 2; ++which) {
         const SvmModel& m = h->svm[which];
