@@ -26,7 +26,9 @@
 namespace {
 
 constexpr int TCT = 256;   // 8 warps: warp&3 = TMEM lane quadrant, warp>>2 = column-slice parity
-enum { EPI_POOL = 0, EPI_UP = 1, EPI_PLAIN = 2, EPI_FINAL = 3 };
+// EPI_PHASE: the layer runs at its INPUT's (pre-upsampling) resolution R with the four output phases
+// (py,px) of the 2x nearest up-sampled grid as column groups: N = 4 * Cout, output is 2R x 2R
+enum { EPI_POOL = 0, EPI_UP = 1, EPI_PLAIN = 2, EPI_FINAL = 3, EPI_PHASE = 4 };
 
 // ---------------------------------------------------------------------------------------
 // PTX wrappers
@@ -385,15 +387,23 @@ conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_l
                         }
                     }
                 } else {
+                    constexpr int CREAL = EPI == EPI_PHASE ? COUT / 4 : COUT;   // real output channels
+                    const int cc = c0 % CREAL;
                     float o[8];
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
-                        float a = fmaf(__uint_as_float(v[k]), inv_scale, __ldg(bias + c0 + k));
+                        float a = fmaf(__uint_as_float(v[k]), inv_scale, __ldg(bias + cc + k));
                         a = fmaxf(a, 0.f);
-                        o[k] = fmaf(a, __ldg(bn_s + c0 + k), __ldg(bn_t + c0 + k));
+                        o[k] = fmaf(a, __ldg(bn_s + cc + k), __ldg(bn_t + cc + k));
                     }
                     if (y < R) {
-                        if (EPI == EPI_UP) {
+                        if (EPI == EPI_PHASE) {
+                            constexpr int RO = 2 * R;
+                            const int ph = c0 / CREAL;
+                            const size_t off = ((((size_t)cell * (CREAL / 8) + cc / 8) * RO + 2 * y + (ph >> 1)) * RO +
+                                                2 * x + (ph & 1)) * 8;
+                            split_store8(o, out_hi + off, nullptr);
+                        } else if (EPI == EPI_UP) {
                             constexpr int RO = 2 * R;
                             const size_t base = (((size_t)cell * (COUT / 8) + sl) * RO + 2 * y) * RO + 2 * x;
                             __align__(16) __half hh[8];
@@ -1336,6 +1346,24 @@ int k_cae_tc_prepare(cia_ctx* h, int which) {
                         }
             sw = scale_exp(kp);
             pack_image(kp, 9, cin, 16, 4, sw, hi, lo);
+        } else if (L == 5) {
+            // same phase form with all Cout channels: N = 4 phases x Cout, run at the low (input) resolution --
+            // 2 tiles x 9 taps instead of 8 tiles x 9 taps of MMAs per cell
+            const int N = 4 * cout;
+            std::vector<float> kp((size_t)9 * cin * N, 0.f);
+            for (int py = 0; py < 2; ++py)
+                for (int px = 0; px < 2; ++px)
+                    for (int dy = 0; dy < 3; ++dy)
+                        for (int dx = 0; dx < 3; ++dx) {
+                            const int oy = (int)std::floor((py + dy - 1) / 2.0), ox = (int)std::floor((px + dx - 1) / 2.0);
+                            const int tl = (oy + 1) * 3 + (ox + 1);
+                            for (int c = 0; c < cin; ++c)
+                                for (int co = 0; co < cout; ++co)
+                                    kp[((size_t)tl * cin + c) * N + (py * 2 + px) * cout + co] +=
+                                        k[((size_t)(dy * 3 + dx) * cin + c) * cout + co];
+                        }
+            sw = scale_exp(kp);
+            pack_image(kp, 9, cin, N, N, sw, hi, lo);
         } else {
             sw = scale_exp(k);
             pack_image(k, 9, cin, cout, cout, sw, hi, lo);
@@ -1435,7 +1463,7 @@ int k_cae_forward_tc(cia_ctx* h, const float* crops, int n, const int32_t* n_dev
         }
         if ((rc = launch_tc<32, 32, 8, EPI_PLAIN, 1>(h, ae, 3, a3h, nullptr, a4, nullptr, nullptr, nullptr, nullptr, nullptr, n, n_dev, c0, chunk, s))) return rc;
         if ((rc = launch_tc<32, 64, 16, EPI_PLAIN, 1, true>(h, ae, 4, a4, nullptr, a5, nullptr, nullptr, nullptr, nullptr, nullptr, n, n_dev, c0, chunk, s))) return rc;
-        if ((rc = launch_tc<64, 32, 32, EPI_PLAIN, 1, true>(h, ae, 5, a5, nullptr, a6p, nullptr, nullptr, nullptr, nullptr, nullptr, n, n_dev, c0, chunk, s))) return rc;
+        if ((rc = launch_tc<64, 128, 16, EPI_PHASE, 1>(h, ae, 5, a5, nullptr, a6p, nullptr, nullptr, nullptr, nullptr, nullptr, n, n_dev, c0, chunk, s))) return rc;
         if ((rc = launch_tc<32, 16, 32, EPI_FINAL, 1>(h, ae, 6, a6p, nullptr, nullptr, nullptr, nullptr, crops, mse, mae, n, n_dev, c0, chunk, s))) return rc;
     }
     if (side_encoder) CIA_CUDA(cudaStreamWaitEvent(s, h->ev_join, 0));
