@@ -1393,7 +1393,13 @@ int k_cae_forward_tc(cia_ctx* h, const float* crops, int n, const int32_t* n_dev
     // mode 3: L1 + L2 on tensor cores with split operands, fp32 tap of the 16x16x64 activation,
     // L3 (the layer whose long RZ-accumulated K=576 chains dominate the feature error) in exact fp32
     const bool l3_exact = mode == 3 && !sep;
-    const int CH = 1024;
+    // cells per pass over the seven layers.  Measured (profiles/r1_cae_chunk_sweep.txt): every launch
+    // pays a fixed prologue (37-147 KB of weights into each CTA's shared memory, TMEM allocation,
+    // pipeline fill, a ragged last wave), and keeping a chunk's activations L2-resident buys nothing
+    // because the layers are tensor-pipe / issue bound, not DRAM bound: 296 cells/pass -> 67 ms,
+    // 1024 -> 49 ms, 16576 (112 per SM) -> 39.6 ms for the same 121k cells.  303 KB of workspace per cell.
+    static const int CH_MAX = [] { const char* e = getenv("CIA_CAE_CHUNK"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 16576; }();
+    const int CH = n < CH_MAX ? (n + 147) / 148 * 148 : CH_MAX;
     // halves per cell; A4 / A5 are stored at their own (pre-upsampling) resolution
     const size_t a1 = 4 * 32 * 32 * 8, a2 = 8 * 16 * 16 * 8, a3 = 4 * 8 * 8 * 8, a4u = 4 * 8 * 8 * 8,
                  a5u = 8 * 16 * 16 * 8, a6 = 4 * 32 * 32 * 8;

@@ -52,7 +52,7 @@ def main():
     x = torch.from_numpy(X).to(eng.tdev)
     mse, mae, feat = eng.cae_forward(x, n, precision=prec)
     torch.cuda.synchronize()
-    CH = 1024          # cells per chunk in k_cae_forward_tc
+    CH = min(16576, (n + 147) // 148 * 148)     # cells per pass in k_cae_forward_tc (buffer stride)
     sizes = dict(a1=4 * 32 * 32 * 8, a2=8 * 16 * 16 * 8, a3=4 * 8 * 8 * 8, a4u=4 * 8 * 8 * 8,
                  a5u=8 * 16 * 16 * 8, a6=4 * 32 * 32 * 8)
     order = [("A1h", "a1"), ("A1l", "a1"), ("A2h", "a2"), ("A2l", "a2"), ("A3h", "a3"), ("A4u", "a4u"),
