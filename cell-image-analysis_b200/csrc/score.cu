@@ -98,11 +98,13 @@ scaler_pca_kernel(const float* __restrict__ feat, int n_cells, const int32_t* __
 // register-tiled kernel above reaches ~9 because every 32-feature stage first waits for its
 // global loads.  Here the components come through cp.async into a second buffer and the raw
 // features of the next stage are prefetched into registers while the current stage computes.
-// Block = 4 warps = 64 cells x 104 components (13 n8 tiles; blockIdx.y tiles wider PCAs);
-// warp = 16 cells x 104 components = 26 accumulator tiles.  Shared-memory pitches put the 64-bit
+// Block = 16 warps = 64 cells x 104 components (13 n8 tiles; blockIdx.y tiles wider PCAs);
+// warp = 16 cells x 3-4 n8 tiles (4 cell groups x 4 component groups).  A call scores ~15k cells =
+// 236 blocks on 148 SMs, so the warps have to come from inside the block: with 4 warps per SM the
+// DMMA pipe was 21 % active (ncu), latency bound.  Shared-memory pitches put the 64-bit
 // fragment loads of a half-warp on 16 distinct bank pairs (x: 36 doubles per cell row, w: 108
 // per feature row).  comp_pad is the [F rounded to 32][C rounded to 104] zero-padded copy.
-constexpr int DT = 128;          // threads
+constexpr int DT = 512;          // threads
 constexpr int DM = 64;           // cells per block
 constexpr int DK = 32;           // features per stage
 constexpr int DN = 104;          // components per block tile
@@ -115,7 +117,7 @@ __device__ __forceinline__ void dmma884(double (&d)[2], double a, double b) {
                  : "+d"(d[0]), "+d"(d[1]) : "d"(a), "d"(b));
 }
 
-__global__ void __launch_bounds__(DT)
+__global__ void __launch_bounds__(DT, 2)
 scaler_pca_dmma_kernel(const float* __restrict__ feat, int n_cells, const int32_t* __restrict__ n_dev,
                        int F, int C, int CP, const double* __restrict__ center, const double* __restrict__ scale,
                        int center_is_f32, const double* __restrict__ comp_pad,
@@ -130,11 +132,15 @@ scaler_pca_dmma_kernel(const float* __restrict__ feat, int n_cells, const int32_
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int gid = lane >> 2, tig = lane & 3;
     const int n_stages = (F + DK - 1) / DK;
-    double acc[2][DN / 8][2];
+    // component group of this warp: n8 tiles [nt0, nt0 + ntc) = {0-3, 4-6, 7-9, 10-12}
+    const int mg = warp & 3, ng = warp >> 2;
+    const int nt0 = ng == 0 ? 0 : 1 + 3 * ng, ntc = ng == 0 ? 4 : 3;
+    static_assert(DN / 8 == 13 && DT == 512, "warp tiling below assumes 13 n8 tiles over 4 component groups");
+    double acc[2][4][2];
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-        for (int nt = 0; nt < DN / 8; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+        for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
 
     auto issue_w = [&](int stage, int buf) {          // DK x DN doubles as 16-byte chunks
         const double* src = comp_pad + (size_t)stage * DK * CP + c_tile0;
@@ -192,14 +198,16 @@ scaler_pca_dmma_kernel(const float* __restrict__ feat, int n_cells, const int32_
         const double* wb = ws + buf * DK * DWP;
 #pragma unroll
         for (int k4 = 0; k4 < DK / 4; ++k4) {
-            const double a0 = xb[(warp * 16 + gid) * DXP + k4 * 4 + tig];
-            const double a1 = xb[(warp * 16 + 8 + gid) * DXP + k4 * 4 + tig];
-            const double* wrow = wb + (k4 * 4 + tig) * DWP + gid;
+            const double a0 = xb[(mg * 16 + gid) * DXP + k4 * 4 + tig];
+            const double a1 = xb[(mg * 16 + 8 + gid) * DXP + k4 * 4 + tig];
+            const double* wrow = wb + (k4 * 4 + tig) * DWP + nt0 * 8 + gid;
 #pragma unroll
-            for (int nt = 0; nt < DN / 8; ++nt) {
-                const double b = wrow[nt * 8];
-                dmma884(acc[0][nt], a0, b);
-                dmma884(acc[1][nt], a1, b);
+            for (int nt = 0; nt < 4; ++nt) {
+                if (nt < ntc) {
+                    const double b = wrow[nt * 8];
+                    dmma884(acc[0][nt], a0, b);
+                    dmma884(acc[1][nt], a1, b);
+                }
             }
         }
         if (more) {
@@ -210,14 +218,14 @@ scaler_pca_dmma_kernel(const float* __restrict__ feat, int n_cells, const int32_
     }
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt) {
-        const int cell = cell0 + warp * 16 + mt * 8 + gid;
+        const int cell = cell0 + mg * 16 + mt * 8 + gid;
         if (cell >= n) continue;
 #pragma unroll
-        for (int nt = 0; nt < DN / 8; ++nt)
+        for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-                const int c = c_tile0 + nt * 8 + 2 * tig + j;
-                if (c >= C) continue;
+                const int c = c_tile0 + (nt0 + nt) * 8 + 2 * tig + j;
+                if (nt >= ntc || c >= C) continue;
                 const double off = offset[c];
                 double z;
                 if (f32_flow) z = (double)__fsub_rn((float)acc[mt][nt][j], (float)off);
