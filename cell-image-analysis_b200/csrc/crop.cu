@@ -41,6 +41,16 @@ __device__ __forceinline__ int mirror_idx(int i, int n) {    // ndimage 'mirror'
     return i >= n ? p - i : i;
 }
 
+// ndimage 'mirror' for an index at most one period out of range (all the resize taps are:
+// |offset| <= gaussian radius + 1 << n whenever blurring is on); anything else takes the
+// general path.  No integer modulo on the hot path.
+__device__ __forceinline__ int mirror_near(int i, int n) {
+    int j = i < 0 ? -i : i;
+    if (j >= n) j = 2 * n - 2 - j;
+    if ((unsigned)j >= (unsigned)n) j = mirror_idx(i, n);
+    return j;
+}
+
 __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 __host__ __device__ inline size_t cell_bytes(int h, int w, int ntr, int ntc) {
     const size_t hw = (size_t)h * w;
@@ -203,9 +213,10 @@ crop_clahe_resize_kernel(const uint16_t* __restrict__ images, int H, int W,
         const uint16_t* img = images + ((size_t)C.field * H + C.minr) * (size_t)W + C.minc;
 
         // ---- A: load bbox, min / max ----
+        const unsigned w_magic = 0xFFFFFFFFu / (unsigned)g.w + 1u;      // i / w for i * w < 2^32 (hw <= 2^20, w <= 2^10)
         int mn = 65535, mx = 0;
         for (int i = tid; i < hw; i += K2_THREADS) {
-            const int y = i / g.w, x = i - y * g.w;
+            const int y = (g.w == 1) ? i : (int)__umulhi((unsigned)i, w_magic), x = i - y * g.w;
             const int v = __ldg(img + (size_t)y * W + x);
             rimg[i] = (uint16_t)v;
             mn = min(mn, v); mx = max(mx, v);
@@ -268,7 +279,6 @@ crop_clahe_resize_kernel(const uint16_t* __restrict__ images, int H, int W,
             for (int a = tid; a < g.kh; a += K2_THREADS) ctab_s[0][a] = __ddiv_rn((double)a, (double)g.kh);
             for (int b = tid; b < g.kw; b += K2_THREADS) ctab_s[1][b] = __ddiv_rn((double)b, (double)g.kw);
             __syncthreads();
-            const unsigned w_magic = 0xFFFFFFFFu / (unsigned)g.w + 1u;      // exact for i < 2^16 * ... (hw <= 2^20, w <= 2^10)
             const unsigned kh_magic = 0xFFFFFFFFu / (unsigned)g.kh + 1u;
             for (int i = tid; i < hw; i += K2_THREADS) {
                 const int y = (g.w == 1) ? i : (int)__umulhi((unsigned)i, w_magic), x = i - y * g.w;
@@ -309,6 +319,16 @@ crop_clahe_resize_kernel(const uint16_t* __restrict__ images, int H, int W,
         const bool blur_r = sig_r > 1e-15, blur_c = sig_c > 1e-15;
         const int rad_r = blur_r ? (int)(4.0 * sig_r + 0.5) : 0;
         const int rad_c = blur_c ? (int)(4.0 * sig_c + 0.5) : 0;
+        // source coordinate of each of the 64 output rows / columns: integer part and weight, once
+        // per cell (ctab_s and hist_s are free after stage D / C)
+        int* coord_i = reinterpret_cast<int*>(&hist_s[0][0]);
+        if (tid >= 64 && tid < 64 + 2 * CIA_CROP) {
+            const int k = tid - 64, axis = k >> 6, o = k & 63;
+            const double cc = ((double)o + 0.5) * (axis == 0 ? fr : fc) - 0.5;
+            const double fl = floor(cc);
+            ctab_s[axis][o] = cc - fl;
+            coord_i[axis * CIA_CROP + o] = (int)fl;
+        }
         if (wid < 2) {
             const bool on = wid == 0 ? blur_r : blur_c;
             const int rad = wid == 0 ? rad_r : rad_c;
@@ -333,28 +353,33 @@ crop_clahe_resize_kernel(const uint16_t* __restrict__ images, int H, int W,
         const double den = (double)(rmx - rmn);
         const double lo = degenerate ? fmin(fmax((double)rmn, 0.0), 1.0) : 0.0;
         const double hi = degenerate ? lo : 1.0;
+        // (r - rmn) / den with both operands integers <= 16383: reciprocal, product and one FMA
+        // correction give the correctly rounded quotient (Markstein); exhaustively checked against
+        // IEEE division over the whole domain by tests/test_exact_division.py
+        const double den_rcp = degenerate ? 0.0 : __drcp_rn(den);
         auto value = [&](int y, int x) -> double {
             const double r = (double)rimg[y * g.w + x];
-            return degenerate ? fmin(fmax(r, 0.0), 1.0) : __ddiv_rn(r - (double)rmn, den);
+            if (degenerate) return fmin(fmax(r, 0.0), 1.0);
+            const double a = r - (double)rmn;
+            const double q0 = __dmul_rn(a, den_rcp);
+            return __fma_rn(__fma_rn(-q0, den, a), den_rcp, q0);
         };
 
         // ---- F: rows: (zoom o gaussian) along axis 0 -> T[64][w] ----
         for (int i = tid; i < CIA_CROP * g.w; i += K2_THREADS) {
-            const int oy = i / g.w, x = i - oy * g.w;
-            const double cc = ((double)oy + 0.5) * fr - 0.5;
-            const double fl = floor(cc);
-            const double t = cc - fl;
-            const int i0 = (int)fl;
+            const int oy = (g.w == 1) ? i : (int)__umulhi((unsigned)i, w_magic), x = i - oy * g.w;
+            const double t = ctab_s[0][oy];
+            const int i0 = coord_i[oy];
             double v[2];
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int yy = i0 + e;
                 if (!blur_r) {
-                    v[e] = value(mirror_idx(yy, g.h), x);
+                    v[e] = value(mirror_near(yy, g.h), x);
                 } else {
                     double acc = 0.0;
                     for (int j = 0; j <= 2 * rad_r; ++j)
-                        acc += gw_s[0][j] * value(mirror_idx(mirror_idx(yy, g.h) + j - rad_r, g.h), x);
+                        acc += gw_s[0][j] * value(mirror_near(mirror_near(yy, g.h) + j - rad_r, g.h), x);
                     v[e] = acc;
                 }
             }
@@ -365,21 +390,19 @@ crop_clahe_resize_kernel(const uint16_t* __restrict__ images, int H, int W,
         // ---- G: columns -> 64x64, clip, store ----
         for (int i = tid; i < CIA_CROP * CIA_CROP; i += K2_THREADS) {
             const int oy = i >> 6, ox = i & 63;
-            const double cc = ((double)ox + 0.5) * fc - 0.5;
-            const double fl = floor(cc);
-            const double t = cc - fl;
-            const int j0 = (int)fl;
+            const double t = ctab_s[1][ox];
+            const int j0 = coord_i[CIA_CROP + ox];
             const double* Trow = T + (size_t)oy * g.w;
             double v[2];
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int xx = j0 + e;
                 if (!blur_c) {
-                    v[e] = Trow[mirror_idx(xx, g.w)];
+                    v[e] = Trow[mirror_near(xx, g.w)];
                 } else {
                     double acc = 0.0;
                     for (int j = 0; j <= 2 * rad_c; ++j)
-                        acc += gw_s[1][j] * Trow[mirror_idx(mirror_idx(xx, g.w) + j - rad_c, g.w)];
+                        acc += gw_s[1][j] * Trow[mirror_near(mirror_near(xx, g.w) + j - rad_c, g.w)];
                     v[e] = acc;
                 }
             }
