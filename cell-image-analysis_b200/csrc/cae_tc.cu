@@ -1101,6 +1101,11 @@ conv1_fp32_planar_kernel(const float* __restrict__ crops, const float* __restric
     for (int k = 0; k < 8; ++k) {
         b8[k] = __ldg(bias + cg * 8 + k); s8[k] = __ldg(bn_s + cg * 8 + k); t8[k] = __ldg(bn_t + cg * 8 + k);
     }
+    // BN after ReLU is monotone in the conv output when its scale is >= 0, so the 2x2 max can be taken
+    // first and ReLU + BN applied once (bit-identical); a negative scale keeps the per-pixel form
+    bool scale_pos = true;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) scale_pos = scale_pos && s8[k] >= 0.f;
     for (int unit = blockIdx.x; unit < n * 4; unit += gridDim.x) {
         const int cell = cell0 + (unit >> 2), qy = (unit >> 1) & 1, qx = unit & 1;
         const float* xr = crops + (size_t)cell * 4096;
@@ -1163,12 +1168,20 @@ conv1_fp32_planar_kernel(const float* __restrict__ crops, const float* __restric
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) unpack2(acc2[q][kk], acc[q][2 * kk], acc[q][2 * kk + 1]);
             float o[8];
+            if (scale_pos) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                float m = -INFINITY;
+                for (int k = 0; k < 8; ++k) {
+                    const float m = fmaxf(fmaxf(acc[0][k], acc[1][k]), fmaxf(acc[2][k], acc[3][k]));
+                    o[k] = fmaf(fmaxf(m, 0.f), s8[k], t8[k]);
+                }
+            } else {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) m = fmaxf(m, fmaf(fmaxf(acc[q][k], 0.f), s8[k], t8[k]));
-                o[k] = m;
+                for (int k = 0; k < 8; ++k) {
+                    float m = -INFINITY;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) m = fmaxf(m, fmaf(fmaxf(acc[q][k], 0.f), s8[k], t8[k]));
+                    o[k] = m;
+                }
             }
             const size_t off = ((((size_t)cell * 4 + cg) * 32 + (16 * qy + Y)) * 32 + (16 * qx + X)) * 8;
             split_store8(o, out_hi + off, out_lo ? out_lo + off : nullptr);
