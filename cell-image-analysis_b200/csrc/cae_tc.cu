@@ -132,7 +132,9 @@ struct Cfg {
     static constexpr int SBO_A = POOL ? 2 * ROW_B : ROW_B;
     static constexpr int TILES = POOL ? 4 : (UNIT_COLS >= 8 ? UNIT_COLS / 8 : 1);
     static constexpr int UNITS_PER_CELL = POOL ? (R >= 32 ? 2 : 1) : (R >= 32 ? 2 : 1) * COL_BLOCKS;
-    static constexpr int TMEM_COLS = pow2_cols(TILES * COUT);
+    static constexpr int TBUF_COLS = TILES * COUT;                    // one accumulator set
+    // single-pass layers double-buffer the accumulators: the MMAs of unit u+1 run under the epilogue of u
+    static constexpr int TMEM_COLS = pow2_cols((NPASS == 1 ? 2 : 1) * TBUF_COLS);
     static constexpr int W_B = 9 * NCH * COUT * 16;
     static constexpr int PARTS = NPASS > 1 ? 2 : 1;
     static constexpr int SMEM_B = PARTS * (REGION_B + W_B);
@@ -200,9 +202,9 @@ conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_l
                int chunk_cells) {
     using C = Cfg<CIN, COUT, R, EPI, NPASS>;
     extern __shared__ __align__(1024) unsigned char smem[];
-    __shared__ __align__(8) uint64_t bar;
+    __shared__ __align__(8) uint64_t bar[2];
     __shared__ uint32_t tmem_base_s;
-    __shared__ float red_s[2][TCT / 32];
+    __shared__ float red_s[2][2][TCT / 32];    // [unit parity][mse | mae][warp]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     unsigned char* a_part[2] = {smem, smem + C::REGION_B};
@@ -215,7 +217,7 @@ conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_l
 
     if (warp == 0) tmem_alloc(&tmem_base_s, C::TMEM_COLS);
     constexpr int NISS = C::TILES;           // issuing warps (TILES <= 4 <= warps)
-    if (tid == 32) { mbar_init(&bar, NISS); fence_barrier_init(); }
+    if (tid == 32) { mbar_init(&bar[0], NISS); mbar_init(&bar[1], NISS); fence_barrier_init(); }
     // weights: linear copy of the prepared UMMA images
     for (int i = tid; i < C::W_B / 16; i += TCT) {
         reinterpret_cast<uint4*>(w_part[0])[i] = __ldg(w_hi + i);
@@ -226,7 +228,6 @@ conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_l
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
     constexpr uint32_t IDESC = make_idesc(128, COUT);
-    uint32_t parity = 0;
 
     // ---- input staging as a software pipeline (single-pass layers): the 16-byte loads of unit
     // u+1 are issued into registers right after the MMAs of unit u and parked in shared memory
@@ -269,25 +270,14 @@ conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_l
             }
         }
     };
-    if (PIPE && (int)blockIdx.x < n_units) prefetch(blockIdx.x);
-
-    for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-        const int cell = cell0 + unit / C::UNITS_PER_CELL;
-        const int sub = unit % C::UNITS_PER_CELL;   // POOL: pooled X half; else: 16-row band
-
-        // ---- stage the zero-padded input block ----
-        if (PIPE) {
+    auto park = [&]() {              // prefetched registers -> the shared-memory input block
 #pragma unroll
-            for (int j = 0; j < S_IT; ++j)
-                if (s_dst[j] != 0xFFFFFFFFu) *reinterpret_cast<uint4*>(a_part[0] + s_dst[j]) = s_val[j];
-        } else {
-            stage_block<C, R, NPASS, TCT, 8, UPSIN>(in_hi, in_lo, a_part[0], a_part[1], cell, sub, tid);
-        }
-        fence_async_smem();
-        __syncthreads();
-
-        // ---- MMA issue: one lane of one warp PER TILE (a single thread sustains only ~one
-        // tcgen05.mma per 60 cycles; the tiles' accumulators are independent) ----
+        for (int j = 0; j < S_IT; ++j)
+            if (s_dst[j] != 0xFFFFFFFFu) *reinterpret_cast<uint4*>(a_part[0] + s_dst[j]) = s_val[j];
+    };
+    // MMA issue: one lane of one warp PER TILE (a single thread sustains only ~one tcgen05.mma per
+    // 60 cycles; the tiles' accumulators are independent); each commits to the buffer's barrier
+    auto issue_mmas = [&](uint32_t tbuf) {
         if (lane == 0 && warp < NISS) {
             tc_fence_after();
             const int t = warp, py = t >> 1, px = t & 1;
@@ -297,6 +287,7 @@ conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_l
                 dxo[dx] = C::POOL ? (uint64_t)((((px + dx) & 1) * C::PLANE_B + ((px + dx) >> 1) * 16) >> 4)
                                   : (uint64_t)dx;
             const uint32_t tile_off = C::POOL ? (uint32_t)(py * C::ROW_B) : (uint32_t)(t * 8 * 16);
+            const uint32_t d_tmem = tmem_base + tbuf * C::TBUF_COLS + (uint32_t)(t * COUT);
 #pragma unroll 1
             for (int pass = 0; pass < NPASS; ++pass) {
                 const uint64_t ad0 = make_smem_desc(smem_u32(a_part[pass == 2 ? 1 : 0]) + tile_off, C::CHUNK_B, C::SBO_A);
@@ -309,21 +300,57 @@ conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_l
                     for (int s = 0; s < CIN / 16; ++s) {
                         const uint64_t ad = ad0 + dxo[dx] + (uint64_t)((dy * C::ROW_B + 2 * s * C::CHUNK_B) >> 4);
                         const uint64_t bd = bd0 + (uint64_t)(((tap * C::NCH + 2 * s) * COUT * 16) >> 4);
-                        umma_f16(tmem_base + (uint32_t)(t * COUT), ad, bd, IDESC, (tap == 0 && s == 0) ? acc0 : 1u);
+                        umma_f16(d_tmem, ad, bd, IDESC, (tap == 0 && s == 0) ? acc0 : 1u);
                     }
                 }
             }
-            umma_commit(&bar);
+            umma_commit(&bar[tbuf]);
         }
-        if (PIPE && unit + (int)gridDim.x < n_units) prefetch(unit + gridDim.x);   // overlaps the MMAs + epilogue
-        mbar_wait(&bar, parity);
-        parity ^= 1;
-        tc_fence_after();
+    };
+
+    if (PIPE && (int)blockIdx.x < n_units) {
+        // prologue: first unit staged and its MMAs in flight, second unit's loads in registers
+        prefetch(blockIdx.x);
+        park();
+        fence_async_smem();
+        __syncthreads();
+        issue_mmas(0);
+        if ((int)(blockIdx.x + gridDim.x) < n_units) prefetch(blockIdx.x + gridDim.x);
+    }
+
+    uint32_t it = 0;
+    for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++it) {
+        const int cell = cell0 + unit / C::UNITS_PER_CELL;
+        const int sub = unit % C::UNITS_PER_CELL;   // POOL: pooled X half; else: 16-row band
+        const uint32_t tbuf = PIPE ? (it & 1) : 0u;
+
+        if (PIPE) {
+            // MMAs of this unit done -> the input block is free: park the next unit, start its MMAs into
+            // the other accumulator set, fetch the unit after that; all of it runs under this unit's epilogue.
+            // The barrier also orders the previous epilogue's TMEM reads before the MMAs that overwrite them.
+            mbar_wait(&bar[tbuf], (it >> 1) & 1);
+            tc_fence_after();
+            if (unit + (int)gridDim.x < n_units) {
+                park();
+                fence_async_smem();
+                tc_fence_before();
+                __syncthreads();
+                issue_mmas(tbuf ^ 1);
+                if (unit + 2 * (int)gridDim.x < n_units) prefetch(unit + 2 * gridDim.x);
+            }
+        } else {
+            stage_block<C, R, NPASS, TCT, 8, UPSIN>(in_hi, in_lo, a_part[0], a_part[1], cell, sub, tid);
+            fence_async_smem();
+            __syncthreads();
+            issue_mmas(0);
+            mbar_wait(&bar[0], it & 1);
+            tc_fence_after();
+        }
 
         // ---- epilogue: TMEM -> registers -> bias/ReLU/BN (-> pool) -> global ----
         const int q = warp & 3, half_sel = warp >> 2;
         const int r = 32 * q + lane;                   // MMA row = TMEM lane
-        const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * q) << 16);
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * q) << 16) + tbuf * C::TBUF_COLS;
         float se = 0.f, ae = 0.f;
         if (EPI == EPI_POOL) {
             constexpr int RO = R / 2;
@@ -360,6 +387,43 @@ conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_l
                     }
                 }
             }
+        } else if (EPI == EPI_PHASE) {
+            // N = 4 phases x CREAL channels: a thread serves the channel slices of its warp-half for all
+            // tiles and phases, so the bias / BN constants of a slice are fetched once
+            constexpr int CREAL = COUT / 4, RO = 2 * R;
+            const int y = 16 * (sub / C::COL_BLOCKS) + (r >> 3);
+            const int xblk = C::UNIT_COLS * (sub % C::COL_BLOCKS);
+#pragma unroll 1
+            for (int cs = half_sel; cs < CREAL / 8; cs += 2) {
+                float b8[8], s8[8], t8[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    b8[k] = __ldg(bias + cs * 8 + k); s8[k] = __ldg(bn_s + cs * 8 + k); t8[k] = __ldg(bn_t + cs * 8 + k);
+                }
+#pragma unroll 1
+                for (int t = 0; t < C::TILES; ++t) {
+                    const int x = xblk + 8 * t + (r & 7);
+                    uint32_t v[4][8];
+#pragma unroll
+                    for (int ph = 0; ph < 4; ++ph) TMEM_LD8(lane_addr + (uint32_t)(t * COUT + ph * CREAL + cs * 8), v[ph]);
+#pragma unroll
+                    for (int ph = 0; ph < 4; ++ph) TMEM_WAIT8(v[ph]);
+                    if (y < R) {
+#pragma unroll
+                        for (int ph = 0; ph < 4; ++ph) {
+                            float o[8];
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) {
+                                const float a = fmaxf(fmaf(__uint_as_float(v[ph][k]), inv_scale, b8[k]), 0.f);
+                                o[k] = fmaf(a, s8[k], t8[k]);
+                            }
+                            const size_t off = ((((size_t)cell * (CREAL / 8) + cs) * RO + 2 * y + (ph >> 1)) * RO +
+                                                2 * x + (ph & 1)) * 8;
+                            split_store8(o, out_hi + off, nullptr);
+                        }
+                    }
+                }
+            }
         } else {
             const int y = 16 * (sub / C::COL_BLOCKS) + (r >> 3);
             const int xblk = C::UNIT_COLS * (sub % C::COL_BLOCKS);
@@ -387,23 +451,15 @@ conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_l
                         }
                     }
                 } else {
-                    constexpr int CREAL = EPI == EPI_PHASE ? COUT / 4 : COUT;   // real output channels
-                    const int cc = c0 % CREAL;
                     float o[8];
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
-                        float a = fmaf(__uint_as_float(v[k]), inv_scale, __ldg(bias + cc + k));
+                        float a = fmaf(__uint_as_float(v[k]), inv_scale, __ldg(bias + c0 + k));
                         a = fmaxf(a, 0.f);
-                        o[k] = fmaf(a, __ldg(bn_s + cc + k), __ldg(bn_t + cc + k));
+                        o[k] = fmaf(a, __ldg(bn_s + c0 + k), __ldg(bn_t + c0 + k));
                     }
                     if (y < R) {
-                        if (EPI == EPI_PHASE) {
-                            constexpr int RO = 2 * R;
-                            const int ph = c0 / CREAL;
-                            const size_t off = ((((size_t)cell * (CREAL / 8) + cc / 8) * RO + 2 * y + (ph >> 1)) * RO +
-                                                2 * x + (ph & 1)) * 8;
-                            split_store8(o, out_hi + off, nullptr);
-                        } else if (EPI == EPI_UP) {
+                        if (EPI == EPI_UP) {
                             constexpr int RO = 2 * R;
                             const size_t base = (((size_t)cell * (COUT / 8) + sl) * RO + 2 * y) * RO + 2 * x;
                             __align__(16) __half hh[8];
@@ -422,19 +478,24 @@ conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_l
         }
         if (EPI == EPI_FINAL) {
             se = warp_sum(se); ae = warp_sum(ae);
-            if (lane == 0) { red_s[0][warp] = se; red_s[1][warp] = ae; }
+            if (lane == 0) { red_s[it & 1][0][warp] = se; red_s[it & 1][1][warp] = ae; }
         }
-        tc_fence_before();
-        __syncthreads();
+        // single-pass layers need no barrier here (the one before the next MMA issue orders the TMEM
+        // reads); the final layer's block reduction does, with red_s alternating between units
+        if (!PIPE || EPI == EPI_FINAL) {
+            tc_fence_before();
+            __syncthreads();
+        }
         if (EPI == EPI_FINAL && tid == 0) {
             float s = 0.f, a = 0.f;
 #pragma unroll
-            for (int w = 0; w < TCT / 32; ++w) { s += red_s[0][w]; a += red_s[1][w]; }
+            for (int w = 0; w < TCT / 32; ++w) { s += red_s[it & 1][0][w]; a += red_s[it & 1][1][w]; }
             // two bands per cell: two commutative float adds onto a zeroed slot -> deterministic
             atomicAdd(mse + cell, s * (1.f / 4096.f));
             atomicAdd(mae + cell, a * (1.f / 4096.f));
         }
     }
+    tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
