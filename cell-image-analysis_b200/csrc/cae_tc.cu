@@ -866,21 +866,23 @@ conv_tc_acc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
 // half-unit k+2 is issued by one thread the moment the last MMAs of half-unit k (same buffer)
 // have completed, i.e. a whole half-unit ahead of its use; no warp stages anything.
 // ---------------------------------------------------------------------------------------
-template <int CIN, int COUT>
+template <int CIN, int COUT, int R_>
 struct Acc2Cfg {
-    static constexpr int R = 32;
+    static constexpr int R = R_;                          // 32: two half blocks per cell, two buffers; 16: one block, one buffer
     static constexpr int NCH = CIN / 8;
     static constexpr int FILL_ROWS = R + 2;
-    static constexpr int BOX_X = R / 2 + 2;               // columns a box spans (every second one is read)
+    static constexpr int HALVES = R / 16;                 // 16-column blocks per cell = shared-memory buffers
+    static constexpr bool ROWPAIR = R == 16;              // see conv_tc_acc_kernel: tiles take both row phases
+    static constexpr int BOX_X = 16 + 2;                  // columns a box spans (every second one is read)
     static constexpr int ROW_UNITS = BOX_X / 2;           // 16-byte units per parity-plane row
     static constexpr int ROW_B = ROW_UNITS * 16;
     static constexpr int PLANE_B = FILL_ROWS * ROW_B;     // one (parity, chunk) plane = LBO of A
     static constexpr int PAR_B = NCH * PLANE_B;           // one TMA box: all chunks of one column parity
     static constexpr int REGION_B = 2 * PAR_B;            // hi or lo part of a block
-    static constexpr int SBO_A = 2 * ROW_B;
-    static constexpr int BUF_B = 2 * REGION_B;            // hi + lo of one half block
+    static constexpr int SBO_A = ROWPAIR ? ROW_B : 2 * ROW_B;
+    static constexpr int BUF_B = 2 * REGION_B;            // hi + lo of one block
     static constexpr int W_B = 9 * NCH * COUT * 16;
-    static constexpr int SMEM_B = 2 * BUF_B + 2 * W_B;
+    static constexpr int SMEM_B = HALVES * BUF_B + 2 * W_B;
     static_assert(PAR_B % 128 == 0, "TMA destinations must be 128-byte aligned");
 };
 
@@ -900,13 +902,13 @@ __device__ __forceinline__ void tma_load_half_block(const CUtensorMap* tm_hi, co
     mbar_expect_tx(bar, A::BUF_B);
 #pragma unroll
     for (int par = 0; par < 2; ++par) {
-        const int x0 = half * (A::R / 2) - 1 + par;
+        const int x0 = half * 16 - 1 + par;
         tma_load_5d(buf + par * A::PAR_B, tm_hi, 0, x0, -1, 0, cell_rel, bar);
         tma_load_5d(buf + A::REGION_B + par * A::PAR_B, tm_lo, 0, x0, -1, 0, cell_rel, bar);
     }
 }
 
-template <int CIN, int COUT, int G>
+template <int CIN, int COUT, int R, int G>
 __global__ void __launch_bounds__(ACC_THREADS, 1)
 conv_tc_acc2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
                     const uint4* __restrict__ w_hi, const uint4* __restrict__ w_lo, float inv_scale,
@@ -914,9 +916,10 @@ conv_tc_acc2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
                     const float* __restrict__ bn_t, __half* __restrict__ out_hi, __half* __restrict__ out_lo,
                     float* __restrict__ feat, int n_cells, const int32_t* __restrict__ n_dev, int cell0,
                     int chunk_cells) {
-    using C = Acc2Cfg<CIN, COUT>;
-    constexpr int R = C::R;
-    constexpr int STAGE_COLS = 4 * COUT;
+    using C = Acc2Cfg<CIN, COUT, R>;
+    constexpr bool ROWPAIR = C::ROWPAIR;
+    constexpr int NT = ROWPAIR ? 2 : 4;          // accumulator tiles per stage = issuing warps
+    constexpr int STAGE_COLS = NT * COUT;
     constexpr int TMEM_COLS = pow2_cols(2 * STAGE_COLS);
     constexpr int CW = COUT / 4;                 // columns per epilogue warp
     constexpr int NGRP = (9 + G - 1) / G;        // TMEM flushes per pooled tile (G filter taps each)
@@ -925,7 +928,7 @@ conv_tc_acc2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
     __shared__ uint32_t tmem_base_s;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    unsigned char* w_part[2] = {smem + 2 * C::BUF_B, smem + 2 * C::BUF_B + C::W_B};
+    unsigned char* w_part[2] = {smem + C::HALVES * C::BUF_B, smem + C::HALVES * C::BUF_B + C::W_B};
 
     int n = dev_count(n_cells, n_dev) - cell0;
     if (n > chunk_cells) n = chunk_cells;
@@ -934,7 +937,7 @@ conv_tc_acc2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
 
     if (warp == 0) tmem_alloc(&tmem_base_s, TMEM_COLS);
     if (tid == 32) {
-        mbar_init(&full_bar[0], ACC_MMA_WARPS); mbar_init(&full_bar[1], ACC_MMA_WARPS);
+        mbar_init(&full_bar[0], NT); mbar_init(&full_bar[1], NT);
         mbar_init(&empty_bar[0], ACC_EPI_WARPS); mbar_init(&empty_bar[1], ACC_EPI_WARPS);
         mbar_init(&ready_bar[0], 1); mbar_init(&ready_bar[1], 1);
         fence_barrier_init();
@@ -953,8 +956,8 @@ conv_tc_acc2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
 
     if (warp >= ACC_EPI_WARPS) {
         // ================= MMA issuers: one warp per phase tile =================
-        if (lane == 0) {
-            const int t = warp - ACC_EPI_WARPS, py = t >> 1, px = t & 1;
+        if (lane == 0 && warp - ACC_EPI_WARPS < NT) {
+            const int t = warp - ACC_EPI_WARPS, py = ROWPAIR ? 0 : t >> 1, px = t & 1;
             const uint64_t b_hi0 = make_smem_desc(smem_u32(w_part[0]), COUT * 16, 128);
             const uint64_t b_lo0 = make_smem_desc(smem_u32(w_part[1]), COUT * 16, 128);
             uint64_t dxo[3];                   // (parity plane, half-column shift) of tap column dx, in 16-byte units
@@ -966,7 +969,7 @@ conv_tc_acc2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
 #endif
             for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
+                for (int half = 0; half < C::HALVES; ++half) {
                     const uint32_t abase = sbase + half * C::BUF_B + py * C::ROW_B;
                     const uint64_t a_hi0 = make_smem_desc(abase, C::PLANE_B, C::SBO_A);
                     const uint64_t a_lo0 = make_smem_desc(abase + C::REGION_B, C::PLANE_B, C::SBO_A);
@@ -1028,9 +1031,9 @@ conv_tc_acc2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
 #ifdef CIA_ACC_TIMING
         long long e_stage = 0, e_full = 0, e_ld = 0, e_add = 0, e_final = 0, e_units = 0;
 #endif
-        if (tid == 0 && (int)blockIdx.x < n_units) {          // prologue: both half blocks of the first cell
-            tma_load_half_block<C>(&tm_hi, &tm_lo, sbase, blockIdx.x, 0, &ready_bar[0]);
-            tma_load_half_block<C>(&tm_hi, &tm_lo, sbase + C::BUF_B, blockIdx.x, 1, &ready_bar[1]);
+        if (tid == 0 && (int)blockIdx.x < n_units) {          // prologue: all blocks of the first cell
+            for (int hb = 0; hb < C::HALVES; ++hb)
+                tma_load_half_block<C>(&tm_hi, &tm_lo, sbase + hb * C::BUF_B, blockIdx.x, hb, &ready_bar[hb]);
         }
         for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
             const int cell = cell0 + unit;
@@ -1038,10 +1041,10 @@ conv_tc_acc2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
             ++e_units;
 #endif
 #pragma unroll 1
-            for (int sub = 0; sub < 2; ++sub) {
-                float acc[4][CW];
+            for (int sub = 0; sub < C::HALVES; ++sub) {
+                float acc[NT][CW];
 #pragma unroll
-                for (int ph = 0; ph < 4; ++ph)
+                for (int ph = 0; ph < NT; ++ph)
 #pragma unroll
                     for (int k = 0; k < CW; ++k) acc[ph][k] = 0.f;
 #pragma unroll 1
@@ -1058,7 +1061,7 @@ conv_tc_acc2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
                                                &ready_bar[sub]);
                     // two phases at a time keeps the live registers under the 102-per-thread budget
 #pragma unroll
-                    for (int hp = 0; hp < 2; ++hp) {
+                    for (int hp = 0; hp < NT / 2; ++hp) {
                         uint32_t v[2][CW / 8][8];
 #pragma unroll
                         for (int p2 = 0; p2 < 2; ++p2)
@@ -1069,7 +1072,7 @@ conv_tc_acc2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
                         for (int p2 = 0; p2 < 2; ++p2)
 #pragma unroll
                             for (int k8 = 0; k8 < CW / 8; ++k8) TMEM_WAIT8(v[p2][k8]);
-                        if (hp == 1) {
+                        if (hp == NT / 2 - 1) {
                             tc_fence_before();
                             __syncwarp();
                             if (lane == 0) mbar_arrive(&empty_bar[st]);
@@ -1092,7 +1095,7 @@ conv_tc_acc2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
                 DBG_T(e6);
                 // final epilogue from registers: bias -> ReLU -> BN -> 2x2 max -> hi/lo fp16 (+ fp32 tap)
                 constexpr int RO = R / 2;
-                const int Y = r >> 3, X = 8 * sub + (r & 7);
+                const int Y = ROWPAIR ? r >> 4 : r >> 3, X = 8 * sub + (r & 7);
 #pragma unroll
                 for (int k8 = 0; k8 < CW / 8; ++k8) {
                     const int c0 = cq * CW + k8 * 8;
@@ -1102,13 +1105,15 @@ conv_tc_acc2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
                         const float b = __ldg(bias + c0 + k), sc = __ldg(bn_s + c0 + k), sh = __ldg(bn_t + c0 + k);
                         float m = -INFINITY;
 #pragma unroll
-                        for (int ph = 0; ph < 4; ++ph) {
+                        for (int ph = 0; ph < NT; ++ph) {
                             float a = fmaf(acc[ph][k8 * 8 + k], inv_scale, b);
                             a = fmaxf(a, 0.f);
                             m = fmaxf(m, fmaf(a, sc, sh));
                         }
+                        if (ROWPAIR) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));   // conv rows 2Y, 2Y+1
                         o[k] = m;
                     }
+                    if (ROWPAIR && (r & 8)) continue;      // the even conv row's lane stores the pooled pixel
                     const size_t off = ((((size_t)cell * (COUT / 8) + c0 / 8) * RO + Y) * RO + X) * 8;
                     split_store8(o, out_hi + off, out_lo ? out_lo + off : nullptr);
                     if (feat) {
@@ -1336,13 +1341,13 @@ static int encode_act_map(cia_ctx* h, CUtensorMap* tm, const __half* base, int n
 
 // R = 32 pooling layer with TMA-fed double-buffered half-cell blocks (conv_tc_acc2_kernel).
 // in_hi / in_lo are the chunk buffers' own base addresses (cell 0 of the chunk).
-template <int CIN, int COUT, int G>
+template <int CIN, int COUT, int R, int G>
 int launch_tc_acc2(cia_ctx* h, const CaeWeights& w, int layer, const __half* in_hi, const __half* in_lo,
                    int buf_cells, __half* out_hi, __half* out_lo, float* feat, int n, const int32_t* n_dev,
                    int cell0, int chunk, cudaStream_t s) {
-    using C = Acc2Cfg<CIN, COUT>;
+    using C = Acc2Cfg<CIN, COUT, R>;
     static_assert(C::SMEM_B + 1280 <= 227 * 1024, "double-buffered blocks do not fit in shared memory");
-    auto kern = conv_tc_acc2_kernel<CIN, COUT, G>;
+    auto kern = conv_tc_acc2_kernel<CIN, COUT, R, G>;
     if (first_use(h, (const void*)kern))
         CIA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_B));
     CUtensorMap tm_hi, tm_lo;
@@ -1356,7 +1361,7 @@ int launch_tc_acc2(cia_ctx* h, const CaeWeights& w, int layer, const __half* in_
                                               w.bn_scale[layer], w.bn_shift[layer], out_hi, out_lo, feat, n, n_dev,
                                               cell0, chunk);
     CIA_LAUNCH_CHECK();
-    acc_timing_dump("acc2", CIN, COUT, 32, G, s);
+    acc_timing_dump("acc2", CIN, COUT, R, G, s);
     return CIA_OK;
 }
 
@@ -1524,15 +1529,21 @@ int k_cae_forward_tc(cia_ctx* h, const float* crops, int n, const int32_t* n_dev
             // whole-cell kernel): 3 keeps the epilogue warps below the tensor pipe's time, see DESIGN.md
             static const int l2_g = [] { const char* e = getenv("CIA_L2_TAPS_PER_FLUSH"); return e ? atoi(e) : 3; }();
             if (l2_g == 0) rc = launch_tc_acc<32, 64, 32, 1>(h, ae, 1, a1h, a1l, a2h, a2l, a2f, n, n_dev, c0, chunk, s);
-            else if (l2_g == 1) rc = launch_tc_acc2<32, 64, 1>(h, ae, 1, A1h, A1l, CH, a2h, a2l, a2f, n, n_dev, c0, chunk, s);
-            else if (l2_g == 2) rc = launch_tc_acc2<32, 64, 2>(h, ae, 1, A1h, A1l, CH, a2h, a2l, a2f, n, n_dev, c0, chunk, s);
-            else rc = launch_tc_acc2<32, 64, 3>(h, ae, 1, A1h, A1l, CH, a2h, a2l, a2f, n, n_dev, c0, chunk, s);
+            else if (l2_g == 1) rc = launch_tc_acc2<32, 64, 32, 1>(h, ae, 1, A1h, A1l, CH, a2h, a2l, a2f, n, n_dev, c0, chunk, s);
+            else if (l2_g == 2) rc = launch_tc_acc2<32, 64, 32, 2>(h, ae, 1, A1h, A1l, CH, a2h, a2l, a2f, n, n_dev, c0, chunk, s);
+            else rc = launch_tc_acc2<32, 64, 32, 3>(h, ae, 1, A1h, A1l, CH, a2h, a2l, a2f, n, n_dev, c0, chunk, s);
             if (rc) return rc;
             if (l3_exact) {
                 if ((rc = launch_tc<64, 32, 16, EPI_POOL, 1>(h, ae, 2, a2h, nullptr, a3h, nullptr, nullptr, nullptr, nullptr, nullptr, n, n_dev, c0, chunk, s))) return rc;
                 if (features && (rc = k_conv3_fp32(h, ae, a2f, n, n_dev, features, c0, chunk, s))) return rc;
             } else {
-                if ((rc = launch_tc_acc<64, 32, 16>(h, ae, 2, a2h, a2l, a3h, nullptr, feat, n, n_dev, c0, chunk, s))) return rc;
+                // CIA_L3_KERNEL=1 selects the TMA-fed kernel (single input buffer -- two do not fit next to the
+                // 74 KB of weights -- refilled the moment the cell's last MMAs complete).  Measured: no gain over
+                // the register-staged kernel (cae 75.6 vs 74.0 ms per 242k cells), which stays the default.
+                static const int l3_tma = [] { const char* e = getenv("CIA_L3_KERNEL"); return e ? atoi(e) : 0; }();
+                if (l3_tma) rc = launch_tc_acc2<64, 32, 16, 1>(h, ae, 2, A2h, A2l, CH, a3h, nullptr, feat, n, n_dev, c0, chunk, s);
+                else rc = launch_tc_acc<64, 32, 16, 1>(h, ae, 2, a2h, a2l, a3h, nullptr, feat, n, n_dev, c0, chunk, s);
+                if (rc) return rc;
             }
         } else {
             conv1_fp32_planar_kernel<<<grid1, 256, 0, s>>>(crops, ae.kernel[0], ae.bias[0], ae.bn_scale[0],
