@@ -9,7 +9,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcia.so")
-SOURCES = ["api.cu", "scan.cu", "crop.cu", "cae_fp32.cu", "cae_tc.cu", "score.cu", "transport.cu"]
+SOURCES = ["api.cu", "scan.cu", "crop.cu", "cae_fp32.cu", "cae_tc.cu", "score.cu", "transport.cu", "host_rle.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 
@@ -35,8 +35,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
     objs = []
     procs = []
     for src in SOURCES:
-        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
         objs.append(obj)
+        if src.endswith(".cpp"):      # host-only sources: the host compiler directly
+            cmd = [shutil.which("g++") or "g++", "-O3", "-std=c++17", "-fPIC", "-c", os.path.join(CSRC, src), "-o", obj]
+            procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+            continue
         cmd = [_nvcc(), *[f for f in NVCC_FLAGS if f != "--use_fast_math=false"],
                *os.environ.get("CIA_NVCC_EXTRA", "").split(), "-c",
                os.path.join(CSRC, src), "-o", obj]

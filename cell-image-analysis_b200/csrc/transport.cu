@@ -22,51 +22,12 @@ namespace {
 
 inline size_t rle_runs_base(int H) { return (size_t)((H + 2) & ~1); }
 
-// Encodes one field; returns the number of words used, or 0 if the slot is too small.
-size_t encode_field(const int32_t* lab, int H, int W, uint32_t* slot, size_t slot_words, int32_t* max_label) {
-    const size_t r0 = rle_runs_base(H);
-    if (slot_words < r0 + 2) return 0;
-    uint32_t* runs = slot + r0;
-    const size_t cap_runs = (slot_words - r0) / 2;
-    size_t n = 0;
-    int32_t mx = 0;
-    if ((H + 1) & 1) slot[H + 1] = 0;   // padding word
-    for (int y = 0; y < H; ++y) {
-        const int32_t* p = lab + (size_t)y * W;
-        slot[y] = (uint32_t)n;
-        if (n + (size_t)W > cap_runs) {
-            // slow path near the end of the slot: check every emit
-            int x = 0;
-            while (x < W) {
-                const int32_t cur = p[x];
-                if (n >= cap_runs) return 0;
-                runs[2 * n] = (uint32_t)x; runs[2 * n + 1] = (uint32_t)cur; ++n;
-                if (cur > mx) mx = cur;
-                while (x < W && p[x] == cur) ++x;
-            }
-            continue;
-        }
-        int x = 0;
-        while (x < W) {
-            const int32_t cur = p[x];
-            runs[2 * n] = (uint32_t)x; runs[2 * n + 1] = (uint32_t)cur; ++n;
-            if (cur > mx) mx = cur;
-            ++x;
-            // skip 8 equal labels (32 bytes) per step while the run lasts
-            const uint64_t pat = (uint64_t)(uint32_t)cur * 0x0000000100000001ULL;
-            while (x + 8 <= W) {
-                uint64_t v[4];
-                std::memcpy(v, p + x, 32);
-                if (((v[0] ^ pat) | (v[1] ^ pat) | (v[2] ^ pat) | (v[3] ^ pat)) != 0) break;
-                x += 8;
-            }
-            while (x < W && p[x] == cur) ++x;
-        }
-    }
-    slot[H] = (uint32_t)n;
-    if (max_label) *max_label = mx;
-    return r0 + 2 * n;
-}
+}  // namespace
+
+// host_rle.cpp (plain C++, AVX2 path selected at run time)
+size_t cia_host_encode_field(const int32_t* lab, int H, int W, uint32_t* slot, size_t slot_words, int32_t* max_label);
+
+namespace {
 
 // One thread per four pixels: binary search for the run covering the first, then walk.
 __global__ void __launch_bounds__(256)
@@ -128,7 +89,7 @@ int cia_rle_encode_fields(const int32_t* labels_host, int n_fields, int H, int W
         for (;;) {
             const int f = next.fetch_add(1);
             if (f >= n_fields) break;
-            const size_t w = encode_field(labels_host + (size_t)f * H * W, H, W, slots_host + (size_t)f * slot_words,
+            const size_t w = cia_host_encode_field(labels_host + (size_t)f * H * W, H, W, slots_host + (size_t)f * slot_words,
                                           slot_words, &mx[f]);
             field_words[f] = (uint32_t)w;
             if (w == 0) overflow.store(1);
