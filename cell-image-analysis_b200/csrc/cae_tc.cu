@@ -16,6 +16,15 @@
 // that the 2x2 max-pool partners of a pooled pixel sit in the SAME TMEM lane (no shuffles).
 // fp32-grade encoder features: operands are split x = hi + lo (two fp16), weights scaled by
 // a power of two; three MMAs (hi*hi, hi*lo, lo*hi) accumulate into one fp32 TMEM tile.
+//
+// Default pass (precision 1), one launch per layer over up to 16576 cells:
+//   L1  1->32 @64  conv1_fp32_planar_kernel     CUDA cores, exact fp32 (FFMA2), writes hi/lo fp16
+//   L2 32->64 @32  conv_tc_acc2_kernel<..,32,3>  TMA-fed double-buffered half-cell blocks, 3 taps per flush
+//   L3 64->32 @16  conv_tc_acc_kernel<..,16,1>   row-pair tiles, register-staged, 1 tap per flush -> features
+//   L4 32->32 @8   conv_tc_kernel<EPI_PLAIN>     single pass, TMEM double-buffered
+//   L5 32->64 @16  conv_tc_kernel<EPI_PLAIN,UPSIN> up-sampling folded into the staging
+//   L6 64->32 @32  conv_tc_kernel<EPI_PHASE>     phase form at 16x16, N = 128
+//   L7 32->1  @64  conv_tc_kernel<EPI_FINAL>     phase form at 32x32 + sigmoid + MSE/MAE reduction
 #include "common.cuh"
 
 #include <cuda.h>          // CUtensorMap (types only; the encoder is fetched through the runtime)
@@ -28,7 +37,7 @@ namespace {
 constexpr int TCT = 256;   // 8 warps: warp&3 = TMEM lane quadrant, warp>>2 = column-slice parity
 // EPI_PHASE: the layer runs at its INPUT's (pre-upsampling) resolution R with the four output phases
 // (py,px) of the 2x nearest up-sampled grid as column groups: N = 4 * Cout, output is 2R x 2R
-enum { EPI_POOL = 0, EPI_UP = 1, EPI_PLAIN = 2, EPI_FINAL = 3, EPI_PHASE = 4 };
+enum { EPI_POOL = 0, EPI_PLAIN = 2, EPI_FINAL = 3, EPI_PHASE = 4 };
 
 // ---------------------------------------------------------------------------------------
 // PTX wrappers
@@ -459,19 +468,8 @@ conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_l
                         o[k] = fmaf(a, __ldg(bn_s + c0 + k), __ldg(bn_t + c0 + k));
                     }
                     if (y < R) {
-                        if (EPI == EPI_UP) {
-                            constexpr int RO = 2 * R;
-                            const size_t base = (((size_t)cell * (COUT / 8) + sl) * RO + 2 * y) * RO + 2 * x;
-                            __align__(16) __half hh[8];
-#pragma unroll
-                            for (int k = 0; k < 8; ++k) hh[k] = __float2half_rn(o[k]);
-                            const uint4 pk = *reinterpret_cast<const uint4*>(hh);
-                            uint4* dst = reinterpret_cast<uint4*>(out_hi);
-                            dst[base] = pk; dst[base + 1] = pk; dst[base + RO] = pk; dst[base + RO + 1] = pk;
-                        } else {
-                            const size_t off = ((((size_t)cell * (COUT / 8) + sl) * R + y) * R + x) * 8;
-                            split_store8(o, out_hi + off, nullptr);
-                        }
+                        const size_t off = ((((size_t)cell * (COUT / 8) + sl) * R + y) * R + x) * 8;
+                        split_store8(o, out_hi + off, nullptr);
                     }
                 }
             }
@@ -1403,14 +1401,8 @@ int k_cae_tc_prepare(cia_ctx* h, int which) {
         CIA_CUDA(cudaMemcpy(k.data(), w.kernel[L], k.size() * sizeof(float), cudaMemcpyDeviceToHost));
         std::vector<__half> hi, lo;
         int sw;
-        if (L == 0) {
-            // K = tap index, padded 9 -> 16: treat as 1 "tap" with 16 "input channels"
-            std::vector<float> kk((size_t)16 * cout, 0.f);
-            for (int tap = 0; tap < 9; ++tap)
-                for (int nn = 0; nn < cout; ++nn) kk[(size_t)tap * cout + nn] = k[(size_t)tap * cout + nn];
-            sw = scale_exp(kk);
-            pack_image(kk, 1, 16, cout, cout, sw, hi, lo);
-        } else if (L == 6) {
+        if (L == 0) continue;   // layer 1 (K = 9) runs on the CUDA cores in exact fp32 (conv1_fp32_planar_kernel)
+        if (L == 6) {
             // phase form: conv on the nearest-up-sampled input == 3x3 conv on the low-res input
             // with 4 outputs (py,px); weights of hi-res taps that fall on the same low-res pixel add up
             std::vector<float> kp((size_t)9 * cin * 4, 0.f);
