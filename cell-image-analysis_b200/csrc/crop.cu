@@ -73,20 +73,22 @@ __device__ __forceinline__ void clip_and_map(int (&hv)[8], int clim, double scal
     ex = __reduce_add_sync(0xffffffffu, ex);          // REDUX: one instruction instead of a 5-step shuffle tree
     if (ex > 0) {
         const int incr = ex / NBINS;
-        const int upper = clim - incr;
-        int nlow = 0;
+        if (incr > 0) {     // with incr == 0 (small tiles: excess < 256) both passes below change nothing
+            const int upper = clim - incr;
+            int nlow = 0;
 #pragma unroll
-        for (int m = 0; m < 8; ++m)
-            if (hv[m] < upper) { hv[m] += incr; ++nlow; }
-        int midsum = 0, nmid = 0;
+            for (int m = 0; m < 8; ++m)
+                if (hv[m] < upper) { hv[m] += incr; ++nlow; }
+            int midsum = 0, nmid = 0;
 #pragma unroll
-        for (int m = 0; m < 8; ++m)
-            if (hv[m] >= upper && hv[m] < clim) { midsum += hv[m]; ++nmid; hv[m] = clim; }
-        // nlow, nmid <= 256 each and midsum <= 256 * clim < 2^17 fit one 32-bit REDUX each way
-        const unsigned cnts = __reduce_add_sync(0xffffffffu, (unsigned)nlow | ((unsigned)nmid << 16));
-        const int msum = __reduce_add_sync(0xffffffffu, midsum);
-        ex -= (int)(cnts & 0xFFFFu) * incr;
-        ex += msum - (int)(cnts >> 16) * clim;
+            for (int m = 0; m < 8; ++m)
+                if (hv[m] >= upper && hv[m] < clim) { midsum += hv[m]; ++nmid; hv[m] = clim; }
+            // nlow, nmid <= 256 each and midsum <= 256 * clim < 2^17 fit one 32-bit REDUX each way
+            const unsigned cnts = __reduce_add_sync(0xffffffffu, (unsigned)nlow | ((unsigned)nmid << 16));
+            const int msum = __reduce_add_sync(0xffffffffu, midsum);
+            ex -= (int)(cnts & 0xFFFFu) * incr;
+            ex += msum - (int)(cnts >> 16) * clim;
+        }
 
         while (ex > 0) {
             const int prev = ex;
@@ -134,9 +136,9 @@ __device__ __forceinline__ void clip_and_map(int (&hv)[8], int clim, double scal
     __align__(16) uint16_t mv16[8];
 #pragma unroll
     for (int m = 0; m < 8; ++m) {
-        double mv = __dmul_rn((double)(base + pre[m]), scale);
-        if (mv > 16383.0) mv = 16383.0;
-        mv16[m] = (uint16_t)(int)mv;
+        // clip after the truncation (same result: both are monotone; the product stays far below 2^31)
+        const int mv = (int)__dmul_rn((double)(base + pre[m]), scale);
+        mv16[m] = (uint16_t)min(mv, 16383);
     }
     *reinterpret_cast<uint4*>(map_out + 8 * lane) = *reinterpret_cast<const uint4*>(mv16);
 }
