@@ -39,6 +39,7 @@ class BatchScreen:
         self.acc = torch.zeros((n_strains, 8), dtype=torch.float64, device=d)
         self.compute = torch.cuda.Stream(device=d)
         self.copy = torch.cuda.Stream(device=d)
+        self.d2h = torch.cuda.Stream(device=d)       # result read-back, off the compute stream
         self._stage = None
 
     # ---- profiling ----
@@ -61,6 +62,9 @@ class BatchScreen:
         assert P % self.Fc == 0 and n_fields % self.Fc == 0
         eng = self.eng
         with torch.cuda.stream(self.compute):
+            if self._stage is not None:                  # a host pass may still be reading self.out back
+                for e in self._stage["out_free"]:
+                    self.compute.wait_event(e)
             for i in range(n_fields // self.Fc):
                 p0 = (i * self.Fc) % P
                 o = self.out[i & 1]
@@ -76,7 +80,9 @@ class BatchScreen:
                 img=[torch.empty((self.Fc, self.H, self.W), dtype=torch.int16, device=d) for _ in range(2)],
                 lab=[torch.empty((self.Fc, self.H, self.W), dtype=torch.int32, device=d) for _ in range(2)],
                 ready=[torch.cuda.Event() for _ in range(2)],
-                done=[torch.cuda.Event() for _ in range(2)])
+                done=[torch.cuda.Event() for _ in range(2)],
+                out_ready=[torch.cuda.Event() for _ in range(2)],
+                out_free=[torch.cuda.Event() for _ in range(2)])
             if self.label_transport == "rle":
                 sw = self.eng.rle_slot_words(self.H, self.W)
                 self._stage.update(
@@ -119,15 +125,16 @@ class BatchScreen:
             b = i & 1
             p0 = (i * self.Fc) % P
             rle = self.label_transport == "rle"
+            with torch.cuda.stream(self.copy):
+                self.copy.wait_event(S["done"][b])
+                S["img"][b].copy_(images_pinned[p0:p0 + self.Fc], non_blocking=True)
             if rle:
-                # the host encodes chunk i while the device still works on chunk i-1; the slot
-                # buffer is reused only after its previous upload (chunk i-2) has finished
+                # the host encodes chunk i while its image copy and the device's work on chunk i-1
+                # are in flight; the slot buffer is reused only after its previous upload (chunk i-2)
                 S["ready"][b].synchronize()
                 rle = eng.rle_encode(labels_pinned[p0:p0 + self.Fc], S["h_rle"][b], S["words"][b],
                                      self.host_threads)
             with torch.cuda.stream(self.copy):
-                self.copy.wait_event(S["done"][b])
-                S["img"][b].copy_(images_pinned[p0:p0 + self.Fc], non_blocking=True)
                 if rle:
                     eng.rle_upload_expand(S["h_rle"][b], S["words"][b], S["d_rle"][b], S["lab"][b])
                     self.h2d_bytes += 2 * px + 4 * int(S["words"][b].sum())
@@ -137,10 +144,14 @@ class BatchScreen:
                 S["ready"][b].record(self.copy)
             with torch.cuda.stream(self.compute):
                 self.compute.wait_event(S["ready"][b])
+                self.compute.wait_event(S["out_free"][b])       # chunk i-2's results have been read back
                 o = self.out[b]
                 st = None if strain_of_visit is None else strain_of_visit[i * self.Fc:(i + 1) * self.Fc]
                 eng.screen_fields(S["img"][b], S["lab"][b], self.max_label, o, field_strain=st, acc=self.acc)
                 S["done"][b].record(self.compute)
+                S["out_ready"][b].record(self.compute)
+            with torch.cuda.stream(self.d2h):
+                self.d2h.wait_event(S["out_ready"][b])
                 self.h_counts[i].copy_(o["counts"], non_blocking=True)
                 self.h_cells[i].copy_(o["cells"], non_blocking=True)
                 self.h_mse[i].copy_(o["mse"], non_blocking=True)
@@ -149,6 +160,7 @@ class BatchScreen:
                 self.h_dm[i].copy_(o["dec_mod"], non_blocking=True)
                 self.h_pc[i].copy_(o["pred_cons"], non_blocking=True)
                 self.h_pm[i].copy_(o["pred_mod"], non_blocking=True)
+                S["out_free"][b].record(self.d2h)
         self._last_chunks = n_chunks
 
     def collect_host(self):
@@ -169,3 +181,4 @@ class BatchScreen:
     def sync(self):
         self.compute.synchronize()
         self.copy.synchronize()
+        self.d2h.synchronize()
