@@ -112,3 +112,32 @@ def test_run_host_rle_equals_raw(golden_config1, model_dir):
     assert a["n_cells"] == b["n_cells"] > 0
     for k in ("cells", "mse", "mae", "dec_cons", "dec_mod", "pred_cons", "pred_mod", "field_counts"):
         assert np.array_equal(a[k], b[k]), k
+
+
+@pytest.mark.gpu
+def test_run_host_incompressible_labels_fall_back_to_raw(model_dir):
+    """A chunk whose labels do not fit the run-length slots is copied raw; results are unchanged."""
+    import torch
+    from cell_image_analysis_b200.artifacts import load_model_dir
+    from cell_image_analysis_b200.batch import BatchScreen
+    from cell_image_analysis_b200.screening import Engine
+    eng = Engine()
+    eng.load_artifacts(load_model_dir(model_dir))
+    H = W = 128
+    rng = np.random.default_rng(3)
+    cells = make_field(11, H, W, 9, 9.0, 14.0)
+    noise = rng.integers(1, 400, (H, W), dtype=np.int32)             # one run per pixel: does not compress
+    g = torch.from_numpy(np.stack([cells[0], cells[0]]).view(np.int16)).pin_memory()
+    lab = torch.from_numpy(np.stack([cells[1], noise])).pin_memory()
+    res = {}
+    for mode in ("raw", "rle"):
+        bs = BatchScreen(eng, H, W, 400, chunk_fields=1, label_transport=mode)
+        bs.run_host(g, lab, 2)
+        bs.sync()
+        res[mode] = bs.collect_host()
+        if mode == "rle":      # field 0 went as runs, field 1 raw
+            assert 2 * H * W * 2 + 4 * H * W < bs.host_bytes_per_pass(2)[0] < 2 * H * W * 6
+    a, b = res["raw"], res["rle"]
+    assert a["n_cells"] == b["n_cells"]
+    for k in ("cells", "mse", "dec_cons", "pred_mod", "field_counts"):
+        assert np.array_equal(a[k], b[k]), k
