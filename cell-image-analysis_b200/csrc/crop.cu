@@ -158,7 +158,33 @@ __device__ __forceinline__ void block_minmax(int& mn, int& mx, int* sh) {
     for (int i = 1; i < K2_WARPS; ++i) { mn = min(mn, sh[i]); mx = max(mx, sh[K2_WARPS + i]); }
 }
 
+__device__ __forceinline__ int cell_class(const cia_cell& C, size_t lo_bytes, size_t hi_bytes) {
+    const int h = C.maxr - C.minr, w = C.maxc - C.minc;
+    if (h > MAX_SIDE || w > MAX_SIDE) return 2;       // refused inside the class-2 launch
+    const int kh = max(h / 8, 1), kw = max(w / 8, 1);
+    const size_t need = cell_bytes(h, w, (h + kh - 1) / kh, (w + kw - 1) / kw);
+    return need <= lo_bytes ? 0 : (need <= hi_bytes ? 1 : 2);
+}
+
+// Work lists of the two rare classes (cells whose working set does not fit the 2-CTA/SM shared
+// memory budget): their launches walk only their own cells instead of every CTA scanning the
+// whole cell table.  cls_counts[0..1] = entries of list 1 / list 2 (zeroed by the caller).
+__global__ void __launch_bounds__(256)
+crop_classify_kernel(const cia_cell* __restrict__ cells, int n_cells,
+                     const int32_t* __restrict__ n_cells_dev, size_t lo_bytes, size_t hi_bytes,
+                     int32_t* __restrict__ cls_counts, int32_t* __restrict__ list1,
+                     int32_t* __restrict__ list2) {
+    const int n = dev_count(n_cells, n_cells_dev);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int c = cell_class(cells[i], lo_bytes, hi_bytes);
+        if (c == 1) list1[atomicAdd(cls_counts + 0, 1)] = i;
+        else if (c == 2) list2[atomicAdd(cls_counts + 1, 1)] = i;
+    }
+}
+
 // cls: 0/1 = shared-memory classes (dynamic smem = smem_bytes), 2 = global-scratch class.
+// cls_list == nullptr: walk every cell and skip the other classes (the common class 0);
+// otherwise walk cls_list[0 .. *cls_count).
 __global__ void __launch_bounds__(K2_THREADS)
 crop_clahe_resize_kernel(const uint16_t* __restrict__ images, int H, int W,
                          const cia_cell* __restrict__ cells, int n_cells,
@@ -167,7 +193,8 @@ crop_clahe_resize_kernel(const uint16_t* __restrict__ images, int H, int W,
                          int cls, size_t lo_bytes, size_t hi_bytes,
                          unsigned char* __restrict__ gscratch, size_t gscratch_per_cta,
                          int32_t* status, uint16_t* __restrict__ levels_out,
-                         const int64_t* __restrict__ level_offsets) {
+                         const int64_t* __restrict__ level_offsets,
+                         const int32_t* __restrict__ cls_list, const int32_t* __restrict__ cls_count) {
     extern __shared__ __align__(16) unsigned char dyn[];
     __shared__ __align__(16) uint32_t hist_s[K2_WARPS][NBINS];
     __shared__ double ctab_s[2][MAX_SIDE / 8];      // a/kh and b/kw interpolation coefficients
@@ -175,9 +202,10 @@ crop_clahe_resize_kernel(const uint16_t* __restrict__ images, int H, int W,
     __shared__ double gw_s[2][2 * MAX_RADIUS + 2];
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int n = dev_count(n_cells, n_cells_dev);
+    const int n = cls_list ? min(*cls_count, n_cells) : dev_count(n_cells, n_cells_dev);
 
-    for (int cell = blockIdx.x; cell < n; cell += gridDim.x) {
+    for (int it = blockIdx.x; it < n; it += gridDim.x) {
+        const int cell = cls_list ? cls_list[it] : it;
         const cia_cell C = cells[cell];
         Geom g;
         g.h = C.maxr - C.minr; g.w = C.maxc - C.minc;
@@ -430,22 +458,37 @@ int k_crop_resize(cia_ctx* h, const uint16_t* images, int H, int W, const cia_ce
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hi_bytes));
     const int huge_ctas = 32;
     const size_t per_cta = cell_bytes(MAX_SIDE, MAX_SIDE, 15, 15);
-    int rc = ws_reserve(h, h->ws_crop_scratch, per_cta * huge_ctas);
+    // [class counters (256 B)] [list 1: n ints] [list 2: n ints] [global scratch of the class-2 CTAs]
+    const size_t list_bytes = (((size_t)n_cells * sizeof(int32_t)) + 255) & ~(size_t)255;
+    int rc = ws_reserve(h, h->ws_crop_scratch, 256 + 2 * list_bytes + per_cta * huge_ctas);
     if (rc) return rc;
+    unsigned char* wsb = (unsigned char*)h->ws_crop_scratch.p;
+    int32_t* cls_counts = (int32_t*)wsb;
+    int32_t* list1 = (int32_t*)(wsb + 256);
+    int32_t* list2 = (int32_t*)(wsb + 256 + list_bytes);
+    unsigned char* gscratch = wsb + 256 + 2 * list_bytes;
+    CIA_CUDA(cudaMemsetAsync(cls_counts, 0, 256, s));
+    {
+        int cb = (n_cells + 255) / 256;
+        if (cb > h->num_sms * 4) cb = h->num_sms * 4;
+        crop_classify_kernel<<<cb, 256, 0, s>>>(cells, n_cells, n_cells_dev, lo_bytes, hi_bytes,
+                                                cls_counts, list1, list2);
+        CIA_LAUNCH_CHECK();
+    }
     int g0 = h->num_sms * 2; if (g0 > n_cells) g0 = n_cells;
     int g1 = h->num_sms;     if (g1 > n_cells) g1 = n_cells;
     int g2 = huge_ctas;      if (g2 > n_cells) g2 = n_cells;
     crop_clahe_resize_kernel<<<g0, K2_THREADS, lo_bytes, s>>>(
         images, H, W, cells, n_cells, n_cells_dev, p->clip_limit, crops32, crops64, 0, lo_bytes,
-        hi_bytes, nullptr, 0, h->status_dev, levels_out, level_offsets);
+        hi_bytes, nullptr, 0, h->status_dev, levels_out, level_offsets, nullptr, nullptr);
     CIA_LAUNCH_CHECK();
     crop_clahe_resize_kernel<<<g1, K2_THREADS, hi_bytes, s>>>(
         images, H, W, cells, n_cells, n_cells_dev, p->clip_limit, crops32, crops64, 1, lo_bytes,
-        hi_bytes, nullptr, 0, h->status_dev, levels_out, level_offsets);
+        hi_bytes, nullptr, 0, h->status_dev, levels_out, level_offsets, list1, cls_counts + 0);
     CIA_LAUNCH_CHECK();
     crop_clahe_resize_kernel<<<g2, K2_THREADS, 0, s>>>(
         images, H, W, cells, n_cells, n_cells_dev, p->clip_limit, crops32, crops64, 2, lo_bytes,
-        hi_bytes, (unsigned char*)h->ws_crop_scratch.p, per_cta, h->status_dev, levels_out, level_offsets);
+        hi_bytes, gscratch, per_cta, h->status_dev, levels_out, level_offsets, list2, cls_counts + 1);
     CIA_LAUNCH_CHECK();
     return CIA_OK;
 }
