@@ -28,6 +28,20 @@ struct Geom {
     int h, w, kh, kw, ntr, ntc, npix, clim;
 };
 
+// ceil(2^32 / s) for s = 2..256: floor(n / s) == umulhi(n, magic[s]) exactly for n < 2^16
+// (the error term n * (magic * s - 2^32) stays below 2^32).  Replaces the generic integer
+// divisions of the redistribution loop, whose operands are warp-uniform and <= 256.
+constexpr int MAGIC_N = 256;
+struct MagicTab { uint32_t v[MAGIC_N + 1]; };
+constexpr MagicTab make_magic() {
+    MagicTab t{};
+    t.v[0] = 0; t.v[1] = 0;
+    for (int s = 2; s <= MAGIC_N; ++s) t.v[s] = 0xFFFFFFFFu / (uint32_t)s + 1u;
+    return t;
+}
+__constant__ MagicTab k_magic = make_magic();
+constexpr int MAPTAB_N = 1024;         // entries of the per-cell count -> level table (2 KB)
+
 __device__ __forceinline__ int reflect_idx(int i, int n) {   // numpy 'reflect'
     if (n == 1) return 0;
     while (i < 0 || i >= n) i = i < 0 ? -i : 2 * (n - 1) - i;
@@ -65,11 +79,14 @@ __host__ __device__ inline size_t cell_bytes(int h, int w, int ntr, int ntc) {
 // uses one reciprocal per iteration (exact for b < 256), the prefix sum is 7 local adds + one
 // warp scan, the 8 uint16 map entries of a lane leave as one 16-byte store.
 __device__ __forceinline__ void clip_and_map(int (&hv)[8], int clim, double scale, int lane,
-                                             uint16_t* __restrict__ map_out) {
+                                             uint16_t* __restrict__ map_out,
+                                             const uint16_t* __restrict__ level_tab) {
     int ex = 0;
 #pragma unroll
-    for (int m = 0; m < 8; ++m)
-        if (hv[m] > clim) { ex += hv[m] - clim; hv[m] = clim; }
+    for (int m = 0; m < 8; ++m) {
+        const int c = min(hv[m], clim);
+        ex += hv[m] - c; hv[m] = c;
+    }
     ex = __reduce_add_sync(0xffffffffu, ex);          // REDUX: one instruction instead of a 5-step shuffle tree
     if (ex > 0) {
         const int incr = ex / NBINS;
@@ -100,9 +117,10 @@ __device__ __forceinline__ void clip_and_map(int (&hv)[8], int clim, double scal
                 // count of under-limit bins over the warp
                 const int cnt = __reduce_add_sync(0xffffffffu, __popc(under));
                 if (cnt == 0) { stuck = true; break; }   // nothing can move any more
-                int step = cnt / ex;
-                if (step < 1) step = 1;
-                const unsigned magic = 0xFFFFFFFFu / (unsigned)step + 1u;   // ceil(2^32 / step)
+                // step = max(cnt / ex, 1) with cnt <= 256: table reciprocal instead of a division
+                int step = 1;
+                if (ex <= cnt) step = ex == 1 ? cnt : (int)__umulhi((unsigned)cnt, k_magic.v[ex]);
+                const unsigned magic = k_magic.v[step];                     // ceil(2^32 / step), step <= 256
                 int moved = 0;
 #pragma unroll
                 for (int m = 0; m < 8; ++m) {
@@ -134,11 +152,18 @@ __device__ __forceinline__ void clip_and_map(int (&hv)[8], int clim, double scal
     }
     const int base = run - pre[7];
     __align__(16) uint16_t mv16[8];
+    if (level_tab) {
+        // the level depends on the cumulative count only: looked up in the per-cell table built
+        // with the very expression of the other branch
 #pragma unroll
-    for (int m = 0; m < 8; ++m) {
-        // clip after the truncation (same result: both are monotone; the product stays far below 2^31)
-        const int mv = (int)__dmul_rn((double)(base + pre[m]), scale);
-        mv16[m] = (uint16_t)min(mv, 16383);
+        for (int m = 0; m < 8; ++m) mv16[m] = level_tab[base + pre[m]];
+    } else {
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            // clip after the truncation (same result: both are monotone; the product stays far below 2^31)
+            const int mv = (int)__dmul_rn((double)(base + pre[m]), scale);
+            mv16[m] = (uint16_t)min(mv, 16383);
+        }
     }
     *reinterpret_cast<uint4*>(map_out + 8 * lane) = *reinterpret_cast<const uint4*>(mv16);
 }
@@ -270,23 +295,44 @@ crop_clahe_resize_kernel(const uint16_t* __restrict__ images, int H, int W,
                 bins[i] = (uint8_t)(q / BIN_SIZE);
             }
         }
-        __syncthreads();
 
         // ---- C: per-tile histogram -> clipped mapping ----
         const int ntiles = g.ntr * g.ntc;
         const double map_scale = __ddiv_rn(16383.0, (double)g.npix);
         const unsigned kw_magic = 0xFFFFFFFFu / (unsigned)g.kw + 1u;       // p / kw for p < 2^16 (npix <= 128*128)
+        // count -> level table (ctab_s is free until stage D).  A tile's counts sum to npix plus at
+        // most one redistribution pass of overshoot (< 256), so npix + 256 entries cover every
+        // cumulative count; larger tiles convert per bin.
+        uint16_t* level_tab = nullptr;
+        if (g.npix + NBINS <= MAPTAB_N) {
+            level_tab = reinterpret_cast<uint16_t*>(&ctab_s[0][0]);
+            for (int c = tid; c < g.npix + NBINS; c += K2_THREADS)
+                level_tab[c] = (uint16_t)min((int)__dmul_rn((double)c, map_scale), 16383);
+        }
+        __syncthreads();
         for (int t = wid; t < ntiles; t += K2_WARPS) {
-            const int ti = t / g.ntc, tj = t - ti * g.ntc;
+            // ntr, ntc <= 16 here only matters for speed: t / ntc via the reciprocal table
+            const int ti = g.ntc == 1 ? t : (g.ntc <= MAGIC_N ? (int)__umulhi((unsigned)t, k_magic.v[g.ntc]) : t / g.ntc);
+            const int tj = t - ti * g.ntc;
             uint32_t* hs = hist_s[wid];
             reinterpret_cast<uint4*>(hs)[2 * lane] = make_uint4(0, 0, 0, 0);
             reinterpret_cast<uint4*>(hs)[2 * lane + 1] = make_uint4(0, 0, 0, 0);
             __syncwarp();
-            for (int p = lane; p < g.npix; p += 32) {
-                const int a = (g.kw == 1) ? p : (int)__umulhi((unsigned)p, kw_magic), b = p - a * g.kw;
-                const int y = reflect_idx(ti * g.kh + a, g.h);
-                const int x = reflect_idx(tj * g.kw + b, g.w);
-                atomicAdd(&hs[bins[y * g.w + x]], 1u);
+            const int y0 = ti * g.kh, x0 = tj * g.kw;
+            if (y0 + g.kh <= g.h && x0 + g.kw <= g.w) {
+                // interior tile: no padding, no reflection
+                const uint8_t* bt = bins + y0 * g.w + x0;
+                for (int p = lane; p < g.npix; p += 32) {
+                    const int a = (g.kw == 1) ? p : (int)__umulhi((unsigned)p, kw_magic), b = p - a * g.kw;
+                    atomicAdd(&hs[bt[a * g.w + b]], 1u);
+                }
+            } else {
+                for (int p = lane; p < g.npix; p += 32) {
+                    const int a = (g.kw == 1) ? p : (int)__umulhi((unsigned)p, kw_magic), b = p - a * g.kw;
+                    const int y = reflect_idx(y0 + a, g.h);
+                    const int x = reflect_idx(x0 + b, g.w);
+                    atomicAdd(&hs[bins[y * g.w + x]], 1u);
+                }
             }
             __syncwarp();
             int hv[8];
@@ -297,7 +343,7 @@ crop_clahe_resize_kernel(const uint16_t* __restrict__ images, int H, int W,
                 hv[4] = (int)h1.x; hv[5] = (int)h1.y; hv[6] = (int)h1.z; hv[7] = (int)h1.w;
             }
             __syncwarp();
-            clip_and_map(hv, g.clim, map_scale, lane, maps + (size_t)t * NBINS);
+            clip_and_map(hv, g.clim, map_scale, lane, maps + (size_t)t * NBINS, level_tab);
         }
         __syncthreads();
 
@@ -389,10 +435,11 @@ crop_clahe_resize_kernel(const uint16_t* __restrict__ images, int H, int W,
         const double den_rcp = degenerate ? 0.0 : __drcp_rn(den);
         auto value = [&](int y, int x) -> double {
             const double r = (double)rimg[y * g.w + x];
-            if (degenerate) return fmin(fmax(r, 0.0), 1.0);
+            // degenerate (constant) image: every pixel equals rmn, i.e. clip(rmn, 0, 1) = lo
             const double a = r - (double)rmn;
             const double q0 = __dmul_rn(a, den_rcp);
-            return __fma_rn(__fma_rn(-q0, den, a), den_rcp, q0);
+            const double q = __fma_rn(__fma_rn(-q0, den, a), den_rcp, q0);
+            return degenerate ? lo : q;
         };
 
         // ---- F: rows: (zoom o gaussian) along axis 0 -> T[64][w] ----
@@ -437,9 +484,13 @@ crop_clahe_resize_kernel(const uint16_t* __restrict__ images, int H, int W,
                 }
             }
             double o = (1.0 - t) * v[0] + t * v[1];
-            o = fmin(fmax(o, lo), hi);
-            crops32[(size_t)cell * 4096 + i] = (float)o;          // det:122 rounding
-            if (crops64) crops64[(size_t)cell * 4096 + i] = o;
+            if (crops64) {
+                o = fmin(fmax(o, lo), hi);
+                crops64[(size_t)cell * 4096 + i] = o;
+            }
+            // det:122 rounding; lo and hi are 0 or 1, exact in fp32, and rounding is monotone, so
+            // clipping after the conversion equals converting the clipped value
+            crops32[(size_t)cell * 4096 + i] = fminf(fmaxf((float)o, (float)lo), (float)hi);
         }
         __syncthreads();
     }
