@@ -70,7 +70,7 @@ def main():
     def rep(name, got, want):
         d = np.abs(got - want)
         print(f"{name:6s} max|d| {d.max():.3e}  rel-to-max {d.max() / max(np.abs(want).max(), 1e-30):.3e}  "
-              f"mean|d| {d.mean():.3e}  mean d {np.mean(got - want):+.3e}  |ref|max {np.abs(want).max():.3f}")
+              f"mean|d| {d.mean():.3e}  mean d {np.mean(got - want):+.3e} (rel {np.mean(got - want) / max(np.abs(want).mean(), 1e-30):+.2e})  |ref|max {np.abs(want).max():.3f}")
 
     a1 = planar_to_nhwc(bufs["A1h"], n, 4, 32)
     rep("A1 hi", a1, ref[0])
