@@ -159,6 +159,9 @@ struct Cfg {
     static constexpr int W_B = 9 * NCH * COUT * 16;
     static constexpr int PARTS = NPASS > 1 ? 2 : 1;
     static constexpr int SMEM_B = PARTS * (REGION_B + W_B);
+    // one CTA per SM, single pass, no pooling phases: a ninth warp issues the MMAs
+    static constexpr bool DED_ISSUER = NPASS == 1 && !POOL && EPI != EPI_FINAL && SMEM_B > 100 * 1024;
+    static constexpr int THREADS = TCT + (DED_ISSUER ? 32 : 0);
 };
 
 // Stage the zero-padded input block of one unit into shared memory (pool layers: columns
@@ -213,7 +216,7 @@ __device__ __forceinline__ void stage_block(const __half* __restrict__ in_hi, co
 }
 
 template <int CIN, int COUT, int R, int EPI, int NPASS, bool UPSIN>
-__global__ void __launch_bounds__(TCT, (Cfg<CIN, COUT, R, EPI, NPASS>::SMEM_B > 100 * 1024) ? 1 : 2)
+__global__ void __launch_bounds__(Cfg<CIN, COUT, R, EPI, NPASS>::THREADS, (Cfg<CIN, COUT, R, EPI, NPASS>::SMEM_B > 100 * 1024) ? 1 : 2)
 conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo,
                const uint4* __restrict__ w_hi, const uint4* __restrict__ w_lo, float inv_scale,
                const float* __restrict__ bias, const float* __restrict__ bn_s,
@@ -237,7 +240,7 @@ conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_l
     const int n_units = n * C::UNITS_PER_CELL;
 
     if (warp == 0) tmem_alloc(&tmem_base_s, C::TMEM_COLS);
-    constexpr int NISS = C::TILES;           // issuing warps (TILES <= 4 <= warps)
+    constexpr int NISS = C::DED_ISSUER ? 1 : C::TILES;           // issuing warps (TILES <= 4 <= warps)
     if (tid == 32) { mbar_init(&bar[0], NISS); mbar_init(&bar[1], NISS); fence_barrier_init(); }
     // weights: linear copy of the prepared UMMA images
     for (int i = tid; i < C::W_B / 16; i += TCT) {
@@ -264,7 +267,7 @@ conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_l
         for (int j = 0; j < S_IT; ++j) {
             const int idx = tid + j * TCT;
             s_dst[j] = 0xFFFFFFFFu; s_crc[j] = 0;
-            if (idx < S_N) {
+            if (idx < S_N && tid < TCT) {
                 const int c = idx / (C::FILL_ROWS * S_COLS);
                 const int rem = idx - c * (C::FILL_ROWS * S_COLS);
                 const int ry = rem / S_COLS, rc = rem - ry * S_COLS;
@@ -299,6 +302,31 @@ conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_l
     // MMA issue: one lane of one warp PER TILE (a single thread sustains only ~one tcgen05.mma per
     // 60 cycles; the tiles' accumulators are independent); each commits to the buffer's barrier
     auto issue_mmas = [&](uint32_t tbuf) {
+        if (C::DED_ISSUER) {
+            // one extra warp issues for all tiles (an N = 128 MMA takes longer than the ~60 cycles a single
+            // thread needs per issue; two issuing warps measured slower): the eight worker warps go straight
+            // to their epilogue instead of two of them first spending the whole MMA time inside the issue loop
+            if (lane == 0 && warp == TCT / 32) {
+                tc_fence_after();
+                const uint64_t ad0 = make_smem_desc(smem_u32(a_part[0]), C::CHUNK_B, C::SBO_A);
+                const uint64_t bd0 = make_smem_desc(smem_u32(w_part[0]), COUT * 16, 128);
+#pragma unroll
+                for (int tap = 0; tap < 9; ++tap) {
+                    const int dy = tap / 3, dx = tap % 3;
+#pragma unroll
+                    for (int s = 0; s < CIN / 16; ++s)
+#pragma unroll
+                        for (int t = 0; t < C::TILES; ++t) {
+                            const uint64_t ad = ad0 + (uint64_t)((t * 8 * 16 + dx * 16 + dy * C::ROW_B + 2 * s * C::CHUNK_B) >> 4);
+                            const uint64_t bd = bd0 + (uint64_t)(((tap * C::NCH + 2 * s) * COUT * 16) >> 4);
+                            umma_f16(tmem_base + tbuf * C::TBUF_COLS + (uint32_t)(t * COUT), ad, bd, IDESC,
+                                     (tap == 0 && s == 0) ? 0u : 1u);
+                        }
+                }
+                umma_commit(&bar[tbuf]);
+            }
+            return;
+        }
         if (lane == 0 && warp < NISS) {
             tc_fence_after();
             const int t = warp, py = t >> 1, px = t & 1;
@@ -369,6 +397,7 @@ conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_l
         }
 
         // ---- epilogue: TMEM -> registers -> bias/ReLU/BN (-> pool) -> global ----
+        if (C::DED_ISSUER && warp >= TCT / 32) continue;     // the issuing warp has no epilogue share
         const int q = warp & 3, half_sel = warp >> 2;
         const int r = 32 * q + lane;                   // MMA row = TMEM lane
         const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * q) << 16) + tbuf * C::TBUF_COLS;
@@ -1549,7 +1578,7 @@ int launch_tc(cia_ctx* h, const CaeWeights& w, int layer, const __half* in_hi, c
     int grid = chunk * C::UNITS_PER_CELL;
     const int cap = h->num_sms * (C::SMEM_B > 100 * 1024 ? 1 : 2);
     if (grid > cap) grid = cap;
-    kern<<<grid, TCT, C::SMEM_B, s>>>(in_hi, in_lo, (const uint4*)w.tc_w[layer][0], (const uint4*)w.tc_w[layer][1],
+    kern<<<grid, C::THREADS, C::SMEM_B, s>>>(in_hi, in_lo, (const uint4*)w.tc_w[layer][0], (const uint4*)w.tc_w[layer][1],
                                       w.tc_inv_scale[layer], w.bias[layer], w.bn_scale[layer], w.bn_shift[layer],
                                       out_hi, out_lo, feat, crops, mse, mae, n, n_dev, cell0, chunk);
     CIA_LAUNCH_CHECK();
@@ -1858,6 +1887,7 @@ int k_cae_forward_tc(cia_ctx* h, const float* crops, int n, const int32_t* n_dev
             static const int l2_g = [] { const char* e = getenv("CIA_L2_TAPS_PER_FLUSH"); return e ? atoi(e) : 3; }();
             if (l2_g == 0) rc = launch_tc_acc<32, 64, 32, 1>(h, ae, 1, a1h, a1l, a2h, a2l, a2f, n, n_dev, c0, chunk, s);
             else if (l2_g == 1) rc = launch_tc_acc2<32, 64, 32, 1>(h, ae, 1, A1h, A1l, CH, a2h, a2l, a2f, n, n_dev, c0, chunk, s);
+            else if (l2_g == 9) rc = launch_tc_acc2<32, 64, 32, 9>(h, ae, 1, A1h, A1l, CH, a2h, a2l, a2f, n, n_dev, c0, chunk, s);
             else if (l2_g == 2) rc = launch_tc_acc2<32, 64, 32, 2>(h, ae, 1, A1h, A1l, CH, a2h, a2l, a2f, n, n_dev, c0, chunk, s);
             else rc = launch_tc_acc2<32, 64, 32, 3>(h, ae, 1, A1h, A1l, CH, a2h, a2l, a2f, n, n_dev, c0, chunk, s);
             if (rc) return rc;
