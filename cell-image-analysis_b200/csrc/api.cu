@@ -42,7 +42,7 @@ int cia_create(int device, cia_handle* out) {
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) { delete h; return CIA_E_CUDA; }
     cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->num_sms = prop.multiProcessorCount;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) { h->num_sms = prop.multiProcessorCount; h->max_smem_optin = (int)prop.sharedMemPerBlockOptin; }
     if (cudaMalloc(&h->status_dev, sizeof(int32_t)) != cudaSuccess ||
         cudaMemset(h->status_dev, 0, sizeof(int32_t)) != cudaSuccess ||
         cudaMallocHost(&h->status_host, sizeof(int32_t)) != cudaSuccess ||
@@ -74,9 +74,9 @@ int cia_destroy(cia_handle h) {
     cudaDeviceSynchronize();
     free_cae(h->cae[0]); free_cae(h->cae[1]);
     cudaFree(h->sp.center); cudaFree(h->sp.scale); cudaFree(h->sp.comp_t); cudaFree(h->sp.comp_pad); cudaFree(h->sp.offset);
-    for (int i = 0; i < 2; ++i) { cudaFree(h->svm[i].sv_t); cudaFree(h->svm[i].coef); }
+    for (int i = 0; i < 2; ++i) { cudaFree(h->svm[i].sv_t); cudaFree(h->svm[i].coef); cudaFree(h->svm[i].sv_pad); cudaFree(h->svm[i].gsn); }
     Workspace* ws[] = {&h->ws_flags, &h->ws_act, &h->ws_crop_scratch, &h->ws_pipe, &h->ws_feat,
-                       &h->ws_misc, &h->ws_stage};
+                       &h->ws_misc, &h->ws_stage, &h->ws_svm};
     for (Workspace* w : ws) cudaFree(w->p);
     cudaFree(h->status_dev);
     cudaFreeHost(h->status_host);
@@ -96,7 +96,7 @@ int64_t cia_launch_count(cia_handle h) { return h ? h->launches : 0; }
 int cia_debug_copy_workspace(cia_handle h, int ws_id, size_t offset, void* dst_host, size_t bytes) {
     if (!h) return bad_handle();
     Workspace* ws[] = {&h->ws_flags, &h->ws_act, &h->ws_crop_scratch, &h->ws_pipe, &h->ws_feat,
-                       &h->ws_misc, &h->ws_stage};
+                       &h->ws_misc, &h->ws_stage, &h->ws_svm};
     if (ws_id < 0 || ws_id >= 7 || !dst_host || offset + bytes > ws[ws_id]->cap) {
         h->err = "cia_debug_copy_workspace: bad argument";
         return CIA_E_ARG;
@@ -196,15 +196,26 @@ int cia_load_svm(cia_handle h, int which, int n_sv, int dim, const double* sv, c
     SvmModel& m = h->svm[which];
     m.loaded = false;
     const int pad = (n_sv + 255) / 256 * 256;
+    const int dpad = (dim + 15) / 16 * 16;
     std::vector<double> t((size_t)dim * pad, 0.0), a((size_t)pad, 0.0);
+    std::vector<double> r((size_t)pad * dpad, 0.0), g((size_t)pad, 0.0);   // row-major copy + -gamma*||s||^2
     for (int i = 0; i < n_sv; ++i) {
         a[i] = coef[i];
-        for (int d = 0; d < dim; ++d) t[(size_t)d * pad + i] = sv[(size_t)i * dim + d];
+        double ss = 0.0;
+        for (int d = 0; d < dim; ++d) {
+            const double v = sv[(size_t)i * dim + d];
+            t[(size_t)d * pad + i] = v;
+            r[(size_t)i * dpad + d] = v;
+            ss += v * v;
+        }
+        g[i] = -gamma * ss;
     }
     int rc;
     if ((rc = upload(h, &m.sv_t, t.data(), t.size()))) return rc;
     if ((rc = upload(h, &m.coef, a.data(), a.size()))) return rc;
-    m.n_sv = n_sv; m.n_sv_pad = pad; m.dim = dim; m.gamma = gamma; m.rho = rho;
+    if ((rc = upload(h, &m.sv_pad, r.data(), r.size()))) return rc;
+    if ((rc = upload(h, &m.gsn, g.data(), g.size()))) return rc;
+    m.n_sv = n_sv; m.n_sv_pad = pad; m.dim = dim; m.dim_pad = dpad; m.gamma = gamma; m.rho = rho;
     m.loaded = true;
     return CIA_OK;
 }

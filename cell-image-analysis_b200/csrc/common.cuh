@@ -36,7 +36,9 @@ struct SvmModel {
     int n_sv = 0, dim = 0;
     double* sv_t = nullptr;   // [dim, n_sv_pad] transposed for coalesced reads
     double* coef = nullptr;   // [n_sv_pad] (zero padded)
-    int n_sv_pad = 0;
+    double* sv_pad = nullptr; // [n_sv_pad, dim_pad] row-major, zero padded (GEMM-form kernel)
+    double* gsn = nullptr;    // [n_sv_pad] -gamma * ||s_i||^2
+    int n_sv_pad = 0, dim_pad = 0;
     double gamma = 0, rho = 0;
 };
 
@@ -60,6 +62,7 @@ struct Workspace {
 struct cia_ctx {
     int device = 0;
     int num_sms = CIA_NUM_SMS_DEFAULT;
+    int max_smem_optin = 227 * 1024;
     std::string err;
     CaeWeights cae[2];
     ScalerPca sp;
@@ -69,7 +72,7 @@ struct cia_ctx {
     int64_t launches = 0;
     std::set<const void*> attr_done;       // kernels whose opt-in smem attribute is set on THIS device
     // grow-only workspaces
-    Workspace ws_flags, ws_act, ws_crop_scratch, ws_pipe, ws_feat, ws_misc, ws_stage;
+    Workspace ws_flags, ws_act, ws_crop_scratch, ws_pipe, ws_feat, ws_misc, ws_stage, ws_svm;
     cudaEvent_t ev = nullptr;
     // side stream: the exact-fp32 encoder pass (FMA pipe) overlaps the tensor-core autoencoder
     cudaStream_t side = nullptr;

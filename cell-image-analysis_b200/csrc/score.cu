@@ -1,10 +1,13 @@
 // score.cu -- K4 RobustScaler -> PCA projection, K5 RBF one-class SVM decision for
-// both detectors (exact fp64 direct-difference path), K6 per-strain accumulators.
+// both detectors (GEMM form on the fp64 tensor pipe with the RBF/dual-coef reduction fused into
+// the tile epilogue; the direct-difference fp64 kernel stays as the wide-D fallback and A/B
+// anchor), K6 per-strain accumulators.
 //
 // Replaces improved_detection.py:134-135 (scaler.transform, pca.transform), :138-142
 // (predict + decision_function of the two OneClassSVMs; libsvm k_function RBF,
 // sklearn/svm/src/libsvm/svm.cpp:461-472, decision sum - rho, sign rule sum > 0) and
 // the reductions behind :151-152 and :202-211.
+#include <algorithm>
 #include "common.cuh"
 
 namespace {
@@ -288,6 +291,164 @@ svm_rbf_kernel(const double* __restrict__ z, int n_cells, const int32_t* __restr
     }
 }
 
+// ---- K5 in GEMM form on the fp64 tensor pipe ------------------------------------------------
+// ||z - s||^2 = ||z||^2 + ||s||^2 - 2 z.s : the z.s^T products of a 64-cell x 128-SV tile run as
+// mma.sync m8n8k4 f64 (same fragment layout as the projection kernel above), and the epilogue of
+// every tile is the fused RBF: arg = -gamma||z||^2 - gamma||s||^2 + 2 gamma z.s (clamped to <= 0),
+// part += coef * exp(arg), kept per thread for its two cell rows.  In fp64 the cancellation costs
+// ~1e-16 * (||z||^2 + ||s||^2) * gamma in the exponent, i.e. ~1e-13 in the decision (gate: 1e-9
+// against libsvm on the same input, tests/test_gpu_parity.py).  The direct-difference kernel above
+// issues a DADD and a DFMA per (cell, SV, dim) on the same fp64 pipe; this form needs one
+// multiply-add, so it halves the fp64 work (north_star: "one GEMM-form kernel with a fused
+// exp/dual-coef reduction").
+// Block = 16 warps: 4 cell groups (16 cells = 2 m8 tiles) x 4 SV groups (32 SVs = 4 n8 tiles).
+// The block's 64 z rows stay in shared memory for the whole launch ([64][DPAD+4], pitch = 4 mod 16
+// doubles -> a half-warp's 64-bit fragment loads hit 16 distinct bank pairs); the support vectors
+// stream through a cp.async double buffer in stages of 128 SVs x 16 dims (pitch 20 doubles).
+// sv_pad is the zero-padded row-major copy [n_sv rounded to 128][D rounded to 16]; gsn[i] =
+// -gamma * ||s_i||^2; padded rows have coef 0.
+constexpr int GT = 512;            // threads
+constexpr int GM = 64;             // cells per block
+constexpr int GN = 128;            // support vectors per tile
+constexpr int GK = 16;             // dims per stage
+constexpr int GSP = GK + 4;        // pitch of a staged SV row (doubles)
+
+__global__ void __launch_bounds__(GT, 2)
+svm_rbf_dmma_kernel(const double* __restrict__ z, int n_cells, const int32_t* __restrict__ n_dev, int D,
+                    int DPAD, const double* __restrict__ sv_pad, const double* __restrict__ coef,
+                    const double* __restrict__ gsn, int n_tiles, double gamma, double rho,
+                    double* __restrict__ dec, int8_t* __restrict__ pred, double* __restrict__ partial,
+                    int partial_pitch) {
+    extern __shared__ __align__(16) unsigned char svm_smem[];
+    const int ZP = DPAD + 4;
+    double* zs = reinterpret_cast<double*>(svm_smem);       // [GM][ZP]
+    double* sb = zs + GM * ZP;                              // [2][GN][GSP]
+    double* gzn = sb + 2 * GN * GSP;                        // [GM]  -gamma * ||z||^2
+    double* red = gzn + GM;                                 // [4][GM]
+    const int n = dev_count(n_cells, n_dev);
+    const int cell0 = blockIdx.x * GM;
+    if (cell0 >= n) return;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int gid = lane >> 2, tig = lane & 3;
+    const int mg = warp & 3, ng = warp >> 2;
+    const int nk = DPAD / GK;
+    // blockIdx.y owns a contiguous range of SV tiles (gridDim.y > 1 when a call has too few cell
+    // blocks to fill the SMs; the partial sums are added in a fixed order by svm_finalize_kernel)
+    const int tiles_per = (n_tiles + gridDim.y - 1) / gridDim.y;
+    const int tile_begin = blockIdx.y * tiles_per;
+    const int my_tiles = max(0, min(n_tiles, tile_begin + tiles_per) - tile_begin);
+    const int n_stages = my_tiles * nk;
+
+    auto issue_sv = [&](int stage, int buf) {               // GN rows x GK doubles as 16-byte chunks
+        const int tile = tile_begin + stage / nk, ks = stage % nk;
+        const double* src = sv_pad + (size_t)tile * GN * DPAD + ks * GK;
+        double* dst = sb + buf * GN * GSP;
+        for (int idx = tid; idx < GN * (GK / 2); idx += GT) {
+            const int r = idx / (GK / 2), c2 = idx - r * (GK / 2);
+            const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst + r * GSP + 2 * c2);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src + (size_t)r * DPAD + 2 * c2) : "memory");
+        }
+    };
+    if (n_stages > 0) issue_sv(0, 0);
+    // the block's z rows (zero padded) and their scaled squared norms: 4 rows per warp
+    for (int r = warp; r < GM; r += GT / 32) {
+        const int cell = cell0 + r;
+        double ss = 0.0;
+        for (int d = lane; d < DPAD; d += 32) {
+            const double v = (cell < n && d < D) ? z[(size_t)cell * D + d] : 0.0;
+            zs[r * ZP + d] = v;
+            ss = fma(v, v, ss);
+        }
+        ss = warp_sum(ss);
+        if (lane == 0) gzn[r] = -gamma * ss;
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+
+    const double g2 = 2.0 * gamma;
+    const double* za0 = zs + (mg * 16 + gid) * ZP + tig;
+    const double* za1 = za0 + 8 * ZP;
+    const double gz0 = gzn[mg * 16 + gid], gz1 = gzn[mg * 16 + 8 + gid];
+    double part0 = 0.0, part1 = 0.0;
+    double acc[2][4][2];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+
+    int tile = tile_begin, ks = 0;
+    for (int st = 0; st < n_stages; ++st) {
+        const int buf = st & 1;
+        if (st + 1 < n_stages) issue_sv(st + 1, buf ^ 1);
+        const double* bb = sb + buf * GN * GSP + (ng * 32 + gid) * GSP + tig;
+        const double* a0p = za0 + ks * GK;
+        const double* a1p = za1 + ks * GK;
+#pragma unroll
+        for (int k4 = 0; k4 < GK / 4; ++k4) {
+            const double a0 = a0p[k4 * 4];
+            const double a1 = a1p[k4 * 4];
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                const double b = bb[nt * 8 * GSP + k4 * 4];
+                dmma884(acc[0][nt], a0, b);
+                dmma884(acc[1][nt], a1, b);
+            }
+        }
+        if (++ks == nk) {
+            // fused RBF epilogue of this tile: acc[mt][nt][j] = z_cell . s_sv
+            const int sv0 = tile * GN + ng * 32 + 2 * tig;
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                const double2 cf = __ldg(reinterpret_cast<const double2*>(coef + sv0 + nt * 8));
+                const double2 gs = __ldg(reinterpret_cast<const double2*>(gsn + sv0 + nt * 8));
+                part0 = fma(cf.x, exp(fmin(fma(g2, acc[0][nt][0], gz0 + gs.x), 0.0)), part0);
+                part0 = fma(cf.y, exp(fmin(fma(g2, acc[0][nt][1], gz0 + gs.y), 0.0)), part0);
+                part1 = fma(cf.x, exp(fmin(fma(g2, acc[1][nt][0], gz1 + gs.x), 0.0)), part1);
+                part1 = fma(cf.y, exp(fmin(fma(g2, acc[1][nt][1], gz1 + gs.y), 0.0)), part1);
+                acc[0][nt][0] = acc[0][nt][1] = acc[1][nt][0] = acc[1][nt][1] = 0.0;
+            }
+            ks = 0;
+            ++tile;
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncthreads();
+    }
+    // the 4 lanes of a quad hold different SV columns of the same two cells; then the 4 SV groups
+    part0 += __shfl_xor_sync(0xffffffffu, part0, 1);
+    part0 += __shfl_xor_sync(0xffffffffu, part0, 2);
+    part1 += __shfl_xor_sync(0xffffffffu, part1, 1);
+    part1 += __shfl_xor_sync(0xffffffffu, part1, 2);
+    if (tig == 0) {
+        red[ng * GM + mg * 16 + gid] = part0;
+        red[ng * GM + mg * 16 + 8 + gid] = part1;
+    }
+    __syncthreads();
+    if (tid < GM && cell0 + tid < n) {
+        const double s = (red[tid] + red[GM + tid]) + (red[2 * GM + tid] + red[3 * GM + tid]);
+        if (partial) {
+            partial[(size_t)blockIdx.y * partial_pitch + cell0 + tid] = s;
+        } else {
+            dec[cell0 + tid] = s - rho;
+            pred[cell0 + tid] = s - rho > 0.0 ? 1 : -1;     // svm.cpp:2841
+        }
+    }
+}
+
+// dec = (sum of the SV-range partial sums, in range order) - rho
+__global__ void __launch_bounds__(256)
+svm_finalize_kernel(const double* __restrict__ partial, int partial_pitch, int splits, int n_cells,
+                    const int32_t* __restrict__ n_dev, double rho, double* __restrict__ dec,
+                    int8_t* __restrict__ pred) {
+    const int n = dev_count(n_cells, n_dev);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s = 0.0;
+    for (int k = 0; k < splits; ++k) s += partial[(size_t)k * partial_pitch + i];
+    s -= rho;
+    dec[i] = s;
+    pred[i] = s > 0.0 ? 1 : -1;
+}
+
 // K6: acc[strain] += {1, cons anomalous, mod anomalous, mse, mse^2, mae, mae^2, 0}
 __global__ void __launch_bounds__(256)
 strain_accumulate_kernel(const cia_cell* __restrict__ cells, int n_cells,
@@ -362,13 +523,40 @@ int k_svm_decision(cia_ctx* h, const float* features, int n, const int32_t* n_de
             sp.has_scale ? sp.scale : nullptr, sp.center_is_f32, sp.comp_pad, sp.offset, sp.f32_flow, z);
     }
     CIA_LAUNCH_CHECK();
+    static const bool direct_svm = getenv("CIA_SVM_DIRECT") != nullptr;   // A/B switch: CUDA-core direct-difference form
     for (int which = 0; which < 2; ++which) {
         const SvmModel& m = h->svm[which];
         if (m.dim != sp.C) { h->err = "svm dimension != pca components"; return CIA_E_STATE; }
-        const size_t sm2 = (size_t)SCELLS * m.dim * sizeof(double);
-        svm_rbf_kernel<<<(n + SCELLS - 1) / SCELLS, PT, sm2, s>>>(
-            z, n, n_dev, m.dim, m.sv_t, m.coef, m.n_sv, m.n_sv_pad, m.gamma, m.rho,
-            which == 0 ? dec_cons : dec_mod, which == 0 ? pred_cons : pred_mod);
+        const size_t sm3 = sizeof(double) * ((size_t)GM * (m.dim_pad + 4) + 2 * GN * GSP + GM + 4 * GM);
+        if (!direct_svm && sm3 <= (size_t)h->max_smem_optin) {
+            if (first_use(h, (const void*)svm_rbf_dmma_kernel))
+                CIA_CUDA(cudaFuncSetAttribute(svm_rbf_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
+            // fill the SMs: when the call has few cell blocks, split the SV tiles over blockIdx.y
+            const int bx = (n + GM - 1) / GM, n_tiles = (m.n_sv + GN - 1) / GN;
+            const int per_sm = sm3 * 2 + 4096 <= (size_t)h->max_smem_optin ? 2 : 1;
+            int splits = (h->num_sms * per_sm + bx - 1) / bx;
+            splits = std::max(1, std::min(splits, n_tiles / 4));     // at least 4 tiles per block
+            double* partial = nullptr;
+            if (splits > 1) {
+                int rc = ws_reserve(h, h->ws_svm, (size_t)splits * n * sizeof(double));
+                if (rc) return rc;
+                partial = (double*)h->ws_svm.p;
+            }
+            double* dec = which == 0 ? dec_cons : dec_mod;
+            int8_t* pred = which == 0 ? pred_cons : pred_mod;
+            svm_rbf_dmma_kernel<<<dim3(bx, splits), GT, sm3, s>>>(
+                z, n, n_dev, m.dim, m.dim_pad, m.sv_pad, m.coef, m.gsn, n_tiles, m.gamma, m.rho,
+                dec, pred, partial, n);
+            if (splits > 1) {
+                CIA_LAUNCH_CHECK();
+                svm_finalize_kernel<<<(n + 255) / 256, 256, 0, s>>>(partial, n, splits, n, n_dev, m.rho, dec, pred);
+            }
+        } else {   // very wide feature spaces (z tile does not fit) and the A/B switch
+            const size_t sm2 = (size_t)SCELLS * m.dim * sizeof(double);
+            svm_rbf_kernel<<<(n + SCELLS - 1) / SCELLS, PT, sm2, s>>>(
+                z, n, n_dev, m.dim, m.sv_t, m.coef, m.n_sv, m.n_sv_pad, m.gamma, m.rho,
+                which == 0 ? dec_cons : dec_mod, which == 0 ? pred_cons : pred_mod);
+        }
         CIA_LAUNCH_CHECK();
     }
     return CIA_OK;

@@ -1,0 +1,7 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
+timeout 300 python scratch/svm_time.py 2>&1 | tail -2
+CIA_SVM_DIRECT=1 timeout 300 python scratch/svm_time.py 2>&1 | tail -2
+timeout 600 python bench.py --no-cpu-baseline --steps 2 --warmup 3 2>/dev/null | python -c "
+import json,sys;d=json.loads(sys.stdin.read());print(d['value'],d['e2e']['value'],d['stages_ms_per_step'])"
