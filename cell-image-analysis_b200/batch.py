@@ -24,11 +24,19 @@ STAGES = ("scan", "gates", "crop", "cae", "svm", "accumulate")
 class BatchScreen:
     def __init__(self, engine, H: int, W: int, max_label: int, chunk_fields: int = 16,
                  n_strains: int = 1, cells_per_field_cap: int | None = None,
-                 label_transport: str = "rle", host_threads: int = 0):
+                 label_transport: str = "rle", host_threads: int = 0, rle_fraction: float = 1.0,
+                 scan_runs: bool = True):
         """``label_transport``: "rle" run-length encodes the int32 label fields on the host
-        cores (csrc/transport.cu) so that only the runs cross PCIe; "raw" copies them as is."""
+        cores (csrc/transport.cu) so that only the runs cross PCIe; "raw" copies them as is.
+        ``rle_fraction`` < 1 sends only that share of the chunks as runs and the rest raw (several
+        ranks sharing the host cores: the encoder and the PCIe link then work side by side).
+        ``scan_runs``: build the region table from the runs themselves (``cia_screen_fields_rle``);
+        False expands them to the dense field first (``cia_rle_expand``)."""
         assert label_transport in ("rle", "raw")
         self.label_transport, self.host_threads = label_transport, host_threads
+        self.rle_fraction = 1.0 if label_transport == "rle" and rle_fraction >= 1.0 else \
+            (0.0 if label_transport == "raw" else max(0.0, float(rle_fraction)))
+        self.scan_runs = scan_runs
         self.eng = engine
         self.H, self.W, self.max_label = H, W, max_label
         self.Fc = chunk_fields
@@ -124,7 +132,8 @@ class BatchScreen:
         for i in range(n_chunks):
             b = i & 1
             p0 = (i * self.Fc) % P
-            rle = self.label_transport == "rle"
+            f = self.rle_fraction
+            rle = self.label_transport == "rle" and int((i + 1) * f) > int(i * f)
             with torch.cuda.stream(self.copy):
                 self.copy.wait_event(S["done"][b])
                 S["img"][b].copy_(images_pinned[p0:p0 + self.Fc], non_blocking=True)
@@ -136,7 +145,10 @@ class BatchScreen:
                                      self.host_threads)
             with torch.cuda.stream(self.copy):
                 if rle:
-                    eng.rle_upload_expand(S["h_rle"][b], S["words"][b], S["d_rle"][b], S["lab"][b])
+                    if self.scan_runs:
+                        eng.rle_upload(S["h_rle"][b], S["words"][b], S["d_rle"][b])
+                    else:
+                        eng.rle_upload_expand(S["h_rle"][b], S["words"][b], S["d_rle"][b], S["lab"][b])
                     self.h2d_bytes += 2 * px + 4 * int(S["words"][b].sum())
                 else:
                     S["lab"][b].copy_(labels_pinned[p0:p0 + self.Fc], non_blocking=True)
@@ -147,7 +159,8 @@ class BatchScreen:
                 self.compute.wait_event(S["out_free"][b])       # chunk i-2's results have been read back
                 o = self.out[b]
                 st = None if strain_of_visit is None else strain_of_visit[i * self.Fc:(i + 1) * self.Fc]
-                eng.screen_fields(S["img"][b], S["lab"][b], self.max_label, o, field_strain=st, acc=self.acc)
+                eng.screen_fields(S["img"][b], S["lab"][b], self.max_label, o, field_strain=st, acc=self.acc,
+                                  rle_slots=S["d_rle"][b] if rle and self.scan_runs else None)
                 S["done"][b].record(self.compute)
                 S["out_ready"][b].record(self.compute)
             with torch.cuda.stream(self.d2h):

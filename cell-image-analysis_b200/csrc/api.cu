@@ -286,14 +286,18 @@ int cia_strain_accumulate(cia_handle h, const cia_cell* cells, int n_cells,
 }
 
 // ---- fused path ---------------------------------------------------------------
-int cia_screen_fields(cia_handle h, const uint16_t* images, const int32_t* labels, int n_fields,
+}  // extern "C"
+
+// labels (dense int32) or rle_slots (run-length transport format) -- exactly one is given
+static int screen_fields_impl(cia_handle h, const uint16_t* images, const int32_t* labels,
+                              const uint32_t* rle_slots, size_t slot_words, int n_fields,
                       int H, int W, int max_label, const cia_params* params, int precision,
                       cia_cell* cells, int cells_cap, int32_t* n_cells_dev,
                       int32_t* field_counts_dev, const cia_scores* scores, float* crops32,
                       float* features, const int32_t* field_strain, double* acc, int n_strains,
                       void* stream) {
     if (!h) return bad_handle();
-    if (!images || !labels || !params || !cells || !n_cells_dev || !scores) {
+    if (!images || (!labels && !rle_slots) || !params || !cells || !n_cells_dev || !scores) {
         h->err = "cia_screen_fields: null pointer";
         return CIA_E_ARG;
     }
@@ -316,7 +320,9 @@ int cia_screen_fields(cia_handle h, const uint16_t* images, const int32_t* label
         pe = &h->prof_ev[(size_t)(h->prof_used++) * CIA_PROF_MARKS];
 #define CIA_MARK(i) do { if (pe) CIA_CUDA(cudaEventRecord(pe[i], s)); } while (0)
     CIA_MARK(0);
-    if ((rc = k_label_scan(h, labels, n_fields, H, W, max_label, regions, s))) return rc;
+    if (labels) rc = k_label_scan(h, labels, n_fields, H, W, max_label, regions, s);
+    else rc = k_label_scan_rle(h, rle_slots, slot_words, n_fields, H, W, max_label, regions, s);
+    if (rc) return rc;
     CIA_MARK(1);
     if ((rc = k_filter(h, images, n_fields, H, W, max_label, regions, params, cells, cells_cap,
                        n_cells_dev, field_counts_dev, s))) return rc;
@@ -337,6 +343,39 @@ int cia_screen_fields(cia_handle h, const uint16_t* images, const int32_t* label
     CIA_MARK(6);
 #undef CIA_MARK
     return CIA_OK;
+}
+
+extern "C" {
+
+int cia_screen_fields(cia_handle h, const uint16_t* images, const int32_t* labels, int n_fields,
+                      int H, int W, int max_label, const cia_params* params, int precision,
+                      cia_cell* cells, int cells_cap, int32_t* n_cells_dev,
+                      int32_t* field_counts_dev, const cia_scores* scores, float* crops32,
+                      float* features, const int32_t* field_strain, double* acc, int n_strains,
+                      void* stream) {
+    if (h && !labels) { h->err = "cia_screen_fields: null pointer"; return CIA_E_ARG; }
+    return screen_fields_impl(h, images, labels, nullptr, 0, n_fields, H, W, max_label, params, precision,
+                              cells, cells_cap, n_cells_dev, field_counts_dev, scores, crops32, features,
+                              field_strain, acc, n_strains, stream);
+}
+
+int cia_screen_fields_rle(cia_handle h, const uint16_t* images, const uint32_t* rle_slots,
+                          size_t slot_words, int n_fields, int H, int W, int max_label,
+                          const cia_params* params, int precision, cia_cell* cells, int cells_cap,
+                          int32_t* n_cells_dev, int32_t* field_counts_dev, const cia_scores* scores,
+                          float* crops32, float* features, const int32_t* field_strain, double* acc,
+                          int n_strains, void* stream) {
+    if (h && !rle_slots) { h->err = "cia_screen_fields_rle: null pointer"; return CIA_E_ARG; }
+    return screen_fields_impl(h, images, nullptr, rle_slots, slot_words, n_fields, H, W, max_label, params,
+                              precision, cells, cells_cap, n_cells_dev, field_counts_dev, scores, crops32,
+                              features, field_strain, acc, n_strains, stream);
+}
+
+int cia_label_scan_rle(cia_handle h, const uint32_t* rle_slots, size_t slot_words, int n_fields, int H,
+                       int W, int max_label, cia_region* regions, void* stream) {
+    if (!h) return bad_handle();
+    if (!rle_slots || !regions) { h->err = "cia_label_scan_rle: null pointer"; return CIA_E_ARG; }
+    return k_label_scan_rle(h, rle_slots, slot_words, n_fields, H, W, max_label, regions, (cudaStream_t)stream);
 }
 
 int cia_profile_begin(cia_handle h, int max_records) {

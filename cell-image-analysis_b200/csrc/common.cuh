@@ -137,6 +137,8 @@ __device__ __forceinline__ T warp_sum(T v) {
 }
 
 // stage-level forward declarations (one per .cu)
+int k_label_scan_rle(cia_ctx* h, const uint32_t* slots, size_t slot_words, int n_fields, int H, int W,
+                     int max_label, cia_region* regions, cudaStream_t s);
 int k_label_scan(cia_ctx* h, const int32_t* labels, int n_fields, int H, int W, int max_label,
                  cia_region* regions, cudaStream_t s);
 int k_filter(cia_ctx* h, const uint16_t* images, int n_fields, int H, int W, int max_label,

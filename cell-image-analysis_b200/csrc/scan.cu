@@ -102,6 +102,56 @@ label_scan_kernel(const int32_t* __restrict__ labels, int n_fields, int H, int W
     }
 }
 
+// K1 on run-length encoded label fields (the transport format of transport.cu): regionprops'
+// bbox / area / raw moments are sums over pixels, and over a run (row r, columns [x0, x1), one
+// label) they have closed forms, so the region table comes straight from the runs -- the dense
+// int32 field (16.8 MB per 2048^2 field) is neither rebuilt in HBM nor read back.  One thread per
+// run (grid-stride over the field's run list), row found by binary search in row_off.  Same
+// table, same complement convention and same label check as label_scan_kernel: bit-identical.
+__global__ void __launch_bounds__(SCAN_THREADS)
+label_scan_rle_kernel(const uint32_t* __restrict__ slots, size_t slot_words, int H, int W, int max_label,
+                      cia_region* __restrict__ regions, int32_t* status) {
+    const int f = blockIdx.y;
+    const uint32_t* slot = slots + (size_t)f * slot_words;
+    const uint32_t* runs = slot + ((H + 2) & ~1);     // (x0, label) word pairs; 4-byte loads: a caller's
+                                                      // slot stride may be odd
+    const uint32_t n_runs = __ldg(slot + H);
+    const size_t cap_runs = (slot_words - (size_t)((H + 2) & ~1)) / 2;
+    if (n_runs > cap_runs) { if (threadIdx.x == 0 && blockIdx.x == 0) raise_status(status, CIA_E_ARG); return; }
+    cia_region* tab = regions + (size_t)f * max_label;
+    for (uint32_t j = blockIdx.x * SCAN_THREADS + threadIdx.x; j < n_runs; j += gridDim.x * SCAN_THREADS) {
+        const int l = (int)__ldg(runs + 2 * (size_t)j + 1);
+        if (l == 0) continue;
+        if (l < 0 || l > max_label) { raise_status(status, CIA_E_LABEL); continue; }
+        int lo = 0, hi = H;                                   // largest r with row_off[r] <= j
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (__ldg(slot + mid) <= j) lo = mid; else hi = mid;
+        }
+        const int r = lo;
+        const int x0 = (int)__ldg(runs + 2 * (size_t)j);
+        int x1 = W;
+        if (j + 1 < __ldg(slot + r + 1)) x1 = min(W, (int)__ldg(runs + 2 * (size_t)j + 2));
+        if (x0 < 0 || x1 <= x0) continue;
+        const long long a = x0, b = x1;
+        const unsigned long long cnt = (unsigned long long)(b - a);
+        const unsigned long long sc = (unsigned long long)((a + b - 1) * (b - a) / 2);
+        const unsigned long long sc2 = (unsigned long long)(((b - 1) * b * (2 * b - 1) - (a - 1) * a * (2 * a - 1)) / 6);
+        const unsigned long long rr = (unsigned long long)r;
+        cia_region* R = tab + (l - 1);
+        atomicAdd(&R->area, (uint32_t)cnt);
+        atomicMax(&R->minr, H - r);
+        atomicMax(&R->maxr, r + 1);
+        atomicMax(&R->minc, W - x0);
+        atomicMax(&R->maxc, x1);
+        atomicAdd((unsigned long long*)&R->m10, rr * cnt);
+        atomicAdd((unsigned long long*)&R->m01, sc);
+        atomicAdd((unsigned long long*)&R->m20, rr * rr * cnt);
+        atomicAdd((unsigned long long*)&R->m02, sc2);
+        atomicAdd((unsigned long long*)&R->m11, rr * sc);
+    }
+}
+
 __global__ void finalize_regions_kernel(cia_region* regions, long long n_slots, int H, int W) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_slots) return;
@@ -278,6 +328,27 @@ int k_label_scan(cia_ctx* h, const int32_t* labels, int n_fields, int H, int W, 
     if (bx < 1) bx = 1;
     label_scan_kernel<<<dim3(bx, n_fields), SCAN_THREADS, 0, s>>>(labels, n_fields, H, W, max_label,
                                                                  regions, h->status_dev, vec_ok);
+    CIA_LAUNCH_CHECK();
+    finalize_regions_kernel<<<(int)((n_slots + 255) / 256), 256, 0, s>>>(regions, (long long)n_slots, H, W);
+    CIA_LAUNCH_CHECK();
+    return CIA_OK;
+}
+
+int k_label_scan_rle(cia_ctx* h, const uint32_t* slots, size_t slot_words, int n_fields, int H, int W,
+                     int max_label, cia_region* regions, cudaStream_t s) {
+    if (n_fields <= 0 || H <= 0 || W <= 0 || max_label <= 0 || H > 32767 || W > 32767 ||
+        slot_words < (size_t)((H + 2) & ~1) + 2) {
+        h->err = "cia_label_scan_rle: bad shape (need 0 < H,W <= 32767, max_label > 0, slot_words >= H + 4)";
+        return CIA_E_ARG;
+    }
+    if (n_fields > 65535) { h->err = "cia_label_scan_rle: at most 65535 fields per call"; return CIA_E_ARG; }
+    const size_t n_slots = (size_t)n_fields * max_label;
+    CIA_CUDA(cudaMemsetAsync(regions, 0, n_slots * sizeof(cia_region), s));
+    int bx = (h->num_sms * 8 + n_fields - 1) / n_fields;
+    if (bx > 128) bx = 128;
+    if (bx < 1) bx = 1;
+    label_scan_rle_kernel<<<dim3(bx, n_fields), SCAN_THREADS, 0, s>>>(slots, slot_words, H, W, max_label,
+                                                                     regions, h->status_dev);
     CIA_LAUNCH_CHECK();
     finalize_regions_kernel<<<(int)((n_slots + 255) / 256), 256, 0, s>>>(regions, (long long)n_slots, H, W);
     CIA_LAUNCH_CHECK();

@@ -190,6 +190,21 @@ class Engine:
         self._check(self.lib.cia_rle_expand(self.h, slots_dev.data_ptr(), F, sw, H, W, labels_dev.data_ptr(),
                                             self._stream()))
 
+    def rle_upload(self, slots_host: torch.Tensor, field_words: np.ndarray, slots_dev: torch.Tensor):
+        """Async: copy the used words of every slot (no expansion: ``label_scan_rle`` /
+        ``screen_fields(rle_slots=...)`` read the runs themselves)."""
+        F, sw = slots_host.shape
+        self._check(self.lib.cia_rle_upload(self.h, slots_host.data_ptr(), F, sw, field_words.ctypes.data,
+                                            slots_dev.data_ptr(), self._stream()))
+
+    def label_scan_rle(self, slots_dev: torch.Tensor, H: int, W: int, max_label: int) -> torch.Tensor:
+        """``label_scan`` from run-length encoded fields [F, slot_words] (int32-viewed words)."""
+        F, sw = slots_dev.shape
+        regions = torch.empty((F, max_label, 64), dtype=torch.uint8, device=self.tdev)
+        self._check(self.lib.cia_label_scan_rle(self.h, _ptr(slots_dev), sw, F, H, W, max_label, _ptr(regions),
+                                                self._stream()))
+        return regions
+
     # ---- fused path ----
     def alloc_outputs(self, cells_cap: int, n_fields: int, keep_crops=False, keep_features=False):
         d = self.tdev
@@ -214,12 +229,22 @@ class Engine:
                            out["pred_mod"].data_ptr())
 
     def screen_fields(self, images: torch.Tensor, labels: torch.Tensor, max_label: int, out: dict,
-                      field_strain: torch.Tensor = None, acc: torch.Tensor = None, precision=None):
-        """Enqueue the whole path for device-resident fields (no host sync)."""
+                      field_strain: torch.Tensor = None, acc: torch.Tensor = None, precision=None,
+                      rle_slots: torch.Tensor = None):
+        """Enqueue the whole path for device-resident fields (no host sync).  With ``rle_slots``
+        ([F, slot_words] device words of the run-length transport) ``labels`` is ignored and the
+        region scan runs on the runs themselves."""
         F, H, W = images.shape
         sc = self._scores(out)
         prec = self.precision if precision is None else precision
         ns = 0 if acc is None else acc.shape[0]
+        if rle_slots is not None:
+            self._check(self.lib.cia_screen_fields_rle(
+                self.h, _ptr(images), _ptr(rle_slots), rle_slots.shape[1], F, H, W, max_label,
+                C.byref(self.params), prec, _ptr(out["cells"]), out["cap"], _ptr(out["counts"]),
+                C.c_void_p(out["counts"].data_ptr() + 4), C.byref(sc), _ptr(out["crops"]),
+                _ptr(out["features"]), _ptr(field_strain), _ptr(acc), ns, self._stream()))
+            return
         self._check(self.lib.cia_screen_fields(
             self.h, _ptr(images), _ptr(labels), F, H, W, max_label, C.byref(self.params), prec,
             _ptr(out["cells"]), out["cap"], _ptr(out["counts"]), C.c_void_p(out["counts"].data_ptr() + 4),

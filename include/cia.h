@@ -201,7 +201,12 @@ int cia_screen_fields_host(cia_handle h, const uint16_t* images_host,
  *                        *max_label = largest label seen (may be NULL).  CIA_E_CAPACITY if a
  *                        field does not fit its slot (send that batch as raw int32 instead).
  *   cia_rle_upload       one async copy per field of exactly the words used
- *   cia_rle_expand       device slots -> dense int32 labels [n_fields, H, W] */
+ *   cia_rle_expand       device slots -> dense int32 labels [n_fields, H, W]
+ *   cia_label_scan_rle   cia_label_scan computed from the runs themselves: bbox / area / raw
+ *                        moments are sums over pixels with closed forms over a run, so the
+ *                        region table (bit-identical to cia_label_scan of the expanded field)
+ *                        needs neither the dense field in HBM nor its 4 B/pixel read
+ *   cia_screen_fields_rle cia_screen_fields with the label fields given as device slots */
 size_t cia_rle_slot_words(int H, int W);
 int cia_rle_encode_fields(const int32_t* labels_host, int n_fields, int H, int W,
                           uint32_t* slots_host, size_t slot_words, uint32_t* field_words,
@@ -210,6 +215,16 @@ int cia_rle_upload(cia_handle h, const uint32_t* slots_host, int n_fields, size_
                    const uint32_t* field_words, uint32_t* slots_dev, void* stream);
 int cia_rle_expand(cia_handle h, const uint32_t* slots_dev, int n_fields, size_t slot_words,
                    int H, int W, int32_t* labels_dev, void* stream);
+int cia_label_scan_rle(cia_handle h, const uint32_t* rle_slots, size_t slot_words, int n_fields,
+                       int H, int W, int max_label, cia_region* regions, void* stream);
+int cia_screen_fields_rle(cia_handle h, const uint16_t* images, const uint32_t* rle_slots,
+                          size_t slot_words, int n_fields, int H, int W, int max_label,
+                          const cia_params* params, int precision,
+                          cia_cell* cells, int cells_cap, int32_t* n_cells_dev,
+                          int32_t* field_counts_dev, const cia_scores* scores,
+                          float* crops32, float* features,
+                          const int32_t* field_strain, double* acc, int n_strains,
+                          void* stream);
 
 /* Stage timing of the fused path with CUDA events recorded in-stream (no host sync is
  * added to the timed region): after cia_profile_begin(h, R) the next R calls of

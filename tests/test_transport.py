@@ -87,6 +87,77 @@ def test_rle_expand_gpu(shape):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(64, 64), (37, 101), (128, 1030), (512, 2048)])
+def test_label_scan_from_runs_equals_dense_scan_gpu(shape):
+    """cia_label_scan_rle (closed-form sums over runs) builds the same region table, byte for
+    byte, as cia_label_scan over the dense field -- including labels outside [0, max_label]
+    (ignored + CIA_E_LABEL raised) and fields with one run per 2 pixels."""
+    import torch
+    from cell_image_analysis_b200.screening import Engine
+    eng = Engine()
+    H, W = shape
+    labs_np = _fields(H, W)
+    labs_np[4] = labs_np[0][::-1].copy()                      # replace the 2^31-1 field: keep labels in range here
+    labs_np[3] %= 997
+    labs = torch.from_numpy(np.ascontiguousarray(labs_np))
+    F = labs.shape[0]
+    max_label = int(labs.max())
+    sw = 2 * H * W + H + 4
+    h_slots = torch.zeros((F, sw), dtype=torch.int32).pin_memory()
+    d_slots = torch.zeros((F, sw), dtype=torch.int32, device="cuda")
+    words = np.zeros(F, np.uint32)
+    assert eng.rle_encode(labs, h_slots, words, 2)
+    eng.rle_upload(h_slots, words, d_slots)
+    dense = eng.label_scan(labs.cuda(), max_label)
+    runs = eng.label_scan_rle(d_slots, H, W, max_label)
+    torch.cuda.synchronize()
+    eng.check_status()
+    assert int((dense != 0).sum()) > 0
+    assert torch.equal(dense, runs)
+    # out-of-range labels: same table as the dense scan, and the status word is raised
+    dense2 = eng.label_scan(labs.cuda(), max_label // 2)
+    with pytest.raises(_lib.CiaError):
+        eng.check_status()
+    runs2 = eng.label_scan_rle(d_slots, H, W, max_label // 2)
+    torch.cuda.synchronize()
+    with pytest.raises(_lib.CiaError):
+        eng.check_status()
+    assert torch.equal(dense2, runs2)
+    eng.close()
+
+
+@pytest.mark.gpu
+def test_run_host_transport_variants_agree(model_dir):
+    """runs scanned directly, runs expanded first, and a mixed raw/run-length pass: same results."""
+    import torch
+    from cell_image_analysis_b200.artifacts import load_model_dir
+    from cell_image_analysis_b200.batch import BatchScreen
+    from cell_image_analysis_b200.screening import Engine
+    from cell_image_analysis_b200.synth import make_fields
+    eng = Engine()
+    eng.load_artifacts(load_model_dir(model_dir))
+    fields = make_fields(range(6), "tiny")
+    g = torch.from_numpy(np.stack([f[0] for f in fields]).view(np.int16)).pin_memory()
+    lab = torch.from_numpy(np.stack([f[1] for f in fields])).pin_memory()
+    H, W = lab.shape[1:]
+    res = []
+    for kw in (dict(label_transport="raw"), dict(label_transport="rle"),
+               dict(label_transport="rle", scan_runs=False), dict(label_transport="rle", rle_fraction=0.5)):
+        bs = BatchScreen(eng, H, W, int(lab.max()), chunk_fields=1, **kw)
+        bs.run_host(g, lab, 6)
+        bs.sync()
+        eng.check_status()
+        res.append(bs.collect_host())
+        h2d = bs.host_bytes_per_pass(6)[0]
+        if kw.get("rle_fraction") == 0.5:      # three chunks raw, three as runs
+            assert 3 * H * W * 6 + 3 * H * W * 2 < h2d < 3 * H * W * 6 + 3 * H * W * 3
+    assert res[0]["n_cells"] > 0
+    for r in res[1:]:
+        for k in ("cells", "mse", "mae", "dec_cons", "dec_mod", "pred_cons", "pred_mod", "field_counts"):
+            assert np.array_equal(res[0][k], r[k]), k
+
+
+@pytest.mark.gpu
 def test_run_host_rle_equals_raw(golden_config1, model_dir):
     """The whole host pass gives identical cells and scores with either label transport."""
     import torch
