@@ -17,6 +17,8 @@ FULL_METRICS = [
     "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
     "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
     "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__cycles_active.avg", "sm__cycles_elapsed.avg",
     "sm__inst_executed_pipe_tensor.sum",
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
     "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
