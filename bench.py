@@ -220,20 +220,13 @@ def run_native(args):
     visit_strain = (torch.arange(NF, dtype=torch.int32) * n_strains // NF).to(dev)   # contiguous blocks
     rle_fraction = args.rle_fraction
     if args.label_transport == "auto":
-        # One GPU: every chunk crosses PCIe as runs (all host cores encode, 99 GB/s of labels).
-        # Several ranks share the host cores, so each rank encodes with cores/world threads and
-        # sends only the share f of its chunks as runs, the rest raw: the encoder then works
-        # beside the rank's own PCIe link instead of in front of it.  f balances the two
-        # (per 2048^2 field: image 16.8/2 MB + raw labels 16.8 MB at ~55 GB/s per link against
-        # 16.8 MB of labels at ~4.5 GB/s per encoder thread when several ranks encode at once --
-        # both measured on this box type; 2 GPUs / 24 cores: f = 1.0 / 0.87 / 0.7 / 0.5 / raw gave
-        # 3.08M / 3.18M / 3.31M / 2.75M / 2.08M cells/s end to end, the formula picks 0.75).
+        # Every chunk crosses PCIe as runs.  One GPU: the 16 host cores encode faster than the device
+        # screens.  Several ranks share the host cores AND the host DRAM: two ranks reach 3.3M
+        # cells/s end to end whether all chunks or 85 % of them are encoded (raw copies: 2.1M), i.e.
+        # the hosts memory bandwidth, read once by the encoder or by the DMA engine, is the limit.
         args.label_transport = "rle"
-        if world > 1 and rle_fraction < 0:
-            if args.host_threads <= 0:
-                args.host_threads = max(1, (os.cpu_count() or 1) // world)
-            t_enc = 16.8 / (4.5 * args.host_threads)              # ms per encoded field
-            rle_fraction = min(1.0, (8.4 + 16.8) / 55.0 / (t_enc + 16.5 / 55.0))
+        if world > 1 and args.host_threads <= 0:
+            args.host_threads = max(1, (os.cpu_count() or 1) // world)
     if rle_fraction < 0:
         rle_fraction = 1.0
     bs = BatchScreen(eng, H, W, max_label, chunk_fields=Fc, n_strains=n_strains,
@@ -394,11 +387,10 @@ def main():
                     help="CAE path: 0 exact fp32 CUDA cores, 1 tcgen05 (split-precision encoder), 2 tcgen05 + fp32 encoder")
     ap.add_argument("--label-transport", default="auto", choices=["auto", "rle", "raw"],
                     help="e2e arm: how the int32 label fields cross PCIe (rle = lossless host run-length encode; "
-                         "auto = rle, with --rle-fraction < 1 when several ranks share the host cores)")
+                         "auto = rle, with cores/ranks encoder threads per rank)")
     ap.add_argument("--host-threads", type=int, default=0, help="host threads of the RLE encoder (0 = all cores / ranks)")
     ap.add_argument("--rle-fraction", type=float, default=-1.0,
-                    help="share of the chunks sent as runs (rest raw); < 0 = auto (1 on one GPU, balanced against "
-                         "the PCIe link when several ranks share the host cores)")
+                    help="share of the chunks sent as runs (rest raw); < 0 = all of them")
     ap.add_argument("--cpu-fields", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
