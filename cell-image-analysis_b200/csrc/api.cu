@@ -73,7 +73,7 @@ int cia_destroy(cia_handle h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     free_cae(h->cae[0]); free_cae(h->cae[1]);
-    cudaFree(h->sp.center); cudaFree(h->sp.scale); cudaFree(h->sp.comp_t); cudaFree(h->sp.comp_pad); cudaFree(h->sp.offset);
+    cudaFree(h->sp.center); cudaFree(h->sp.scale); cudaFree(h->sp.rscale); cudaFree(h->sp.comp_t); cudaFree(h->sp.comp_pad); cudaFree(h->sp.offset);
     for (int i = 0; i < 2; ++i) { cudaFree(h->svm[i].sv_t); cudaFree(h->svm[i].coef); cudaFree(h->svm[i].sv_pad); cudaFree(h->svm[i].gsn); }
     Workspace* ws[] = {&h->ws_flags, &h->ws_act, &h->ws_crop_scratch, &h->ws_pipe, &h->ws_feat,
                        &h->ws_misc, &h->ws_stage, &h->ws_svm};
@@ -170,6 +170,15 @@ int cia_load_scaler_pca(cia_handle h, int F, int C, const double* center, const 
     sp.has_center = center != nullptr; sp.has_scale = scale != nullptr;
     if (center && (rc = upload(h, &sp.center, center, (size_t)F))) return rc;
     if (scale && (rc = upload(h, &sp.scale, scale, (size_t)F))) return rc;
+    if (scale) {
+        std::vector<double> rs((size_t)F);
+        sp.rscale_ok = true;
+        for (int f = 0; f < F; ++f) {
+            rs[f] = 1.0 / scale[f];
+            if (!std::isnormal(scale[f]) || !std::isnormal(rs[f])) sp.rscale_ok = false;
+        }
+        if ((rc = upload(h, &sp.rscale, rs.data(), rs.size()))) return rc;
+    }
     std::vector<double> t((size_t)F * C);
     for (int c = 0; c < C; ++c)
         for (int f = 0; f < F; ++f) t[(size_t)f * C + c] = components[(size_t)c * F + f];

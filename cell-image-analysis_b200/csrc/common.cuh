@@ -48,6 +48,8 @@ struct ScalerPca {
     int center_is_f32 = 1, f32_flow = 1, has_center = 0, has_scale = 0;
     double* center = nullptr;   // [F]
     double* scale = nullptr;    // [F]
+    double* rscale = nullptr;   // [F] 1 / scale, correctly rounded on the host (division by FMA correction)
+    bool rscale_ok = false;     // every scale and reciprocal is a normal number
     double* comp_t = nullptr;   // [F, C] transposed components
     double* comp_pad = nullptr; // [F rounded up to 32, CP] zero-padded copy for the cp.async-fed DMMA kernel
     int CP = 0;                 // C rounded up to a multiple of 104

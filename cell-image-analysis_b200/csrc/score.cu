@@ -8,6 +8,7 @@
 // sklearn/svm/src/libsvm/svm.cpp:461-472, decision sum - rho, sign rule sum > 0) and
 // the reductions behind :151-152 and :202-211.
 #include <algorithm>
+#include <type_traits>
 #include "common.cuh"
 
 namespace {
@@ -123,7 +124,7 @@ __device__ __forceinline__ void dmma884(double (&d)[2], double a, double b) {
 __global__ void __launch_bounds__(DT, 2)
 scaler_pca_dmma_kernel(const float* __restrict__ feat, int n_cells, const int32_t* __restrict__ n_dev,
                        int F, int C, int CP, const double* __restrict__ center, const double* __restrict__ scale,
-                       int center_is_f32, const double* __restrict__ comp_pad,
+                       const double* __restrict__ rscale, int center_is_f32, const double* __restrict__ comp_pad,
                        const double* __restrict__ offset, int f32_flow, double* __restrict__ z_out) {
     extern __shared__ __align__(16) unsigned char pca_smem[];
     double* xs = reinterpret_cast<double*>(pca_smem);                 // [2][DM][DXP]
@@ -148,10 +149,13 @@ scaler_pca_dmma_kernel(const float* __restrict__ feat, int n_cells, const int32_
     auto issue_w = [&](int stage, int buf) {          // DK x DN doubles as 16-byte chunks
         const double* src = comp_pad + (size_t)stage * DK * CP + c_tile0;
         double* dst = ws + buf * DK * DWP;
-        for (int idx = tid; idx < DK * (DN / 2); idx += DT) {
-            const int ff = idx / (DN / 2), c2 = idx - ff * (DN / 2);
-            const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst + ff * DWP + 2 * c2);
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src + (size_t)ff * CP + 2 * c2) : "memory");
+        // 64 chunk slots per feature row (52 used): row / chunk from shifts, no division by 52
+        for (int idx = tid; idx < DK * 64; idx += DT) {
+            const int ff = idx >> 6, c2 = idx & 63;
+            if (c2 < DN / 2) {
+                const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst + ff * DWP + 2 * c2);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src + (size_t)ff * CP + 2 * c2) : "memory");
+            }
         }
     };
     float xr[DXR];
@@ -165,10 +169,10 @@ scaler_pca_dmma_kernel(const float* __restrict__ feat, int n_cells, const int32_
     };
     auto store_x = [&](int stage, int buf) {          // scaler applied on the way (sklearn's float32 flow)
         const int f = stage * DK + lane;
-        double cen = 0.0, sc = 1.0;
+        double cen = 0.0, sc = 1.0, rsc = 1.0;
         if (f < F) {
             if (center) cen = center[f];
-            if (scale) sc = scale[f];
+            if (scale) { sc = scale[f]; if (rscale) rsc = rscale[f]; }
         }
         double* dst = xs + buf * DM * DXP;
 #pragma unroll
@@ -179,7 +183,20 @@ scaler_pca_dmma_kernel(const float* __restrict__ feat, int n_cells, const int32_
                     if (center_is_f32) v = __fsub_rn(v, (float)cen);
                     else v = (float)__dsub_rn((double)v, cen);
                 }
-                if (scale) v = (float)__ddiv_rn((double)v, sc);
+                if (scale) {
+                    // RN(v / sc) without the division sequence: q = RN(v * RN(1/sc)) is within one
+                    // ulp, the remainder v - q*sc is exact in one FMA, and q + rem * RN(1/sc) rounds
+                    // to the correctly rounded quotient (Markstein); the fp32 rounding follows as in
+                    // sklearn's in-place float32 division
+                    const double a = (double)v;
+                    if (rscale) {
+                        const double q = __dmul_rn(a, rsc);
+                        const double rem = __fma_rn(-q, sc, a);
+                        v = (float)__fma_rn(rem, rsc, q);
+                    } else {                      // a scale whose reciprocal is not a normal number
+                        v = (float)__ddiv_rn(a, sc);
+                    }
+                }
             }
             dst[(warp + j * (DT / 32)) * DXP + lane] = (double)v;
         }
@@ -197,22 +214,26 @@ scaler_pca_dmma_kernel(const float* __restrict__ feat, int n_cells, const int32_
             issue_w(st + 1, buf ^ 1);
             load_x(st + 1);
         }
-        const double* xb = xs + buf * DM * DXP;
-        const double* wb = ws + buf * DK * DWP;
+        const double* xb = xs + buf * DM * DXP + (mg * 16 + gid) * DXP + tig;
+        const double* wb = ws + buf * DK * DWP + tig * DWP + nt0 * 8 + gid;
+        // the tile count of a warp (4 or 3) is a compile-time constant inside each branch: no
+        // predicate, branch or WARPSYNC in front of the MMAs
+        auto mma_stage = [&](auto ntc_c) {
+            constexpr int NTC = decltype(ntc_c)::value;
 #pragma unroll
-        for (int k4 = 0; k4 < DK / 4; ++k4) {
-            const double a0 = xb[(mg * 16 + gid) * DXP + k4 * 4 + tig];
-            const double a1 = xb[(mg * 16 + 8 + gid) * DXP + k4 * 4 + tig];
-            const double* wrow = wb + (k4 * 4 + tig) * DWP + nt0 * 8 + gid;
+            for (int k4 = 0; k4 < DK / 4; ++k4) {
+                const double a0 = xb[k4 * 4];
+                const double a1 = xb[8 * DXP + k4 * 4];
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt) {
-                if (nt < ntc) {
-                    const double b = wrow[nt * 8];
+                for (int nt = 0; nt < NTC; ++nt) {
+                    const double b = wb[k4 * 4 * DWP + nt * 8];
                     dmma884(acc[0][nt], a0, b);
                     dmma884(acc[1][nt], a1, b);
                 }
             }
-        }
+        };
+        if (ng == 0) mma_stage(std::integral_constant<int, 4>{});
+        else mma_stage(std::integral_constant<int, 3>{});
         if (more) {
             store_x(st + 1, buf ^ 1);
             asm volatile("cp.async.wait_all;" ::: "memory");
@@ -520,7 +541,8 @@ int k_svm_decision(cia_ctx* h, const float* features, int n, const int32_t* n_de
         const size_t sm1 = sizeof(double) * 2 * (DM * DXP + DK * DWP);
         scaler_pca_dmma_kernel<<<dim3((n + DM - 1) / DM, sp.CP / DN), DT, sm1, s>>>(
             features, n, n_dev, sp.F, sp.C, sp.CP, sp.has_center ? sp.center : nullptr,
-            sp.has_scale ? sp.scale : nullptr, sp.center_is_f32, sp.comp_pad, sp.offset, sp.f32_flow, z);
+            sp.has_scale ? sp.scale : nullptr, sp.has_scale && sp.rscale_ok ? sp.rscale : nullptr, sp.center_is_f32, sp.comp_pad,
+            sp.offset, sp.f32_flow, z);
     }
     CIA_LAUNCH_CHECK();
     static const bool direct_svm = getenv("CIA_SVM_DIRECT") != nullptr;   // A/B switch: CUDA-core direct-difference form
