@@ -43,14 +43,15 @@ label_scan_kernel(const int32_t* __restrict__ labels, int n_fields, int H, int W
 #pragma unroll
             for (int k = 0; k < 4; ++k) lab[k] = (c0 + k < W) ? __ldg(row + c0 + k) : 0;
         }
+        // background-only segments (the majority) leave before the range check: 0 is in range
+        const unsigned any = __ballot_sync(0xffffffffu, (lab[0] | lab[1] | lab[2] | lab[3]) != 0);
+        if (any == 0) continue;
         bool bad = false;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            if (lab[k] < 0 || lab[k] > max_label) { bad = true; lab[k] = 0; }
+            if ((unsigned)lab[k] > (unsigned)max_label) { bad = true; lab[k] = 0; }
         }
         if (bad) raise_status(status, CIA_E_LABEL);
-        const unsigned any = __ballot_sync(0xffffffffu, (lab[0] | lab[1] | lab[2] | lab[3]) != 0);
-        if (any == 0) continue;
 
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
