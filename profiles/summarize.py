@@ -18,6 +18,10 @@ FULL_METRICS = [
     "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
     "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
     "sm__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_tc_cycles_active.avg.pct_of_peak_sustained_active",
+    "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+    "l1tex__throughput.avg.pct_of_peak_sustained_active",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active",
     "sm__cycles_active.avg", "sm__cycles_elapsed.avg",
     "sm__inst_executed_pipe_tensor.sum",
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
