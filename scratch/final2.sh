@@ -12,6 +12,6 @@ CMD="python bench.py --steps 1 --warmup 1 --fields 32 --pool 16 --chunk 16 --no-
 $CMD > gpurun_out/plain_$TAG.log 2>&1 &&
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv \
     --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_list_$TAG.log 2>&1
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:'scaler_pca|svm_rbf|label_scan' -s 8 -c 6 \
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:"scaler_pca|svm_rbf|label_scan|gate_kernel" -s 10 -c 7 \
     -o gpurun_out/prof_score_$TAG $CMD > gpurun_out/ncu_full_score_$TAG.log 2>&1
 ls -la gpurun_out | tail -8
