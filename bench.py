@@ -35,6 +35,7 @@ METRIC = "cells scored/sec (crop+resize+CAE+SVM)"
 UNIT = "cells/s"
 MODEL_DIR = os.path.join(ROOT, "tests", "golden", "model_dir")
 FLOP_PER_CELL = 100.27e6          # L1..L7 conv MACs*2
+LAYER_MFLOP = [2.359, 37.749, 9.437, 1.180, 9.437, 37.749, 2.359]
 ISSUED_FLOP_RATIO = (3 * (2.359 + 37.749 + 9.437) + (1.180 + 9.437 + 37.749 + 2.359)) / 100.27   # split-precision encoder
 H = W = 2048
 N_CELLS_PER_FIELD = 520
@@ -274,6 +275,12 @@ def run_native(args):
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     clocks = sampler.stop()
     launches = eng.launch_count - l0
+    layer_ms = None
+    if args.precision != 0:
+        try:
+            layer_ms = bs.profile_layers()        # CAE stage split by conv layer (first pass of every call)
+        except Exception:
+            layer_ms = None
     stage_ms, nrec = bs.profile_end()
     eng.check_status()
     # cells per step on this rank: one extra untimed pass without the all-reduce
@@ -326,6 +333,41 @@ def run_native(args):
         if os.path.exists(tp):
             traffic = json.load(open(tp)).get("cae_stage_dram_bytes_per_cell")
             traffic = None if traffic is None else traffic * cells_per_step_local
+        split = 3.0 if args.precision == 1 else 1.0       # fp16 MMAs per encoder product (hi*lo, lo*hi, hi*hi)
+        stage_roofline = {"kernel": "CAE forward stage (7 conv layers + error reduction)", "bound": "tensor",
+                          "achieved": tf, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": tf / pk["tf_sust"],
+                          "traffic": traffic, "peak_source": pk["source"] + ", bf16 dense sustained",
+                          # what the tensor pipe executes: the encoder (49.55 of the 100.27 MFLOP) runs three
+                          # fp16 MMAs per product to deliver fp32-grade features
+                          "issued_tflops": tf * ISSUED_FLOP_RATIO if args.precision == 1 else tf,
+                          "issued_frac": (tf * ISSUED_FLOP_RATIO if args.precision == 1 else tf) / pk["tf_sust"],
+                          "share_of_step": cae_ms / (t_ms / args.steps)}
+        roofline = stage_roofline
+        layers = None
+        if layer_ms is not None and layer_ms[1] > 0:
+            # the dominant kernel: layer 2 (conv_tc_acc2_kernel, 32 -> 64 channels at 32x32, one launch per
+            # chunk); its time comes from CUDA events recorded in-stream around that launch
+            l2_ms = layer_ms[1] / args.steps
+            l2_tf = LAYER_MFLOP[1] * 1e6 * cells_per_step_local / (l2_ms * 1e-3) / 1e12
+            l2_traffic = None
+            if os.path.exists(tp):
+                l2_traffic = json.load(open(tp)).get("l2_kernel_dram_bytes_per_cell")
+                l2_traffic = None if l2_traffic is None else l2_traffic * cells_per_step_local / chunks_per_step
+            roofline = {"kernel": "conv_tc_acc2_kernel<32,64,32,3> (CAE layer 2, tcgen05 implicit GEMM, split-precision)",
+                        "bound": "tensor", "achieved": l2_tf, "peak": pk["tf_sust"], "unit": "TFLOP/s",
+                        "frac": l2_tf / pk["tf_sust"], "traffic": l2_traffic,
+                        "peak_source": pk["source"] + ", bf16 dense sustained",
+                        "algorithmic_mflop_per_cell": LAYER_MFLOP[1], "launches_per_step": chunks_per_step,
+                        "avg_launch_ms": l2_ms / chunks_per_step,
+                        "issued_tflops": l2_tf * split, "issued_frac": l2_tf * split / pk["tf_sust"],
+                        "note": "achieved = algorithmic FLOPs (37.749 MFLOP per cell x cells per launch) / launch "
+                                "time; the kernel issues 3 fp16 MMAs per product for fp32-grade features "
+                                "(issued_*), and ncu shows its tensor-core pipe 90 % busy, bound by operand reads "
+                                "from shared memory at N = 64 (profiles/r1j_cae_full.txt); traffic per launch",
+                        "share_of_step": l2_ms / (t_ms / args.steps)}
+            layers = {f"L{i + 1}": {"ms_per_step": layer_ms[i] / args.steps,
+                                    "tflops": LAYER_MFLOP[i] * 1e6 * cells_per_step_local / (layer_ms[i] / args.steps * 1e-3) / 1e12}
+                      for i in range(7) if layer_ms[i] > 0}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": t_ms / args.steps, "higher_is_better": True,
@@ -349,16 +391,11 @@ def run_native(args):
                            "from the runs on the device, the rest crosses PCIe raw; double-buffered H2D)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"kernel": "CAE forward stage (7 conv layers + error reduction)", "bound": "tensor",
-                         "achieved": tf, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": tf / pk["tf_sust"],
-                         "traffic": traffic, "peak_source": pk["source"] + ", bf16 dense sustained",
-                         # what the tensor pipe executes: the encoder (49.55 of the 100.27 MFLOP) runs three
-                         # fp16 MMAs per product (hi*lo, lo*hi, hi*hi) to deliver fp32-grade features
-                         "issued_tflops": tf * ISSUED_FLOP_RATIO if args.precision == 1 else tf,
-                         "issued_frac": (tf * ISSUED_FLOP_RATIO if args.precision == 1 else tf) / pk["tf_sust"],
-                         "share_of_step": cae_ms / (t_ms / args.steps)},
+            "roofline": roofline,
             "stages_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
+            "cae_layers": layers,
             "stage_rooflines": {
+                "cae_stage": stage_roofline,
                 "label_scan": {"bound": "hbm", "achieved": scan_gbs, "peak": pk["hbm"], "unit": "GB/s",
                                "frac": scan_gbs / pk["hbm"]},
                 "crop_clahe_resize": {"bound": "hbm", "achieved": crop_gbs, "peak": pk["hbm"], "unit": "GB/s",

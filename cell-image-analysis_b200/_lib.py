@@ -88,6 +88,7 @@ SIGNATURES = {
                                    C.POINTER(Scores), _P, _P, _P, _P, _I, _P]),
     "cia_profile_begin": (_I, [_P, _I]),
     "cia_profile_end": (_I, [_P, C.POINTER(C.c_double), C.POINTER(_I)]),
+    "cia_profile_layers": (_I, [_P, C.POINTER(C.c_double)]),
     "cia_debug_copy_workspace": (_I, [_P, _I, C.c_size_t, _P, C.c_size_t]),
     "cia_launch_count": (C.c_int64, [_P]),
 }

@@ -66,6 +66,12 @@ class BatchScreen:
     def profile_begin(self, n_calls: int):
         self.eng._check(self.eng.lib.cia_profile_begin(self.eng.h, n_calls))
 
+    def profile_layers(self):
+        """CAE stage split by conv layer (ms summed over the recorded calls); before ``profile_end``."""
+        ms = (C.c_double * 7)()
+        self.eng._check(self.eng.lib.cia_profile_layers(self.eng.h, ms))
+        return [float(v) for v in ms]
+
     def profile_end(self):
         ms = (C.c_double * 6)()
         n = C.c_int(0)

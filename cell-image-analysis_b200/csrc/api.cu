@@ -85,6 +85,7 @@ int cia_destroy(cia_handle h) {
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->side) cudaStreamDestroy(h->side);
     for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->prof_layer_ev) cudaEventDestroy(e);
     delete h;
     return CIA_OK;
 }
@@ -339,7 +340,12 @@ static int screen_fields_impl(cia_handle h, const uint16_t* images, const int32_
     if ((rc = k_crop_resize(h, images, H, W, cells, cells_cap, n_cells_dev, params, crops, nullptr, s))) return rc;
     CIA_MARK(3);
     if (precision == 0) rc = k_cae_forward_fp32(h, crops, cells_cap, n_cells_dev, scores->mse, scores->mae, feats, s);
-    else rc = k_cae_forward_tc(h, crops, cells_cap, n_cells_dev, scores->mse, scores->mae, feats, precision, s);
+    else {
+        h->layer_ev = pe ? &h->prof_layer_ev[(size_t)(h->prof_used - 1) * CIA_LAYER_MARKS] : nullptr;
+        rc = k_cae_forward_tc(h, crops, cells_cap, n_cells_dev, scores->mse, scores->mae, feats, precision, s);
+        h->layer_ev = nullptr;
+        h->prof_layers_valid = pe != nullptr;
+    }
     if (rc) return rc;
     CIA_MARK(4);
     if ((rc = k_svm_decision(h, feats, cells_cap, n_cells_dev, scores->dec_conservative,
@@ -397,8 +403,31 @@ int cia_profile_begin(cia_handle h, int max_records) {
         CIA_CUDA(cudaEventCreate(&e));
         h->prof_ev.push_back(e);
     }
+    while (h->prof_layer_ev.size() < (size_t)max_records * CIA_LAYER_MARKS) {
+        cudaEvent_t e;
+        CIA_CUDA(cudaEventCreate(&e));
+        h->prof_layer_ev.push_back(e);
+    }
     h->prof_records = max_records;
     h->prof_used = 0;
+    h->prof_layers_valid = false;
+    return CIA_OK;
+}
+
+int cia_profile_layers(cia_handle h, double* layer_ms /* [7] */) {
+    if (!h) return bad_handle();
+    if (!layer_ms) { h->err = "cia_profile_layers: null pointer"; return CIA_E_ARG; }
+    for (int k = 0; k < CIA_LAYER_MARKS - 1; ++k) layer_ms[k] = 0.0;
+    if (!h->prof_layers_valid) { h->err = "cia_profile_layers: no tensor-core pass was profiled"; return CIA_E_STATE; }
+    for (int r = 0; r < h->prof_used; ++r) {
+        cudaEvent_t* le = &h->prof_layer_ev[(size_t)r * CIA_LAYER_MARKS];
+        CIA_CUDA(cudaEventSynchronize(le[CIA_LAYER_MARKS - 1]));
+        for (int k = 0; k < CIA_LAYER_MARKS - 1; ++k) {
+            float ms = 0.f;
+            CIA_CUDA(cudaEventElapsedTime(&ms, le[k], le[k + 1]));
+            layer_ms[k] += ms;
+        }
+    }
     return CIA_OK;
 }
 

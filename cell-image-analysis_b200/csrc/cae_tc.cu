@@ -1863,6 +1863,9 @@ int k_cae_forward_tc(cia_ctx* h, const float* crops, int n, const int32_t* n_dev
         float* feat = tc_feat ? features : nullptr;
         int grid1 = chunk * 4;
         if (grid1 > h->num_sms * 8) grid1 = h->num_sms * 8;
+        // per-layer event marks of the first pass (cia_profile_layers): L1..L7 boundaries
+#define CIA_LMARK(i) do { if (h->layer_ev && c0 == 0) CIA_CUDA(cudaEventRecord(h->layer_ev[i], s)); } while (0)
+        CIA_LMARK(0);
         if (tc_feat || l3_exact) {
             // CIA_L1_KERNEL=0 keeps layer 1 on the CUDA cores (exact fp32 FMA chains) for A/B runs;
             // CIA_L1_DEBIAS scales the half-ulp truncation compensation (default 0.5 * 2^-24 measured against the exact kernel, 0 = off)
@@ -1881,6 +1884,7 @@ int k_cae_forward_tc(cia_ctx* h, const float* crops, int n, const int32_t* n_dev
                                                                ae.bn_shift[0], a1h, a1l, n, n_dev, c0, chunk);
             }
             CIA_LAUNCH_CHECK();
+            CIA_LMARK(1);
             float* a2f = l3_exact ? A2f - (size_t)c0 * (16 * 16 * 64) : nullptr;
             // taps per TMEM flush of layer 2 (CIA_L2_TAPS_PER_FLUSH=1|2|3; 0 = the single-buffered
             // whole-cell kernel): 3 keeps the epilogue warps below the tensor pipe's time, see DESIGN.md
@@ -1891,6 +1895,7 @@ int k_cae_forward_tc(cia_ctx* h, const float* crops, int n, const int32_t* n_dev
             else if (l2_g == 2) rc = launch_tc_acc2<32, 64, 32, 2>(h, ae, 1, A1h, A1l, CH, a2h, a2l, a2f, n, n_dev, c0, chunk, s);
             else rc = launch_tc_acc2<32, 64, 32, 3>(h, ae, 1, A1h, A1l, CH, a2h, a2l, a2f, n, n_dev, c0, chunk, s);
             if (rc) return rc;
+            CIA_LMARK(2);
             if (l3_exact) {
                 if ((rc = launch_tc<64, 32, 16, EPI_POOL, 1>(h, ae, 2, a2h, nullptr, a3h, nullptr, nullptr, nullptr, nullptr, nullptr, n, n_dev, c0, chunk, s))) return rc;
                 if (features && (rc = k_conv3_fp32(h, ae, a2f, n, n_dev, features, c0, chunk, s))) return rc;
@@ -1909,13 +1914,21 @@ int k_cae_forward_tc(cia_ctx* h, const float* crops, int n, const int32_t* n_dev
             conv1_fp32_planar_kernel<<<grid1, 256, 0, s>>>(crops, ae.kernel[0], ae.bias[0], ae.bn_scale[0],
                                                            ae.bn_shift[0], a1h, nullptr, n, n_dev, c0, chunk);
             CIA_LAUNCH_CHECK();
+            CIA_LMARK(1);
             if ((rc = launch_tc<32, 64, 32, EPI_POOL, 1>(h, ae, 1, a1h, nullptr, a2h, nullptr, nullptr, nullptr, nullptr, nullptr, n, n_dev, c0, chunk, s))) return rc;
+            CIA_LMARK(2);
             if ((rc = launch_tc<64, 32, 16, EPI_POOL, 1>(h, ae, 2, a2h, nullptr, a3h, nullptr, nullptr, nullptr, nullptr, nullptr, n, n_dev, c0, chunk, s))) return rc;
         }
+        CIA_LMARK(3);
         if ((rc = launch_tc<32, 32, 8, EPI_PLAIN, 1>(h, ae, 3, a3h, nullptr, a4, nullptr, nullptr, nullptr, nullptr, nullptr, n, n_dev, c0, chunk, s))) return rc;
+        CIA_LMARK(4);
         if ((rc = launch_tc<32, 64, 16, EPI_PLAIN, 1, true>(h, ae, 4, a4, nullptr, a5, nullptr, nullptr, nullptr, nullptr, nullptr, n, n_dev, c0, chunk, s))) return rc;
+        CIA_LMARK(5);
         if ((rc = launch_tc<64, 128, 16, EPI_PHASE, 1>(h, ae, 5, a5, nullptr, a6p, nullptr, nullptr, nullptr, nullptr, nullptr, n, n_dev, c0, chunk, s))) return rc;
+        CIA_LMARK(6);
         if ((rc = launch_tc<32, 16, 32, EPI_FINAL, 1>(h, ae, 6, a6p, nullptr, nullptr, nullptr, nullptr, crops, mse, mae, n, n_dev, c0, chunk, s))) return rc;
+        CIA_LMARK(7);
+#undef CIA_LMARK
     }
     if (side_encoder) CIA_CUDA(cudaStreamWaitEvent(s, h->ev_join, 0));
     return CIA_OK;

@@ -233,6 +233,10 @@ int cia_screen_fields_rle(cia_handle h, const uint16_t* images, const uint32_t* 
  * (synchronises on the last event of each). */
 int cia_profile_begin(cia_handle h, int max_records);
 int cia_profile_end(cia_handle h, double* stage_ms /* [6] */, int* n_records);
+/* Per-layer split of the CAE stage of the same recorded calls (tensor-core precisions; first
+ * pass of each call): elapsed milliseconds of the seven conv layers L1..L7, summed over the
+ * records.  Call it BEFORE cia_profile_end (which closes the recording). */
+int cia_profile_layers(cia_handle h, double* layer_ms /* [7] */);
 
 /* Test tap: copy `bytes` at `offset` of internal workspace `ws_id` to host (synchronises).
  * ws_id 5 holds the tensor-core path's fp16 activations (layout in cae_tc.cu). */
