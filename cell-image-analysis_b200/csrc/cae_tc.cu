@@ -1820,7 +1820,9 @@ int k_cae_forward_tc(cia_ctx* h, const float* crops, int n, const int32_t* n_dev
     // pipeline fill, a ragged last wave), and keeping a chunk's activations L2-resident buys nothing
     // because the layers are tensor-pipe / issue bound, not DRAM bound: 296 cells/pass -> 67 ms,
     // 1024 -> 49 ms, 16576 (112 per SM) -> 39.6 ms for the same 121k cells.  303 KB of workspace per cell.
-    static const int CH_MAX = [] { const char* e = getenv("CIA_CAE_CHUNK"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 16576; }();
+    // The cap is 128 cells per SM so that a 32-field chunk (capacity 32 x ~520 labels = 16640 cells) is ONE
+    // pass: with 16576 every chunk launched a second, empty pass of all seven kernels.
+    static const int CH_MAX = [] { const char* e = getenv("CIA_CAE_CHUNK"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 18944; }();
     const int CH = n < CH_MAX ? (n + 147) / 148 * 148 : CH_MAX;
     // halves per cell; A4 / A5 are stored at their own (pre-upsampling) resolution
     const size_t a1 = 4 * 32 * 32 * 8, a2 = 8 * 16 * 16 * 8, a3 = 4 * 8 * 8 * 8, a4u = 4 * 8 * 8 * 8,
