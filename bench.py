@@ -418,7 +418,7 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--fields", type=int, default=1024, help="field visits per GPU per step (config 2: ~1000)")
     ap.add_argument("--pool", type=int, default=64, help="distinct resident fields per GPU")
-    ap.add_argument("--chunk", type=int, default=32, help="fields per fused call")
+    ap.add_argument("--chunk", type=int, default=64, help="fields per fused call (measured: 32 -> 2.45M, 64 -> 2.49M cells/s)")
     ap.add_argument("--strains", type=int, default=4)
     ap.add_argument("--precision", type=int, default=1,
                     help="CAE path: 0 exact fp32 CUDA cores, 1 tcgen05 (split-precision encoder), 2 tcgen05 + fp32 encoder")
