@@ -341,8 +341,10 @@ static int screen_fields_impl(cia_handle h, const uint16_t* images, const int32_
     CIA_MARK(3);
     if (precision == 0) rc = k_cae_forward_fp32(h, crops, cells_cap, n_cells_dev, scores->mse, scores->mae, feats, s);
     else {
-        h->layer_ev = pe ? &h->prof_layer_ev[(size_t)(h->prof_used - 1) * CIA_LAYER_MARKS] : nullptr;
+        h->layer_ev = pe ? &h->prof_layer_ev[(size_t)(h->prof_used - 1) * CIA_LAYER_PASSES * CIA_LAYER_MARKS] : nullptr;
+        h->layer_passes = 0;
         rc = k_cae_forward_tc(h, crops, cells_cap, n_cells_dev, scores->mse, scores->mae, feats, precision, s);
+        if (pe) h->prof_layer_passes[(size_t)(h->prof_used - 1)] = h->layer_passes;
         h->layer_ev = nullptr;
         h->prof_layers_valid = pe != nullptr;
     }
@@ -403,7 +405,8 @@ int cia_profile_begin(cia_handle h, int max_records) {
         CIA_CUDA(cudaEventCreate(&e));
         h->prof_ev.push_back(e);
     }
-    while (h->prof_layer_ev.size() < (size_t)max_records * CIA_LAYER_MARKS) {
+    h->prof_layer_passes.assign((size_t)max_records, 0);
+    while (h->prof_layer_ev.size() < (size_t)max_records * CIA_LAYER_PASSES * CIA_LAYER_MARKS) {
         cudaEvent_t e;
         CIA_CUDA(cudaEventCreate(&e));
         h->prof_layer_ev.push_back(e);
@@ -420,12 +423,14 @@ int cia_profile_layers(cia_handle h, double* layer_ms /* [7] */) {
     for (int k = 0; k < CIA_LAYER_MARKS - 1; ++k) layer_ms[k] = 0.0;
     if (!h->prof_layers_valid) { h->err = "cia_profile_layers: no tensor-core pass was profiled"; return CIA_E_STATE; }
     for (int r = 0; r < h->prof_used; ++r) {
-        cudaEvent_t* le = &h->prof_layer_ev[(size_t)r * CIA_LAYER_MARKS];
-        CIA_CUDA(cudaEventSynchronize(le[CIA_LAYER_MARKS - 1]));
-        for (int k = 0; k < CIA_LAYER_MARKS - 1; ++k) {
-            float ms = 0.f;
-            CIA_CUDA(cudaEventElapsedTime(&ms, le[k], le[k + 1]));
-            layer_ms[k] += ms;
+        for (int p = 0; p < h->prof_layer_passes[(size_t)r]; ++p) {
+            cudaEvent_t* le = &h->prof_layer_ev[((size_t)r * CIA_LAYER_PASSES + p) * CIA_LAYER_MARKS];
+            CIA_CUDA(cudaEventSynchronize(le[CIA_LAYER_MARKS - 1]));
+            for (int k = 0; k < CIA_LAYER_MARKS - 1; ++k) {
+                float ms = 0.f;
+                CIA_CUDA(cudaEventElapsedTime(&ms, le[k], le[k + 1]));
+                layer_ms[k] += ms;
+            }
         }
     }
     return CIA_OK;

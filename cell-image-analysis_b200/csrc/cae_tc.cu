@@ -1865,8 +1865,10 @@ int k_cae_forward_tc(cia_ctx* h, const float* crops, int n, const int32_t* n_dev
         float* feat = tc_feat ? features : nullptr;
         int grid1 = chunk * 4;
         if (grid1 > h->num_sms * 8) grid1 = h->num_sms * 8;
-        // per-layer event marks of the first pass (cia_profile_layers): L1..L7 boundaries
-#define CIA_LMARK(i) do { if (h->layer_ev && c0 == 0) CIA_CUDA(cudaEventRecord(h->layer_ev[i], s)); } while (0)
+        // per-layer event marks of every pass (cia_profile_layers): L1..L7 boundaries
+        const int pass = c0 / CH;
+        if (h->layer_ev && pass < CIA_LAYER_PASSES) h->layer_passes = pass + 1;
+#define CIA_LMARK(i) do { if (h->layer_ev && pass < CIA_LAYER_PASSES) CIA_CUDA(cudaEventRecord(h->layer_ev[pass * CIA_LAYER_MARKS + (i)], s)); } while (0)
         CIA_LMARK(0);
         if (tc_feat || l3_exact) {
             // CIA_L1_KERNEL=0 keeps layer 1 on the CUDA cores (exact fp32 FMA chains) for A/B runs;

@@ -81,12 +81,15 @@ struct cia_ctx {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // stage profiler: ring of CUDA events recorded in-stream by the fused path
     std::vector<cudaEvent_t> prof_ev;     // [records][CIA_PROF_MARKS]
-    std::vector<cudaEvent_t> prof_layer_ev;   // [records][CIA_LAYER_MARKS]: CAE layer boundaries of the first pass
+    std::vector<cudaEvent_t> prof_layer_ev;   // [records][CIA_LAYER_PASSES][CIA_LAYER_MARKS]: CAE layer boundaries
+    std::vector<int> prof_layer_passes;       // [records] passes recorded
+    int layer_passes = 0;
     cudaEvent_t* layer_ev = nullptr;      // the current call's layer marks (null: not profiling)
     bool prof_layers_valid = false;
     int prof_records = 0, prof_used = 0;
 };
 #define CIA_LAYER_MARKS 8  // before L1, after L1 .. L7
+#define CIA_LAYER_PASSES 8 // passes of one call that carry marks (cells_cap <= 8 x 18944)
 #define CIA_PROF_MARKS 7   // before scan, after scan, gates, crop, cae, svm, accumulate
 
 #define CIA_CUDA(call)                                                              \

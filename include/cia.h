@@ -233,8 +233,8 @@ int cia_screen_fields_rle(cia_handle h, const uint16_t* images, const uint32_t* 
  * (synchronises on the last event of each). */
 int cia_profile_begin(cia_handle h, int max_records);
 int cia_profile_end(cia_handle h, double* stage_ms /* [6] */, int* n_records);
-/* Per-layer split of the CAE stage of the same recorded calls (tensor-core precisions; first
- * pass of each call): elapsed milliseconds of the seven conv layers L1..L7, summed over the
+/* Per-layer split of the CAE stage of the same recorded calls (tensor-core precisions; up to 8
+ * passes of each call): elapsed milliseconds of the seven conv layers L1..L7, summed over the
  * records.  Call it BEFORE cia_profile_end (which closes the recording). */
 int cia_profile_layers(cia_handle h, double* layer_ms /* [7] */);
 
