@@ -4,9 +4,11 @@
 // (improved_detection.py:66-70).  A B200 screens a 2048 x 2048 field in ~0.3 ms, less than the
 // 0.30 ms its 16.8 MB of int32 labels take over PCIe Gen5 -- the host->device copy, not a
 // kernel, bounds the end-to-end rate.  Label images are piecewise constant along rows, so the
-// host side run-length encodes them (multi-threaded, one pass at memory speed), only the runs
-// (~0.4 MB per field) cross the bus, and a kernel expands them back into the dense int32
-// field in HBM that the scan / gate kernels read.  Lossless: expand(encode(L)) == L bit for bit.
+// host side run-length encodes them (multi-threaded, one pass at memory speed) and only the runs
+// (~0.3 MB per field) cross the bus.  The fused path then builds the region table straight from
+// the runs (label_scan_rle_kernel in scan.cu: labels are read by the scan only, and its sums have
+// closed forms per run); rle_expand_kernel below rebuilds the dense int32 field in HBM for callers
+// that want it.  Lossless: expand(encode(L)) == L bit for bit.
 //
 // Slot layout per field (uint32 words; slot stride chosen by the caller):
 //   [0 .. H]      row_off: index of the first run of each row, row_off[H] = number of runs
