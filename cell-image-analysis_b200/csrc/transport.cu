@@ -39,24 +39,25 @@ rle_expand_kernel(const uint32_t* __restrict__ slots, size_t slot_words, int H, 
     const int x = 4 * (blockIdx.x * 256 + threadIdx.x);
     if (x >= W) return;
     const uint32_t* slot = slots + (size_t)f * slot_words;
-    const uint2* runs = reinterpret_cast<const uint2*>(slot + ((H + 2) & ~1));
+    const uint32_t* runs = slot + ((H + 2) & ~1);               // (x0, label) word pairs; 4-byte loads only,
+                                                                // a caller's slot stride may be odd
     uint32_t lo = __ldg(slot + y), hi = __ldg(slot + y + 1);    // runs of this row: [lo, hi)
     const uint32_t end = hi;
     while (hi - lo > 1) {                                       // largest j with runs[j].x0 <= x
         const uint32_t mid = (lo + hi) >> 1;
-        if (__ldg(&runs[mid]).x <= (uint32_t)x) lo = mid; else hi = mid;
+        if (__ldg(runs + 2 * (size_t)mid) <= (uint32_t)x) lo = mid; else hi = mid;
     }
-    uint2 cur = __ldg(&runs[lo]);
-    uint32_t next_x0 = lo + 1 < end ? __ldg(&runs[lo + 1]).x : 0xFFFFFFFFu;
+    uint32_t cur_label = __ldg(runs + 2 * (size_t)lo + 1);
+    uint32_t next_x0 = lo + 1 < end ? __ldg(runs + 2 * (size_t)lo + 2) : 0xFFFFFFFFu;
     int32_t out[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         while ((uint32_t)(x + k) >= next_x0) {
             ++lo;
-            cur = __ldg(&runs[lo]);
-            next_x0 = lo + 1 < end ? __ldg(&runs[lo + 1]).x : 0xFFFFFFFFu;
+            cur_label = __ldg(runs + 2 * (size_t)lo + 1);
+            next_x0 = lo + 1 < end ? __ldg(runs + 2 * (size_t)lo + 2) : 0xFFFFFFFFu;
         }
-        out[k] = (int32_t)cur.y;
+        out[k] = (int32_t)cur_label;
     }
     int32_t* dst = labels + ((size_t)f * H + y) * W + x;
     if (x + 4 <= W && (W & 3) == 0) {
