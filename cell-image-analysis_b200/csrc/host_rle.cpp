@@ -3,6 +3,7 @@
 // form (chosen at run time) compares 32 labels with their left neighbours per step.
 #include <cstddef>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 
 #if defined(__x86_64__) && defined(__GNUC__)
@@ -123,7 +124,8 @@ __attribute__((target("avx2"))) size_t encode_field_avx2(const int32_t* lab, int
 size_t cia_host_encode_field(const int32_t* lab, int H, int W, uint32_t* slot, size_t slot_words,
                              int32_t* max_label) {
 #if CIA_HAVE_AVX2_PATH
-    static const bool avx2 = __builtin_cpu_supports("avx2");
+    // CIA_HOST_RLE_SCALAR=1 forces the portable path (tests compare the two word for word)
+    static const bool avx2 = __builtin_cpu_supports("avx2") && getenv("CIA_HOST_RLE_SCALAR") == nullptr;
     if (avx2) return encode_field_avx2(lab, H, W, slot, slot_words, max_label);
 #endif
     return encode_field_impl(lab, H, W, slot, slot_words, max_label, run_end_scalar);

@@ -66,6 +66,46 @@ def test_rle_encode_capacity_cpu():
     assert lib.cia_rle_encode_fields(None, 1, H, W, slots.ctypes.data, sw, words.ctypes.data, None, 1) == _lib.CIA_E_ARG
 
 
+_DIGEST_SNIPPET = """
+import hashlib, sys
+import numpy as np
+sys.path.insert(0, {root!r})
+from cell_image_analysis_b200 import _lib
+lib = _lib.load()
+rng = np.random.default_rng(11)
+h = hashlib.sha256()
+for H, W in ((3, 31), (5, 32), (4, 33), (7, 64), (6, 97), (9, 1030), (64, 2048)):
+    # runs of random lengths, boundaries on and around the 8- and 32-label steps, repeated labels
+    lens = rng.integers(1, 70, size=H * W)
+    vals = rng.integers(0, 5, size=H * W, dtype=np.int32) * rng.integers(1, 2**30, size=H * W, dtype=np.int32)
+    lab = np.ascontiguousarray(np.repeat(vals, lens)[:H * W].reshape(1, H, W))
+    sw = 2 * H * W + H + 4
+    slots = np.zeros((1, sw), np.uint32); words = np.zeros(1, np.uint32)
+    assert lib.cia_rle_encode_fields(lab.ctypes.data, 1, H, W, slots.ctypes.data, sw, words.ctypes.data, None, 1) == 0
+    h.update(slots[0, :words[0]].tobytes())
+print(h.hexdigest())
+"""
+
+
+def test_rle_encoder_avx2_and_scalar_paths_agree_cpu():
+    """The streaming AVX2 encoder and the portable run-by-run encoder emit identical slots."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = _DIGEST_SNIPPET.format(root=root)
+    outs = []
+    for scalar in (False, True):
+        env = dict(os.environ)
+        env.pop("CIA_HOST_RLE_SCALAR", None)
+        if scalar:
+            env["CIA_HOST_RLE_SCALAR"] = "1"
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(r.stdout.strip().splitlines()[-1])
+    assert len(outs[0]) == 64 and outs[0] == outs[1]
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("shape", [(64, 64), (37, 101), (128, 1030), (512, 2048)])
 def test_rle_expand_gpu(shape):
