@@ -66,6 +66,43 @@ def test_rle_encode_capacity_cpu():
     assert lib.cia_rle_encode_fields(None, 1, H, W, slots.ctypes.data, sw, words.ctypes.data, None, 1) == _lib.CIA_E_ARG
 
 
+def test_run_closed_forms_equal_pixel_sums_cpu():
+    """The algebra of label_scan_rle_kernel (scan.cu) restated in integers: per run (row r,
+    columns [x0, x1)) area += x1-x0, m01 += (x0+x1-1)(x1-x0)/2, m02 by the cubic formula, m10/m20/m11
+    from r -- summed over the encoded runs they equal the per-pixel sums and bboxes of the field."""
+    H, W = 96, 200
+    lab = np.ascontiguousarray(make_field(8, H, W, 12, 5.0, 12.0)[1][None])
+    lib = _lib.load()
+    sw = 2 * H * W + H + 4
+    slots = np.zeros((1, sw), np.uint32); words = np.zeros(1, np.uint32)
+    assert lib.cia_rle_encode_fields(lab.ctypes.data, 1, H, W, slots.ctypes.data, sw, words.ctypes.data, None, 1) == 0
+    slot, r0 = slots[0].astype(np.int64), (H + 2) & ~1
+    acc = {}
+    for r in range(H):
+        lo, hi = int(slot[r]), int(slot[r + 1])
+        for j in range(lo, hi):
+            x0, l = int(slot[r0 + 2 * j]), int(slot[r0 + 2 * j + 1])
+            x1 = int(slot[r0 + 2 * j + 2]) if j + 1 < hi else W
+            if l == 0:
+                continue
+            a = acc.setdefault(l, dict(area=0, m10=0, m01=0, m20=0, m02=0, m11=0, minr=H, minc=W, maxr=0, maxc=0))
+            cnt = x1 - x0
+            sc = (x0 + x1 - 1) * cnt // 2
+            sc2 = ((x1 - 1) * x1 * (2 * x1 - 1) - (x0 - 1) * x0 * (2 * x0 - 1)) // 6
+            a["area"] += cnt; a["m10"] += r * cnt; a["m01"] += sc
+            a["m20"] += r * r * cnt; a["m02"] += sc2; a["m11"] += r * sc
+            a["minr"] = min(a["minr"], r); a["maxr"] = max(a["maxr"], r + 1)
+            a["minc"] = min(a["minc"], x0); a["maxc"] = max(a["maxc"], x1)
+    present = [int(v) for v in np.unique(lab) if v != 0]
+    assert sorted(acc) == present and len(present) >= 5
+    for l in present:
+        rr, cc = np.nonzero(lab[0] == l)
+        rr, cc = rr.astype(np.int64), cc.astype(np.int64)
+        want = dict(area=len(rr), m10=rr.sum(), m01=cc.sum(), m20=(rr * rr).sum(), m02=(cc * cc).sum(),
+                    m11=(rr * cc).sum(), minr=rr.min(), minc=cc.min(), maxr=rr.max() + 1, maxc=cc.max() + 1)
+        assert {k: int(v) for k, v in want.items()} == acc[l], l
+
+
 _DIGEST_SNIPPET = """
 import hashlib, sys
 import numpy as np
