@@ -11,7 +11,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcia.so")
 SOURCES = ["api.cu", "scan.cu", "crop.cu", "cae_fp32.cu", "cae_tc.cu", "score.cu", "transport.cu", "host_rle.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "--use_fast_math=false"]
+              "-Xcompiler", "-fPIC"]
 
 
 def _nvcc():
@@ -41,8 +41,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             cmd = [shutil.which("g++") or "g++", "-O3", "-std=c++17", "-fPIC", "-c", os.path.join(CSRC, src), "-o", obj]
             procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
             continue
-        cmd = [_nvcc(), *[f for f in NVCC_FLAGS if f != "--use_fast_math=false"],
-               *os.environ.get("CIA_NVCC_EXTRA", "").split(), "-c",
+        cmd = [_nvcc(), *NVCC_FLAGS, *os.environ.get("CIA_NVCC_EXTRA", "").split(), "-c",
                os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")

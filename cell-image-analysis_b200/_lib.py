@@ -37,7 +37,7 @@ class Cell(C.Structure):
 class Params(C.Structure):
     _fields_ = [("border_margin", C.c_int32), ("area_min", C.c_int32), ("area_max", C.c_int32),
                 ("ecc_max", C.c_double), ("mean_min", C.c_double), ("std_min", C.c_double),
-                ("clip_limit", C.c_double)]
+                ("clip_limit", C.c_double), ("intensity_inv", C.c_double)]
 
 
 class Scores(C.Structure):
@@ -65,6 +65,7 @@ SIGNATURES = {
     "cia_last_error": (C.c_char_p, [_P]),
     "cia_default_params": (None, [C.POINTER(Params)]),
     "cia_check_status": (_I, [_P, _P]),
+    "cia_set_option": (_I, [_P, C.c_char_p, C.c_double]),
     "cia_load_cae": (_I, [_P, _I, _I, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.c_float]),
     "cia_load_scaler_pca": (_I, [_P, _I, _I, _P, _P, _I, _P, _P, _I]),
     "cia_load_svm": (_I, [_P, _I, _I, _I, _P, _P, C.c_double, C.c_double]),

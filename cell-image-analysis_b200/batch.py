@@ -25,29 +25,18 @@ STAGES = ("scan", "gates", "crop", "cae", "svm", "accumulate")
 class BatchScreen:
     def __init__(self, engine, H: int, W: int, max_label: int, chunk_fields: int = 16,
                  n_strains: int = 1, cells_per_field_cap: int | None = None,
-                 label_transport: str = "rle", host_threads: int = 0, rle_fraction: float | str = 1.0,
-                 scan_runs: bool = True, pcie_gbs: float = 55.0):
+                 label_transport: str = "rle", host_threads: int = 0, rle_fraction: float = 1.0,
+                 scan_runs: bool = True):
         """``label_transport``: "rle" run-length encodes the int32 label fields on the host
         cores (csrc/transport.cu) so that only the runs cross PCIe; "raw" copies them as is.
         ``rle_fraction`` < 1 sends only that share of the chunks as runs and the rest raw (several
         ranks sharing the host cores: the encoder and the PCIe link then work side by side).
-        "auto" picks the share during the pass from what it measures: the host time of every
-        encode call and the H2D rate of every image copy (CUDA events on the copy stream); the
-        pass is bound by max(encoder, link), the encoder's time grows and the link's shrinks with
-        f, so f = (t_image + t_raw_labels) / (t_encode + t_raw_labels - t_runs), clipped to
-        [0.1, 1] -- 1 on a host whose cores keep up, less on a slow or shared one.  (Measured on
-        one GPU it is no better than f = 1: with two staging buffers a whole raw chunk is a 15 ms
-        burst on the link that the pipeline cannot smooth, so ``bench.py`` uses fixed shares.)
         ``scan_runs``: build the region table from the runs themselves (``cia_screen_fields_rle``);
         False expands them to the dense field first (``cia_rle_expand``)."""
         assert label_transport in ("rle", "raw")
         self.label_transport, self.host_threads = label_transport, host_threads
-        self.auto_fraction = label_transport == "rle" and rle_fraction == "auto"
-        if self.auto_fraction:
-            rle_fraction = 1.0
         self.rle_fraction = 1.0 if label_transport == "rle" and rle_fraction >= 1.0 else \
             (0.0 if label_transport == "raw" else max(0.0, float(rle_fraction)))
-        self._t_enc, self._pcie_rate, self._rle_bytes, self._credit = None, pcie_gbs * 1e9, 0.0, 0.0
         self.scan_runs = scan_runs
         self.eng = engine
         self.H, self.W, self.max_label = H, W, max_label
@@ -108,9 +97,7 @@ class BatchScreen:
                 ready=[torch.cuda.Event() for _ in range(2)],
                 done=[torch.cuda.Event() for _ in range(2)],
                 out_ready=[torch.cuda.Event() for _ in range(2)],
-                out_free=[torch.cuda.Event() for _ in range(2)],
-                c0=[torch.cuda.Event(enable_timing=True) for _ in range(2)],
-                c1=[torch.cuda.Event(enable_timing=True) for _ in range(2)], timed=[False, False])
+                out_free=[torch.cuda.Event() for _ in range(2)])
             if self.label_transport == "rle":
                 sw = self.eng.rle_slot_words(self.H, self.W)
                 self._stage.update(
@@ -149,32 +136,16 @@ class BatchScreen:
         S, eng = self._stage, self.eng
         px = self.Fc * self.H * self.W
         self.h2d_bytes = 0
+        self.encode_seconds = 0.0          # host time spent inside the run-length encoder this pass
         n_rle = 0
         for i in range(n_chunks):
             b = i & 1
             p0 = (i * self.Fc) % P
-            if self.auto_fraction:
-                if S["timed"][b] and S["c1"][b].query():       # H2D rate of this buffer's previous image copy
-                    ms = S["c0"][b].elapsed_time(S["c1"][b])
-                    if ms > 0:
-                        self._pcie_rate = 0.7 * self._pcie_rate + 0.3 * (2 * px / (ms * 1e-3))
-                if self._t_enc is not None:
-                    r = self._pcie_rate
-                    f = (6 * px / r) / (self._t_enc + (4 * px - self._rle_bytes) / r)
-                    self.rle_fraction = min(1.0, max(0.1, f))
-                self._credit += self.rle_fraction
-                rle = self._credit >= 1.0 - 1e-9
-                if rle:
-                    self._credit -= 1.0
-            else:
-                f = self.rle_fraction
-                rle = self.label_transport == "rle" and int((i + 1) * f) > int(i * f)
+            f = self.rle_fraction
+            rle = self.label_transport == "rle" and int((i + 1) * f) > int(i * f)
             with torch.cuda.stream(self.copy):
                 self.copy.wait_event(S["done"][b])
-                S["c0"][b].record(self.copy)
                 S["img"][b].copy_(images_pinned[p0:p0 + self.Fc], non_blocking=True)
-                S["c1"][b].record(self.copy)
-                S["timed"][b] = True
             if rle:
                 # the host encodes chunk i while its image copy and the device's work on chunk i-1
                 # are in flight; the slot buffer is reused only after its previous upload (chunk i-2)
@@ -182,10 +153,7 @@ class BatchScreen:
                 t0 = time.perf_counter()
                 rle = eng.rle_encode(labels_pinned[p0:p0 + self.Fc], S["h_rle"][b], S["words"][b],
                                      self.host_threads)
-                dt = time.perf_counter() - t0
-                self._t_enc = dt if self._t_enc is None else 0.7 * self._t_enc + 0.3 * dt
-                if rle:
-                    self._rle_bytes = 4.0 * float(S["words"][b].sum())
+                self.encode_seconds += time.perf_counter() - t0
             with torch.cuda.stream(self.copy):
                 if rle:
                     n_rle += 1
@@ -222,10 +190,16 @@ class BatchScreen:
         self.last_rle_share = n_rle / max(n_chunks, 1)        # share of the chunks that crossed PCIe as runs
 
     def collect_host(self):
-        """Compact the per-chunk host buffers of the last ``run_host`` into flat arrays."""
+        """Compact the per-chunk host buffers of the last ``run_host`` into flat arrays.  Raises if
+        a kernel of the pass reported a capacity overflow, an out-of-range label or an unsupported
+        bbox (nothing is truncated silently)."""
+        self.sync()
         n_chunks = self._last_chunks
         counts = self.h_counts[:n_chunks].numpy()
-        ks = np.minimum(counts[:, 0], self.cap)
+        if (counts[:, 0] > self.cap).any():
+            raise _lib.CiaError(_lib.CIA_E_CAPACITY, f"a chunk produced {int(counts[:, 0].max())} cells, capacity "
+                                f"{self.cap} (raise cells_per_field_cap)")
+        ks = counts[:, 0]
         cat = lambda t: np.concatenate([t[i, :ks[i]].numpy() for i in range(n_chunks)])
         cells = np.concatenate([self.h_cells[i, :ks[i]].numpy().view(_lib.CELL_DTYPE).reshape(-1)
                                 for i in range(n_chunks)])
@@ -237,6 +211,8 @@ class BatchScreen:
                     dec_mod=cat(self.h_dm), pred_cons=cat(self.h_pc), pred_mod=cat(self.h_pm))
 
     def sync(self):
-        self.compute.synchronize()
+        """Wait for every stream of the pass and raise on a device-side status (CIA_E_CAPACITY /
+        _LABEL / _UNSUPPORTED) raised by any of its kernels."""
         self.copy.synchronize()
         self.d2h.synchronize()
+        self.eng.check_status(self.compute)

@@ -3,6 +3,7 @@
 #include "common.cuh"
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -31,6 +32,7 @@ void cia_default_params(cia_params* p) {
     p->mean_min = 0.5;          // det:94
     p->std_min = 0.1;
     p->clip_limit = 0.02;       // det:98
+    p->intensity_inv = 1.0 / 65535.0;   // img_as_float of a uint16 image (inside det:98)
 }
 
 int cia_create(int device, cia_handle* out) {
@@ -53,7 +55,29 @@ int cia_create(int device, cia_handle* out) {
         delete h;
         return CIA_E_CUDA;
     }
+    // run-time defaults of the options (A/B scripts): see cia_set_option
+    if (const char* e = getenv("CIA_CAE_CHUNK")) { const int v = atoi(e); if (v > 0) h->cae_pass_cells = v; }
+    if (const char* e = getenv("CIA_L1_DEBIAS")) h->cae_debias[0] = (float)atof(e);
+    if (const char* e = getenv("CIA_L2_DEBIAS")) h->cae_debias[1] = (float)atof(e);
+    if (const char* e = getenv("CIA_L3_DEBIAS")) h->cae_debias[2] = (float)atof(e);
     *out = h;
+    return CIA_OK;
+}
+
+int cia_set_option(cia_handle h, const char* name, double value) {
+    if (!h) return bad_handle();
+    if (!name) { h->err = "cia_set_option: null name"; return CIA_E_ARG; }
+    const std::string n(name);
+    if (n == "cae_pass_cells") {
+        if (!(value >= 1 && value <= 1 << 20)) { h->err = "cia_set_option: cae_pass_cells must be in [1, 2^20]"; return CIA_E_ARG; }
+        h->cae_pass_cells = (int)value;
+    } else if (n == "cae_l1_debias" || n == "cae_l2_debias" || n == "cae_l3_debias") {
+        if (!(value >= 0 && value <= 64)) { h->err = "cia_set_option: debias must be in [0, 64] (units of 2^-24)"; return CIA_E_ARG; }
+        h->cae_debias[n[5] - '1'] = (float)value;
+    } else {
+        h->err = "cia_set_option: unknown option '" + n + "'";
+        return CIA_E_ARG;
+    }
     return CIA_OK;
 }
 
@@ -98,7 +122,7 @@ int cia_debug_copy_workspace(cia_handle h, int ws_id, size_t offset, void* dst_h
     if (!h) return bad_handle();
     Workspace* ws[] = {&h->ws_flags, &h->ws_act, &h->ws_crop_scratch, &h->ws_pipe, &h->ws_feat,
                        &h->ws_misc, &h->ws_stage, &h->ws_svm};
-    if (ws_id < 0 || ws_id >= 7 || !dst_host || offset + bytes > ws[ws_id]->cap) {
+    if (ws_id < 0 || ws_id >= (int)(sizeof(ws) / sizeof(ws[0])) || !dst_host || offset + bytes > ws[ws_id]->cap) {
         h->err = "cia_debug_copy_workspace: bad argument";
         return CIA_E_ARG;
     }

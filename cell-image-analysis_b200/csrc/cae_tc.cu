@@ -118,7 +118,9 @@ __host__ __device__ constexpr int pow2_cols(int c) { return c <= 32 ? 32 : c <= 
 // deficit of the whole sum is a fixed fraction of the sum and is added back here with the bias.
 __device__ __forceinline__ float pooled_act(float folded_max, float inv_scale, float invd, float b, float s, float t) {
     const float m = __uint_as_float(__float_as_uint(folded_max) ^ (__float_as_uint(s) & 0x80000000u));
-    return fmaf(fmaxf(fmaf(m, inv_scale, fmaf(m, invd, b)), 0.f), s, t);
+    // BatchNormalization as Keras evaluates it: x * inv + offset, a product and a sum rounded
+    // separately (not one FMA) -- the oracle and the exact-fp32 path do the same
+    return __fadd_rn(__fmul_rn(fmaxf(fmaf(m, inv_scale, fmaf(m, invd, b)), 0.f), s), t);
 }
 
 __device__ __forceinline__ void split_store8(const float (&o)[8], __half* hi_dst, __half* lo_dst) {
@@ -460,7 +462,7 @@ conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_l
 #pragma unroll
                             for (int k = 0; k < 8; ++k) {
                                 const float a = fmaxf(fmaf(__uint_as_float(v[ph][k]), inv_scale, b8[k]), 0.f);
-                                o[k] = fmaf(a, s8[k], t8[k]);
+                                o[k] = __fadd_rn(__fmul_rn(a, s8[k]), t8[k]);
                             }
                             const size_t off = ((((size_t)cell * (CREAL / 8) + cs) * RO + 2 * y + (ph >> 1)) * RO +
                                                 2 * x + (ph & 1)) * 8;
@@ -501,7 +503,7 @@ conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_l
                     for (int k = 0; k < 8; ++k) {
                         float a = fmaf(__uint_as_float(v[k]), inv_scale, __ldg(bias + c0 + k));
                         a = fmaxf(a, 0.f);
-                        o[k] = fmaf(a, __ldg(bn_s + c0 + k), __ldg(bn_t + c0 + k));
+                        o[k] = __fadd_rn(__fmul_rn(a, __ldg(bn_s + c0 + k)), __ldg(bn_t + c0 + k));
                     }
                     if (y < R) {
                         const size_t off = ((((size_t)cell * (COUT / 8) + sl) * R + y) * R + x) * 8;
@@ -1322,14 +1324,14 @@ conv1_fp32_planar_kernel(const float* __restrict__ crops, const float* __restric
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     const float m = fmaxf(fmaxf(acc[0][k], acc[1][k]), fmaxf(acc[2][k], acc[3][k]));
-                    o[k] = fmaf(fmaxf(m, 0.f), s8[k], t8[k]);
+                    o[k] = __fadd_rn(__fmul_rn(fmaxf(m, 0.f), s8[k]), t8[k]);
                 }
             } else {
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     float m = -INFINITY;
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) m = fmaxf(m, fmaf(fmaxf(acc[q][k], 0.f), s8[k], t8[k]));
+                    for (int q = 0; q < 4; ++q) m = fmaxf(m, __fadd_rn(__fmul_rn(fmaxf(acc[q][k], 0.f), s8[k]), t8[k]));
                     o[k] = m;
                 }
             }
@@ -1604,12 +1606,8 @@ static inline void acc_timing_dump(const char*, int, int, int, int, cudaStream_t
 #endif
 
 // mean relative deficit of the accumulating kernels' truncated sums, in units of 2^-24
-// (CIA_L2_DEBIAS / CIA_L3_DEBIAS; calibrated against the correctly rounded oracle, 0 = off)
-static float acc_debias(int layer) {
-    static const float d2 = [] { const char* e = getenv("CIA_L2_DEBIAS"); return (e ? (float)atof(e) : 2.4f) * 5.9604645e-8f; }();
-    static const float d3 = [] { const char* e = getenv("CIA_L3_DEBIAS"); return (e ? (float)atof(e) : 1.2f) * 5.9604645e-8f; }();
-    return layer == 1 ? d2 : d3;
-}
+// (cia_set_option "cae_l2_debias" / "cae_l3_debias", 0 = off; derivation in DESIGN.md section 5)
+static float acc_debias(const cia_ctx* h, int layer) { return h->cae_debias[layer == 1 ? 1 : 2] * 5.9604645e-8f; }
 
 template <int CIN, int COUT, int R, int G = 1>
 int launch_tc_acc(cia_ctx* h, const CaeWeights& w, int layer, const __half* in_hi, const __half* in_lo,
@@ -1623,7 +1621,7 @@ int launch_tc_acc(cia_ctx* h, const CaeWeights& w, int layer, const __half* in_h
     if (grid > h->num_sms) grid = h->num_sms;
     kern<<<grid, ACC_THREADS, C::SMEM_B, s>>>(in_hi, in_lo, (const uint4*)w.tc_w[layer][0],
                                               (const uint4*)w.tc_w[layer][1], w.tc_inv_scale[layer],
-                                              w.tc_inv_scale[layer] * acc_debias(layer), w.bias[layer],
+                                              w.tc_inv_scale[layer] * acc_debias(h, layer), w.bias[layer],
                                               w.bn_scale[layer], w.bn_shift[layer], out_hi, out_lo, feat, n, n_dev,
                                               cell0, chunk);
     CIA_LAUNCH_CHECK();
@@ -1676,7 +1674,7 @@ int launch_tc_acc2(cia_ctx* h, const CaeWeights& w, int layer, const __half* in_
     if (grid > h->num_sms) grid = h->num_sms;
     kern<<<grid, ACC_THREADS, C::SMEM_B, s>>>(tm_hi, tm_lo, (const uint4*)w.tc_w[layer][0],
                                               (const uint4*)w.tc_w[layer][1], w.tc_inv_scale[layer],
-                                              w.tc_inv_scale[layer] * acc_debias(layer), w.bias[layer],
+                                              w.tc_inv_scale[layer] * acc_debias(h, layer), w.bias[layer],
                                               w.bn_scale[layer], w.bn_shift[layer], out_hi, out_lo, feat, n, n_dev,
                                               cell0, chunk);
     CIA_LAUNCH_CHECK();
@@ -1822,7 +1820,7 @@ int k_cae_forward_tc(cia_ctx* h, const float* crops, int n, const int32_t* n_dev
     // 1024 -> 49 ms, 16576 (112 per SM) -> 39.6 ms for the same 121k cells.  303 KB of workspace per cell.
     // The cap is 128 cells per SM so that a 32-field chunk (capacity 32 x ~520 labels = 16640 cells) is ONE
     // pass: with 16576 every chunk launched a second, empty pass of all seven kernels.
-    static const int CH_MAX = [] { const char* e = getenv("CIA_CAE_CHUNK"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 18944; }();
+    const int CH_MAX = h->cae_pass_cells;
     const int CH = n < CH_MAX ? (n + 147) / 148 * 148 : CH_MAX;
     // halves per cell; A4 / A5 are stored at their own (pre-upsampling) resolution
     const size_t a1 = 4 * 32 * 32 * 8, a2 = 8 * 16 * 16 * 8, a3 = 4 * 8 * 8 * 8, a4u = 4 * 8 * 8 * 8,
@@ -1872,9 +1870,9 @@ int k_cae_forward_tc(cia_ctx* h, const float* crops, int n, const int32_t* n_dev
         CIA_LMARK(0);
         if (tc_feat || l3_exact) {
             // CIA_L1_KERNEL=0 keeps layer 1 on the CUDA cores (exact fp32 FMA chains) for A/B runs;
-            // CIA_L1_DEBIAS scales the half-ulp truncation compensation (default 0.5 * 2^-24 measured against the exact kernel, 0 = off)
+            // the half-ulp truncation compensation of its single accumulation: cia_set_option "cae_l1_debias"
             static const int l1_tc = [] { const char* e = getenv("CIA_L1_KERNEL"); return e ? atoi(e) : 1; }();
-            static const float l1_debias = [] { const char* e = getenv("CIA_L1_DEBIAS"); return (e ? (float)atof(e) : 0.5f) * 5.9604645e-8f; }();
+            const float l1_debias = h->cae_debias[0] * 5.9604645e-8f;
             if (l1_tc) {
                 if (first_use(h, (const void*)conv1_tc_split_kernel))
                     CIA_CUDA(cudaFuncSetAttribute(conv1_tc_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, l1tc::SMEM_B));

@@ -87,6 +87,10 @@ struct cia_ctx {
     cudaEvent_t* layer_ev = nullptr;      // the current call's layer marks (null: not profiling)
     bool prof_layers_valid = false;
     int prof_records = 0, prof_used = 0;
+    // cia_set_option: cells per pass of the tensor-core autoencoder (303 KB of activations per cell)
+    // and the truncation compensation of its accumulating layers in units of 2^-24 (cae_tc.cu)
+    int cae_pass_cells = 18944;
+    float cae_debias[3] = {0.5f, 2.4f, 1.2f};   // L1, L2, L3
 };
 #define CIA_LAYER_MARKS 8  // before L1, after L1 .. L7
 #define CIA_LAYER_PASSES 8 // passes of one call that carry marks (cells_cap <= 8 x 18944)

@@ -213,7 +213,7 @@ crop_classify_kernel(const cia_cell* __restrict__ cells, int n_cells,
 __global__ void __launch_bounds__(K2_THREADS)
 crop_clahe_resize_kernel(const uint16_t* __restrict__ images, int H, int W,
                          const cia_cell* __restrict__ cells, int n_cells,
-                         const int32_t* __restrict__ n_cells_dev, double clip_limit,
+                         const int32_t* __restrict__ n_cells_dev, double clip_limit, double intensity_inv,
                          float* __restrict__ crops32, double* __restrict__ crops64,
                          int cls, size_t lo_bytes, size_t hi_bytes,
                          unsigned char* __restrict__ gscratch, size_t gscratch_per_cta,
@@ -280,7 +280,7 @@ crop_clahe_resize_kernel(const uint16_t* __restrict__ images, int H, int W,
 
         // ---- B: 14-bit quantise (round half even) and bin ----
         {
-            const double inv = 1.0 / 65535.0;
+            const double inv = intensity_inv;
             const double vmin = __dmul_rn((double)mn, inv), vmax = __dmul_rn((double)mx, inv);
             const double den = __dsub_rn(vmax, vmin);
             for (int i = tid; i < hw; i += K2_THREADS) {
@@ -530,15 +530,15 @@ int k_crop_resize(cia_ctx* h, const uint16_t* images, int H, int W, const cia_ce
     int g1 = h->num_sms;     if (g1 > n_cells) g1 = n_cells;
     int g2 = huge_ctas;      if (g2 > n_cells) g2 = n_cells;
     crop_clahe_resize_kernel<<<g0, K2_THREADS, lo_bytes, s>>>(
-        images, H, W, cells, n_cells, n_cells_dev, p->clip_limit, crops32, crops64, 0, lo_bytes,
+        images, H, W, cells, n_cells, n_cells_dev, p->clip_limit, p->intensity_inv, crops32, crops64, 0, lo_bytes,
         hi_bytes, nullptr, 0, h->status_dev, levels_out, level_offsets, nullptr, nullptr);
     CIA_LAUNCH_CHECK();
     crop_clahe_resize_kernel<<<g1, K2_THREADS, hi_bytes, s>>>(
-        images, H, W, cells, n_cells, n_cells_dev, p->clip_limit, crops32, crops64, 1, lo_bytes,
+        images, H, W, cells, n_cells, n_cells_dev, p->clip_limit, p->intensity_inv, crops32, crops64, 1, lo_bytes,
         hi_bytes, nullptr, 0, h->status_dev, levels_out, level_offsets, list1, cls_counts + 0);
     CIA_LAUNCH_CHECK();
     crop_clahe_resize_kernel<<<g2, K2_THREADS, 0, s>>>(
-        images, H, W, cells, n_cells, n_cells_dev, p->clip_limit, crops32, crops64, 2, lo_bytes,
+        images, H, W, cells, n_cells, n_cells_dev, p->clip_limit, p->intensity_inv, crops32, crops64, 2, lo_bytes,
         hi_bytes, gscratch, per_cta, h->status_dev, levels_out, level_offsets, list2, cls_counts + 1);
     CIA_LAUNCH_CHECK();
     return CIA_OK;

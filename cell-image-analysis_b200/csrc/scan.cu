@@ -46,10 +46,13 @@ label_scan_kernel(const int32_t* __restrict__ labels, int n_fields, int H, int W
         // background-only segments (the majority) leave before the range check: 0 is in range
         const unsigned any = __ballot_sync(0xffffffffu, (lab[0] | lab[1] | lab[2] | lab[3]) != 0);
         if (any == 0) continue;
+        // negative labels are background, as scipy.ndimage.find_objects (behind regionprops, det:67)
+        // treats them; a label above max_label cannot come from labels.max() and is reported
         bool bad = false;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            if ((unsigned)lab[k] > (unsigned)max_label) { bad = true; lab[k] = 0; }
+            if (lab[k] > max_label) bad = true;
+            if ((unsigned)lab[k] > (unsigned)max_label) lab[k] = 0;
         }
         if (bad) raise_status(status, CIA_E_LABEL);
 
@@ -122,8 +125,8 @@ label_scan_rle_kernel(const uint32_t* __restrict__ slots, size_t slot_words, int
     cia_region* tab = regions + (size_t)f * max_label;
     for (uint32_t j = blockIdx.x * SCAN_THREADS + threadIdx.x; j < n_runs; j += gridDim.x * SCAN_THREADS) {
         const int l = (int)__ldg(runs + 2 * (size_t)j + 1);
-        if (l == 0) continue;
-        if (l < 0 || l > max_label) { raise_status(status, CIA_E_LABEL); continue; }
+        if (l <= 0) continue;                                 // negative labels: background (find_objects)
+        if (l > max_label) { raise_status(status, CIA_E_LABEL); continue; }
         int lo = 0, hi = H;                                   // largest r with row_off[r] <= j
         while (hi - lo > 1) {
             const int mid = (lo + hi) >> 1;

@@ -69,8 +69,14 @@ class Engine:
     def _check(self, rc):
         _lib.check(self.h, rc)
 
-    def check_status(self):
-        self._check(self.lib.cia_check_status(self.h, self._stream()))
+    def check_status(self, stream=None):
+        """Raise if a kernel reported CIA_E_CAPACITY / _LABEL / _UNSUPPORTED since the last check
+        (synchronises ``stream``, default torch's current stream)."""
+        s = self._stream() if stream is None else C.c_void_p(stream.cuda_stream)
+        self._check(self.lib.cia_check_status(self.h, s))
+
+    def set_option(self, name: str, value: float):
+        self._check(self.lib.cia_set_option(self.h, name.encode(), float(value)))
 
     @property
     def launch_count(self) -> int:
@@ -123,12 +129,12 @@ class Engine:
         return cells, counts
 
     def crop_resize(self, images: torch.Tensor, cells: torch.Tensor, n: int, n_dev=None,
-                    want64: bool = False):
+                    want64: bool = False, params=None):
         F, H, W = images.shape
         c32 = torch.empty((max(n, 1), 64, 64), dtype=torch.float32, device=self.tdev)
         c64 = torch.empty((max(n, 1), 64, 64), dtype=torch.float64, device=self.tdev) if want64 else None
         self._check(self.lib.cia_crop_resize(self.h, _ptr(images), H, W, _ptr(cells), n, _ptr(n_dev),
-                                             C.byref(self.params), _ptr(c32), _ptr(c64), self._stream()))
+                                             C.byref(params or self.params), _ptr(c32), _ptr(c64), self._stream()))
         return c32, c64
 
     def debug_clahe_levels(self, images: torch.Tensor, cells: torch.Tensor, n: int, sizes):
@@ -298,6 +304,12 @@ def _default_imread(path):
         return img
 
 
+class UnsupportedImageError(TypeError):
+    """The analysis channel has a dtype the CUDA path does not take (anything but 8- / 16-bit
+    unsigned).  Raised THROUGH the catch-all of ``extract_quality_cells`` (det:113-115) so that
+    such a file is not silently counted as "0 cells"."""
+
+
 class ProductionMutantScreening:
     """Drop-in for the reference class of the same name (improved_detection.py:18).
 
@@ -349,6 +361,8 @@ class ProductionMutantScreening:
                 green_channel = image
             labels = self._segment(seg_channel)
             return self.extract_quality_cells_from_labels(green_channel, labels)
+        except UnsupportedImageError:
+            raise
         except Exception as e:                                   # det:113-115
             print(f"Error processing {image_path}: {e}")
             return [], []
@@ -357,8 +371,18 @@ class ProductionMutantScreening:
     def extract_quality_cells_from_labels(self, green_channel, labels, return_regions=False):
         eng = self.engine
         green = np.ascontiguousarray(green_channel)
-        if green.dtype != np.uint16:
-            raise TypeError("green channel must be uint16 (16-bit TIFF field)")
+        params = self.engine.params
+        if green.dtype == np.uint8:
+            # 8-bit fields: same arithmetic on the widened values; only img_as_float's factor inside
+            # equalize_adapthist (det:98) differs (1/255 instead of 1/65535)
+            green = green.astype(np.uint16)
+            params = _lib.default_params()
+            C.memmove(C.byref(params), C.byref(self.engine.params), C.sizeof(params))
+            params.intensity_inv = 1.0 / 255.0
+        elif green.dtype != np.uint16:
+            raise UnsupportedImageError(
+                f"analysis channel dtype {green.dtype}: the CUDA path takes uint16 (16-bit TIFF fields) and "
+                "uint8 images; convert float / signed images before screening")
         lab = np.ascontiguousarray(labels, dtype=np.int32)
         if lab.shape != green.shape or lab.ndim != 2:
             raise ValueError("labels and image must be 2-D arrays of the same shape")
@@ -373,7 +397,7 @@ class ProductionMutantScreening:
         eng.check_status()
         if n == 0:
             return ([], [], regions) if return_regions else ([], [])
-        _c32, c64 = eng.crop_resize(g, cells, n, want64=True)
+        _c32, c64 = eng.crop_resize(g, cells, n, want64=True, params=params)
         eng.check_status()
         crops = c64[:n].cpu().numpy()
         rec = cells[:n].cpu().numpy().view(_lib.CELL_DTYPE).reshape(-1)

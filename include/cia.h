@@ -75,6 +75,9 @@ typedef struct cia_params {
     double  ecc_max;                /* 0.95                                          */
     double  mean_min, std_min;      /* 0.5, 0.1                                      */
     double  clip_limit;             /* 0.02                                          */
+    double  intensity_inv;          /* 1/65535: img_as_float's factor inside equalize_adapthist
+                                     * (det:98) for 16-bit fields; 1/255 when an 8-bit field was
+                                     * widened to uint16 by the caller                              */
 } cia_params;
 
 /* Per-cell scores, the arrays of the dict at det:144-153 (signs as libsvm returns
@@ -97,6 +100,16 @@ void cia_default_params(cia_params* p);
 /* Reads back the device status word (synchronises `stream`): 0 or a CIA_E_* code
  * raised by a kernel since the last check (capacity / label / unsupported). */
 int  cia_check_status(cia_handle h, void* stream);
+/* Tuning knobs of the handle (no reference counterpart; defaults reproduce the documented
+ * behaviour).  Unknown names / out-of-range values give CIA_E_ARG.
+ *   "cae_pass_cells"  cells per pass of the tensor-core autoencoder over its seven layers
+ *                     (default 18944 = 128 per SM; 303 KB of fp16 activations per cell);
+ *                     results do not depend on it (tests/test_gpu_multipass.py)
+ *   "cae_l1_debias", "cae_l2_debias", "cae_l3_debias"
+ *                     compensation of tcgen05's round-toward-zero accumulation in the
+ *                     split-precision encoder layers, in units of 2^-24 relative
+ *                     (defaults 0.5 / 2.4 / 1.2, 0 = off) */
+int  cia_set_option(cia_handle h, const char* name, double value);
 
 /* ---- artifacts (replaces load_trained_models, det:23-41) ----------------- */
 /* which = 0: best_autoencoder.keras (7 Conv2D, 6 BatchNormalization);

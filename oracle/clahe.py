@@ -17,8 +17,12 @@ BIN_SIZE = 1 + NR_OF_GRAY // NBINS       # 65 -> bins 0..252
 
 def quantise(cell: np.ndarray) -> np.ndarray:
     """A.2 steps 1-2: img_as_float then rescale to 0..16383 and round half even."""
-    v = cell.astype(np.float64) * (1.0 / 65535.0) if cell.dtype == np.uint16 \
-        else cell.astype(np.float64)
+    if cell.dtype == np.uint16:
+        v = cell.astype(np.float64) * (1.0 / 65535.0)
+    elif cell.dtype == np.uint8:                # img_as_float: multiply by 1 / imax_in
+        v = cell.astype(np.float64) * (1.0 / 255.0)
+    else:
+        v = cell.astype(np.float64)
     vmin, vmax = float(v.min()), float(v.max())
     if vmin != vmax:
         v = (v - vmin) / (vmax - vmin)

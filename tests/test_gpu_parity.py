@@ -362,25 +362,3 @@ def test_tc_hybrid_meets_svm_gate(screener, golden_config1, field_config1):
         d = np.abs(-r[f"{key}_scores"] - g[dec])
         assert d.max() <= 1e-4, f"{key}: max |d dec| {d.max():.3e}"
         assert np.array_equal(r[f"{key}_predictions"], g[pred])
-
-
-def test_tc_split_precision_features(screener, golden_config1, field_config1):
-    """precision 1: encoder on tensor cores with hi/lo fp16 operand splitting (3 MMAs).  The
-    features are fp32-grade but not bit-identical to an fp32 pipeline; the one-class SVM amplifies
-    1e-6 relative feature noise to ~7e-5 in the decision value, so this mode is held to a
-    documented looser bound (5e-4) and to identical signs away from the boundary."""
-    green, labels = field_config1
-    cells, _ = screener.extract_quality_cells_from_labels(green, labels)
-    old = screener.engine.precision
-    screener.engine.precision = 1
-    try:
-        r = screener.compute_anomaly_scores(cells)
-    finally:
-        screener.engine.precision = old
-    g = golden_config1
-    for key, dec, pred in (("conservative", "dec_cons", "pred_cons"), ("moderate", "dec_mod", "pred_mod")):
-        d = np.abs(-r[f"{key}_scores"] - g[dec])
-        print(f"precision 1 {key}: max |d dec| {d.max():.3e}, median {np.median(d):.3e}")
-        assert d.max() <= 5e-4
-        far = np.abs(g[dec]) > 5e-4
-        assert np.array_equal(r[f"{key}_predictions"][far], g[pred][far])

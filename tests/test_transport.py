@@ -219,8 +219,7 @@ def test_run_host_transport_variants_agree(model_dir):
     H, W = lab.shape[1:]
     res = []
     for kw in (dict(label_transport="raw"), dict(label_transport="rle"),
-               dict(label_transport="rle", scan_runs=False), dict(label_transport="rle", rle_fraction=0.5),
-               dict(label_transport="rle", rle_fraction="auto"), dict(label_transport="rle", rle_fraction="auto", pcie_gbs=1e6)):
+               dict(label_transport="rle", scan_runs=False), dict(label_transport="rle", rle_fraction=0.5)):
         bs = BatchScreen(eng, H, W, int(lab.max()), chunk_fields=1, **kw)
         bs.run_host(g, lab, 6)
         bs.sync()
@@ -230,8 +229,6 @@ def test_run_host_transport_variants_agree(model_dir):
         if kw.get("rle_fraction") == 0.5:      # three chunks raw, three as runs
             assert 3 * H * W * 6 + 3 * H * W * 2 < h2d < 3 * H * W * 6 + 3 * H * W * 3
             assert bs.last_rle_share == 0.5
-        if kw.get("pcie_gbs") == 1e6:          # an (assumed) infinitely fast link: mostly raw chunks after the first
-            assert 0.0 < bs.last_rle_share < 1.0
     assert res[0]["n_cells"] > 0
     for r in res[1:]:
         for k in ("cells", "mse", "mae", "dec_cons", "dec_mod", "pred_cons", "pred_mod", "field_counts"):
