@@ -191,25 +191,8 @@ __device__ __forceinline__ int cell_class(const cia_cell& C, size_t lo_bytes, si
     return need <= lo_bytes ? 0 : (need <= hi_bytes ? 1 : 2);
 }
 
-// Work lists of the two rare classes (cells whose working set does not fit the 2-CTA/SM shared
-// memory budget): their launches walk only their own cells instead of every CTA scanning the
-// whole cell table.  cls_counts[0..1] = entries of list 1 / list 2 (zeroed by the caller).
-__global__ void __launch_bounds__(256)
-crop_classify_kernel(const cia_cell* __restrict__ cells, int n_cells,
-                     const int32_t* __restrict__ n_cells_dev, size_t lo_bytes, size_t hi_bytes,
-                     int32_t* __restrict__ cls_counts, int32_t* __restrict__ list1,
-                     int32_t* __restrict__ list2) {
-    const int n = dev_count(n_cells, n_cells_dev);
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const int c = cell_class(cells[i], lo_bytes, hi_bytes);
-        if (c == 1) list1[atomicAdd(cls_counts + 0, 1)] = i;
-        else if (c == 2) list2[atomicAdd(cls_counts + 1, 1)] = i;
-    }
-}
-
 // cls: 0/1 = shared-memory classes (dynamic smem = smem_bytes), 2 = global-scratch class.
-// cls_list == nullptr: walk every cell and skip the other classes (the common class 0);
-// otherwise walk cls_list[0 .. *cls_count).
+// Walks cls_list[0 .. *cls_count) (cls_list == nullptr: every cell, skipping the other classes).
 __global__ void __launch_bounds__(K2_THREADS)
 crop_clahe_resize_kernel(const uint16_t* __restrict__ images, int H, int W,
                          const cia_cell* __restrict__ cells, int n_cells,
@@ -496,6 +479,395 @@ crop_clahe_resize_kernel(const uint16_t* __restrict__ images, int H, int W,
     }
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Fast path: cells whose CLAHE clip limit is 1 (tiles of < 100 pixels at clip_limit 0.02 --
+// every cell with sides up to ~80 px, i.e. all of BASELINE config 2).
+//
+// ncu on the general kernel above (profiles/r1j_crop_full.txt): 57k warp instructions per ~34x34
+// cell, half of them in the per-tile stage -- a warp clips, redistributes and prefix-sums a dense
+// 256-bin histogram for a tile that holds 16 pixels.  With clip limit 1 the clipped histogram is
+// an OCCUPANCY SET: every bin is 0 or 1, the excess is npix - popcount, `excess // 256` is 0 (so
+// the two bulk passes of clip_histogram change nothing) and the serial redistribution only ever
+// turns zero bins into ones.  A tile is therefore a 256-bit mask: ONE THREAD per tile builds it
+// with shared-memory ORs, runs skimage's redistribution loop on the bits, and stores per 32-bin
+// word the number of bits set below it; the mapping of a bin is then
+//     level_tab[ bits_below(word) + popc(word & mask_up_to(bin)) ]
+// evaluated where the interpolation needs it -- 72 bytes per tile instead of a 512-byte table,
+// ~10 KB of shared memory per typical cell, 13-16 resident CTAs of 128 threads per SM.
+// The bbox is fetched with aligned 16-byte loads (8 pixels each) straight into shared memory,
+// the two resize passes stream through a per-warp row block (no 64 x w intermediate, no block
+// barrier), and cells are handed out by an atomic work counter (bbox areas vary 20x).
+// Arithmetic is the general kernel's, operation for operation: same uint16 levels, bit for bit.
+// ---------------------------------------------------------------------------------------
+constexpr int KF_THREADS = 128;
+constexpr int KF_WARPS = KF_THREADS / 32;
+constexpr int KF_TILE_WORDS = 18;      // 8 x (mask word, bits set below it) + 2 pad words (bank spread, 8-byte aligned)
+constexpr int KF_TBUF = 176;           // doubles per warp: the row block of the resize passes
+constexpr int KF_MAX_SIDE = 96;        // gaussian radius <= 1 up to here
+constexpr int KF_MAX_NPIX = 256;       // excess < 256 => the bulk passes of clip_histogram are no-ops
+constexpr int KF_CLASSES = 2;
+
+struct FastLayout {
+    int pitch;                          // uint16 elements per staged row (multiple of 8)
+    int o_bins, o_tiles, o_coef, o_ltab, o_rinfo, o_cinfo, total;
+};
+__host__ __device__ inline FastLayout fast_layout(int h, int w, int ntiles, int npix) {
+    FastLayout L;
+    L.pitch = ((w + 14) >> 3) << 3;
+    int o = (int)align16((size_t)h * L.pitch * 2);       // raw pixels, later the dense uint16 levels
+    const int u0 = o;                                    // everything below is dead after stage D ...
+    L.o_bins = o;  o += (int)align16((size_t)h * w);
+    L.o_tiles = o; o += (int)align16((size_t)ntiles * KF_TILE_WORDS * 4);
+    L.o_coef = o;  o += npix * 32;
+    L.o_ltab = o;  o += (int)align16((KF_MAX_NPIX + 1) * 2);
+    L.o_rinfo = o; o += (int)align16((size_t)h * 4);
+    L.o_cinfo = o; o += (int)align16((size_t)w * 4);
+    const int tb = u0 + KF_WARPS * KF_TBUF * 8;          // ... and shares its space with the row blocks
+    L.total = o > tb ? o : tb;
+    return L;
+}
+
+// class of a cell: 0..KF_CLASSES-1 fast (by shared-memory need), KF_CLASSES + {0,1,2} general
+__device__ __forceinline__ int cell_class_all(const cia_cell& C, double clip_limit, const int* fast_bytes,
+                                              size_t lo_bytes, size_t hi_bytes) {
+    const int h = C.maxr - C.minr, w = C.maxc - C.minc;
+    if (h >= 1 && w >= 1 && h <= KF_MAX_SIDE && w <= KF_MAX_SIDE) {
+        const int kh = max(h / 8, 1), kw = max(w / 8, 1), npix = kh * kw;
+        double cl = __dmul_rn(clip_limit, (double)npix);
+        if (!(cl >= 1.0)) cl = 1.0;
+        if (clip_limit > 0.0 && (int)cl == 1 && npix <= KF_MAX_NPIX) {
+            const int need = fast_layout(h, w, ((h + kh - 1) / kh) * ((w + kw - 1) / kw), npix).total;
+            for (int c = 0; c < KF_CLASSES; ++c)
+                if (need <= fast_bytes[c]) return c;
+        }
+    }
+    return KF_CLASSES + cell_class(C, lo_bytes, hi_bytes);
+}
+
+struct FastBytes { int v[KF_CLASSES]; };
+
+// Work lists of all classes.  cls_counts[c] = entries of list c (zeroed by the caller).
+__global__ void __launch_bounds__(256)
+crop_classify_all_kernel(const cia_cell* __restrict__ cells, int n_cells,
+                         const int32_t* __restrict__ n_cells_dev, double clip_limit, FastBytes fb,
+                         size_t lo_bytes, size_t hi_bytes, int32_t* __restrict__ cls_counts,
+                         int32_t* __restrict__ lists, size_t list_stride) {
+    const int n = dev_count(n_cells, n_cells_dev);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int c = cell_class_all(cells[i], clip_limit, fb.v, lo_bytes, hi_bytes);
+        lists[(size_t)c * list_stride + atomicAdd(cls_counts + c, 1)] = i;
+    }
+}
+
+__global__ void __launch_bounds__(KF_THREADS, 8)
+crop_fast_kernel(const uint16_t* __restrict__ images, int H, int W, const cia_cell* __restrict__ cells,
+                 double intensity_inv, float* __restrict__ crops32, double* __restrict__ crops64,
+                 const int32_t* __restrict__ list, const int32_t* __restrict__ count,
+                 int32_t* __restrict__ work_counter, uint16_t* __restrict__ levels_out,
+                 const int64_t* __restrict__ level_offsets) {
+    extern __shared__ __align__(16) unsigned char dyn[];
+    __shared__ double ctab_s[2][CIA_CROP];        // interpolation weight of each output row / column
+    __shared__ int coord_s[2][CIA_CROP];          // integer source coordinate
+    __shared__ double gw_s[2][4];                 // gaussian taps (radius <= 1)
+    __shared__ int red_s[2 * KF_WARPS];
+    __shared__ int work_s;
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int n = *count;
+
+    for (;;) {
+        __syncthreads();                          // the previous cell's shared memory is free
+        if (tid == 0) work_s = atomicAdd(work_counter, 1);
+        __syncthreads();
+        const int it = work_s;
+        if (it >= n) break;
+        const int cell = list[it];
+        const cia_cell C = cells[cell];
+        const int h = C.maxr - C.minr, w = C.maxc - C.minc;
+        const int kh = max(h / 8, 1), kw = max(w / 8, 1);
+        const int ntr = (h + kh - 1) / kh, ntc = (w + kw - 1) / kw;
+        const int npix = kh * kw, ntiles = ntr * ntc, hw = h * w;
+        const FastLayout L = fast_layout(h, w, ntiles, npix);
+        uint16_t* raw = reinterpret_cast<uint16_t*>(dyn);        // staged rows; from stage D on: dense levels
+        uint8_t* bins = dyn + L.o_bins;
+        uint32_t* tiles = reinterpret_cast<uint32_t*>(dyn + L.o_tiles);
+        double* coef = reinterpret_cast<double*>(dyn + L.o_coef);
+        uint16_t* level_tab = reinterpret_cast<uint16_t*>(dyn + L.o_ltab);
+        uint32_t* rinfo = reinterpret_cast<uint32_t*>(dyn + L.o_rinfo);
+        uint32_t* cinfo = reinterpret_cast<uint32_t*>(dyn + L.o_cinfo);
+        double* tbuf = reinterpret_cast<double*>(dyn + L.o_bins) + wid * KF_TBUF;
+
+        const unsigned w_magic = 0xFFFFFFFFu / (unsigned)w + 1u;         // i / w for i < 2^16
+        const long long base_elem = ((long long)C.field * H + C.minr) * (long long)W + C.minc;
+        const long long end_elem = (long long)(C.field + 1) * H * (long long)W;
+        // element alignment (mod 8) of the first pixel of bbox row 0 / increment per row
+        const int e00 = (int)((((unsigned long long)(uintptr_t)images >> 1) + (unsigned long long)base_elem) & 7ull);
+        const int wlow = W & 7;
+
+        // ---- A: bbox -> shared memory with aligned 16-byte loads; min / max ----
+        int mn = 65535, mx = 0;
+        {
+            const int chunks = L.pitch >> 3;
+            const unsigned c_magic = k_magic.v[chunks];                  // chunks in 2..13
+            for (int i = tid; i < h * chunks; i += KF_THREADS) {
+                const int y = (int)__umulhi((unsigned)i, c_magic), c = i - y * chunks;
+                const int e0 = (e00 + y * wlow) & 7;
+                const int first = 8 * c - e0;                            // bbox column of the chunk's first pixel
+                if (first >= w) continue;
+                const long long g0 = base_elem + (long long)y * W + first;
+                uint4 v;
+                if (g0 >= 0 && g0 + 8 <= end_elem) {
+                    v = __ldg(reinterpret_cast<const uint4*>(images + g0));
+                } else {                                                 // chunk straddles the buffer's ends
+                    uint16_t t[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        t[k] = (first + k >= 0 && first + k < w) ? __ldg(images + g0 + k) : (uint16_t)0;
+                    v = make_uint4(t[0] | ((uint32_t)t[1] << 16), t[2] | ((uint32_t)t[3] << 16),
+                                   t[4] | ((uint32_t)t[5] << 16), t[6] | ((uint32_t)t[7] << 16));
+                }
+                *reinterpret_cast<uint4*>(raw + y * L.pitch + 8 * c) = v;
+                const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int px = (int)((vv[k >> 1] >> (16 * (k & 1))) & 0xFFFFu);
+                    if ((unsigned)(first + k) < (unsigned)w) { mn = min(mn, px); mx = max(mx, px); }
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        }
+        if (lane == 0) { red_s[wid] = mn; red_s[KF_WARPS + wid] = mx; }
+        // per-cell tables (independent of the pixels): count -> level, interpolation coefficients,
+        // row / column -> (tile pair, in-tile offset)
+        {
+            const double map_scale = __ddiv_rn(16383.0, (double)npix);
+            for (int c = tid; c <= KF_MAX_NPIX; c += KF_THREADS)
+                level_tab[c] = (uint16_t)min((int)__dmul_rn((double)c, map_scale), 16383);
+            for (int p = tid; p < npix; p += KF_THREADS) {
+                const int a = p / kw, b = p - a * kw;
+                const double cr = __ddiv_rn((double)a, (double)kh), cc = __ddiv_rn((double)b, (double)kw);
+                const double icr = __dsub_rn(1.0, cr), icc = __dsub_rn(1.0, cc);
+                coef[4 * p + 0] = __dmul_rn(icc, icr);
+                coef[4 * p + 1] = __dmul_rn(cc, icr);
+                coef[4 * p + 2] = __dmul_rn(icc, cr);
+                coef[4 * p + 3] = __dmul_rn(cc, cr);
+            }
+            const int pr = kh / 2, pc = kw / 2;
+            for (int y = tid; y < h; y += KF_THREADS) {
+                const int Y = y + pr, I = Y / kh, a = Y - I * kh;
+                const int t0 = min(max(I - 1, 0), ntr - 1), t1 = min(I, ntr - 1);
+                rinfo[y] = (uint32_t)(t0 * ntc) | ((uint32_t)(t1 * ntc) << 8) | ((uint32_t)(a * kw) << 16);
+            }
+            for (int x = tid; x < w; x += KF_THREADS) {
+                const int X = x + pc, J = X / kw, b = X - J * kw;
+                const int u0 = min(max(J - 1, 0), ntc - 1), u1 = min(J, ntc - 1);
+                cinfo[x] = (uint32_t)u0 | ((uint32_t)u1 << 8) | ((uint32_t)b << 16);
+            }
+        }
+        __syncthreads();
+        mn = red_s[0]; mx = red_s[KF_WARPS];
+#pragma unroll
+        for (int i = 1; i < KF_WARPS; ++i) { mn = min(mn, red_s[i]); mx = max(mx, red_s[KF_WARPS + i]); }
+
+        // ---- B: 14-bit quantise (round half even) and bin ----
+        {
+            const double vmin = __dmul_rn((double)mn, intensity_inv), vmax = __dmul_rn((double)mx, intensity_inv);
+            const double den = __dsub_rn(vmax, vmin);
+            for (int i = tid; i < hw; i += KF_THREADS) {
+                const int y = (w == 1) ? i : (int)__umulhi((unsigned)i, w_magic), x = i - y * w;
+                const double v = __dmul_rn((double)raw[y * L.pitch + ((e00 + y * wlow) & 7) + x], intensity_inv);
+                int q;
+                if (mn != mx) q = __double2int_rn(__dmul_rn(__ddiv_rn(__dsub_rn(v, vmin), den), 16383.0));
+                else q = __double2int_rn(fmin(fmax(v, 0.0), 16383.0));
+                bins[i] = (uint8_t)(q / BIN_SIZE);
+            }
+        }
+        __syncthreads();
+
+        // ---- C: one thread per tile: occupancy mask, redistribution on the bits, prefix counts ----
+        for (int t = tid; t < ntiles; t += KF_THREADS) {
+            const int ti = ntc == 1 ? t : (int)__umulhi((unsigned)t, k_magic.v[ntc]), tj = t - ti * ntc;
+            uint32_t* tw = tiles + t * KF_TILE_WORDS;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) tw[2 * k] = 0u;
+            const int y0 = ti * kh, x0 = tj * kw;
+            for (int a = 0; a < kh; ++a) {
+                const int y = reflect_idx(y0 + a, h);
+                const uint8_t* brow = bins + y * w;
+                for (int b = 0; b < kw; ++b) {
+                    const int bin = brow[reflect_idx(x0 + b, w)];
+                    tw[2 * (bin >> 5)] |= 1u << (bin & 31);
+                }
+            }
+            int set = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) set += __popc(tw[2 * k]);
+            int ex = npix - set;                  // clip at 1: every bin above the limit gives up its surplus
+            while (ex > 0) {                      // skimage clip_histogram's redistribution loop, on bits
+                const int prev = ex;
+                for (int index = 0; index < NBINS; ++index) {
+                    const int under = NBINS - set;
+                    if (under == 0) break;
+                    int step = 1;
+                    if (ex <= under) step = ex == 1 ? under : (int)__umulhi((unsigned)under, k_magic.v[ex]);
+                    int moved = 0;
+                    for (int p = index; p < NBINS; p += step) {
+                        uint32_t* wp = tw + 2 * (p >> 5);
+                        const uint32_t m = 1u << (p & 31), v = *wp;
+                        if (!(v & m)) { *wp = v | m; ++moved; }
+                    }
+                    ex -= moved; set += moved;
+                    if (ex <= 0) break;
+                }
+                if (prev == ex) break;
+            }
+            int run = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { tw[2 * k + 1] = (uint32_t)run; run += __popc(tw[2 * k]); }
+        }
+        __syncthreads();
+
+        // ---- D: 4-corner interpolation, fp32 accumulation, truncate to uint16 (dense, over `raw`) ----
+        // (the raw pixels are dead: stage B was their last reader)
+        int rmn = 65535, rmx = 0;
+        for (int i = tid; i < hw; i += KF_THREADS) {
+            const int y = (w == 1) ? i : (int)__umulhi((unsigned)i, w_magic), x = i - y * w;
+            const uint32_t ri = rinfo[y], ci = cinfo[x];
+            const int bin = bins[i];
+            const int wsel = 2 * (bin >> 5);
+            const uint32_t below = 0xFFFFFFFFu >> (31 - (bin & 31));
+            const double* cf = coef + 4 * ((ri >> 16) + (ci >> 16));
+            const int tr[2] = {(int)(ri & 255u), (int)((ri >> 8) & 255u)};
+            const int tc[2] = {(int)(ci & 255u), (int)((ci >> 8) & 255u)};
+            float res = 0.f;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const uint2 mw = *reinterpret_cast<const uint2*>(tiles + (tr[e >> 1] + tc[e & 1]) * KF_TILE_WORDS + wsel);
+                const double m = (double)level_tab[mw.y + __popc(mw.x & below)];
+                res = __fadd_rn(res, __double2float_rn(__dmul_rn(m, cf[e])));
+            }
+            const int r = (int)res;
+            rmn = min(rmn, r); rmx = max(rmx, r);
+            // `raw` still holds staged pixels that OTHER threads may be reading?  No: stage B finished
+            // before the barrier above, and stage C / D read bins only.
+            raw[i] = (uint16_t)r;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            rmn = min(rmn, __shfl_xor_sync(0xffffffffu, rmn, o));
+            rmx = max(rmx, __shfl_xor_sync(0xffffffffu, rmx, o));
+        }
+        if (lane == 0) { red_s[wid] = rmn; red_s[KF_WARPS + wid] = rmx; }
+
+        // ---- E: source coordinates of the 64 output rows / columns, gaussian taps ----
+        const double fr = __ddiv_rn((double)h, 64.0), fc = __ddiv_rn((double)w, 64.0);
+        double sig_r = __dmul_rn(__dsub_rn(fr, 1.0), 0.5), sig_c = __dmul_rn(__dsub_rn(fc, 1.0), 0.5);
+        if (sig_r < 0.0) sig_r = 0.0;
+        if (sig_c < 0.0) sig_c = 0.0;
+        const bool blur_r = sig_r > 1e-15, blur_c = sig_c > 1e-15;
+        const int rad_r = blur_r ? (int)(4.0 * sig_r + 0.5) : 0;
+        const int rad_c = blur_c ? (int)(4.0 * sig_c + 0.5) : 0;
+        {
+            const int axis = tid >> 6, o = tid & 63;              // 128 threads = 2 axes x 64 outputs
+            const double cc = ((double)o + 0.5) * (axis == 0 ? fr : fc) - 0.5;
+            const double fl = floor(cc);
+            ctab_s[axis][o] = cc - fl;
+            coord_s[axis][o] = (int)fl;
+        }
+        if (wid < 2 && lane == 0) {
+            const bool on = wid == 0 ? blur_r : blur_c;
+            const int rad = wid == 0 ? rad_r : rad_c;
+            const double sg = wid == 0 ? sig_r : sig_c;
+            if (on) {                                              // same sums as the general kernel's warp_sum for <= 3 taps
+                const double cf = -0.5 / (sg * sg);
+                double e[3] = {0.0, 0.0, 0.0}, ssum = 0.0;
+                for (int j = 0; j <= 2 * rad; ++j) { const double xx = (double)(j - rad); e[j] = exp(cf * xx * xx); }
+                // warp_sum adds lane values pairwise (xor tree): lanes 0..2 hold e0,e1,e2 -> (e0+e1)+(e2+0)
+                ssum = (e[0] + e[1]) + e[2];
+                for (int j = 0; j <= 2 * rad; ++j) gw_s[wid][j] = e[j] / ssum;
+            }
+        }
+        __syncthreads();
+        rmn = red_s[0]; rmx = red_s[KF_WARPS];
+#pragma unroll
+        for (int i = 1; i < KF_WARPS; ++i) { rmn = min(rmn, red_s[i]); rmx = max(rmx, red_s[KF_WARPS + i]); }
+        if (levels_out) {                          // test tap: the bit-exact integer core
+            uint16_t* dst = levels_out + level_offsets[cell];
+            for (int i = tid; i < hw; i += KF_THREADS) dst[i] = raw[i];
+        }
+
+        const bool degenerate = rmn == rmx;
+        const double den = (double)(rmx - rmn);
+        const double lo = degenerate ? fmin(fmax((double)rmn, 0.0), 1.0) : 0.0;
+        const double hi = degenerate ? lo : 1.0;
+        const double den_rcp = degenerate ? 0.0 : __drcp_rn(den);
+        auto value = [&](int y, int x) -> double {               // (r - rmn) / den, correctly rounded (Markstein)
+            const double a = (double)raw[y * w + x] - (double)rmn;
+            const double q0 = __dmul_rn(a, den_rcp);
+            const double q = __fma_rn(__fma_rn(-q0, den, a), den_rcp, q0);
+            return degenerate ? lo : q;
+        };
+
+        // ---- F + G: a warp takes a block of RB output rows: zoom(+blur) along axis 0 into its row
+        // block, then along axis 1, clip, store ----
+        const int RB = w <= 11 ? 16 : (w <= 22 ? 8 : (w <= 44 ? 4 : (w <= 88 ? 2 : 1)));
+        double sx[2]; int jx[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) { sx[e] = ctab_s[1][lane + 32 * e]; jx[e] = coord_s[1][lane + 32 * e]; }
+        for (int oy0 = wid * RB; oy0 < CIA_CROP; oy0 += KF_WARPS * RB) {
+            for (int i = lane; i < RB * w; i += 32) {
+                const int r = (w == 1) ? i : (int)__umulhi((unsigned)i, w_magic), x = i - r * w;
+                const double t = ctab_s[0][oy0 + r];
+                const int i0 = coord_s[0][oy0 + r];
+                double v[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int yy = i0 + e;
+                    if (!blur_r) {
+                        v[e] = value(mirror_near(yy, h), x);
+                    } else {
+                        double acc = 0.0;
+                        for (int j = 0; j <= 2 * rad_r; ++j)
+                            acc += gw_s[0][j] * value(mirror_near(mirror_near(yy, h) + j - rad_r, h), x);
+                        v[e] = acc;
+                    }
+                }
+                tbuf[i] = (1.0 - t) * v[0] + t * v[1];
+            }
+            __syncwarp();
+            for (int r = 0; r < RB; ++r) {
+                const double* Trow = tbuf + r * w;
+#pragma unroll
+                for (int e2 = 0; e2 < 2; ++e2) {
+                    double v[2];
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int xx = jx[e2] + e;
+                        if (!blur_c) {
+                            v[e] = Trow[mirror_near(xx, w)];
+                        } else {
+                            double acc = 0.0;
+                            for (int j = 0; j <= 2 * rad_c; ++j)
+                                acc += gw_s[1][j] * Trow[mirror_near(mirror_near(xx, w) + j - rad_c, w)];
+                            v[e] = acc;
+                        }
+                    }
+                    double o = (1.0 - sx[e2]) * v[0] + sx[e2] * v[1];
+                    const size_t off = (size_t)cell * 4096 + (size_t)(oy0 + r) * 64 + lane + 32 * e2;
+                    if (crops64) { o = fmin(fmax(o, lo), hi); crops64[off] = o; }
+                    crops32[off] = fminf(fmaxf((float)o, (float)lo), (float)hi);
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
 }  // namespace
 
 int k_crop_resize(cia_ctx* h, const uint16_t* images, int H, int W, const cia_cell* cells,
@@ -504,42 +876,56 @@ int k_crop_resize(cia_ctx* h, const uint16_t* images, int H, int W, const cia_ce
                   const int64_t* level_offsets) {
     if (n_cells <= 0) return CIA_OK;
     const size_t lo_bytes = 92 * 1024, hi_bytes = 206 * 1024;   // 2 CTAs/SM and 1 CTA/SM with the 19.5 KB static part
+    // fast-path classes by shared-memory need: 8 (the register limit at 64 per thread) / 5 resident CTAs per SM
+    const FastBytes fb = {{26 * 1024, 42 * 1024}};
+    const int fast_ctas[KF_CLASSES] = {8, 5};
     if (first_use(h, (const void*)crop_clahe_resize_kernel))
         CIA_CUDA(cudaFuncSetAttribute(crop_clahe_resize_kernel,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hi_bytes));
+    if (first_use(h, (const void*)crop_fast_kernel)) {
+        CIA_CUDA(cudaFuncSetAttribute(crop_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fb.v[KF_CLASSES - 1]));
+        CIA_CUDA(cudaFuncSetAttribute(crop_fast_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    }
     const int huge_ctas = 32;
     const size_t per_cta = cell_bytes(MAX_SIDE, MAX_SIDE, 15, 15);
-    // [class counters (256 B)] [list 1: n ints] [list 2: n ints] [global scratch of the class-2 CTAs]
-    const size_t list_bytes = (((size_t)n_cells * sizeof(int32_t)) + 255) & ~(size_t)255;
-    int rc = ws_reserve(h, h->ws_crop_scratch, 256 + 2 * list_bytes + per_cta * huge_ctas);
+    // [class counters + work counters (256 B)] [6 lists of n ints] [global scratch of the class-2 CTAs]
+    constexpr int NCLS = KF_CLASSES + 3;
+    const size_t list_stride = (((size_t)n_cells + 63) / 64) * 64;
+    const size_t list_bytes = list_stride * sizeof(int32_t);
+    int rc = ws_reserve(h, h->ws_crop_scratch, 256 + NCLS * list_bytes + per_cta * huge_ctas);
     if (rc) return rc;
     unsigned char* wsb = (unsigned char*)h->ws_crop_scratch.p;
-    int32_t* cls_counts = (int32_t*)wsb;
-    int32_t* list1 = (int32_t*)(wsb + 256);
-    int32_t* list2 = (int32_t*)(wsb + 256 + list_bytes);
-    unsigned char* gscratch = wsb + 256 + 2 * list_bytes;
+    int32_t* cls_counts = (int32_t*)wsb;                 // [0..NCLS): list lengths, [16..16+KF_CLASSES): work counters
+    int32_t* work = cls_counts + 16;
+    int32_t* lists = (int32_t*)(wsb + 256);
+    unsigned char* gscratch = wsb + 256 + NCLS * list_bytes;
     CIA_CUDA(cudaMemsetAsync(cls_counts, 0, 256, s));
     {
         int cb = (n_cells + 255) / 256;
         if (cb > h->num_sms * 4) cb = h->num_sms * 4;
-        crop_classify_kernel<<<cb, 256, 0, s>>>(cells, n_cells, n_cells_dev, lo_bytes, hi_bytes,
-                                                cls_counts, list1, list2);
+        crop_classify_all_kernel<<<cb, 256, 0, s>>>(cells, n_cells, n_cells_dev, p->clip_limit, fb, lo_bytes,
+                                                    hi_bytes, cls_counts, lists, list_stride);
+        CIA_LAUNCH_CHECK();
+    }
+    for (int c = 0; c < KF_CLASSES; ++c) {
+        int g = h->num_sms * fast_ctas[c];
+        if (g > n_cells) g = n_cells;
+        crop_fast_kernel<<<g, KF_THREADS, fb.v[c], s>>>(images, H, W, cells, p->intensity_inv, crops32, crops64,
+                                                        lists + c * list_stride, cls_counts + c, work + c,
+                                                        levels_out, level_offsets);
         CIA_LAUNCH_CHECK();
     }
     int g0 = h->num_sms * 2; if (g0 > n_cells) g0 = n_cells;
     int g1 = h->num_sms;     if (g1 > n_cells) g1 = n_cells;
     int g2 = huge_ctas;      if (g2 > n_cells) g2 = n_cells;
-    crop_clahe_resize_kernel<<<g0, K2_THREADS, lo_bytes, s>>>(
-        images, H, W, cells, n_cells, n_cells_dev, p->clip_limit, p->intensity_inv, crops32, crops64, 0, lo_bytes,
-        hi_bytes, nullptr, 0, h->status_dev, levels_out, level_offsets, nullptr, nullptr);
-    CIA_LAUNCH_CHECK();
-    crop_clahe_resize_kernel<<<g1, K2_THREADS, hi_bytes, s>>>(
-        images, H, W, cells, n_cells, n_cells_dev, p->clip_limit, p->intensity_inv, crops32, crops64, 1, lo_bytes,
-        hi_bytes, nullptr, 0, h->status_dev, levels_out, level_offsets, list1, cls_counts + 0);
-    CIA_LAUNCH_CHECK();
-    crop_clahe_resize_kernel<<<g2, K2_THREADS, 0, s>>>(
-        images, H, W, cells, n_cells, n_cells_dev, p->clip_limit, p->intensity_inv, crops32, crops64, 2, lo_bytes,
-        hi_bytes, gscratch, per_cta, h->status_dev, levels_out, level_offsets, list2, cls_counts + 1);
-    CIA_LAUNCH_CHECK();
+    const int gg[3] = {g0, g1, g2};
+    const size_t gsm[3] = {lo_bytes, hi_bytes, 0};
+    for (int c = 0; c < 3; ++c) {
+        crop_clahe_resize_kernel<<<gg[c], K2_THREADS, gsm[c], s>>>(
+            images, H, W, cells, n_cells, n_cells_dev, p->clip_limit, p->intensity_inv, crops32, crops64, c,
+            lo_bytes, hi_bytes, c == 2 ? gscratch : nullptr, c == 2 ? per_cta : 0, h->status_dev, levels_out,
+            level_offsets, lists + (KF_CLASSES + c) * list_stride, cls_counts + KF_CLASSES + c);
+        CIA_LAUNCH_CHECK();
+    }
     return CIA_OK;
 }
