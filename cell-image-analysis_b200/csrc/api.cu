@@ -88,6 +88,7 @@ static void free_cae(CaeWeights& w) {
     }
     for (int i = 0; i < CAE_NCONV; ++i)
         for (int j = 0; j < 2; ++j) { cudaFree(w.tc_w[i][j]); w.tc_w[i][j] = nullptr; }
+    cudaFree(w.tc_w7); w.tc_w7 = nullptr;
     w.tc_ready = false;
     w.loaded = false;
 }

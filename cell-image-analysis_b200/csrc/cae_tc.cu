@@ -1567,6 +1567,181 @@ conv1_tc_split_kernel(const float* __restrict__ crops, const uint4* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------
+// Layer 7 (32 -> 1 channel on the 2x up-sampled 64x64 map) with the filter taps on the N axis.
+//
+// In phase form the layer is a 3x3 conv on the 32x32 low-resolution map with four outputs
+// (py,px) per pixel, and each output only sees a 2x2 block of low-resolution neighbours (the
+// nine high-resolution taps collapse onto them).  As an implicit GEMM that is N = 16 with four
+// real columns and K = 9 taps x 32 channels: 144 MMAs per cell whose cost is the 4 KB A-operand
+// fetch (ncu: tensor-core pipe 87 % busy for 18 % math, profiles/r1j_cae_full.txt).  Here the
+// contraction over channels and the sum over taps swap places:
+//     P[pixel][(py,px),(ty,tx)] = sum_c A6[pixel][c] * Weff[c][(py,px),(ty,tx)]      (16 columns)
+//     out[2Y+py][2X+px] = sum_{ty,tx} P[(Y+py-1+ty, X+px-1+tx)][(py,px),(ty,tx)] + bias
+// -- ONE tap, K = 32: 16 MMAs per cell, no halo, and the A operand of a cell is its 64 KB of
+// activations exactly as they lie in HBM ([chunk][y][x][8] = K-major core matrices), fetched by
+// one bulk copy (TMA) into one of two buffers.  The weights ride as [hi | lo] fp16 pairs on 32
+// columns (the A fetch bounds an MMA whatever N is), so this layer's weights are exact.  The
+// shifted tap sum runs on the CUDA cores through shared-memory planes [column][pixel], fused
+// with sigmoid, (x - y)^2, |x - y| and the per-cell reduction.
+//   warps 0..15: epilogue (TMEM lane quadrant = warp & 3, tiles (warp >> 2) and (warp >> 2) + 4)
+//   warp 16:     lane 0 issues the bulk copies and the MMAs
+// ---------------------------------------------------------------------------------------
+namespace l7 {
+constexpr int EPI_WARPS = 16;
+constexpr int NT = (EPI_WARPS + 1) * 32;
+constexpr int A_B = 1024 * 32 * 2;                 // one cell: 4 chunks x 1024 pixels x 8 halves
+constexpr int W_B = 4 * 32 * 16;                   // [chunk][32 columns][8 halves]
+constexpr int PL_B = 16 * 1024 * 4;                // tap-sum planes [column][pixel] fp32
+constexpr int SMEM_B = 2 * A_B + W_B + PL_B;
+constexpr int STAGE_COLS = 8 * 32;                 // 8 tiles x (16 hi + 16 lo columns)
+}  // namespace l7
+
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(l7::NT, 1)
+final_tapsum_kernel(const __half* __restrict__ a6, const uint4* __restrict__ w_img, float inv_scale,
+                    const float* __restrict__ bias, const float* __restrict__ crops,
+                    float* __restrict__ mse, float* __restrict__ mae, int n_cells,
+                    const int32_t* __restrict__ n_dev, int cell0, int chunk_cells) {
+    using namespace l7;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ __align__(8) uint64_t a_full[2], d_full[2], d_empty[2];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ float red_s[2][2][EPI_WARPS];
+    unsigned char* const w_s = smem + 2 * A_B;
+    float* const planes = reinterpret_cast<float*>(smem + 2 * A_B + W_B);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    int n = dev_count(n_cells, n_dev) - cell0;
+    if (n > chunk_cells) n = chunk_cells;
+    if (n <= 0) return;
+    const int stride = (int)gridDim.x;
+
+    if (warp == 0) tmem_alloc(&tmem_base_s, 2 * STAGE_COLS);
+    if (tid == 32) {
+        for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 1); mbar_init(&d_full[i], 1); mbar_init(&d_empty[i], EPI_WARPS); }
+        fence_barrier_init();
+    }
+    for (int i = tid; i < W_B / 16; i += NT) reinterpret_cast<uint4*>(w_s)[i] = __ldg(w_img + i);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == EPI_WARPS) {
+        if (lane == 0) {
+            constexpr uint32_t IDESC = make_idesc(128, 32);
+            const uint64_t bd0 = make_smem_desc(smem_u32(w_s), 32 * 16, 128);
+            const __half* src0 = a6 + (size_t)cell0 * (A_B / 2);
+            // prologue: the first two cells' activations
+            for (int k = 0; k < 2; ++k) {
+                const int unit = (int)blockIdx.x + k * stride;
+                if (unit < n) {
+                    mbar_expect_tx(&a_full[k], A_B);
+                    bulk_load(smem_u32(smem) + k * A_B, src0 + (size_t)unit * (A_B / 2), A_B, &a_full[k]);
+                }
+            }
+            uint32_t it = 0;
+            for (int unit = blockIdx.x; unit < n; unit += stride, ++it) {
+                const uint32_t st = it & 1, ph = (it >> 1) & 1;
+                mbar_wait(&a_full[st], ph);
+                mbar_wait(&d_empty[st], ph ^ 1);            // the epilogue of two cells ago has drained this stage
+                tc_fence_after();
+                const uint64_t ad0 = make_smem_desc(smem_u32(smem) + st * A_B, 1024 * 16, 128);
+#pragma unroll
+                for (int t = 0; t < 8; ++t)
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks)
+                        umma_f16(tmem_base + st * STAGE_COLS + (uint32_t)(t * 32),
+                                 ad0 + (uint64_t)((t * 128 * 16 + 2 * ks * 1024 * 16) >> 4),
+                                 bd0 + (uint64_t)((2 * ks * 32 * 16) >> 4), IDESC, ks);
+                umma_commit(&d_full[st]);
+                // the MMAs have read the buffer: refill it with the cell after next
+                mbar_wait(&d_full[st], ph);
+                if (unit + 2 * stride < n) {
+                    mbar_expect_tx(&a_full[st], A_B);
+                    bulk_load(smem_u32(smem) + st * A_B, src0 + (size_t)(unit + 2 * stride) * (A_B / 2), A_B, &a_full[st]);
+                }
+            }
+        }
+    } else {
+        const int q = warp & 3, g = warp >> 2;
+        const float b = __ldg(bias);
+        uint32_t it = 0;
+        for (int unit = blockIdx.x; unit < n; unit += stride, ++it) {
+            const uint32_t st = it & 1, ph = (it >> 1) & 1;
+            const int cell = cell0 + unit;
+            mbar_wait(&d_full[st], ph);
+            tc_fence_after();
+            // planes of the previous cell have been consumed (barrier 2 of the previous iteration)
+#pragma unroll
+            for (int tt = 0; tt < 2; ++tt) {
+                const int t = g + 4 * tt;
+                const int p = 128 * t + 32 * q + lane;
+                const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + st * STAGE_COLS + (uint32_t)(t * 32);
+                uint32_t v[4][8];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) TMEM_LD8(taddr + 8 * k, v[k]);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) TMEM_WAIT8(v[k]);
+#pragma unroll
+                for (int c = 0; c < 16; ++c)
+                    planes[c * 1024 + p] = __uint_as_float(v[c >> 3][c & 7]) + __uint_as_float(v[2 + (c >> 3)][c & 7]);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&d_empty[st]);
+            asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");      // planes complete
+            float se = 0.f, ae = 0.f;
+            const float* xr = crops + (size_t)cell * 4096;
+#pragma unroll
+            for (int tt = 0; tt < 2; ++tt) {
+                const int p = 128 * (g + 4 * tt) + 32 * q + lane;
+                const int Y = p >> 5, X = p & 31;
+#pragma unroll
+                for (int py = 0; py < 2; ++py) {
+                    const float2 xv = __ldg(reinterpret_cast<const float2*>(xr + (2 * Y + py) * 64 + 2 * X));
+#pragma unroll
+                    for (int px = 0; px < 2; ++px) {
+                        float sum = 0.f;
+#pragma unroll
+                        for (int ty = 0; ty < 2; ++ty)
+#pragma unroll
+                            for (int tx = 0; tx < 2; ++tx) {
+                                const int yy = Y + py - 1 + ty, xx = X + px - 1 + tx;
+                                if ((unsigned)yy < 32u && (unsigned)xx < 32u)
+                                    sum += planes[(4 * (2 * py + px) + 2 * ty + tx) * 1024 + yy * 32 + xx];
+                            }
+                        const float a = fmaf(sum, inv_scale, b);
+                        const float rec = __fdividef(1.f, 1.f + __expf(-a));   // |err| ~1e-6, MSE gate is 1e-3
+                        const float d = (px ? xv.y : xv.x) - rec;
+                        se = fmaf(d, d, se);
+                        ae += fabsf(d);
+                    }
+                }
+            }
+            se = warp_sum(se); ae = warp_sum(ae);
+            if (lane == 0) { red_s[it & 1][0][warp] = se; red_s[it & 1][1][warp] = ae; }
+            asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");      // planes free, partial sums visible
+            if (tid == 0) {
+                float s = 0.f, a = 0.f;
+#pragma unroll
+                for (int w = 0; w < EPI_WARPS; ++w) { s += red_s[it & 1][0][w]; a += red_s[it & 1][1][w]; }
+                mse[cell] = s * (1.f / 4096.f);
+                mae[cell] = a * (1.f / 4096.f);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 2 * l7::STAGE_COLS);
+}
+
+// ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
 template <int CIN, int COUT, int R, int EPI, int NPASS, bool UPSIN = false>
@@ -1766,6 +1941,32 @@ int k_cae_tc_prepare(cia_ctx* h, int which) {
                         }
             sw = scale_exp(kp);
             pack_image(kp, 9, cin, 16, 4, sw, hi, lo);
+            // final_tapsum_kernel's image: ONE tap, the (phase, low-resolution neighbour) pairs on 16 columns
+            // + their fp16 remainders on 16 more: [chunk][32][8]
+            {
+                std::vector<float> kt((size_t)cin * 16, 0.f);
+                for (int py = 0; py < 2; ++py)
+                    for (int px = 0; px < 2; ++px)
+                        for (int dy = 0; dy < 3; ++dy)
+                            for (int dx = 0; dx < 3; ++dx) {
+                                const int oy = (int)std::floor((py + dy - 1) / 2.0), ox = (int)std::floor((px + dx - 1) / 2.0);
+                                const int ty = oy - (py - 1), tx = ox - (px - 1);
+                                for (int c = 0; c < cin; ++c)
+                                    kt[(size_t)c * 16 + 4 * (2 * py + px) + 2 * ty + tx] += k[((size_t)(dy * 3 + dx) * cin + c)];
+                            }
+                std::vector<__half> img((size_t)(cin / 8) * 32 * 8, __float2half_rn(0.f));
+                const float sc = std::ldexp(1.f, sw);        // the same scale: kt's entries are kp's (sums of the same taps)
+                for (int c = 0; c < cin; ++c)
+                    for (int col = 0; col < 16; ++col) {
+                        const float v = kt[(size_t)c * 16 + col] * sc;
+                        const __half hv = __float2half_rn(v);
+                        img[((size_t)(c / 8) * 32 + col) * 8 + (c % 8)] = hv;
+                        img[((size_t)(c / 8) * 32 + 16 + col) * 8 + (c % 8)] = __float2half_rn(v - __half2float(hv));
+                    }
+                cudaFree(w.tc_w7); w.tc_w7 = nullptr;
+                CIA_CUDA(cudaMalloc(&w.tc_w7, img.size() * sizeof(__half)));
+                CIA_CUDA(cudaMemcpy(w.tc_w7, img.data(), img.size() * sizeof(__half), cudaMemcpyHostToDevice));
+            }
         } else if (L == 5) {
             // same phase form with all Cout channels: N = 4 phases x Cout, run at the low (input) resolution --
             // 2 tiles x 9 taps instead of 8 tiles x 9 taps of MMAs per cell
@@ -1928,7 +2129,16 @@ int k_cae_forward_tc(cia_ctx* h, const float* crops, int n, const int32_t* n_dev
         CIA_LMARK(5);
         if ((rc = launch_tc<64, 128, 16, EPI_PHASE, 1>(h, ae, 5, a5, nullptr, a6p, nullptr, nullptr, nullptr, nullptr, nullptr, n, n_dev, c0, chunk, s))) return rc;
         CIA_LMARK(6);
-        if ((rc = launch_tc<32, 16, 32, EPI_FINAL, 1>(h, ae, 6, a6p, nullptr, nullptr, nullptr, nullptr, crops, mse, mae, n, n_dev, c0, chunk, s))) return rc;
+        // CIA_L7_KERNEL=0: the nine-tap implicit GEMM (conv_tc_kernel<EPI_FINAL>, 144 MMAs per cell) for A/B runs
+        static const int l7_tapsum = [] { const char* e = getenv("CIA_L7_KERNEL"); return e ? atoi(e) : 1; }();
+        if (l7_tapsum) {
+            if (first_use(h, (const void*)final_tapsum_kernel))
+                CIA_CUDA(cudaFuncSetAttribute(final_tapsum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, l7::SMEM_B));
+            int g7 = chunk < h->num_sms ? chunk : h->num_sms;
+            final_tapsum_kernel<<<g7, l7::NT, l7::SMEM_B, s>>>(a6p, (const uint4*)ae.tc_w7, ae.tc_inv_scale[6], ae.bias[6],
+                                                              crops, mse, mae, n, n_dev, c0, chunk);
+            CIA_LAUNCH_CHECK();
+        } else if ((rc = launch_tc<32, 16, 32, EPI_FINAL, 1>(h, ae, 6, a6p, nullptr, nullptr, nullptr, nullptr, crops, mse, mae, n, n_dev, c0, chunk, s))) return rc;
         CIA_LMARK(7);
 #undef CIA_LMARK
     }

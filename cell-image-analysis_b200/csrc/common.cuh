@@ -27,6 +27,7 @@ struct CaeWeights {
     // tensor-core operand images (built at load time, see cae_tc.cu): per layer the fp16
     // hi / lo parts of the power-of-two scaled weights in UMMA K-major core-matrix order
     void* tc_w[CAE_NCONV][2] = {};
+    void* tc_w7 = nullptr;           // layer 7 as one tap with the (phase, neighbour) pairs on N (final_tapsum_kernel)
     float tc_inv_scale[CAE_NCONV] = {};
     bool tc_ready = false;
 };

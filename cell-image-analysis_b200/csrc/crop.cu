@@ -560,6 +560,7 @@ crop_classify_all_kernel(const cia_cell* __restrict__ cells, int n_cells,
     }
 }
 
+template <bool WANT64>
 __global__ void __launch_bounds__(KF_THREADS, 8)
 crop_fast_kernel(const uint16_t* __restrict__ images, int H, int W, const cia_cell* __restrict__ cells,
                  double intensity_inv, float* __restrict__ crops32, double* __restrict__ crops64,
@@ -569,7 +570,10 @@ crop_fast_kernel(const uint16_t* __restrict__ images, int H, int W, const cia_ce
     extern __shared__ __align__(16) unsigned char dyn[];
     __shared__ double ctab_s[2][CIA_CROP];        // interpolation weight of each output row / column
     __shared__ int coord_s[2][CIA_CROP];          // integer source coordinate
+    __shared__ int src0_s[2][CIA_CROP], src1_s[2][CIA_CROP];   // unblurred axis: mirrored source line offsets
     __shared__ double gw_s[2][4];                 // gaussian taps (radius <= 1)
+    __shared__ double scale_s[2];
+    __shared__ int rad_s[2];                      // gaussian radius per axis, -1 = not blurred
     __shared__ int red_s[2 * KF_WARPS];
     __shared__ int work_s;
 
@@ -764,103 +768,122 @@ crop_fast_kernel(const uint16_t* __restrict__ images, int H, int W, const cia_ce
         }
         if (lane == 0) { red_s[wid] = rmn; red_s[KF_WARPS + wid] = rmx; }
 
-        // ---- E: source coordinates of the 64 output rows / columns, gaussian taps ----
-        const double fr = __ddiv_rn((double)h, 64.0), fc = __ddiv_rn((double)w, 64.0);
-        double sig_r = __dmul_rn(__dsub_rn(fr, 1.0), 0.5), sig_c = __dmul_rn(__dsub_rn(fc, 1.0), 0.5);
-        if (sig_r < 0.0) sig_r = 0.0;
-        if (sig_c < 0.0) sig_c = 0.0;
-        const bool blur_r = sig_r > 1e-15, blur_c = sig_c > 1e-15;
-        const int rad_r = blur_r ? (int)(4.0 * sig_r + 0.5) : 0;
-        const int rad_c = blur_c ? (int)(4.0 * sig_c + 0.5) : 0;
-        {
-            const int axis = tid >> 6, o = tid & 63;              // 128 threads = 2 axes x 64 outputs
-            const double cc = ((double)o + 0.5) * (axis == 0 ? fr : fc) - 0.5;
-            const double fl = floor(cc);
-            ctab_s[axis][o] = cc - fl;
-            coord_s[axis][o] = (int)fl;
-        }
-        if (wid < 2 && lane == 0) {
-            const bool on = wid == 0 ? blur_r : blur_c;
-            const int rad = wid == 0 ? rad_r : rad_c;
-            const double sg = wid == 0 ? sig_r : sig_c;
-            if (on) {                                              // same sums as the general kernel's warp_sum for <= 3 taps
-                const double cf = -0.5 / (sg * sg);
-                double e[3] = {0.0, 0.0, 0.0}, ssum = 0.0;
-                for (int j = 0; j <= 2 * rad; ++j) { const double xx = (double)(j - rad); e[j] = exp(cf * xx * xx); }
-                // warp_sum adds lane values pairwise (xor tree): lanes 0..2 hold e0,e1,e2 -> (e0+e1)+(e2+0)
-                ssum = (e[0] + e[1]) + e[2];
-                for (int j = 0; j <= 2 * rad; ++j) gw_s[wid][j] = e[j] / ssum;
+        // ---- E: per-cell resize tables: source rows / columns, weights, gaussian taps ----
+        // (one thread does the scalar fp64 set-up; the loops below read plain integers)
+        if (tid == 0) {
+            const double fr = __ddiv_rn((double)h, 64.0), fc = __ddiv_rn((double)w, 64.0);
+            for (int axis = 0; axis < 2; ++axis) {
+                double sg = __dmul_rn(__dsub_rn(axis == 0 ? fr : fc, 1.0), 0.5);
+                if (sg < 0.0) sg = 0.0;
+                const bool on = sg > 1e-15;
+                const int rad = on ? (int)(4.0 * sg + 0.5) : 0;
+                rad_s[axis] = on ? rad : -1;                           // -1: this axis is not blurred
+                if (on) {
+                    // same sums as the general kernel's warp_sum for <= 3 taps: (e0 + e1) + (e2 + 0)
+                    const double cf = -0.5 / (sg * sg);
+                    double e[3] = {0.0, 0.0, 0.0};
+                    for (int k = 0; k <= 2 * rad; ++k) { const double xx = (double)(k - rad); e[k] = exp(cf * xx * xx); }
+                    const double ssum = (e[0] + e[1]) + e[2];
+                    for (int k = 0; k <= 2 * rad; ++k) gw_s[axis][k] = e[k] / ssum;
+                }
             }
+            scale_s[0] = fr; scale_s[1] = fc;
         }
         __syncthreads();
         rmn = red_s[0]; rmx = red_s[KF_WARPS];
 #pragma unroll
         for (int i = 1; i < KF_WARPS; ++i) { rmn = min(rmn, red_s[i]); rmx = max(rmx, red_s[KF_WARPS + i]); }
+        {
+            const int axis = tid >> 6, o = tid & 63;                   // 128 threads = 2 axes x 64 outputs
+            const int nn = axis == 0 ? h : w;
+            const double cc = ((double)o + 0.5) * scale_s[axis] - 0.5;
+            const double fl = floor(cc);
+            const int i0 = (int)fl;
+            ctab_s[axis][o] = cc - fl;
+            coord_s[axis][o] = i0;
+            // unblurred axis: the two (mirrored) source lines of this output line, as element offsets
+            src0_s[axis][o] = mirror_near(i0, nn) * (axis == 0 ? w : 1);
+            src1_s[axis][o] = mirror_near(i0 + 1, nn) * (axis == 0 ? w : 1);
+        }
         if (levels_out) {                          // test tap: the bit-exact integer core
             uint16_t* dst = levels_out + level_offsets[cell];
             for (int i = tid; i < hw; i += KF_THREADS) dst[i] = raw[i];
         }
+        __syncthreads();
+        const int rad_r = rad_s[0], rad_c = rad_s[1];
 
+        // The interpolation weights of every output sum to one, so (r - rmn) / den commutes with
+        // them: the passes run on the integer levels and the affine map is applied once per output
+        // pixel (the general kernel normalises first; the difference is ~1e-16, the gate 1e-5).
         const bool degenerate = rmn == rmx;
-        const double den = (double)(rmx - rmn);
         const double lo = degenerate ? fmin(fmax((double)rmn, 0.0), 1.0) : 0.0;
         const double hi = degenerate ? lo : 1.0;
-        const double den_rcp = degenerate ? 0.0 : __drcp_rn(den);
-        auto value = [&](int y, int x) -> double {               // (r - rmn) / den, correctly rounded (Markstein)
-            const double a = (double)raw[y * w + x] - (double)rmn;
-            const double q0 = __dmul_rn(a, den_rcp);
-            const double q = __fma_rn(__fma_rn(-q0, den, a), den_rcp, q0);
-            return degenerate ? lo : q;
-        };
+        const double den_rcp = degenerate ? 0.0 : __drcp_rn((double)(rmx - rmn));
+        const double nrm_off = degenerate ? lo : -(double)rmn * den_rcp;      // o = raw * den_rcp + nrm_off
 
         // ---- F + G: a warp takes a block of RB output rows: zoom(+blur) along axis 0 into its row
-        // block, then along axis 1, clip, store ----
+        // block, then along axis 1, normalise, clip, store ----
         const int RB = w <= 11 ? 16 : (w <= 22 ? 8 : (w <= 44 ? 4 : (w <= 88 ? 2 : 1)));
-        double sx[2]; int jx[2];
+        double sx[2]; int c0[2], c1[2];
 #pragma unroll
-        for (int e = 0; e < 2; ++e) { sx[e] = ctab_s[1][lane + 32 * e]; jx[e] = coord_s[1][lane + 32 * e]; }
+        for (int e = 0; e < 2; ++e) {
+            sx[e] = ctab_s[1][lane + 32 * e];
+            c0[e] = rad_c < 0 ? src0_s[1][lane + 32 * e] : coord_s[1][lane + 32 * e];
+            c1[e] = src1_s[1][lane + 32 * e];
+        }
         for (int oy0 = wid * RB; oy0 < CIA_CROP; oy0 += KF_WARPS * RB) {
-            for (int i = lane; i < RB * w; i += 32) {
-                const int r = (w == 1) ? i : (int)__umulhi((unsigned)i, w_magic), x = i - r * w;
-                const double t = ctab_s[0][oy0 + r];
-                const int i0 = coord_s[0][oy0 + r];
-                double v[2];
+            if (rad_r < 0) {
+                for (int i = lane; i < RB * w; i += 32) {
+                    const int r = (w == 1) ? i : (int)__umulhi((unsigned)i, w_magic), x = i - r * w;
+                    const double t = ctab_s[0][oy0 + r];
+                    const double v0 = (double)raw[src0_s[0][oy0 + r] + x], v1 = (double)raw[src1_s[0][oy0 + r] + x];
+                    tbuf[i] = (1.0 - t) * v0 + t * v1;
+                }
+            } else {
+                for (int i = lane; i < RB * w; i += 32) {
+                    const int r = (w == 1) ? i : (int)__umulhi((unsigned)i, w_magic), x = i - r * w;
+                    const double t = ctab_s[0][oy0 + r];
+                    const int i0 = coord_s[0][oy0 + r];
+                    double v[2];
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int yy = i0 + e;
-                    if (!blur_r) {
-                        v[e] = value(mirror_near(yy, h), x);
-                    } else {
+                    for (int e = 0; e < 2; ++e) {
+                        const int yc = mirror_near(i0 + e, h);
                         double acc = 0.0;
-                        for (int j = 0; j <= 2 * rad_r; ++j)
-                            acc += gw_s[0][j] * value(mirror_near(mirror_near(yy, h) + j - rad_r, h), x);
+                        for (int k = 0; k <= 2 * rad_r; ++k)
+                            acc += gw_s[0][k] * (double)raw[mirror_near(yc + k - rad_r, h) * w + x];
                         v[e] = acc;
                     }
+                    tbuf[i] = (1.0 - t) * v[0] + t * v[1];
                 }
-                tbuf[i] = (1.0 - t) * v[0] + t * v[1];
             }
             __syncwarp();
             for (int r = 0; r < RB; ++r) {
                 const double* Trow = tbuf + r * w;
+                float* dst32 = crops32 + (size_t)cell * 4096 + (size_t)(oy0 + r) * 64 + lane;
 #pragma unroll
                 for (int e2 = 0; e2 < 2; ++e2) {
-                    double v[2];
+                    double v0, v1;
+                    if (rad_c < 0) {
+                        v0 = Trow[c0[e2]]; v1 = Trow[c1[e2]];
+                    } else {
+                        double v[2];
 #pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int xx = jx[e2] + e;
-                        if (!blur_c) {
-                            v[e] = Trow[mirror_near(xx, w)];
-                        } else {
+                        for (int e = 0; e < 2; ++e) {
+                            const int xc = mirror_near(c0[e2] + e, w);
                             double acc = 0.0;
-                            for (int j = 0; j <= 2 * rad_c; ++j)
-                                acc += gw_s[1][j] * Trow[mirror_near(mirror_near(xx, w) + j - rad_c, w)];
+                            for (int k = 0; k <= 2 * rad_c; ++k)
+                                acc += gw_s[1][k] * Trow[mirror_near(xc + k - rad_c, w)];
                             v[e] = acc;
                         }
+                        v0 = v[0]; v1 = v[1];
                     }
-                    double o = (1.0 - sx[e2]) * v[0] + sx[e2] * v[1];
-                    const size_t off = (size_t)cell * 4096 + (size_t)(oy0 + r) * 64 + lane + 32 * e2;
-                    if (crops64) { o = fmin(fmax(o, lo), hi); crops64[off] = o; }
-                    crops32[off] = fminf(fmaxf((float)o, (float)lo), (float)hi);
+                    double o = (1.0 - sx[e2]) * v0 + sx[e2] * v1;
+                    o = degenerate ? lo : __fma_rn(o, den_rcp, nrm_off);
+                    if (WANT64) {
+                        o = fmin(fmax(o, lo), hi);
+                        crops64[(size_t)cell * 4096 + (size_t)(oy0 + r) * 64 + lane + 32 * e2] = o;
+                    }
+                    dst32[32 * e2] = fminf(fmaxf((float)o, (float)lo), (float)hi);
                 }
             }
             __syncwarp();
@@ -882,9 +905,10 @@ int k_crop_resize(cia_ctx* h, const uint16_t* images, int H, int W, const cia_ce
     if (first_use(h, (const void*)crop_clahe_resize_kernel))
         CIA_CUDA(cudaFuncSetAttribute(crop_clahe_resize_kernel,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hi_bytes));
-    if (first_use(h, (const void*)crop_fast_kernel)) {
-        CIA_CUDA(cudaFuncSetAttribute(crop_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fb.v[KF_CLASSES - 1]));
-        CIA_CUDA(cudaFuncSetAttribute(crop_fast_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    auto fast = crops64 ? crop_fast_kernel<true> : crop_fast_kernel<false>;
+    if (first_use(h, (const void*)fast)) {
+        CIA_CUDA(cudaFuncSetAttribute(fast, cudaFuncAttributeMaxDynamicSharedMemorySize, fb.v[KF_CLASSES - 1]));
+        CIA_CUDA(cudaFuncSetAttribute(fast, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     }
     const int huge_ctas = 32;
     const size_t per_cta = cell_bytes(MAX_SIDE, MAX_SIDE, 15, 15);
@@ -910,7 +934,7 @@ int k_crop_resize(cia_ctx* h, const uint16_t* images, int H, int W, const cia_ce
     for (int c = 0; c < KF_CLASSES; ++c) {
         int g = h->num_sms * fast_ctas[c];
         if (g > n_cells) g = n_cells;
-        crop_fast_kernel<<<g, KF_THREADS, fb.v[c], s>>>(images, H, W, cells, p->intensity_inv, crops32, crops64,
+        fast<<<g, KF_THREADS, fb.v[c], s>>>(images, H, W, cells, p->intensity_inv, crops32, crops64,
                                                         lists + c * list_stride, cls_counts + c, work + c,
                                                         levels_out, level_offsets);
         CIA_LAUNCH_CHECK();
