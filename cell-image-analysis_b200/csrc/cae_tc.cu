@@ -2089,8 +2089,11 @@ int k_cae_forward_tc(cia_ctx* h, const float* crops, int n, const int32_t* n_dev
             CIA_LAUNCH_CHECK();
             CIA_LMARK(1);
             float* a2f = l3_exact ? A2f - (size_t)c0 * (16 * 16 * 64) : nullptr;
-            // taps per TMEM flush of layer 2 (CIA_L2_TAPS_PER_FLUSH=1|2|3; 0 = the single-buffered
-            // whole-cell kernel): 3 keeps the epilogue warps below the tensor pipe's time, see DESIGN.md
+            // taps per TMEM flush of layer 2 (CIA_L2_TAPS_PER_FLUSH=1|2|3|9; 0 = the single-buffered whole-cell
+            // kernel): 3 keeps the epilogue warps below the tensor pipe's time.  An N-stacked variant (hi x [hi|lo]
+            // as one N = 128 instruction: 112 instead of 145 pipe cycles per k-step by profiles/umma_microbench.cu)
+            // was built and measured in round 2: 53.3 vs 51.5 ms -- its flushes double (main + cross column
+            // groups) and the drain of a two-tile stage no longer hides under the other stage's MMAs
             static const int l2_g = [] { const char* e = getenv("CIA_L2_TAPS_PER_FLUSH"); return e ? atoi(e) : 3; }();
             if (l2_g == 0) rc = launch_tc_acc<32, 64, 32, 1>(h, ae, 1, a1h, a1l, a2h, a2l, a2f, n, n_dev, c0, chunk, s);
             else if (l2_g == 1) rc = launch_tc_acc2<32, 64, 32, 1>(h, ae, 1, A1h, A1l, CH, a2h, a2l, a2f, n, n_dev, c0, chunk, s);

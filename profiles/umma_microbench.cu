@@ -25,7 +25,8 @@ __device__ __forceinline__ void mma(uint32_t d, uint64_t ad, uint64_t bd, uint32
                  ::"r"(d), "l"(ad), "l"(bd), "r"(idesc), "r"(acc) : "memory");
 }
 
-// MODE 0: no swizzle (A: SBO=288 pool layout, LBO=9792; B canonical); MODE 2: 128B swizzle
+// MODE 0: no swizzle (A: SBO=288 pool layout, LBO=9792; B canonical); MODE 1: no swizzle, dense A
+// (SBO=128, LBO=2048: the 128 rows of a k-chunk contiguous, as final_tapsum_kernel's); MODE 2: 128B swizzle
 template <int N, int MODE, int NT>
 __global__ void bench(int iters, long long* out) {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -48,15 +49,15 @@ __global__ void bench(int iters, long long* out) {
     constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const uint32_t a0 = smem_u32(smem), b0 = smem_u32(smem + 48 * 1024);
     if (threadIdx.x == 0) {
-        const uint64_t ad0 = MODE == 0 ? desc(a0, 9792, 288, 0) : desc(a0, 16, 1024, 2);
-        const uint64_t bd0 = MODE == 0 ? desc(b0, N * 16, 128, 0) : desc(b0, 16, 1024, 2);
+        const uint64_t ad0 = MODE == 0 ? desc(a0, 9792, 288, 0) : MODE == 1 ? desc(a0, 2048, 128, 0) : desc(a0, 16, 1024, 2);
+        const uint64_t bd0 = MODE != 2 ? desc(b0, N * 16, 128, 0) : desc(b0, 16, 1024, 2);
         const long long t0 = clock64();
         for (int it = 0; it < iters; ++it) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 // constant per-MMA offsets (16-byte units) folded at compile time
-                const uint64_t ad = ad0 + (uint64_t)(MODE == 0 ? (j % 3) + 18 * (j % 5) : 2 * (j % 4));
-                const uint64_t bd = bd0 + (uint64_t)(MODE == 0 ? (j % 9) * N * 2 : 2 * (j % 4));
+                const uint64_t ad = ad0 + (uint64_t)(MODE == 0 ? (j % 3) + 18 * (j % 5) : MODE == 1 ? 256 * (j % 8) : 2 * (j % 4));
+                const uint64_t bd = bd0 + (uint64_t)(MODE != 2 ? (j % (N >= 256 ? 3 : 9)) * N * 2 : 2 * (j % 4));
                 mma(tmem + (uint32_t)((j % NT) * N), ad, bd, idesc, (it > 0 || j >= NT) ? 1u : 0u);
             }
         }
@@ -85,7 +86,7 @@ void run(long long* out) {
     long long mx = 0;
     for (int i = 0; i < grid; ++i) mx = h[i] > mx ? h[i] : mx;
     printf("%s  N=%3d  accumulators=%d : %6.1f cycles/MMA  (tensor ideal %5.1f; smem A+B read %5.1f)\n",
-           MODE == 0 ? "no-swizzle" : "swizzle128", N, NT, (double)mx / (iters * 16), N / 2.0, (4096 + N * 32) / 128.0);
+           MODE == 0 ? "no-swizzle pool " : MODE == 1 ? "no-swizzle dense" : "swizzle128      ", N, NT, (double)mx / (iters * 16), N / 2.0, (4096 + N * 32) / 128.0);
 }
 
 int main() {
@@ -96,6 +97,7 @@ int main() {
     run<64, 0, 1>(out); run<64, 0, 2>(out); run<64, 0, 4>(out); run<64, 0, 8>(out);
     run<128, 0, 1>(out); run<128, 0, 2>(out); run<128, 0, 4>(out);
     run<256, 0, 1>(out); run<256, 0, 2>(out);
+    run<16, 1, 4>(out); run<32, 1, 4>(out); run<64, 1, 4>(out); run<128, 1, 4>(out); run<256, 1, 2>(out);
     run<32, 2, 1>(out); run<32, 2, 4>(out); run<64, 2, 1>(out); run<64, 2, 4>(out);
     run<128, 2, 1>(out); run<128, 2, 4>(out); run<256, 2, 1>(out); run<256, 2, 2>(out);
     return 0;
