@@ -191,6 +191,76 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def host_probe(eng, bs, g_pin, l_pin, host_threads, world, dev, barrier):
+    """Host-memory side of the end-to-end pass, measured on every rank at the same time: streaming
+    reads of the pinned label pool with the encoder's thread count, alone and next to back-to-back
+    H2D copies of the image pool (what the DMA engine does during a pass).  Sums over ranks."""
+    import torch
+    import torch.distributed as dist
+    lib = eng.lib
+    threads = host_threads if host_threads > 0 else (os.cpu_count() or 1)
+    nbytes = l_pin.numel() * 4
+    stage = torch.empty_like(g_pin, device=dev)
+    barrier()
+    alone = lib.cia_host_read_probe(l_pin.data_ptr(), nbytes, threads, 2)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 12
+    with torch.cuda.stream(bs.copy):
+        e0.record(bs.copy)
+        for _ in range(reps):
+            stage.copy_(g_pin, non_blocking=True)
+        e1.record(bs.copy)
+    busy = lib.cia_host_read_probe(l_pin.data_ptr(), nbytes, threads, 2)
+    still_copying = not e1.query()
+    bs.copy.synchronize()
+    h2d_gbs = reps * g_pin.numel() * 2 / (e0.elapsed_time(e1) * 1e-3) / 1e9
+    v = torch.tensor([alone, busy, h2d_gbs], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(v, op=dist.ReduceOp.SUM)
+    return {"read_gbs_alone": float(v[0]), "read_gbs_next_to_h2d": float(v[1]), "h2d_gbs_next_to_reads": float(v[2]),
+            "threads_per_rank": threads, "copies_outlasted_probe": bool(still_copying)}
+
+
+def svm_extras(pk_note="DMMA fp64 peak 37 TFLOP/s (profiles/fp64_peak_test.cu)"):
+    """Scaler/PCA + both detectors timed at detector sizes the golden artifacts do not have:
+    'realistic' (2 x 5000 SVs, 100-d: nu * N_train for a ~50k-100k cell training set) and BASELINE
+    config 4 (2 x 20000 SVs, 256-d).  Synthetic detectors (random SVs), real kernels."""
+    import torch
+    from cell_image_analysis_b200.artifacts import load_model_dir
+    from cell_image_analysis_b200.screening import Engine
+    arts = load_model_dir(MODEL_DIR)
+    out = {}
+    for tag, nsv, dim, n in (("realistic_5k_sv_100d", 5000, 100, 15130), ("config4_20k_sv_256d", 20000, 256, 15130)):
+        rng = np.random.default_rng(1)
+        q, _ = np.linalg.qr(rng.standard_normal((2048, dim)))
+        a = dict(arts)
+        a["scaler_pca"] = dict(arts["scaler_pca"], C=dim, center=None, scale=None, components=np.ascontiguousarray(q.T),
+                               offset=np.zeros(dim), f32_flow=True)
+        for k in ("svm_conservative", "svm_moderate"):
+            a[k] = dict(sv=rng.standard_normal((nsv, dim)) * 3.0, coef=rng.uniform(0, 1, nsv), gamma=1.0 / (dim * 9.0), rho=1.0)
+        eng = Engine(device=0, precision=1)
+        eng.load_artifacts(a)
+        feat = torch.from_numpy((rng.standard_normal((n, 2048)) * 3.0).astype(np.float32)).to(eng.tdev)
+        for _ in range(2):
+            eng.svm_decision(feat, n)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 5
+        e0.record()
+        for _ in range(reps):
+            eng.svm_decision(feat, n)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        flop = (2.0 * dim * 2 * nsv + 2.0 * 2048 * dim) * n
+        out[tag] = {"cells": n, "ms": ms, "cells_per_s": n / (ms * 1e-3), "tflops_fp64": flop / (ms * 1e-3) / 1e12,
+                    "frac_of_dmma_peak": flop / (ms * 1e-3) / 1e12 / 37.0}
+        eng.close()
+    out["note"] = "PCA + 2 detectors per call, GEMM-form fp64 mma.sync (DMMA); " + pk_note
+    return out
+
+
 # ---------------------------------------------------------------------------
 def run_native(args):
     import torch
@@ -218,7 +288,7 @@ def run_native(args):
     g_pin = torch.from_numpy(greens.view(np.int16)).pin_memory()
     l_pin = torch.from_numpy(labels).pin_memory()
     g_dev, l_dev = g_pin.to(dev), l_pin.to(dev)
-    n_strains = args.strains
+    n_strains = args.strains if args.strains > 0 else (100 if world > 1 else 4)
     visit_strain = (torch.arange(NF, dtype=torch.int32) * n_strains // NF).to(dev)   # contiguous blocks
     rle_fraction = args.rle_fraction
     if args.label_transport == "auto":
@@ -319,6 +389,11 @@ def run_native(args):
     e2e_value = cells_per_step * args.steps / (float(ems.item()) * 1e-3)
     h2d, d2h = bs.host_bytes_per_pass(NF)
     eng.check_status()
+    enc_s = getattr(bs, "encode_seconds", 0.0)          # host time inside the encoder during the LAST timed pass
+    host = host_probe(eng, bs, g_pin, l_pin, args.host_threads, world, dev, barrier)
+    enc_gbs = torch.tensor([4.0 * NF * H * W / enc_s / 1e9 if enc_s > 0 else 0.0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(enc_gbs, op=dist.ReduceOp.SUM)
 
     if rank == 0:
         pk = peaks()
@@ -377,16 +452,26 @@ def run_native(args):
             "dtype": "f32 (CAE fp32 FMA, fp64 flush) / f64 (CLAHE+resize, PCA, SVM) / int (scan)"
                      if args.precision == 0 else "f16 tensor core CAE / f64 SVM",
             "data": "synthetic",
-            "config": {"workload": f"config 2: {NF} visits/GPU/step of 2048x2048 uint16 fields + int32 labels "
+            "config": {"workload": ("config 2" if world == 1 else f"config 5 (multi-strain screen, {n_strains} strains, fields "
+                                    f"sharded over {world} GPUs, one all-reduce of the [S,8] accumulator per step)") +
+                                   f": {NF} visits/GPU/step of 2048x2048 uint16 fields + int32 labels "
                                    f"(~{cells_per_step_local / NF:.0f} scored cells/field), resident pool of {P} "
                                    f"distinct seeded fields ({P * 25.2:.0f} MB > 126 MB L2) cycled in chunks of {Fc}",
-                       "fields_per_step_per_gpu": NF, "cells_per_step": cells_per_step,
+                       "fields_per_step_per_gpu": NF, "cells_per_step": cells_per_step, "strains": n_strains,
                        "artifacts": "tests/golden/model_dir (synthetic CAE weights; scaler/PCA(100)/2 SVMs fit with sklearn)",
                        "precision": args.precision, "l2_policy": "inputs larger than L2"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": float(ems.item()) / args.steps,
                     "label_transport": args.label_transport, "rle_fraction": round(getattr(bs, "last_rle_share", bs.rle_fraction), 3),
                     "host_threads": args.host_threads or (os.cpu_count() or 1),
+                    "host": dict(host, encoder_gbs=float(enc_gbs.item()),
+                                 host_dram_traffic_gbs=(4.0 + 2.0) * H * W * (e2e_value / (cells_per_step_local / NF)) / 1e9,
+                                 bound=("gpu" if e2e_value > 0.9 * value else
+                                        ("host-dram" if (4.0 + 2.0) * H * W * (e2e_value / (cells_per_step_local / NF)) / 1e9
+                                         > 0.7 * (host["read_gbs_next_to_h2d"] + host["h2d_gbs_next_to_reads"]) else "host-cores")),
+                                 note="per field the encoder reads 16.8 MB of labels and the DMA engine 8.4 MB of image from "
+                                      "host DRAM; read_gbs_*: cia_host_read_probe on the pinned label pool on all ranks at "
+                                      "once; encoder_gbs: label bytes / host time inside cia_rle_encode_fields"),
                     "api": "BatchScreen.run_host -> cia_screen_fields_rle / cia_screen_fields (pinned host pool of "
                            "uint16 images + int32 labels; with label_transport=rle the share rle_fraction of the "
                            "chunks is run-length encoded by the host cores inside the timed region and scanned "
@@ -404,6 +489,8 @@ def run_native(args):
                                       "frac": crop_gbs / pk["hbm"]},
                 "svm_ms": svm_ms},
         }
+        if world == 1 and not args.no_svm_extras:
+            line["extra"] = {"svm": svm_extras()}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_inline(args.cpu_fields)
         print(json.dumps(line), flush=True)
@@ -421,7 +508,8 @@ def main():
     ap.add_argument("--fields", type=int, default=1024, help="field visits per GPU per step (config 2: ~1000)")
     ap.add_argument("--pool", type=int, default=64, help="distinct resident fields per GPU")
     ap.add_argument("--chunk", type=int, default=64, help="fields per fused call (measured: 32 -> 2.45M, 64 -> 2.49M cells/s)")
-    ap.add_argument("--strains", type=int, default=4)
+    ap.add_argument("--strains", type=int, default=0,
+                    help="strains the field visits are spread over (0 = 4 on one GPU; 100 on several: BASELINE config 5)")
     ap.add_argument("--precision", type=int, default=1,
                     help="CAE path: 0 exact fp32 CUDA cores, 1 tcgen05 (split-precision encoder), 2 tcgen05 + fp32 encoder")
     ap.add_argument("--label-transport", default="auto", choices=["auto", "rle", "raw"],
@@ -432,6 +520,7 @@ def main():
                     help="share of the chunks sent as runs (rest raw); < 0 = all of them")
     ap.add_argument("--cpu-fields", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-svm-extras", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

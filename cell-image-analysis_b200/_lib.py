@@ -82,6 +82,7 @@ SIGNATURES = {
                                     _P, C.POINTER(Scores), _P]),
     "cia_rle_slot_words": (C.c_size_t, [_I, _I]),
     "cia_rle_encode_fields": (_I, [_P, _I, _I, _I, _P, C.c_size_t, _P, _P, _I]),
+    "cia_host_read_probe": (C.c_double, [_P, C.c_size_t, _I, _I]),
     "cia_rle_upload": (_I, [_P, _P, _I, C.c_size_t, _P, _P, _P]),
     "cia_rle_expand": (_I, [_P, _P, _I, C.c_size_t, _I, _I, _P, _P]),
     "cia_label_scan_rle": (_I, [_P, _P, C.c_size_t, _I, _I, _I, _I, _P, _P]),

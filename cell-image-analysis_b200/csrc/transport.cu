@@ -17,6 +17,7 @@
 #include "common.cuh"
 
 #include <atomic>
+#include <chrono>
 #include <cstring>
 #include <thread>
 
@@ -108,6 +109,39 @@ int cia_rle_encode_fields(const int32_t* labels_host, int n_fields, int H, int W
         *max_label = m;
     }
     return overflow.load() ? CIA_E_CAPACITY : CIA_OK;
+}
+
+// Streaming-read bandwidth of host memory as the run-length encoder sees it: n_threads threads each
+// sum their contiguous share of `buf` with 8-byte loads, `reps` passes; returns GB/s (0 on bad input).
+// bench.py runs it on the pinned label pool, alone and next to H2D copies, to say whether the
+// end-to-end rate is bound by the host's cores or by its DRAM.
+double cia_host_read_probe(const void* buf, size_t bytes, int n_threads, int reps) {
+    if (!buf || bytes < 4096 || reps <= 0) return 0.0;
+    if (n_threads <= 0) {
+        const char* e = getenv("CIA_HOST_THREADS");
+        n_threads = e ? atoi(e) : (int)std::thread::hardware_concurrency();
+        if (n_threads <= 0) n_threads = 1;
+        if (n_threads > 64) n_threads = 64;
+    }
+    const size_t words = bytes / 8, per = words / (size_t)n_threads;
+    std::vector<uint64_t> sums((size_t)n_threads, 0);
+    auto work = [&](int t) {
+        const uint64_t* p = (const uint64_t*)buf + (size_t)t * per;
+        uint64_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+        for (int r = 0; r < reps; ++r)
+            for (size_t i = 0; i + 4 <= per; i += 4) { a0 += p[i]; a1 += p[i + 1]; a2 += p[i + 2]; a3 += p[i + 3]; }
+        sums[(size_t)t] = a0 + a1 + a2 + a3;
+    };
+    const auto t0 = std::chrono::steady_clock::now();
+    std::vector<std::thread> pool;
+    for (int t = 1; t < n_threads; ++t) pool.emplace_back(work, t);
+    work(0);
+    for (auto& t : pool) t.join();
+    const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    volatile uint64_t sink = 0;
+    for (uint64_t v : sums) sink = sink + v;
+    (void)sink;
+    return dt > 0 ? (double)per * 8.0 * n_threads * reps / dt / 1e9 : 0.0;
 }
 
 int cia_rle_upload(cia_handle h, const uint32_t* slots_host, int n_fields, size_t slot_words,

@@ -483,6 +483,20 @@ class ProductionMutantScreening:
         return results, detailed_results
 
 
+    # det:155-244 over the ranks of a torch.distributed process group (one process per GPU)
+    def screen_mutant_samples_sharded(self, test_folders_dict, output_dir=None, chunk_fields: int = 16):
+        from .distributed import screen_mutant_samples_sharded
+        return screen_mutant_samples_sharded(self, test_folders_dict, output_dir, chunk_fields)
+
+    def screen_fields_sharded(self, fields, field_strain, n_strains: int, chunk_fields: int = 16):
+        """``fields``: sequence of (green uint16 [H,W], labels int32 [H,W]) of one size, ``field_strain``
+        their strain ids.  Every rank scores fields[rank::world]; returns the all-reduced per-strain
+        accumulator [S,8] and (rank 0) the per-cell rows in reference order (distributed.ShardedScreen)."""
+        from .distributed import GpuFieldScorer, ShardedScreen
+        sh = ShardedScreen(GpuFieldScorer(self.engine, chunk_fields=chunk_fields))
+        return sh.screen(lambda i: fields[i], len(fields), field_strain, n_strains)
+
+
 def summarize_sample(sample_name, files_processed, s):
     """det:202-212."""
     return {

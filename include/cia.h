@@ -224,6 +224,9 @@ size_t cia_rle_slot_words(int H, int W);
 int cia_rle_encode_fields(const int32_t* labels_host, int n_fields, int H, int W,
                           uint32_t* slots_host, size_t slot_words, uint32_t* field_words,
                           int32_t* max_label, int n_threads);
+/* Host-only probe: streaming-read bandwidth (GB/s) of `bytes` at `buf` with n_threads threads
+ * (<= 0: CIA_HOST_THREADS or all cores), `reps` passes -- the memory side of cia_rle_encode_fields. */
+double cia_host_read_probe(const void* buf, size_t bytes, int n_threads, int reps);
 int cia_rle_upload(cia_handle h, const uint32_t* slots_host, int n_fields, size_t slot_words,
                    const uint32_t* field_words, uint32_t* slots_dev, void* stream);
 int cia_rle_expand(cia_handle h, const uint32_t* slots_dev, int n_fields, size_t slot_words,

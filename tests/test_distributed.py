@@ -87,3 +87,73 @@ def test_shard_fields_round_robin():
 def test_allreduce_without_group_is_identity():
     a = torch.arange(16, dtype=torch.float64).reshape(2, 8)
     assert torch.equal(D.allreduce_strain_acc(a.clone()), a)
+
+
+# ---- ShardedScreen: sharding, all-reduce and host-side row assembly with a NumPy scorer ----
+class _FakeScorer:
+    """One 'cell' per label present in a field; scores derived from the label id and the field's
+    first pixel, so that results identify (field, label) uniquely."""
+
+    def score(self, fields, strains, n_strains):
+        acc = np.zeros((n_strains, D.ACC_COLS))
+        out = []
+        for (g, l), s in zip(fields, strains):
+            labs = np.unique(l[l > 0])
+            k = float(g[0, 0])
+            rows = dict(label=labs.astype(np.int32), mse=(labs * 0.001 + k).astype(np.float32),
+                        mae=(labs * 0.002 + k).astype(np.float32), dec_cons=labs * 0.5 - k, dec_mod=labs * 0.25 - k,
+                        pred_cons=np.where(labs % 2 == 0, -1, 1).astype(np.int8),
+                        pred_mod=np.where(labs % 3 == 0, -1, 1).astype(np.int8))
+            D.accumulate_rows(acc, s, rows)
+            out.append(rows)
+        return torch.from_numpy(acc), out
+
+
+def _fake_field(i):
+    g = np.full((8, 8), i, np.uint16)
+    l = np.zeros((8, 8), np.int32)
+    for k in range(1 + i % 4):
+        l[k, k] = 3 * k + 1 + (i % 2)
+    return g, l
+
+
+def _sharded_worker(rank, world, port, n_fields, n_strains, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    strain = [i % n_strains for i in range(n_fields)]
+    loaded = []
+
+    def load(i):
+        loaded.append(i)
+        return _fake_field(i)
+    acc, rows = D.ShardedScreen(_FakeScorer()).screen(load, n_fields, strain, n_strains)
+    q.put((rank, loaded, acc, rows))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_screen_two_ranks_equals_one():
+    n_fields, n_strains, world = 13, 3, 2
+    strain = [i % n_strains for i in range(n_fields)]
+    acc1, rows1 = D.ShardedScreen(_FakeScorer()).screen(_fake_field, n_fields, strain, n_strains)   # no group: 1 rank
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_sharded_worker, args=(r, world, port, n_fields, n_strains, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got[0][1] == list(range(0, n_fields, 2)) and got[1][1] == list(range(1, n_fields, 2))   # only its own fields
+    for _, _, acc, _ in got:
+        assert np.array_equal(acc[:, :3], acc1[:, :3])                   # counts exact on every rank
+        np.testing.assert_allclose(acc, acc1, rtol=1e-13)                # sums within fp64 rounding
+    assert got[1][3] is None                                             # rows are assembled on rank 0 only
+    rows2 = got[0][3]
+    for k in rows1:
+        assert np.array_equal(rows1[k], rows2[k]), k                     # same rows, same (field, label) order
+    assert np.all(np.diff(rows2["field"]) >= 0)
+    same = np.diff(rows2["field"]) == 0
+    assert np.all(np.diff(rows2["label"])[same] > 0)
