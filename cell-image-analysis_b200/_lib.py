@@ -71,6 +71,7 @@ SIGNATURES = {
     "cia_load_svm": (_I, [_P, _I, _I, _I, _P, _P, C.c_double, C.c_double]),
     "cia_label_scan": (_I, [_P, _P, _I, _I, _I, _I, _P, _P]),
     "cia_filter": (_I, [_P, _P, _I, _I, _I, _I, _P, C.POINTER(Params), _P, _I, _P, _P, _P]),
+    "cia_solidity": (_I, [_P, _P, _I, _I, _P, _I, _P, _P, _P]),
     "cia_crop_resize": (_I, [_P, _P, _I, _I, _P, _I, _P, C.POINTER(Params), _P, _P, _P]),
     "cia_debug_clahe_levels": (_I, [_P, _P, _I, _I, _P, _I, C.POINTER(Params), _P, _P, _P, _P]),
     "cia_cae_forward": (_I, [_P, _P, _I, _P, _P, _P, _P, _I, _P]),
@@ -88,6 +89,8 @@ SIGNATURES = {
     "cia_label_scan_rle": (_I, [_P, _P, C.c_size_t, _I, _I, _I, _I, _P, _P]),
     "cia_screen_fields_rle": (_I, [_P, _P, _P, C.c_size_t, _I, _I, _I, _I, C.POINTER(Params), _I, _P, _I, _P, _P,
                                    C.POINTER(Scores), _P, _P, _P, _P, _I, _P]),
+    "cia_tiff_lzw_decode": (C.c_longlong, [_P, C.c_size_t, _P, C.c_size_t]),
+    "cia_tiff_packbits_decode": (C.c_longlong, [_P, C.c_size_t, _P, C.c_size_t]),
     "cia_profile_begin": (_I, [_P, _I]),
     "cia_profile_end": (_I, [_P, C.POINTER(C.c_double), C.POINTER(_I)]),
     "cia_profile_layers": (_I, [_P, C.POINTER(C.c_double)]),

@@ -272,6 +272,13 @@ int cia_filter(cia_handle h, const uint16_t* images, int n_fields, int H, int W,
                     n_cells_dev, field_counts_dev, (cudaStream_t)stream);
 }
 
+int cia_solidity(cia_handle h, const int32_t* labels, int H, int W, const cia_cell* cells, int n_cells,
+                 const int32_t* n_cells_dev, double* solidity, void* stream) {
+    if (!h) return bad_handle();
+    if (!labels || !cells || !solidity) { h->err = "cia_solidity: null pointer"; return CIA_E_ARG; }
+    return k_solidity(h, labels, H, W, cells, n_cells, n_cells_dev, solidity, (cudaStream_t)stream);
+}
+
 int cia_crop_resize(cia_handle h, const uint16_t* images, int H, int W, const cia_cell* cells,
                     int n_cells, const int32_t* n_cells_dev, const cia_params* params,
                     float* crops32, double* crops64, void* stream) {

@@ -158,6 +158,8 @@ int k_label_scan(cia_ctx* h, const int32_t* labels, int n_fields, int H, int W, 
 int k_filter(cia_ctx* h, const uint16_t* images, int n_fields, int H, int W, int max_label,
              cia_region* regions, const cia_params* p, cia_cell* cells, int cells_cap,
              int32_t* n_cells_dev, int32_t* field_counts_dev, cudaStream_t s);
+int k_solidity(cia_ctx* h, const int32_t* labels, int H, int W, const cia_cell* cells, int n_cells,
+               const int32_t* n_dev, double* out, cudaStream_t s);
 int k_crop_resize(cia_ctx* h, const uint16_t* images, int H, int W, const cia_cell* cells,
                   int n_cells, const int32_t* n_cells_dev, const cia_params* p, float* crops32,
                   double* crops64, cudaStream_t s, uint16_t* levels_out = nullptr,

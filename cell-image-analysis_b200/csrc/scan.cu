@@ -9,6 +9,8 @@
 // lanes by label with match.any and issues one set of atomics per (segment, label).
 #include "common.cuh"
 
+#include <climits>
+
 namespace {
 
 constexpr int SCAN_THREADS = 256;
@@ -315,6 +317,103 @@ scatter_kernel(const cia_region* __restrict__ regions, const double* __restrict_
 }
 
 }  // namespace
+
+// ---- K1c: solidity (det:106, train:101) --------------------------------------
+// skimage regionprops: solidity = area / area_convex, area_convex = convex_hull_image(mask).sum() with
+// offset_coordinates (every mask pixel contributes the four midpoints of its edges) and
+// include_borders (pixel centres ON the hull count).  The hull of a pixel set depends only on the
+// leftmost / rightmost pixel of every row, so: lanes find the row extents, doubled coordinates keep
+// everything integer (edge midpoints (2r +- 1, 2c), (2r, 2c +- 1); pixel centres (2r, 2c)), one lane
+// runs the two monotone chains (right = upper envelope of X over Y, left = lower envelope) and
+// counts per pixel row the even X between the envelopes with exact rational floor / ceil.
+// One warp per cell; scratch per warp: 6 * (2h + 1) ints in global memory.
+__global__ void __launch_bounds__(128)
+solidity_kernel(const int32_t* __restrict__ labels, int H, int W, const cia_cell* __restrict__ cells, int n_cells,
+                const int32_t* __restrict__ n_dev, double* __restrict__ out, int32_t* __restrict__ scratch,
+                size_t scratch_per_warp) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int n = dev_count(n_cells, n_dev);
+    int32_t* base = scratch + (size_t)warp * scratch_per_warp;
+    for (int cell = warp; cell < n; cell += nwarps) {
+        const cia_cell C = cells[cell];
+        const int h = C.maxr - C.minr, w = C.maxc - C.minc;
+        const int K = 2 * h + 1;                           // Y = 2r - 1 .. 2r + 1 over the bbox rows, index k = Y + 1
+        int32_t* xr = base;            int32_t* xl = base + K;
+        int32_t* hr = base + 2 * K;    int32_t* hl = base + 4 * K;      // hull stacks: (k, x) pairs
+        const int32_t* lab = labels + ((size_t)C.field * H + C.minr) * (size_t)W + C.minc;
+        for (int k = lane; k < K; k += 32) { xr[k] = INT_MIN; xl[k] = INT_MAX; }
+        __syncwarp();
+        // row extents; columns are local + 1 so that doubled coordinates stay positive
+        for (int r = lane; r < h; r += 32) {
+            int cl = -1, cr = -1;
+            const int32_t* row = lab + (size_t)r * W;
+            for (int c = 0; c < w; ++c)
+                if (__ldg(row + c) == C.label) { if (cl < 0) cl = c; cr = c; }
+            if (cl >= 0) {
+                const int L = 2 * (cl + 1), Rr = 2 * (cr + 1);
+                atomicMax(&xr[2 * r + 1], Rr + 1); atomicMin(&xl[2 * r + 1], L - 1);      // (2r, 2c +- 1)
+                atomicMax(&xr[2 * r], Rr);     atomicMin(&xl[2 * r], L);                 // (2r - 1, 2c)
+                atomicMax(&xr[2 * r + 2], Rr); atomicMin(&xl[2 * r + 2], L);             // (2r + 1, 2c)
+            }
+        }
+        __syncwarp();
+        if (lane == 0) {
+            // monotone chains over k ascending: keep the envelope convex (cross product test, 64-bit)
+            int nr = 0, nl = 0;
+            for (int k = 0; k < K; ++k) {
+                if (xr[k] == INT_MIN) continue;
+                const long long px = xr[k];
+                while (nr >= 2) {
+                    const long long ax = hr[2 * (nr - 2) + 1], ak = hr[2 * (nr - 2)], bx = hr[2 * (nr - 1) + 1], bk = hr[2 * (nr - 1)];
+                    // b lies on or below the chord a -> p: not a vertex of the upper envelope
+                    if ((bx - ax) * (k - ak) <= (px - ax) * (bk - ak)) --nr; else break;
+                }
+                hr[2 * nr] = k; hr[2 * nr + 1] = (int)px; ++nr;
+                const long long qx = xl[k];
+                while (nl >= 2) {
+                    const long long ax = hl[2 * (nl - 2) + 1], ak = hl[2 * (nl - 2)], bx = hl[2 * (nl - 1) + 1], bk = hl[2 * (nl - 1)];
+                    if ((bx - ax) * (k - ak) >= (qx - ax) * (bk - ak)) --nl; else break;
+                }
+                hl[2 * nl] = k; hl[2 * nl + 1] = (int)qx; ++nl;
+            }
+            long long area_convex = 0;
+            int ir = 0, il = 0;
+            for (int r = 0; r < h && nr > 0; ++r) {
+                const int k = 2 * r + 1;                   // Y = 2r
+                if (k < hr[0] || k > hr[2 * (nr - 1)]) continue;
+                while (ir + 1 < nr - 1 && hr[2 * (ir + 1)] <= k) ++ir;
+                while (il + 1 < nl - 1 && hl[2 * (il + 1)] <= k) ++il;
+                long long xmax2, xmin2;                    // floor(X_right / 2), ceil(X_left / 2) in doubled local columns
+                if (nr == 1) { xmax2 = hr[1] / 2; xmin2 = (hl[1] + 1) / 2; }
+                else {
+                    const long long k0 = hr[2 * ir], x0 = hr[2 * ir + 1], k1 = hr[2 * ir + 2], x1 = hr[2 * ir + 3], d = k1 - k0;
+                    xmax2 = (x0 * d + (x1 - x0) * (k - k0)) / (2 * d);                     // numerator >= 0
+                    const long long m0 = hl[2 * il], y0 = hl[2 * il + 1], m1 = hl[2 * il + 2], y1 = hl[2 * il + 3], e = m1 - m0;
+                    const long long num = y0 * e + (y1 - y0) * (k - m0);
+                    xmin2 = (num + 2 * e - 1) / (2 * e);
+                }
+                if (xmax2 >= xmin2) area_convex += xmax2 - xmin2 + 1;
+            }
+            out[cell] = area_convex > 0 ? (double)C.area / (double)area_convex : 0.0;
+        }
+        __syncwarp();
+    }
+}
+
+int k_solidity(cia_ctx* h, const int32_t* labels, int H, int W, const cia_cell* cells, int n_cells,
+               const int32_t* n_dev, double* out, cudaStream_t s) {
+    if (n_cells <= 0) return CIA_OK;
+    if (H <= 0 || W <= 0) { h->err = "cia_solidity: bad shape"; return CIA_E_ARG; }
+    int blocks = (n_cells + 3) / 4;
+    if (blocks > h->num_sms * 4) blocks = h->num_sms * 4;
+    const size_t per_warp = 6 * (size_t)(2 * H + 1);
+    int rc = ws_reserve(h, h->ws_flags, (size_t)blocks * 4 * per_warp * sizeof(int32_t));
+    if (rc) return rc;
+    solidity_kernel<<<blocks, 128, 0, s>>>(labels, H, W, cells, n_cells, n_dev, out, (int32_t*)h->ws_flags.p, per_warp);
+    CIA_LAUNCH_CHECK();
+    return CIA_OK;
+}
 
 int k_label_scan(cia_ctx* h, const int32_t* labels, int n_fields, int H, int W, int max_label,
                  cia_region* regions, cudaStream_t s) {

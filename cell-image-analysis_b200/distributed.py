@@ -104,36 +104,58 @@ class GpuFieldScorer:
         return bs
 
     def score(self, fields, strains, n_strains):
-        """fields: list of (green uint16 [H,W], labels int32 [H,W]); strains: strain id per field.
-        Returns (acc [S,8] float64 tensor on this rank's device, list of per-field row dicts)."""
+        """fields: list of (green uint16 [H,W], labels int32 [H,W]) pairs OR of zero-argument callables
+        returning such a pair (file decode + segmentation); callables of chunk k+1 are resolved by a
+        thread pool while the device scores chunk k, so at most two chunks of fields are alive.
+        strains: strain id per field.  Returns (acc [S,8] float64 tensor on this rank's device, list
+        of per-field row dicts)."""
+        from concurrent.futures import ThreadPoolExecutor
         dev = self.eng.tdev
+        total = torch.zeros((n_strains, ACC_COLS), dtype=torch.float64, device=dev)
         if not fields:
-            return torch.zeros((n_strains, ACC_COLS), dtype=torch.float64, device=dev), []
-        H, W = fields[0][0].shape
-        max_label = max(int(l.max()) if l.size else 0 for _, l in fields)
-        bs = self._batch(H, W, max_label, n_strains)
-        bs.sync()
-        bs.acc.zero_()
+            return total, []
         out = []
-        for c0 in range(0, len(fields), self.Fc):
-            chunk = fields[c0:c0 + self.Fc]
-            self._l.zero_()                                   # a short last chunk is padded with empty fields
-            for j, (g, l) in enumerate(chunk):
-                if g.shape != (H, W) or l.shape != (H, W):
-                    raise ValueError("ShardedScreen needs equally sized fields (pad or group by size)")
-                self._g[j].copy_(torch.from_numpy(np.ascontiguousarray(g, np.uint16).view(np.int16)))
-                self._l[j].copy_(torch.from_numpy(np.ascontiguousarray(l, np.int32)))
-            st = torch.zeros(self.Fc, dtype=torch.int32)
-            st[:len(chunk)] = torch.tensor(strains[c0:c0 + len(chunk)], dtype=torch.int32)
-            bs.run_host(self._g, self._l, self.Fc, st.to(dev))
-            r = bs.collect_host()                             # synchronises, raises on a device-side status
-            starts = np.concatenate([[0], np.cumsum(r["field_counts"])])
-            for j in range(len(chunk)):
-                s0, s1 = int(starts[j]), int(starts[j + 1])
-                rows = {k: r[k][s0:s1].copy() for k in ROW_KEYS}
-                rows["label"] = r["cells"]["label"][s0:s1].copy()
-                out.append(rows)
-        return bs.acc.clone(), out
+        chunks = [list(range(c0, min(c0 + self.Fc, len(fields)))) for c0 in range(0, len(fields), self.Fc)]
+        resolve = lambda f: f() if callable(f) else f
+        with ThreadPoolExecutor(max_workers=min(8, self.Fc)) as pool:
+            pending = [pool.submit(resolve, fields[i]) for i in chunks[0]]
+            for ci, idx in enumerate(chunks):
+                chunk = [p.result() for p in pending]
+                pending = [pool.submit(resolve, fields[i]) for i in chunks[ci + 1]] if ci + 1 < len(chunks) else []
+                ok = [f for f in chunk if f is not None]       # None: the loader gave up on this file (det:113-115)
+                if not ok:
+                    out.extend({**{k: np.zeros(0) for k in ROW_KEYS}, "label": np.zeros(0, np.int32)} for _ in chunk)
+                    continue
+                H, W = ok[0][0].shape
+                blank = (np.zeros((H, W), np.uint16), np.zeros((H, W), np.int32))
+                chunk = [f if f is not None else blank for f in chunk]
+                max_label = max(int(l.max()) if l.size else 0 for _, l in chunk)
+                old = self._bs
+                bs = self._batch(H, W, max_label, n_strains)
+                if bs is not old:                              # first chunk, or a larger label range / field size
+                    bs.sync()
+                    bs.acc.zero_()
+                self._l.zero_()                                # a short last chunk is padded with empty fields
+                for j, (g, l) in enumerate(chunk):
+                    if g.shape != (H, W) or l.shape != (H, W):
+                        raise ValueError("a chunk needs equally sized fields (pad or group by size)")
+                    if g.dtype != np.uint16:
+                        raise TypeError("fields must be uint16 (widen 8-bit fields before screening)")
+                    self._g[j].copy_(torch.from_numpy(np.ascontiguousarray(g).view(np.int16)))
+                    self._l[j].copy_(torch.from_numpy(np.ascontiguousarray(l, np.int32)))
+                st = torch.zeros(self.Fc, dtype=torch.int32)
+                st[:len(chunk)] = torch.tensor([strains[i] for i in idx], dtype=torch.int32)
+                bs.run_host(self._g, self._l, self.Fc, st.to(dev))
+                r = bs.collect_host()                          # synchronises, raises on a device-side status
+                total += bs.acc
+                bs.acc.zero_()
+                starts = np.concatenate([[0], np.cumsum(r["field_counts"])])
+                for j in range(len(chunk)):
+                    s0, s1 = int(starts[j]), int(starts[j + 1])
+                    rows = {k: r[k][s0:s1].copy() for k in ROW_KEYS}
+                    rows["label"] = r["cells"]["label"][s0:s1].copy()
+                    out.append(rows)
+        return total, out
 
 
 class ShardedScreen:
@@ -151,7 +173,7 @@ class ShardedScreen:
         as a dict of arrays with ``field`` (global index), ``strain`` and ``label`` columns
         (``None`` on the other ranks)."""
         mine = shard_fields(n_fields, self.rank, self.world)
-        fields = [load_field(i) for i in mine]
+        fields = [(lambda i=i: load_field(i)) for i in mine]       # resolved chunk by chunk by the scorer
         acc, rows = self.scorer.score(fields, [int(field_strain[i]) for i in mine], n_strains)
         acc = allreduce_strain_acc(acc)                       # the path's only collective
         local = [(i, r) for i, r in zip(mine, rows)]
@@ -198,12 +220,16 @@ def screen_mutant_samples_sharded(screener, test_folders_dict, output_dir=None, 
         return {}, []
 
     def load(i):
-        image = screener.imread(files[i])
-        if image.ndim == 3 and image.shape[-1] >= 3:                      # det:54-59
-            seg, green = image[..., 2], image[..., 1]
-        else:
-            seg = green = image
-        return np.ascontiguousarray(green), np.ascontiguousarray(screener._segment(seg), np.int32)
+        try:
+            image = screener.imread(files[i])
+            if image.ndim == 3 and image.shape[-1] >= 3:                  # det:54-59
+                seg, green = image[..., 2], image[..., 1]
+            else:
+                seg = green = image
+            return np.ascontiguousarray(green), np.ascontiguousarray(screener._segment(seg), np.int32)
+        except Exception as e:                                            # det:113-115: the file contributes no cells
+            print(f"Error processing {files[i]}: {e}")
+            return None
 
     sh = ShardedScreen(GpuFieldScorer(screener.engine, chunk_fields=chunk_fields))
     acc, rows = sh.screen(load, len(files), strain_of, len(names))

@@ -128,6 +128,13 @@ class Engine:
                                         C.c_void_p(counts.data_ptr() + 4), self._stream()))
         return cells, counts
 
+    def solidity(self, labels: torch.Tensor, cells: torch.Tensor, n: int) -> torch.Tensor:
+        """prop.solidity (det:106) of the first ``n`` cells; labels int32 [F,H,W] (cuda)."""
+        F, H, W = labels.shape
+        out = torch.empty(max(n, 1), dtype=torch.float64, device=self.tdev)
+        self._check(self.lib.cia_solidity(self.h, _ptr(labels), H, W, _ptr(cells), n, None, _ptr(out), self._stream()))
+        return out
+
     def crop_resize(self, images: torch.Tensor, cells: torch.Tensor, n: int, n_dev=None,
                     want64: bool = False, params=None):
         F, H, W = images.shape
@@ -398,13 +405,15 @@ class ProductionMutantScreening:
         if n == 0:
             return ([], [], regions) if return_regions else ([], [])
         _c32, c64 = eng.crop_resize(g, cells, n, want64=True, params=params)
+        sol = eng.solidity(l, cells, n)
         eng.check_status()
         crops = c64[:n].cpu().numpy()
+        sol = sol[:n].cpu().numpy()
         rec = cells[:n].cpu().numpy().view(_lib.CELL_DTYPE).reshape(-1)
         quality_cells = [crops[i] for i in range(n)]
         cell_stats = [{"area": float(r["area"]), "eccentricity": float(r["eccentricity"]),
-                       "mean_intensity": float(r["mean_intensity"]),
-                       "std_intensity": float(r["std_intensity"])} for r in rec]     # det:103-109
+                       "solidity": float(sol[i]), "mean_intensity": float(r["mean_intensity"]),
+                       "std_intensity": float(r["std_intensity"])} for i, r in enumerate(rec)]   # det:103-109
         if return_regions:
             return quality_cells, cell_stats, rec
         return quality_cells, cell_stats

@@ -55,8 +55,8 @@ typedef struct cia_region {
 } cia_region;                        /* 64 bytes                                      */
 
 /* One cell that passed the gates, in reference order: fields in call order, labels
- * ascending (det:72).  The stats are the cell_stats dict of det:103-109 (solidity is
- * out of scope: dead in the screening path). */
+ * ascending (det:72).  The stats are the cell_stats dict of det:103-109; its solidity entry
+ * comes from cia_solidity (it needs the label field, which the fused path does not keep). */
 typedef struct cia_cell {
     int32_t field;                  /* index of the field inside the call            */
     int32_t label;
@@ -147,6 +147,11 @@ int cia_filter(cia_handle h, const uint16_t* images, int n_fields, int H, int W,
                int max_label, cia_region* regions, const cia_params* params,
                cia_cell* cells, int cells_cap, int32_t* n_cells_dev,
                int32_t* field_counts_dev, void* stream);
+/* prop.solidity of det:106 / train:101 for the cells that passed the gates: area over the pixel count
+ * of skimage's convex_hull_image of the region mask (edge-midpoint offsets, border included).
+ * labels: int32 [n_fields, H, W] as given to cia_label_scan; solidity: float64 [n_cells]. */
+int cia_solidity(cia_handle h, const int32_t* labels, int H, int W, const cia_cell* cells,
+                 int n_cells, const int32_t* n_cells_dev, double* solidity, void* stream);
 /* det:88 crop + det:98 equalize_adapthist + det:99 resize + det:122 float32 cast.
  * n_cells: host upper bound; n_cells_dev (may be NULL) the device count.
  * crops32: float32 [n,64,64]; crops64 (may be NULL): float64 [n,64,64]. */
@@ -241,6 +246,12 @@ int cia_screen_fields_rle(cia_handle h, const uint16_t* images, const uint32_t* 
                           float* crops32, float* features,
                           const int32_t* field_strain, double* acc, int n_strains,
                           void* stream);
+
+/* Host-only strip / tile decompressors of the TIFF reader that stands in for tiff.imread
+ * (improved_detection.py:51): TIFF-LZW and PackBits.  Return the bytes written
+ * to dst (at most cap) or -1 on a corrupt stream. */
+long long cia_tiff_lzw_decode(const uint8_t* src, size_t n, uint8_t* dst, size_t cap);
+long long cia_tiff_packbits_decode(const uint8_t* src, size_t n, uint8_t* dst, size_t cap);
 
 /* Stage timing of the fused path with CUDA events recorded in-stream (no host sync is
  * added to the timed region): after cia_profile_begin(h, R) the next R calls of

@@ -17,7 +17,7 @@ def extract_quality_cells_from_labels(green: np.ndarray, labels: np.ndarray):
         cell = green[minr:maxr, minc:maxc]                        # det:88
         eq = clahe.equalize_adapthist(cell, clip_limit=0.02)      # det:98
         cells.append(resize.resize(eq, (64, 64)))                 # det:99
-        stats.append({"area": k["area"], "eccentricity": k["eccentricity"],
+        stats.append({"area": k["area"], "eccentricity": k["eccentricity"], "solidity": k["solidity"],
                       "mean_intensity": k["mean_intensity"],
-                      "std_intensity": k["std_intensity"]})       # det:103-109 minus solidity (C10)
+                      "std_intensity": k["std_intensity"]})       # det:103-109
     return cells, stats, kept, tab

@@ -73,6 +73,36 @@ def eccentricity_closed_form(n, m10, m01, m20, m02, m11) -> float:
     return float(np.sqrt(max(1.0 - l2 / l1, 0.0)))
 
 
+def convex_hull_image(mask: np.ndarray) -> np.ndarray:
+    """``skimage.morphology.convex_hull_image(mask)`` with its defaults (``offset_coordinates=True``,
+    ``include_borders=True``) as regionprops' ``image_convex`` uses it: every mask pixel contributes
+    the four midpoints of its edges, the convex hull of those points is computed with the REAL Qhull
+    (scipy.spatial.ConvexHull, the library skimage itself calls) and every pixel centre inside or on
+    the hull is set.  skimage is absent here [R]; pinned by skimage's own unit-test vector
+    (tests/test_oracle.py::test_convex_hull_image_skimage_vector)."""
+    from scipy.spatial import ConvexHull
+    mask = np.asarray(mask, bool)
+    out = np.zeros(mask.shape, bool)
+    rr, cc = np.nonzero(mask)
+    if rr.size == 0:
+        return out
+    pts = np.stack([rr, cc], 1).astype(np.float64)
+    offs = np.array([[-0.5, 0.0], [0.5, 0.0], [0.0, -0.5], [0.0, 0.5]])
+    pts = np.unique((pts[:, None, :] + offs[None]).reshape(-1, 2), axis=0)
+    hull = ConvexHull(pts)
+    gr, gc = np.mgrid[0:mask.shape[0], 0:mask.shape[1]]
+    g = np.stack([gr.ravel(), gc.ravel()], 1).astype(np.float64)
+    # inside or on every facet: normal . x + offset <= 0 (coordinates are multiples of 0.5: a point ON a
+    # facet evaluates to ~1e-16, far inside the tolerance)
+    inside = np.all(g @ hull.equations[:, :2].T + hull.equations[:, 2] <= 1e-9, axis=1)
+    return inside.reshape(mask.shape)
+
+
+def solidity(mask: np.ndarray) -> float:
+    """``prop.solidity`` (det:106, train:101): area / area_convex."""
+    return float(mask.sum()) / float(convex_hull_image(mask).sum())
+
+
 def raw_moments(labels: np.ndarray, lab: int, bbox):
     minr, minc, maxr, maxc = bbox
     rr, cc = np.nonzero(labels[minr:maxr, minc:maxc] == lab)
@@ -107,5 +137,5 @@ def quality_regions(green: np.ndarray, labels: np.ndarray, ecc_fn=None):
         if mean < MEAN_MIN or std < STD_MIN:                       # det:94
             continue
         kept.append(dict(label=lab, bbox=(minr, minc, maxr, maxc), area=area,
-                         eccentricity=ecc, mean_intensity=mean, std_intensity=std))
+                         eccentricity=ecc, solidity=solidity(mask), mean_intensity=mean, std_intensity=std))
     return kept, tab

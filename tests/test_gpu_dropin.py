@@ -63,6 +63,22 @@ def test_screen_mutant_samples_end_to_end(tmp_path, model_dir, artifacts, oracle
         assert d.max() <= 1e-4
     for name in ("screening_summary.csv", "detailed_cell_results.csv", "mutant_screening_report.txt"):
         assert os.path.exists(out / name)
+    # the sharded twin (one rank here; two ranks in tests/test_gpu_sharded.py): same strains, counts and rows
+    results2, rows2 = s.screen_mutant_samples_sharded(folders, str(tmp_path / "out2"), chunk_fields=2)
+    assert list(results2) == list(results)
+    for strain in results:
+        a, b = results[strain], results2[strain]
+        assert list(a) == list(b)                                              # key order of det:202-212
+        for k in ("total_cells", "files_processed", "conservative_anomaly_rate", "moderate_anomaly_rate"):
+            assert a[k] == b[k], (strain, k)
+        for k in ("mean_mse", "std_mse", "mean_mae", "std_mae"):
+            assert abs(float(a[k]) - b[k]) <= 1e-6 * abs(b[k]), (strain, k)    # float32 np.mean vs fp64 accumulator
+    assert len(rows2) == len(rows)
+    for x, y in zip(rows, rows2):
+        assert x["sample_name"] == y["sample_name"] and x["cell_id"] == y["cell_id"]
+        assert x["mse"] == y["mse"] and x["conservative_score"] == y["conservative_score"]
+        assert x["moderate_anomaly"] == y["moderate_anomaly"]
+    assert os.path.exists(tmp_path / "out2" / "screening_summary.csv")
     feats = s.encode_features(cells)
     assert feats.shape == (len(cells), 2048) and feats.dtype == np.float32
     assert np.abs(feats - ref["_features"]).max() <= 1e-5 * max(1.0, np.abs(ref["_features"]).max())

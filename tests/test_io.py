@@ -28,6 +28,80 @@ def test_tiff_matches_opencv_decoder(tmp_path):
     assert np.array_equal(tiff_min.read_tiff(str(tmp_path / "cv.tif")), img)  # and we read its files
 
 
+def _field(shape=(300, 411), seed=0):
+    rng = np.random.default_rng(seed)
+    ramp = np.linspace(0, 30000, shape[1])[None, :]
+    return (rng.integers(0, 4000, shape) + ramp).astype(np.uint16)
+
+
+@pytest.mark.parametrize("compression", [5, 8, 32946, 32773])
+def test_tiff_reads_compressed_files_written_by_libtiff(tmp_path, compression):
+    """LZW (with libtiff's horizontal predictor), Deflate (both tag values) and PackBits strips
+    as OpenCV / libtiff writes them -- an independent encoder."""
+    cv2 = pytest.importorskip("cv2")
+    img = _field()
+    p = str(tmp_path / "c.tif")
+    assert cv2.imwrite(p, img, [cv2.IMWRITE_TIFF_COMPRESSION, compression])
+    assert np.array_equal(tiff_min.read_tiff(p), img)
+    rgb = np.random.default_rng(2).integers(0, 65535, (120, 90, 3)).astype(np.uint16)
+    assert cv2.imwrite(p, rgb, [cv2.IMWRITE_TIFF_COMPRESSION, compression])
+    assert np.array_equal(tiff_min.read_tiff(p), rgb[..., ::-1])            # OpenCV stores BGR as RGB
+
+
+def test_tiff_reads_pillow_files_and_stacks_pages(tmp_path):
+    Image = pytest.importorskip("PIL.Image")
+    img = _field()
+    for comp in ("tiff_lzw", "tiff_adobe_deflate", "packbits", None):
+        p = str(tmp_path / "p.tif")
+        Image.fromarray(img).save(p, compression=comp)
+        assert np.array_equal(tiff_min.read_tiff(p), img), comp
+    pages = [Image.fromarray((img + i).astype(np.uint16)) for i in range(3)]
+    p = str(tmp_path / "stack.tif")
+    pages[0].save(p, save_all=True, append_images=pages[1:], compression="tiff_lzw")
+    back = tiff_min.read_tiff(p)                                             # tifffile.imread returns the stack
+    assert back.shape == (3,) + img.shape and np.array_equal(back[2], img + 2)
+
+
+@pytest.mark.parametrize("kw", [dict(tile=(64, 48 + 16)), dict(tile=(128, 128), compression=8),
+                                dict(compression=8, rows_per_strip=7), dict(bigtiff=True),
+                                dict(bigtiff=True, tile=(32, 32), compression=8)])
+def test_tiff_tiles_deflate_bigtiff_round_trip(tmp_path, kw):
+    for img in (_field((150, 203)), np.random.default_rng(3).integers(0, 65535, (70, 50, 3)).astype(np.uint16)):
+        p = str(tmp_path / "t.tif")
+        tiff_min.write_tiff(p, img, **kw)
+        assert np.array_equal(tiff_min.read_tiff(p), img)
+
+
+def test_tiff_tiled_file_matches_opencv_decoder(tmp_path):
+    cv2 = pytest.importorskip("cv2")
+    img = _field((150, 203))
+    p = str(tmp_path / "t.tif")
+    tiff_min.write_tiff(p, img, tile=(64, 64), compression=8)
+    assert np.array_equal(cv2.imread(p, cv2.IMREAD_UNCHANGED), img)
+
+
+def test_native_and_python_lzw_agree(tmp_path):
+    """The interpreter fallback decodes the same stream to the same bytes as csrc/host_tiff.cpp."""
+    cv2 = pytest.importorskip("cv2")
+    import struct
+    img = _field((64, 200))
+    p = str(tmp_path / "l.tif")
+    cv2.imwrite(p, img, [cv2.IMWRITE_TIFF_COMPRESSION, 5])
+    buf = open(p, "rb").read()
+    # first strip of the file, located through the reader's own IFD parser
+    (ifd,) = struct.unpack("<I", buf[4:8])
+    (n,) = struct.unpack("<H", buf[ifd:ifd + 2])
+    tags = {}
+    for i in range(n):
+        e = buf[ifd + 2 + 12 * i: ifd + 14 + 12 * i]
+        tag, typ, cnt = struct.unpack("<HHI", e[:8])
+        tags[tag] = tiff_min._ifd_values(buf, "<", typ, cnt, e[8:12], struct.unpack("<I", e[8:12])[0])
+    strip = buf[tags[273][0]: tags[273][0] + tags[279][0]]
+    cap = tags[278][0] * 200 * 2
+    native = tiff_min._decompress(strip, 5, cap)
+    assert tiff_min._lzw_python(strip, cap) == native and len(native) == cap
+
+
 def test_tiff_rejects_what_it_cannot_read(tmp_path):
     p = tmp_path / "bad.tif"
     p.write_bytes(b"II*\0" + b"\0" * 3)
