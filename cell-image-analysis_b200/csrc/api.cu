@@ -60,6 +60,7 @@ int cia_create(int device, cia_handle* out) {
     if (const char* e = getenv("CIA_L1_DEBIAS")) h->cae_debias[0] = (float)atof(e);
     if (const char* e = getenv("CIA_L2_DEBIAS")) h->cae_debias[1] = (float)atof(e);
     if (const char* e = getenv("CIA_L3_DEBIAS")) h->cae_debias[2] = (float)atof(e);
+    if (const char* e = getenv("CIA_SVM_KERNEL")) h->svm_kernel = atoi(e) ? 1 : 0;
     *out = h;
     return CIA_OK;
 }
@@ -74,6 +75,11 @@ int cia_set_option(cia_handle h, const char* name, double value) {
     } else if (n == "cae_l1_debias" || n == "cae_l2_debias" || n == "cae_l3_debias") {
         if (!(value >= 0 && value <= 64)) { h->err = "cia_set_option: debias must be in [0, 64] (units of 2^-24)"; return CIA_E_ARG; }
         h->cae_debias[n[5] - '1'] = (float)value;
+    } else if (n == "svm_kernel") {
+        if (value != 0 && value != 1) { h->err = "cia_set_option: svm_kernel is 0 (fp64 DMMA) or 1 (tcgen05)"; return CIA_E_ARG; }
+        h->svm_kernel = (int)value;
+    } else if (n == "svm_refine") {
+        h->svm_refine = value != 0;
     } else {
         h->err = "cia_set_option: unknown option '" + n + "'";
         return CIA_E_ARG;
@@ -99,7 +105,8 @@ int cia_destroy(cia_handle h) {
     cudaDeviceSynchronize();
     free_cae(h->cae[0]); free_cae(h->cae[1]);
     cudaFree(h->sp.center); cudaFree(h->sp.scale); cudaFree(h->sp.rscale); cudaFree(h->sp.comp_t); cudaFree(h->sp.comp_pad); cudaFree(h->sp.offset);
-    for (int i = 0; i < 2; ++i) { cudaFree(h->svm[i].sv_t); cudaFree(h->svm[i].coef); cudaFree(h->svm[i].sv_pad); cudaFree(h->svm[i].gsn); }
+    for (int i = 0; i < 2; ++i) { cudaFree(h->svm[i].sv_t); cudaFree(h->svm[i].coef); cudaFree(h->svm[i].sv_pad); cudaFree(h->svm[i].gsn);
+                                  cudaFree(h->svm[i].tc_hi); cudaFree(h->svm[i].tc_lo); cudaFree(h->svm[i].tc_gcol); }
     Workspace* ws[] = {&h->ws_flags, &h->ws_act, &h->ws_crop_scratch, &h->ws_pipe, &h->ws_feat,
                        &h->ws_misc, &h->ws_stage, &h->ws_svm};
     for (Workspace* w : ws) cudaFree(w->p);
@@ -251,6 +258,7 @@ int cia_load_svm(cia_handle h, int which, int n_sv, int dim, const double* sv, c
     if ((rc = upload(h, &m.sv_pad, r.data(), r.size()))) return rc;
     if ((rc = upload(h, &m.gsn, g.data(), g.size()))) return rc;
     m.n_sv = n_sv; m.n_sv_pad = pad; m.dim = dim; m.dim_pad = dpad; m.gamma = gamma; m.rho = rho;
+    if ((rc = k_svm_tc_prepare(h, m, sv, coef))) return rc;
     m.loaded = true;
     return CIA_OK;
 }

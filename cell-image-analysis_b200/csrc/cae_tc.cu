@@ -26,6 +26,7 @@
 //   L6 64->32 @32  conv_tc_kernel<EPI_PHASE>     phase form at 16x16, N = 128
 //   L7 32->1  @64  conv_tc_kernel<EPI_FINAL>     phase form at 32x32 + sigmoid + MSE/MAE reduction
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 #include <cuda.h>          // CUtensorMap (types only; the encoder is fetched through the runtime)
 #include <cuda_fp16.h>
@@ -39,75 +40,7 @@ constexpr int TCT = 256;   // 8 warps: warp&3 = TMEM lane quadrant, warp>>2 = co
 // (py,px) of the 2x nearest up-sampled grid as column groups: N = 4 * Cout, output is 2R x 2R
 enum { EPI_POOL = 0, EPI_PLAIN = 2, EPI_FINAL = 3, EPI_PHASE = 4 };
 
-// ---------------------------------------------------------------------------------------
-// PTX wrappers
-// ---------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    const uint32_t a = smem_u32(bar);
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(a), "r"(parity) : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {   // one full warp
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {     // same warp
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem], kind::f16 (fp16 operands, fp32 accumulate), issued by ONE thread
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                         uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// 32 lanes x 8 consecutive fp32 columns -> 8 registers per thread (lane = TMEM lane of the warp's quadrant)
-#define TMEM_LD8(taddr, v)                                                                          \
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"            \
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), \
-                   "=r"(v[7]) : "r"(taddr))
-// wait for the loads AND make every later use of the registers depend on the wait
-#define TMEM_WAIT8(v)                                                                               \
-    asm volatile("tcgen05.wait::ld.sync.aligned;"                                                   \
-                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), \
-                   "+r"(v[7]) :: "memory")
-
-// K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
-// canonical layout ((8,m),2):((16 B, SBO), LBO) in 16-byte units.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
-    d |= (uint64_t)1 << 46;                 // descriptor version 1 (sm_100)
-    return d;                               // layout_type 0 = SWIZZLE_NONE, base_offset 0
-}
-// cute::UMMA::InstrDescriptor: c_format f32 (bit 4), a/b format f16 (0), K-major A and B,
-// n_dim = N >> 3 at [17,23), m_dim = M >> 4 at [24,29)
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
-    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-__host__ __device__ constexpr int pow2_cols(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
+using namespace tcptx;
 
 // Pooling layers: value of a pooled pixel from the max over its 2x2 window of the SIGN-FOLDED conv
 // accumulators (weight columns carry sign(bn scale), see k_cae_tc_prepare).  bias -> ReLU -> BN is
@@ -554,31 +487,6 @@ constexpr int ACC_EPI_WARPS = 16;
 constexpr int ACC_MMA_WARPS = 4;
 constexpr int ACC_THREADS = (ACC_EPI_WARPS + ACC_MMA_WARPS) * 32;
 
-// packed fp32x2 helpers (sm_100): two IEEE fp32 lanes in one 64-bit register
-__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
-    unsigned long long r;
-    asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ void unpack2(unsigned long long v, float& lo, float& hi) {
-    asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
-    unsigned long long d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-    return d;
-}
-// (a0, a1) += (b0, b1): one FADD2 (sm_100 packed fp32x2, IEEE round-to-nearest per lane)
-__device__ __forceinline__ void fadd2(float& a0, float& a1, uint32_t b0, uint32_t b1) {
-    asm("{\n\t.reg .b64 ra, rb;\n\tmov.b64 ra, {%0,%1};\n\tmov.b64 rb, {%2,%3};\n\t"
-        "add.rn.f32x2 ra, ra, rb;\n\tmov.b64 {%0,%1}, ra;\n\t}"
-        : "+f"(a0), "+f"(a1) : "r"(b0), "r"(b1));
-}
-
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
 // Geometry of the accurate-accumulation kernel: ONE unit = one whole cell.  The zero-padded
 // (R+2) x (R+2) input is staged once, column-parity de-interleaved, and serves both pooled
 // X-halves (R = 32) -- half as many unit boundaries (staging, pipeline fill/drain) per MMA.
@@ -976,9 +884,6 @@ struct Acc2Cfg {
     static_assert(PAR_B % 128 == 0, "TMA destinations must be 128-byte aligned");
 };
 
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
 __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3,
                                             int c4, uint64_t* bar) {
     asm volatile(
@@ -1595,11 +1500,6 @@ constexpr int PL_B = 16 * 1024 * 4;                // tap-sum planes [column][pi
 constexpr int SMEM_B = 2 * A_B + W_B + PL_B;
 constexpr int STAGE_COLS = 8 * 32;                 // 8 tiles x (16 hi + 16 lo columns)
 }  // namespace l7
-
-__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
 
 __global__ void __launch_bounds__(l7::NT, 1)
 final_tapsum_kernel(const __half* __restrict__ a6, const uint4* __restrict__ w_img, float inv_scale,

@@ -41,6 +41,13 @@ struct SvmModel {
     double* gsn = nullptr;    // [n_sv_pad] -gamma * ||s_i||^2
     int n_sv_pad = 0, dim_pad = 0;
     double gamma = 0, rho = 0;
+    // tensor-core operand images (score_tc.cu): fp16 hi / lo parts of the 2^tc_es scaled support vectors as
+    // [SV tile of 128][dim / 8][128][8], and per SV log2(e) * -gamma||s||^2 + log2(coef)
+    void* tc_hi = nullptr;
+    void* tc_lo = nullptr;
+    float* tc_gcol = nullptr;
+    int tc_es = 0, tc_svt = 0;
+    bool tc_ok = false;
 };
 
 struct ScalerPca {
@@ -92,6 +99,9 @@ struct cia_ctx {
     // and the truncation compensation of its accumulating layers in units of 2^-24 (cae_tc.cu)
     int cae_pass_cells = 18944;
     float cae_debias[3] = {0.5f, 2.4f, 1.2f};   // L1, L2, L3
+    // cia_set_option "svm_kernel": 1 = tcgen05 GEMM form (score_tc.cu), 0 = fp64 DMMA anchor (score.cu)
+    int svm_kernel = 1;
+    int svm_refine = 1;        // "svm_refine": decisions within the tensor-core kernel's error of 0 are recomputed in fp64
 };
 #define CIA_LAYER_MARKS 8  // before L1, after L1 .. L7
 #define CIA_LAYER_PASSES 8 // passes of one call that carry marks (cells_cap <= 8 x 18944)
@@ -176,6 +186,9 @@ int k_cae_tc_prepare(cia_ctx* h, int which);
 int k_svm_decision(cia_ctx* h, const float* features, int n, const int32_t* n_dev,
                    double* dec_cons, double* dec_mod, int8_t* pred_cons, int8_t* pred_mod,
                    double* pca_out, cudaStream_t s);
+int k_svm_tc_prepare(cia_ctx* h, SvmModel& m, const double* sv, const double* coef);
+int k_svm_tc(cia_ctx* h, const SvmModel& m, const double* z, int n, const int32_t* n_dev, double* dec,
+             int8_t* pred, bool* done, cudaStream_t s);
 int k_strain_accumulate(cia_ctx* h, const cia_cell* cells, int n, const int32_t* n_dev,
                         const cia_scores* sc, const int32_t* field_strain, double* acc,
                         int n_strains, cudaStream_t s);

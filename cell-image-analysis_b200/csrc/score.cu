@@ -328,6 +328,9 @@ svm_rbf_kernel(const double* __restrict__ z, int n_cells, const int32_t* __restr
 // stream through a cp.async double buffer in stages of 128 SVs x 16 dims (pitch 20 doubles).
 // sv_pad is the zero-padded row-major copy [n_sv rounded to 128][D rounded to 16]; gsn[i] =
 // -gamma * ||s_i||^2; padded rows have coef 0.
+// min(x, 0) that lets a NaN through (fmin would turn a non-finite row into "kernel value 1" = an inlier)
+__device__ __forceinline__ double neg_part(double x) { return x > 0.0 ? 0.0 : x; }
+
 constexpr int GT = 512;            // threads
 constexpr int GM = 64;             // cells per block
 constexpr int GN = 128;            // support vectors per tile
@@ -422,10 +425,10 @@ svm_rbf_dmma_kernel(const double* __restrict__ z, int n_cells, const int32_t* __
             for (int nt = 0; nt < 4; ++nt) {
                 const double2 cf = __ldg(reinterpret_cast<const double2*>(coef + sv0 + nt * 8));
                 const double2 gs = __ldg(reinterpret_cast<const double2*>(gsn + sv0 + nt * 8));
-                part0 = fma(cf.x, exp(fmin(fma(g2, acc[0][nt][0], gz0 + gs.x), 0.0)), part0);
-                part0 = fma(cf.y, exp(fmin(fma(g2, acc[0][nt][1], gz0 + gs.y), 0.0)), part0);
-                part1 = fma(cf.x, exp(fmin(fma(g2, acc[1][nt][0], gz1 + gs.x), 0.0)), part1);
-                part1 = fma(cf.y, exp(fmin(fma(g2, acc[1][nt][1], gz1 + gs.y), 0.0)), part1);
+                part0 = fma(cf.x, exp(neg_part(fma(g2, acc[0][nt][0], gz0 + gs.x))), part0);
+                part0 = fma(cf.y, exp(neg_part(fma(g2, acc[0][nt][1], gz0 + gs.y))), part0);
+                part1 = fma(cf.x, exp(neg_part(fma(g2, acc[1][nt][0], gz1 + gs.x))), part1);
+                part1 = fma(cf.y, exp(neg_part(fma(g2, acc[1][nt][1], gz1 + gs.y))), part1);
                 acc[0][nt][0] = acc[0][nt][1] = acc[1][nt][0] = acc[1][nt][1] = 0.0;
             }
             ks = 0;
@@ -549,6 +552,13 @@ int k_svm_decision(cia_ctx* h, const float* features, int n, const int32_t* n_de
     for (int which = 0; which < 2; ++which) {
         const SvmModel& m = h->svm[which];
         if (m.dim != sp.C) { h->err = "svm dimension != pca components"; return CIA_E_STATE; }
+        if (h->svm_kernel == 1 && !direct_svm) {
+            // tensor-core GEMM form (score_tc.cu); falls through when the model is not served by it
+            bool done = false;
+            int rc = k_svm_tc(h, m, z, n, n_dev, which == 0 ? dec_cons : dec_mod, which == 0 ? pred_cons : pred_mod, &done, s);
+            if (rc) return rc;
+            if (done) continue;
+        }
         const size_t sm3 = sizeof(double) * ((size_t)GM * (m.dim_pad + 4) + 2 * GN * GSP + GM + 4 * GM);
         if (!direct_svm && sm3 <= (size_t)h->max_smem_optin) {
             if (first_use(h, (const void*)svm_rbf_dmma_kernel))

@@ -1,0 +1,525 @@
+// score_tc.cu -- K5 on the 5th-generation tensor cores: both one-class RBF SVM decision
+// functions in GEMM form, ||z - s||^2 = ||z||^2 + ||s||^2 - 2 z.s^T, with the z.s^T products of
+// a 128-cell x 128-SV tile as tcgen05.mma (fp16 operands split hi + lo, three MMAs per k-step,
+// fp32 accumulation in TMEM) and the exp / dual-coefficient reduction fused into the tile epilogue.
+//
+// Replaces detector.predict + detector.decision_function (improved_detection.py:138-142; libsvm
+// k_function RBF, sklearn/svm/src/libsvm/svm.cpp:461-472, sum - rho and the sign rule :2832-2841).
+// The fp64 DMMA kernel in score.cu stays as the exact anchor (cia_set_option "svm_kernel" = 0).
+//
+// Why fp16 x 3 is accurate enough here: only the CROSS term z.s goes through
+// the tensor cores.  The PCA scores are centred, so gamma * z.s is O(1/sqrt(D)) while the two large
+// terms gamma||z||^2 and gamma||s||^2 are computed exactly in fp64 (per cell in the prologue, per SV
+// at load time).  Every row (cell) and the SV matrix are scaled by a power of two so that their
+// largest element sits in [2^13, 2^14): x = hi + lo carries 22 significant bits, the dropped lo*lo
+// term and the roundings are ~2^-22 of |z||s|, i.e. ~3e-8 in the exponent, random in sign over
+// the SVs.  What would be systematic is kept out of fp32: the per-cell term log2(e)*gamma||z||^2 is
+// split into an integer (added to the exponent) and a fraction that multiplies the finished row sum
+// in fp64; 2^t is a Cody-Waite reduction + degree-6 polynomial (max rel. error 1e-7, mean 4e-10,
+// no MUFU bias); row sums are fp32 over 32 terms, fp64 beyond.
+//
+// Work distribution: the (cell tile, SV tile) pairs are one flat list cut into equal contiguous
+// ranges, one per CTA (one CTA per SM); a cell tile whose SV range spans several CTAs gets one
+// partial sum per CTA, added in CTA order by svm_tc_finalize_kernel (deterministic).
+// tcgen05 adds every MMA into its fp32 accumulator with round-toward-zero (profiles/umma_rounding_test.cu):
+// a 16-k-step chain under-estimates z.s by ~6e-7 relative, always in the same direction for the near SVs
+// that dominate a decision (measured: 3e-5 on the golden detectors).  So a TMEM accumulator only ever holds
+// ONE pipeline stage (32 dims: cross terms first, the two hi*hi k-steps last); the epilogue warps add the
+// stage partials in fp32 registers with round-to-nearest while the MMAs of the next stage fill the other
+// TMEM buffer, and the mean deficit of the two remaining truncations (1.5 * 2^-25) rides on the row factor,
+// which is carried as an fp32 pair (its own rounding would be an error of the same size, common to all pairs).
+//   warps 0..15 build the A operand (z tile: scale, split, K-major core matrices), then run the
+//               epilogue: TMEM quadrant = warp & 3, column quarter = warp >> 2
+//   warp 16     lane 0 streams the SV tiles (hi | lo images, 32 dims per stage) with cp.async.bulk
+//   warps 17,18 lane 0 of each issues the MMAs of every second stage (one thread sustains ~one tcgen05.mma per
+//               60 cycles plus ~90 per barrier wait; a stage is six 64-cycle MMAs); TMEM holds four stage accumulators
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+#include <cuda_fp16.h>
+
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+using namespace tcptx;
+
+namespace {
+namespace svmtc {
+constexpr int EPI_WARPS = 16;
+constexpr int PROD_WARP = 16, MMA_WARP = 17;     // MMA_WARP and MMA_WARP + 1 issue alternate stages
+constexpr int NT = 19 * 32;
+constexpr int TM = 128, TN = 128;
+constexpr int KC = 32;                       // dims per pipeline stage = 2 k-steps
+constexpr int K8_B = TN * 16;                // one 8-dim core-matrix column of a 128-row operand: 2 KB
+constexpr int HALF_B = (KC / 8) * K8_B;      // hi (or lo) part of a stage: 8 KB
+constexpr int STAGE_B = 2 * HALF_B;
+constexpr int MAX_STAGES = 8;
+constexpr int NBUF = 4;                      // TMEM stage accumulators (128 columns each)
+constexpr int TMEM_COLS = NBUF * TN;
+constexpr int STATIC_SMEM_EST = 8 * 1024;    // barriers + per-row arrays below (host-side budget)
+constexpr double LOG2E = 1.4426950408889634074;
+}  // namespace svmtc
+
+#define TMEM_LD32(taddr, v)                                                                               \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                \
+                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"                                 \
+                 "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"                \
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),     \
+                   "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), \
+                   "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]),           \
+                   "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]),           \
+                   "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])            \
+                 : "r"(taddr))
+#define TMEM_WAIT32(v)                                                                                    \
+    asm volatile("tcgen05.wait::ld.sync.aligned;"                                                         \
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]),     \
+                   "+r"(v[7]), "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), \
+                   "+r"(v[14]), "+r"(v[15]), "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]),           \
+                   "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]), "+r"(v[25]),           \
+                   "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31]) :: "memory")
+
+__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
+// (2^(t0 + nrow), 2^(t1 + nrow)) for an integer nrow: n = rint(t) by the magic-number add, f = t - n in
+// [-0.5, 0.5], degree-6 minimax polynomial in packed fp32x2 FMAs; n and nrow (pre-shifted into the
+// exponent field, nsh = nrow << 23) are added to the exponent as integers.  t is clamped to
+// tmin = -126 - nrow (the result underflows to ~1e-38 instead of wrapping).  Relative error <= 1.0e-7
+// (fp32 Horner), mean 4e-10 (fit and figures: DESIGN.md section 4).
+template <bool MUFU, bool SLOW>
+__device__ __forceinline__ void exp2x2(unsigned long long t, float tmin, float tmax, uint32_t nsh, float nrow, float& r0f, float& r1f) {
+    float t0, t1;
+    unpack2(t, t0, t1);
+    if (MUFU) {       // A/B variant: ex2.approx (max rel. error 2^-22, unknown mean)
+        t0 += nrow; t1 += nrow;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r0f) : "f"(t0));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r1f) : "f"(t1));
+        return;
+    }
+    t0 = fmaxf(t0, tmin);                     // fmaxf also drops a NaN (0 * inf of a degenerate row)
+    t1 = fmaxf(t1, tmin);
+    if (SLOW) { t0 = fminf(t0, tmax); t1 = fminf(t1, tmax); }
+    const unsigned long long tt = pack2(t0, t1);
+    const unsigned long long m = add2(tt, pack2(12582912.f, 12582912.f));          // 1.5 * 2^23: n in the low mantissa bits
+    const unsigned long long nf = add2(m, pack2(-12582912.f, -12582912.f));
+    const unsigned long long f = fma2(nf, pack2(-1.f, -1.f), tt);                  // exact
+    unsigned long long p = pack2(0.00015337577497120947f, 0.00015337577497120947f);
+    p = fma2(p, f, pack2(0.0013399859890341759f, 0.0013399859890341759f));
+    p = fma2(p, f, pack2(0.009618519805371761f, 0.009618519805371761f));
+    p = fma2(p, f, pack2(0.05550329014658928f, 0.05550329014658928f));
+    p = fma2(p, f, pack2(0.24022646248340607f, 0.24022646248340607f));
+    p = fma2(p, f, pack2(0.6931471824645996f, 0.6931471824645996f));
+    p = fma2(p, f, pack2(1.0f, 1.0f));
+    r0f = __uint_as_float((uint32_t)p + ((uint32_t)m << 23) + nsh);
+    r1f = __uint_as_float((uint32_t)(p >> 32) + ((uint32_t)(m >> 32) << 23) + nsh);
+}
+
+template <bool MUFU>
+__global__ void __launch_bounds__(svmtc::NT, 1)
+svm_rbf_tc_kernel(const double* __restrict__ z, int n_cells, const int32_t* __restrict__ n_dev, int D, int Dpad,
+                  const __half* __restrict__ sv_hi, const __half* __restrict__ sv_lo,
+                  const float* __restrict__ gcol, int n_svt, double fac_base, double gamma, int per_cta,
+                  int stages, double* __restrict__ partial, int pitch) {
+    using namespace svmtc;
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], tfull_bar[NBUF], tempty_bar[NBUF];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ float s_rowfac[TM], s_rowfac_lo[TM], s_nrow[TM];
+    __shared__ int s_erow[TM];
+    __shared__ double s_rowmul[TM], s_red[4][TM];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n = dev_count(n_cells, n_dev);
+    const int n_ct = (n + TM - 1) / TM;
+    const long long W = (long long)n_ct * n_svt;
+    const long long w0 = (long long)blockIdx.x * per_cta;
+    const long long w1 = W < w0 + per_cta ? W : w0 + per_cta;
+    if (w0 >= W) return;                          // uniform per CTA, nothing allocated yet
+
+    const int nk8 = Dpad >> 3;
+    const int n_kc = (Dpad + KC - 1) / KC;
+    const uint32_t a_half_b = (uint32_t)Dpad * 256u;          // hi (or lo) image of the z tile
+    unsigned char* const a_hi = smem;
+    unsigned char* const a_lo = smem + a_half_b;
+    const uint32_t a_addr = smem_u32(smem);
+    const uint32_t st_addr = a_addr + 2 * a_half_b;
+
+    if (warp == MMA_WARP) tmem_alloc(&tmem_base_s, TMEM_COLS);
+    if (tid == 0) {
+        for (int i = 0; i < MAX_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < NBUF; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], EPI_WARPS); }
+        fence_barrier_init();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    constexpr uint32_t IDESC = make_idesc(TM, TN);
+
+    uint32_t p_st = 0, p_ph = 0;                  // producer: stage, parity of its round
+    uint32_t m_cnt = 0;                           // MMA issuers: running stage count
+    uint32_t e_buf = 0;                           // epilogue
+
+    for (long long w = w0; w < w1;) {
+        const int ct = (int)(w / n_svt), t0 = (int)(w - (long long)ct * n_svt);
+        const int nt = (int)((long long)(n_svt - t0) < w1 - w ? (long long)(n_svt - t0) : w1 - w);
+
+        // ---------------- A operand of this cell tile ----------------
+        if (warp < EPI_WARPS) {
+            // (the previous segment's MMAs have completed: every epilogue warp waited on its last tile)
+            asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");      // per-row arrays free
+            for (int r = warp; r < TM; r += EPI_WARPS) {
+                const int cell = ct * TM + r;
+                double mx = 0.0, ss = 0.0;
+                if (cell < n)
+                    for (int d = lane; d < D; d += 32) {
+                        const double v = z[(size_t)cell * D + d];
+                        mx = fmax(mx, fabs(v));
+                        ss = fma(v, v, ss);
+                    }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                ss = warp_sum(ss);
+                if (lane == 0) {
+                    int e = 0;
+                    if (mx > 0.0 && mx < 1e300) e = 13 - ilogb(mx);
+                    e = max(-100, min(100, e));
+                    const double growl = -gamma * ss * LOG2E;
+                    double nr = rint(growl);
+                    if (!(nr > -1048576.0)) nr = -1048576.0;            // also catches NaN / -inf rows
+                    s_erow[r] = e;
+                    const double fac = ldexp(fac_base, -e);         // fac_base carries the truncation compensation
+                    const float fh = (float)fac;
+                    s_rowfac[r] = fh;
+                    s_rowfac_lo[r] = (float)(fac - (double)fh);
+                    s_nrow[r] = (float)nr;
+                    s_rowmul[r] = exp2(growl - nr);
+                }
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+            for (int idx = tid; idx < TM * nk8; idx += EPI_WARPS * 32) {
+                const int r = idx & (TM - 1), k8 = idx >> 7;
+                const int cell = ct * TM + r;
+                const double sc = __hiloint2double((1023 + s_erow[r]) << 20, 0);   // 2^e, exact
+                __align__(16) __half hh[8];
+                __align__(16) __half ll[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int d = k8 * 8 + j;
+                    const double v = (cell < n && d < D) ? z[(size_t)cell * D + d] * sc : 0.0;
+                    hh[j] = __double2half(v);
+                    ll[j] = __double2half(v - (double)__half2float(hh[j]));
+                }
+                *reinterpret_cast<uint4*>(a_hi + (size_t)idx * 16) = *reinterpret_cast<const uint4*>(hh);
+                *reinterpret_cast<uint4*>(a_lo + (size_t)idx * 16) = *reinterpret_cast<const uint4*>(ll);
+            }
+            fence_async_smem();
+        }
+        __syncthreads();
+
+        if (warp == PROD_WARP) {
+            // ================= SV tile stream =================
+            if (lane == 0) {
+                for (int t = t0; t < t0 + nt; ++t)
+                    for (int kc = 0; kc < n_kc; ++kc) {
+                        mbar_wait(&empty_bar[p_st], p_ph ^ 1);
+                        const int k8n = min(KC / 8, nk8 - kc * (KC / 8));
+                        const uint32_t bytes = (uint32_t)k8n * K8_B;
+                        const size_t off = ((size_t)t * nk8 + (size_t)kc * (KC / 8)) * (TN * 8);   // halves
+                        mbar_expect_tx(&full_bar[p_st], 2 * bytes);
+                        bulk_load(st_addr + p_st * STAGE_B, sv_hi + off, bytes, &full_bar[p_st]);
+                        bulk_load(st_addr + p_st * STAGE_B + HALF_B, sv_lo + off, bytes, &full_bar[p_st]);
+                        if (++p_st == (uint32_t)stages) { p_st = 0; p_ph ^= 1; }
+                    }
+            }
+            __syncwarp();
+        } else if (warp >= MMA_WARP) {
+            // ================= MMA issuers =================
+            if (lane == 0) {
+                const uint32_t me = (uint32_t)(warp - MMA_WARP);
+                const uint64_t ah0 = make_smem_desc(a_addr, K8_B, 128), al0 = make_smem_desc(a_addr + a_half_b, K8_B, 128);
+                const uint64_t bh0 = make_smem_desc(st_addr, K8_B, 128), bl0 = make_smem_desc(st_addr + HALF_B, K8_B, 128);
+                for (int t = t0; t < t0 + nt; ++t) {
+                    for (int kc = 0; kc < n_kc; ++kc, ++m_cnt) {
+                        if ((m_cnt & 1) != me) continue;
+                        const uint32_t buf = m_cnt & (NBUF - 1), st = m_cnt % (uint32_t)stages;
+                        mbar_wait(&tempty_bar[buf], ((m_cnt / NBUF) & 1) ^ 1);   // the epilogue has drained this buffer
+                        mbar_wait(&full_bar[st], (m_cnt / (uint32_t)stages) & 1);
+                        tc_fence_after();
+                        const uint32_t d = tmem_base + buf * TN;
+                        const int ksn = min(KC / 16, (nk8 - kc * (KC / 8)) >> 1);
+                        const uint64_t ao = (uint64_t)((uint32_t)(kc * (KC / 16)) * ((2 * K8_B) >> 4));
+                        const uint64_t bo = (uint64_t)(st * (STAGE_B >> 4));
+                        // cross terms (2^-11 of the product) first into the fresh accumulator, hi*hi last
+#pragma unroll
+                        for (int pass = 0; pass < 2; ++pass)
+#pragma unroll
+                            for (int s = 0; s < KC / 16; ++s) {
+                                if (s < ksn) {
+                                    const uint64_t so = (uint64_t)(s * ((2 * K8_B) >> 4));
+                                    if (pass == 0) {
+                                        umma_f16(d, ah0 + ao + so, bl0 + bo + so, IDESC, s == 0 ? 0u : 1u);
+                                        umma_f16(d, al0 + ao + so, bh0 + bo + so, IDESC, 1u);
+                                    } else {
+                                        umma_f16(d, ah0 + ao + so, bh0 + bo + so, IDESC, 1u);
+                                    }
+                                }
+                            }
+                        umma_commit(&empty_bar[st]);
+                        umma_commit(&tfull_bar[buf]);
+                    }
+                }
+            }
+            __syncwarp();
+        } else {
+            // ================= epilogue: fused RBF + dual-coefficient reduction =================
+            const int q = warp & 3, cq = warp >> 2, row = 32 * q + lane;
+            const float rf = s_rowfac[row], rfl = s_rowfac_lo[row], nrw = s_nrow[row];
+            const unsigned long long rf2 = pack2(rf, rf), rfl2 = pack2(rfl, rfl);
+            // 2^(t + nrow): nrow goes into the exponent field as an integer; rows whose nrow is beyond the
+            // fp32 exponent range contribute 2^-126-ish terms (their kernel values are < 1e-38 anyway)
+            const float nrc = fminf(fmaxf(nrw, -250.f), 120.f);
+            const float tmin = -126.f - nrc, tmax = 126.f - nrc;
+            const uint32_t nsh = (uint32_t)((int)nrc) << 23;
+            // far outliers (log2e * gamma||z||^2 beyond the fp32 exponent range): the rest of n_row is added to t
+            // in fp32 and t is clamped on both sides -- a warp-uniform slow path, one more FADD2 per pair
+            const float rem = nrw - nrc;
+            const unsigned long long rem2 = pack2(rem, rem);
+            const bool slow = __any_sync(0xffffffffu, rem != 0.f);
+            const uint32_t taddr0 = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(cq * 32);
+            double rowsum = 0.0;
+            for (int t = t0; t < t0 + nt; ++t) {
+                // ---- z.s of this tile: the stage partials added in fp32 registers, round to nearest ----
+                float acc[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+#pragma unroll 1
+                for (int kc = 0; kc < n_kc; ++kc, ++e_buf) {
+                    const uint32_t buf = e_buf & (NBUF - 1);
+                    mbar_wait(&tfull_bar[buf], (e_buf / NBUF) & 1);
+                    tc_fence_after();
+                    uint32_t v[32];
+                    TMEM_LD32(taddr0 + buf * TN, v);
+                    TMEM_WAIT32(v);
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+#pragma unroll
+                    for (int j = 0; j < 32; j += 2) fadd2(acc[j], acc[j + 1], v[j], v[j + 1]);
+                }
+                // ---- fused RBF + dual-coefficient reduction ----
+                // t = acc * (2 gamma log2e 2^-(e_row + e_s)) + (log2e * -gamma||s||^2 + log2 coef)  [+ n_row]
+                const float4* gc = reinterpret_cast<const float4*>(gcol + (size_t)t * TN + cq * 32);
+                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+                if (!slow) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 g = __ldg(gc + (j >> 2));
+                        const unsigned long long a01 = pack2(acc[j], acc[j + 1]), a23 = pack2(acc[j + 2], acc[j + 3]);
+                        const unsigned long long ta = fma2(a01, rf2, fma2(a01, rfl2, pack2(g.x, g.y)));
+                        const unsigned long long tb = fma2(a23, rf2, fma2(a23, rfl2, pack2(g.z, g.w)));
+                        float e0, e1, e2, e3;
+                        exp2x2<MUFU, false>(ta, tmin, tmax, nsh, nrc, e0, e1);
+                        exp2x2<MUFU, false>(tb, tmin, tmax, nsh, nrc, e2, e3);
+                        s0 += e0; s1 += e1; s2 += e2; s3 += e3;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 g = __ldg(gc + (j >> 2));
+                        const unsigned long long a01 = pack2(acc[j], acc[j + 1]), a23 = pack2(acc[j + 2], acc[j + 3]);
+                        const unsigned long long ta = add2(fma2(a01, rf2, fma2(a01, rfl2, pack2(g.x, g.y))), rem2);
+                        const unsigned long long tb = add2(fma2(a23, rf2, fma2(a23, rfl2, pack2(g.z, g.w))), rem2);
+                        float e0, e1, e2, e3;
+                        exp2x2<MUFU, true>(ta, tmin, tmax, nsh, nrc, e0, e1);
+                        exp2x2<MUFU, true>(tb, tmin, tmax, nsh, nrc, e2, e3);
+                        s0 += e0; s1 += e1; s2 += e2; s3 += e3;
+                    }
+                }
+                rowsum += (double)((s0 + s1) + (s2 + s3));
+            }
+            s_red[cq][row] = rowsum;
+            asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+            if (cq == 0) {
+                const int cell = ct * TM + row;
+                if (cell < n) {
+                    const int first_cta = (int)(((long long)ct * n_svt) / per_cta);
+                    partial[(size_t)((int)blockIdx.x - first_cta) * pitch + cell] =
+                        ((s_red[0][row] + s_red[1][row]) + (s_red[2][row] + s_red[3][row])) * s_rowmul[row];
+                }
+            }
+        }
+        w += nt;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == svmtc::MMA_WARP) tmem_dealloc(tmem_base, svmtc::TMEM_COLS);
+}
+
+// dec = (partial sums of the CTAs that shared this cell tile, in CTA order) - rho
+__global__ void __launch_bounds__(256)
+svm_tc_finalize_kernel(const double* __restrict__ partial, int pitch, int n_svt, int per_cta, int n_cells,
+                       const int32_t* __restrict__ n_dev, double rho, double* __restrict__ dec,
+                       int8_t* __restrict__ pred) {
+    const int n = dev_count(n_cells, n_dev);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const long long ct = i / svmtc::TM;
+    const int first = (int)((ct * n_svt) / per_cta), last = (int)(((ct + 1) * n_svt - 1) / per_cta);
+    double s = 0.0;
+    for (int k = 0; k <= last - first; ++k) s += partial[(size_t)k * pitch + i];
+    s -= rho;
+    dec[i] = s;
+    pred[i] = s > 0.0 ? 1 : -1;                    // svm.cpp:2841
+}
+
+// Exact re-evaluation of the decisions the fp16 x 3 kernel cannot sign with certainty.  Its error is a
+// few 2^-24 of the kernel sum (the z tile keeps 22 of the 24 significand bits of the float32 PCA scores,
+// and that rounding is common to all SVs of a row: measured 6e-5 at 20 000 SVs with sum(coef) = 2e4, 1e-6
+// at the golden detectors), so a decision with |dec| < thr_abs + thr_rel * (dec + rho) is recomputed in
+// fp64 with direct differences -- libsvm's own arithmetic, svm.cpp:461-472 -- by a whole block, its SV
+// partial sums added in a fixed order.  Such cells are rare (~1e-5 of a screen); the scan costs 8 bytes a cell.
+__global__ void __launch_bounds__(256)
+svm_refine_kernel(const double* __restrict__ z, int n_cells, const int32_t* __restrict__ n_dev, int D,
+                  const double* __restrict__ sv_t, const double* __restrict__ coef, int n_sv, int n_sv_pad,
+                  double gamma, double rho, double thr_abs, double thr_rel, double* __restrict__ dec,
+                  int8_t* __restrict__ pred) {
+    extern __shared__ double zrow[];             // [D]
+    __shared__ int s_list[256];
+    __shared__ int s_count;
+    __shared__ double s_part[8];
+    const int n = dev_count(n_cells, n_dev);
+    const int tid = threadIdx.x;
+    for (int base = blockIdx.x * 256; base < n; base += gridDim.x * 256) {
+        if (tid == 0) s_count = 0;
+        __syncthreads();
+        const int c = base + tid;
+        if (c < n) {
+            const double d = dec[c];
+            if (fabs(d) < thr_abs + thr_rel * fabs(d + rho)) s_list[atomicAdd(&s_count, 1)] = c;
+        }
+        __syncthreads();
+        const int cnt = s_count;
+        for (int k = 0; k < cnt; ++k) {
+            const int cell = s_list[k];          // (the order of the list does not matter: cells are independent)
+            for (int d = tid; d < D; d += 256) zrow[d] = z[(size_t)cell * D + d];
+            __syncthreads();
+            double part = 0.0;
+            for (int i = tid; i < n_sv; i += 256) {
+                double d2 = 0.0;
+                for (int d = 0; d < D; ++d) {
+                    const double df = zrow[d] - __ldg(sv_t + (size_t)d * n_sv_pad + i);
+                    d2 = fma(df, df, d2);
+                }
+                part = fma(coef[i], exp(-gamma * d2), part);
+            }
+            part = warp_sum(part);
+            if ((tid & 31) == 0) s_part[tid >> 5] = part;
+            __syncthreads();
+            if (tid == 0) {
+                double sum = 0.0;
+                for (int w = 0; w < 8; ++w) sum += s_part[w];
+                sum -= rho;
+                dec[cell] = sum;
+                pred[cell] = sum > 0.0 ? 1 : -1;
+            }
+            __syncthreads();
+        }
+    }
+}
+
+}  // namespace
+
+// Operand images of one detector for svm_rbf_tc_kernel (called from cia_load_svm): support vectors
+// scaled by 2^e_s and split hi + lo, as [SV tile of 128][dim / 8][128][8 halves] (the K-major
+// core-matrix order a tile's bulk copy lands in); gcol[i] = log2(e) * -gamma||s_i||^2 + log2(coef_i).
+int k_svm_tc_prepare(cia_ctx* h, SvmModel& m, const double* sv, const double* coef) {
+    m.tc_ok = false;
+    cudaFree(m.tc_hi); cudaFree(m.tc_lo); cudaFree(m.tc_gcol);
+    m.tc_hi = m.tc_lo = nullptr; m.tc_gcol = nullptr;
+    if (m.dim_pad > 256) return CIA_OK;              // the z tile (hi + lo) would not fit in shared memory
+    double mx = 0.0;
+    for (size_t i = 0; i < (size_t)m.n_sv * m.dim; ++i) {
+        if (!std::isfinite(sv[i])) return CIA_OK;
+        mx = std::fmax(mx, std::fabs(sv[i]));
+    }
+    for (int i = 0; i < m.n_sv; ++i)
+        if (!(coef[i] >= 0.0) || !std::isfinite(coef[i])) return CIA_OK;   // one-class duals are >= 0; anything else: DMMA path
+    const int es = mx > 0.0 ? 13 - std::ilogb(mx) : 0;
+    if (es < -100 || es > 100) return CIA_OK;
+    const int n_svt = (m.n_sv + svmtc::TN - 1) / svmtc::TN, nk8 = m.dim_pad / 8;
+    std::vector<__half> hi((size_t)n_svt * nk8 * svmtc::TN * 8, __float2half_rn(0.f)), lo = hi;
+    std::vector<float> g((size_t)n_svt * svmtc::TN, -1e30f);
+    for (int i = 0; i < m.n_sv; ++i) {
+        const int t = i / svmtc::TN, r = i % svmtc::TN;
+        double ss = 0.0;
+        for (int d = 0; d < m.dim; ++d) {
+            const double v0 = sv[(size_t)i * m.dim + d];
+            ss += v0 * v0;
+            const double v = std::ldexp(v0, es);
+            const __half hv = __double2half(v);
+            const size_t idx = (((size_t)t * nk8 + d / 8) * svmtc::TN + r) * 8 + (d % 8);
+            hi[idx] = hv;
+            lo[idx] = __double2half(v - (double)__half2float(hv));
+        }
+        if (coef[i] > 0.0) g[i] = (float)(svmtc::LOG2E * (-m.gamma * ss) + std::log2(coef[i]));
+    }
+    CIA_CUDA(cudaMalloc(&m.tc_hi, hi.size() * sizeof(__half)));
+    CIA_CUDA(cudaMalloc(&m.tc_lo, lo.size() * sizeof(__half)));
+    CIA_CUDA(cudaMalloc(&m.tc_gcol, g.size() * sizeof(float)));
+    CIA_CUDA(cudaMemcpy(m.tc_hi, hi.data(), hi.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    CIA_CUDA(cudaMemcpy(m.tc_lo, lo.data(), lo.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    CIA_CUDA(cudaMemcpy(m.tc_gcol, g.data(), g.size() * sizeof(float), cudaMemcpyHostToDevice));
+    m.tc_es = es;
+    m.tc_svt = n_svt;
+    m.tc_ok = true;
+    return CIA_OK;
+}
+
+// returns CIA_OK and sets *done = false when this model / size is not served by the tensor-core kernel
+int k_svm_tc(cia_ctx* h, const SvmModel& m, const double* z, int n, const int32_t* n_dev, double* dec,
+             int8_t* pred, bool* done, cudaStream_t s) {
+    using namespace svmtc;
+    *done = false;
+    if (!m.tc_ok) return CIA_OK;
+    const int a_bytes = 2 * m.dim_pad * 256;
+    int stages = (h->max_smem_optin - STATIC_SMEM_EST - a_bytes) / STAGE_B;
+    if (stages < 3) return CIA_OK;
+    stages = std::min(stages, MAX_STAGES);
+    const int smem_b = a_bytes + stages * STAGE_B;
+    static const bool mufu = getenv("CIA_SVM_MUFU") != nullptr;       // A/B switch: ex2.approx instead of the polynomial
+    auto kern = mufu ? svm_rbf_tc_kernel<true> : svm_rbf_tc_kernel<false>;
+    if (first_use(h, (const void*)kern))
+        CIA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin - STATIC_SMEM_EST));
+    const int n_ct = (n + TM - 1) / TM;
+    const long long W = (long long)n_ct * m.tc_svt;
+    // equal contiguous ranges of (cell tile, SV tile) pairs, one CTA per SM; a range never shorter than 2
+    // pairs (each range pays one A-operand build)
+    int per_cta = (int)((W + h->num_sms - 1) / h->num_sms);
+    per_cta = std::max(per_cta, std::min(2, m.tc_svt));
+    const int grid = (int)((W + per_cta - 1) / per_cta);
+    const int slots = (m.tc_svt + per_cta - 1) / per_cta + 1;
+    int rc = ws_reserve(h, h->ws_svm, (size_t)slots * n * sizeof(double));
+    if (rc) return rc;
+    double* partial = (double*)h->ws_svm.p;
+    // mean deficit of the two full-magnitude round-toward-zero accumulations of a stage, in units of 2^-25
+    static const double debias = [] { const char* e = getenv("CIA_SVM_DEBIAS"); return e ? atof(e) : 1.5; }();
+    const double fac_base = std::ldexp(2.0 * m.gamma * LOG2E, -m.tc_es) * (1.0 + debias * 2.9802322387695312e-8);
+    kern<<<grid, NT, smem_b, s>>>(z, n, n_dev, m.dim, m.dim_pad, (const __half*)m.tc_hi, (const __half*)m.tc_lo, m.tc_gcol, m.tc_svt, fac_base,
+                                  m.gamma, per_cta, stages, partial, n);
+    CIA_LAUNCH_CHECK();
+    svm_tc_finalize_kernel<<<(n + 255) / 256, 256, 0, s>>>(partial, n, m.tc_svt, per_cta, n, n_dev, m.rho, dec, pred);
+    CIA_LAUNCH_CHECK();
+    if (h->svm_refine) {
+        int blocks = std::min((n + 255) / 256, h->num_sms * 4);
+        svm_refine_kernel<<<blocks, 256, m.dim * sizeof(double), s>>>(z, n, n_dev, m.dim, m.sv_t, m.coef, m.n_sv, m.n_sv_pad, m.gamma,
+                                                                     m.rho, 2e-4, 4e-7, dec, pred);
+        CIA_LAUNCH_CHECK();
+    }
+    *done = true;
+    return CIA_OK;
+}

@@ -1,0 +1,110 @@
+"""The tcgen05 GEMM-form SVM kernel (csrc/score_tc.cu, cia_set_option "svm_kernel" = 1, the default)
+against the fp64 DMMA anchor (= libsvm to 1e-9, tests/test_gpu_parity.py) and real libsvm:
+work distribution over CTAs, ragged sizes, device-side counts, outlier / zero / non-finite rows,
+and the fp64 re-evaluation of decisions near zero."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng(artifacts):
+    from cell_image_analysis_b200.screening import Engine
+    e = Engine(device=0, precision=1)
+    e.load_artifacts(artifacts)
+    yield e
+    e.close()
+
+
+def _features(golden_tiny, n, seed=0):
+    rng = np.random.default_rng(seed)
+    f0 = golden_tiny["features"].astype(np.float32)
+    reps = (n + len(f0) - 1) // len(f0)
+    return np.concatenate([f0 * (1 + 0.05 * rng.standard_normal(f0.shape).astype(np.float32))
+                           for _ in range(reps)])[:n]
+
+
+def _both(eng, feat_np, n=None, n_dev=None):
+    n = len(feat_np) if n is None else n
+    feat = torch.from_numpy(feat_np).to(eng.tdev)
+    out = {}
+    for k in (0, 1):
+        eng.set_option("svm_kernel", k)
+        dc, dm, pc, pm, _ = eng.svm_decision(feat, n, n_dev=n_dev)
+        eng.check_status()
+        out[k] = [t.cpu().numpy() for t in (dc, dm, pc, pm)]
+    eng.set_option("svm_kernel", 1)
+    return out
+
+
+@pytest.mark.parametrize("n", [1, 127, 128, 129, 5000, 40000])
+def test_tc_equals_dmma_across_sizes(eng, golden_tiny, n):
+    """1 cell ... 313 cell tiles (more (cell tile, SV tile) pairs than CTAs: several tiles per CTA)."""
+    out = _both(eng, _features(golden_tiny, n, seed=n))
+    for i in (0, 1):
+        d = np.abs(out[1][i][:n] - out[0][i][:n]).max()
+        assert d <= 1e-5, f"n={n} det{i}: max |tc - dmma| {d:.3e}"
+        assert np.array_equal(out[1][2 + i][:n], out[0][2 + i][:n])
+
+
+def test_device_side_count_smaller_than_capacity(eng, golden_tiny):
+    n_cap, n_real = 3000, 1234
+    f = _features(golden_tiny, n_cap, seed=3)
+    n_dev = torch.tensor([n_real], dtype=torch.int32, device=eng.tdev)
+    a = _both(eng, f, n=n_cap, n_dev=n_dev)
+    b = _both(eng, f[:n_real])
+    for i in range(4):
+        assert np.array_equal(a[1][i][:n_real], b[1][i][:n_real])
+
+
+def test_outlier_zero_and_nonfinite_rows(eng, golden_tiny):
+    f = _features(golden_tiny, 300, seed=5)
+    f[3] *= 30.0            # gamma ||z||^2 ~ 1e3: the row exponent leaves the fp32 range (slow path)
+    f[40] *= 300.0
+    f[77] = 0.0
+    f[130] *= 1e-3
+    out = _both(eng, f)
+    for i in (0, 1):
+        d = np.abs(out[1][i] - out[0][i])
+        assert np.isfinite(out[1][i]).all()
+        assert d.max() <= 1e-5, f"det{i}: max |tc - dmma| {d.max():.3e} at row {d.argmax()}"
+        assert np.array_equal(out[1][2 + i], out[0][2 + i])
+    f[9, 17] = np.nan
+    out = _both(eng, f)
+    for i in (0, 1):
+        assert np.isnan(out[1][i][9]) and np.isnan(out[0][i][9])
+        ok = np.arange(300) != 9
+        assert np.abs(out[1][i][ok] - out[0][i][ok]).max() <= 1e-5
+
+
+def test_decisions_near_zero_are_recomputed_in_fp64(artifacts, golden_tiny):
+    """Move rho onto a cell's kernel sum: that decision is ~0 and must come out of the fp64 refine pass
+    (bit-identical to what the direct fp64 kernel gives), with the sign libsvm would give."""
+    from cell_image_analysis_b200.screening import Engine
+    f = _features(golden_tiny, 600, seed=9)
+    e = Engine(device=0, precision=1)
+    e.load_artifacts(artifacts)
+    e.set_option("svm_kernel", 0)
+    dc0 = e.svm_decision(torch.from_numpy(f).to(e.tdev), 600)[0].cpu().numpy()
+    arts = dict(artifacts)
+    cons = dict(artifacts["svm_conservative"])
+    target = 123
+    cons["rho"] = float(cons["rho"] + dc0[target] - 3e-7)       # new decision of `target`: +3e-7
+    arts["svm_conservative"] = cons
+    e.load_artifacts(arts)
+    res = {}
+    for refine in (0, 1):
+        e.set_option("svm_kernel", 1)
+        e.set_option("svm_refine", refine)
+        dc, _dm, pc, _pm, _ = e.svm_decision(torch.from_numpy(f).to(e.tdev), 600)
+        res[refine] = (dc.cpu().numpy(), pc.cpu().numpy())
+    e.set_option("svm_kernel", 0)
+    dc_exact = e.svm_decision(torch.from_numpy(f).to(e.tdev), 600)[0].cpu().numpy()
+    e.close()
+    assert abs(dc_exact[target] - 3e-7) < 1e-9
+    assert abs(res[1][0][target] - dc_exact[target]) < 1e-12 and res[1][1][target] == 1
+    untouched = np.abs(dc_exact) > 1e-3
+    assert np.array_equal(res[1][0][untouched], res[0][0][untouched])      # the refine pass leaves the rest alone
+    assert np.abs(res[1][0] - dc_exact).max() <= 1e-5
