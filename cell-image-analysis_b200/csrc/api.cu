@@ -61,6 +61,7 @@ int cia_create(int device, cia_handle* out) {
     if (const char* e = getenv("CIA_L2_DEBIAS")) h->cae_debias[1] = (float)atof(e);
     if (const char* e = getenv("CIA_L3_DEBIAS")) h->cae_debias[2] = (float)atof(e);
     if (const char* e = getenv("CIA_SVM_KERNEL")) h->svm_kernel = atoi(e) ? 1 : 0;
+    if (const char* e = getenv("CIA_PCA_KERNEL")) h->pca_kernel = atoi(e) ? 1 : 0;
     *out = h;
     return CIA_OK;
 }
@@ -78,6 +79,9 @@ int cia_set_option(cia_handle h, const char* name, double value) {
     } else if (n == "svm_kernel") {
         if (value != 0 && value != 1) { h->err = "cia_set_option: svm_kernel is 0 (fp64 DMMA) or 1 (tcgen05)"; return CIA_E_ARG; }
         h->svm_kernel = (int)value;
+    } else if (n == "pca_kernel") {
+        if (value != 0 && value != 1) { h->err = "cia_set_option: pca_kernel is 0 (fp64 DMMA) or 1 (tcgen05)"; return CIA_E_ARG; }
+        h->pca_kernel = (int)value;
     } else if (n == "svm_refine") {
         h->svm_refine = value != 0;
     } else {
@@ -104,7 +108,7 @@ int cia_destroy(cia_handle h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     free_cae(h->cae[0]); free_cae(h->cae[1]);
-    cudaFree(h->sp.center); cudaFree(h->sp.scale); cudaFree(h->sp.rscale); cudaFree(h->sp.comp_t); cudaFree(h->sp.comp_pad); cudaFree(h->sp.offset);
+    cudaFree(h->sp.center); cudaFree(h->sp.scale); cudaFree(h->sp.rscale); cudaFree(h->sp.comp_t); cudaFree(h->sp.comp_pad); cudaFree(h->sp.offset); cudaFree(h->sp.tc_img); cudaFree(h->sp.tc_par);
     for (int i = 0; i < 2; ++i) { cudaFree(h->svm[i].sv_t); cudaFree(h->svm[i].coef); cudaFree(h->svm[i].sv_pad); cudaFree(h->svm[i].gsn);
                                   cudaFree(h->svm[i].tc_hi); cudaFree(h->svm[i].tc_lo); cudaFree(h->svm[i].tc_gcol); }
     Workspace* ws[] = {&h->ws_flags, &h->ws_act, &h->ws_crop_scratch, &h->ws_pipe, &h->ws_feat,
@@ -226,6 +230,7 @@ int cia_load_scaler_pca(cia_handle h, int F, int C, const double* center, const 
     }
     if ((rc = upload(h, &sp.offset, pca_offset, (size_t)C))) return rc;
     sp.F = F; sp.C = C; sp.center_is_f32 = center_is_f32; sp.f32_flow = f32_flow;
+    if ((rc = k_pca_tc_prepare(h, sp, components))) return rc;
     sp.loaded = true;
     return CIA_OK;
 }

@@ -62,6 +62,11 @@ struct ScalerPca {
     double* comp_pad = nullptr; // [F rounded up to 32, CP] zero-padded copy for the cp.async-fed DMMA kernel
     int CP = 0;                 // C rounded up to a multiple of 104
     double* offset = nullptr;   // [C]
+    // tensor-core operand image of the components (score_tc.cu): fp16 hi | lo of the 2^tc_ew scaled rows
+    void* tc_img = nullptr;
+    void* tc_par = nullptr;     // per feature {center, RN(1/scale), scale hi, scale lo} as fp32 (the kernel's fp32-only scaler)
+    int tc_ew = 0;
+    bool tc_ok = false;
 };
 
 struct Workspace {
@@ -101,6 +106,7 @@ struct cia_ctx {
     float cae_debias[3] = {0.5f, 2.4f, 1.2f};   // L1, L2, L3
     // cia_set_option "svm_kernel": 1 = tcgen05 GEMM form (score_tc.cu), 0 = fp64 DMMA anchor (score.cu)
     int svm_kernel = 1;
+    int pca_kernel = 1;        // "pca_kernel": 1 = tcgen05 projection (score_tc.cu), 0 = fp64 DMMA anchor
     int svm_refine = 1;        // "svm_refine": decisions within the tensor-core kernel's error of 0 are recomputed in fp64
 };
 #define CIA_LAYER_MARKS 8  // before L1, after L1 .. L7
@@ -186,6 +192,8 @@ int k_cae_tc_prepare(cia_ctx* h, int which);
 int k_svm_decision(cia_ctx* h, const float* features, int n, const int32_t* n_dev,
                    double* dec_cons, double* dec_mod, int8_t* pred_cons, int8_t* pred_mod,
                    double* pca_out, cudaStream_t s);
+int k_pca_tc_prepare(cia_ctx* h, ScalerPca& sp, const double* components);
+int k_pca_tc(cia_ctx* h, const float* features, int n, const int32_t* n_dev, double* z, bool* done, cudaStream_t s);
 int k_svm_tc_prepare(cia_ctx* h, SvmModel& m, const double* sv, const double* coef);
 int k_svm_tc(cia_ctx* h, const SvmModel& m, const double* z, int n, const int32_t* n_dev, double* dec,
              int8_t* pred, bool* done, cudaStream_t s);

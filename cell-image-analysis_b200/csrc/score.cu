@@ -535,7 +535,13 @@ int k_svm_decision(cia_ctx* h, const float* features, int n, const int32_t* n_de
         CIA_CUDA(cudaFuncSetAttribute(scaler_pca_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     }
     static const bool vector_pca = getenv("CIA_PCA_VECTOR") != nullptr;   // A/B switch: CUDA-core fp64 tile
-    if (vector_pca) {
+    bool pca_done = false;
+    if (h->pca_kernel == 1 && !vector_pca) {          // tensor-core projection (score_tc.cu)
+        int rc = k_pca_tc(h, features, n, n_dev, z, &pca_done, s);
+        if (rc) return rc;
+    }
+    if (pca_done) {
+    } else if (vector_pca) {
         const size_t sm1 = sizeof(double) * PFT * (PCT + XPAD);
         scaler_pca_kernel<<<dim3((n + PB - 1) / PB, (sp.C + PCT - 1) / PCT), PT, sm1, s>>>(
             features, n, n_dev, sp.F, sp.C, sp.has_center ? sp.center : nullptr,
@@ -547,7 +553,7 @@ int k_svm_decision(cia_ctx* h, const float* features, int n, const int32_t* n_de
             sp.has_scale ? sp.scale : nullptr, sp.has_scale && sp.rscale_ok ? sp.rscale : nullptr, sp.center_is_f32, sp.comp_pad,
             sp.offset, sp.f32_flow, z);
     }
-    CIA_LAUNCH_CHECK();
+    if (!pca_done) CIA_LAUNCH_CHECK();
     static const bool direct_svm = getenv("CIA_SVM_DIRECT") != nullptr;   // A/B switch: CUDA-core direct-difference form
     for (int which = 0; which < 2; ++which) {
         const SvmModel& m = h->svm[which];

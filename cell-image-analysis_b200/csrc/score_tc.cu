@@ -377,6 +377,261 @@ svm_tc_finalize_kernel(const double* __restrict__ partial, int pitch, int n_svt,
     pred[i] = s > 0.0 ? 1 : -1;                    // svm.cpp:2841
 }
 
+// ---------------------------------------------------------------------------------------------
+// K4 on the tensor cores: RobustScaler -> PCA projection, z = x2 @ components^T - offset.
+//
+// M = 128 cells, N = 128 components (blockIdx.y walks wider PCAs), K = the 2048 encoder features in
+// stages of 32.  The A operand cannot be copied, it has to be COMPUTED: four producer warps (one
+// thread per cell row) read the raw float32 features, apply the scaler exactly as sklearn's in-place
+// float32 flow does (x1 = f32(x - center), x2 = f32(f64(x1) / scale), the division as reciprocal +
+// exact-remainder FMA, bit-identical to the DMMA kernel in score.cu), scale the row's 32 values by a
+// power of two so that the largest sits in [2^13, 2^14), split them into fp16 hi + lo and store them
+// as K-major core matrices; the power of two goes to the epilogue through a small ring.  The
+// components arrive pre-split ([stage][hi | lo][4][128][8]) by cp.async.bulk.  Per stage six MMAs
+// (cross terms first, hi*hi last) fill one of four TMEM accumulators; eight epilogue warps add the
+// stage partial, times the row's power of two, into fp32 registers with round-to-nearest (FFMA2) --
+// tcgen05's own accumulation truncates (see above) -- and finish with sklearn's float32 subtraction
+// of the offset.  Error against the exactly rounded projection: ~2e-7 of |z| (the oracle's own
+// float32 sgemm is at 7e-7), tests/test_gpu_svm_tc.py.
+// ---------------------------------------------------------------------------------------------
+namespace pcatc {
+constexpr int PROD_WARPS = 8, EPI_WARPS = 8;            // producers: two groups of four warps, alternate stages
+constexpr int EPI_WARP0 = PROD_WARPS;
+constexpr int MMA_WARP = PROD_WARPS + EPI_WARPS;        // and MMA_WARP + 1: alternate stages
+constexpr int BULK_WARP = MMA_WARP + 2;
+constexpr int NT = (BULK_WARP + 1) * 32;
+constexpr int TM = 128, TN = 128, KC = 32;
+constexpr int K8_B = 128 * 16;
+constexpr int HALF_B = (KC / 8) * K8_B;                 // 8 KB: hi (or lo) of one operand stage
+constexpr int STAGE_B = 4 * HALF_B;                     // A hi | A lo | B hi | B lo
+constexpr int STAGES = 4;
+constexpr int NBUF = 4;
+constexpr int RING = 16;                                // row-scale ring (>= STAGES + NBUF stages in flight)
+constexpr int PAR_F = 2048;                             // scaler constants of up to this many features live in shared memory
+constexpr int SMEM_B = STAGES * STAGE_B + RING * TM * 4 + PAR_F * 16;
+}  // namespace pcatc
+
+#define TMEM_LD16(taddr, v)                                                                               \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "                                                \
+                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"                         \
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),     \
+                   "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), \
+                   "=r"(v[14]), "=r"(v[15]) : "r"(taddr))
+#define TMEM_WAIT16(v)                                                                                    \
+    asm volatile("tcgen05.wait::ld.sync.aligned;"                                                         \
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]),     \
+                   "+r"(v[7]), "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), \
+                   "+r"(v[14]), "+r"(v[15]) :: "memory")
+
+__global__ void __launch_bounds__(pcatc::NT, 1)
+scaler_pca_tc_kernel(const float* __restrict__ feat, int n_cells, const int32_t* __restrict__ n_dev, int F, int C,
+                     const float4* __restrict__ par_g /* {center, RN(1/scale), scale hi, scale lo} per feature */,
+                     const __half* __restrict__ comp_img,
+                     float w_unscale, const double* __restrict__ offset, int f32_flow, double* __restrict__ z_out) {
+    using namespace pcatc;
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tfull_bar[NBUF], tempty_bar[NBUF];
+    __shared__ uint32_t tmem_base_s;
+    float* const ring = reinterpret_cast<float*>(smem + STAGES * STAGE_B);      // [RING][TM]
+    float4* const par = reinterpret_cast<float4*>(smem + STAGES * STAGE_B + RING * TM * 4);   // scaler constants
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n = dev_count(n_cells, n_dev);
+    const int n_ct = (n + TM - 1) / TM;
+    if ((int)blockIdx.x >= n_ct) return;
+    const int n_kc = F / KC;                                  // F is a multiple of 32 (host checks)
+    const int cb = blockIdx.y;                                // component block of 128
+    const uint32_t s_addr = smem_u32(smem);
+    const bool par_s = F <= PAR_F;                            // scaler constants staged in shared memory
+
+    if (warp == MMA_WARP) tmem_alloc(&tmem_base_s, NBUF * TN);
+    if (tid == 0) {
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], PROD_WARPS / 2 + 1); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < NBUF; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], EPI_WARPS); }
+        fence_barrier_init();
+    }
+    if (par_s)
+        for (int i = tid; i < F; i += NT) par[i] = __ldg(par_g + i);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    constexpr uint32_t IDESC = make_idesc(TM, TN);
+
+    uint32_t cnt = 0;                                         // running stage count of this CTA (every role keeps its own copy)
+    if (warp < PROD_WARPS) {
+        // ================= A producers: scaler + power-of-two scaling + hi/lo split =================
+        // a warp owns 32 cell rows of the tile, 32 features per stage.  Loads are coalesced: instruction i of a lane
+        // reads row 4i + lane/8, features 4(lane%8)..+3 (8 lanes = one 128-byte line; a thread-per-row layout costs
+        // 32 L1 wavefronts per instruction and bound the kernel at ~1000 cycles a stage).  The two groups of four
+        // warps take alternate stages and every thread fetches its NEXT stage before it works on the current one.
+        const int grp = warp >> 2, r0 = 32 * (warp & 3) + (lane >> 3), ch = lane & 7;
+        const long long total = (long long)((n_ct - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) * n_kc;   // stages of this CTA
+        auto fetch = [&](long long sidx, float4 (&x)[8]) {
+            const int ct = (int)blockIdx.x + (int)(sidx / n_kc) * (int)gridDim.x, kc = (int)(sidx % n_kc);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int cell = ct * TM + r0 + 4 * i;
+                x[i] = (sidx < total && cell < n)
+                           ? __ldg(reinterpret_cast<const float4*>(feat + (size_t)cell * F + kc * KC) + ch)
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        float4 xn[8];
+        fetch(grp, xn);
+        for (long long sidx = grp; sidx < total; sidx += 2) {
+            const uint32_t c = (uint32_t)sidx, st = c % STAGES;
+            const int kc = (int)(sidx % n_kc);
+            float4 x[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] = xn[i];
+            fetch(sidx + 2, xn);
+            // RobustScaler in fp32 only (fp64 conversions run at a fraction of the fp32 rate and bound this kernel
+            // otherwise): x1 = RN(x - center) as sklearn's float32 subtraction; x2 = RN(x1 / scale) with the float64
+            // scale as an fp32 pair: q = RN(x1 * RN(1/scale)) is within an ulp, x1 - q * scale_hi is exact in one FMA,
+            // the scale_lo part and the final fma(rem, 1/scale, q) follow -- the correctly rounded quotient except
+            // within 2^-49 of a rounding boundary (1 element in ~10^7 differs by an ulp from the float64 division)
+            float4 pf[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) pf[k] = par_s ? par[kc * KC + 4 * ch + k] : __ldg(par_g + kc * KC + 4 * ch + k);
+            auto scaler = [](float xv, const float4& p) {
+                const float x1 = __fsub_rn(xv, p.x);
+                const float q = __fmul_rn(x1, p.y);
+                const float rem = __fmaf_rn(-q, p.w, __fmaf_rn(-q, p.z, x1));
+                return __fmaf_rn(rem, p.y, q);
+            };
+            float up[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                x[i].x = scaler(x[i].x, pf[0]); x[i].y = scaler(x[i].y, pf[1]);
+                x[i].z = scaler(x[i].z, pf[2]); x[i].w = scaler(x[i].w, pf[3]);
+                // (a NaN feature is dropped by fmaxf here and comes back through hi)
+                float mx = fmaxf(fmaxf(fabsf(x[i].x), fabsf(x[i].y)), fmaxf(fabsf(x[i].z), fabsf(x[i].w)));
+                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
+                // 2^e with the largest |x2| of the row's stage in [2^13, 2^14); e in [-100, 100]
+                int e = 0;
+                if (mx > 0.f && mx < 3e38f) e = 13 - (int)((__float_as_uint(mx) >> 23) & 0xFF) + 127;
+                e = max(-100, min(100, e));
+                up[i] = __uint_as_float((uint32_t)(127 + e) << 23);
+            }
+            mbar_wait(&empty_bar[st], ((c / STAGES) & 1) ^ 1);
+            unsigned char* a_hi = smem + st * STAGE_B + ((ch >> 1) * TM) * 16 + (ch & 1) * 8;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int r = r0 + 4 * i;
+                const float v0 = x[i].x * up[i], v1 = x[i].y * up[i], v2 = x[i].z * up[i], v3 = x[i].w * up[i];   // exact
+                const __half2 h01 = __floats2half2_rn(v0, v1), h23 = __floats2half2_rn(v2, v3);
+                const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                const __half2 l01 = __floats2half2_rn(v0 - f01.x, v1 - f01.y), l23 = __floats2half2_rn(v2 - f23.x, v3 - f23.y);
+                *reinterpret_cast<uint2*>(a_hi + r * 16) = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+                *reinterpret_cast<uint2*>(a_hi + HALF_B + r * 16) = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+                if (ch == 0) ring[(c % RING) * TM + r] = __uint_as_float(0x7F000000u - __float_as_uint(up[i])) * w_unscale;   // 2^-e, exact
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full_bar[st]);
+        }
+    } else
+    for (int ct = blockIdx.x; ct < n_ct; ct += gridDim.x) {
+        if (warp == BULK_WARP) {
+            // ================= component stream =================
+            if (lane == 0) {
+                for (int kc = 0; kc < n_kc; ++kc, ++cnt) {
+                    const uint32_t st = cnt % STAGES;
+                    mbar_wait(&empty_bar[st], ((cnt / STAGES) & 1) ^ 1);
+                    mbar_expect_tx(&full_bar[st], 2 * HALF_B);
+                    bulk_load(s_addr + st * STAGE_B + 2 * HALF_B, comp_img + ((size_t)cb * n_kc + kc) * (2 * HALF_B / 2),
+                              2 * HALF_B, &full_bar[st]);
+                }
+            }
+            __syncwarp();
+        } else if (warp >= MMA_WARP) {
+            // ================= MMA issuers (alternate stages) =================
+            if (lane == 0) {
+                const uint32_t me = (uint32_t)(warp - MMA_WARP);
+                const uint64_t d0 = make_smem_desc(s_addr, K8_B, 128);
+                for (int kc = 0; kc < n_kc; ++kc, ++cnt) {
+                    if ((cnt & 1) != me) continue;
+                    const uint32_t st = cnt % STAGES, buf = cnt % NBUF;
+                    mbar_wait(&tempty_bar[buf], ((cnt / NBUF) & 1) ^ 1);
+                    mbar_wait(&full_bar[st], (cnt / STAGES) & 1);
+                    tc_fence_after();
+                    const uint32_t d = tmem_base + buf * TN;
+                    const uint64_t ah = d0 + (uint64_t)((st * STAGE_B) >> 4), al = ah + (HALF_B >> 4);
+                    const uint64_t bh = ah + (2 * HALF_B >> 4), bl = ah + (3 * HALF_B >> 4);
+#pragma unroll
+                    for (int s = 0; s < KC / 16; ++s) {
+                        const uint64_t so = (uint64_t)(s * ((2 * K8_B) >> 4));
+                        umma_f16(d, ah + so, bl + so, IDESC, s == 0 ? 0u : 1u);
+                        umma_f16(d, al + so, bh + so, IDESC, 1u);
+                    }
+#pragma unroll
+                    for (int s = 0; s < KC / 16; ++s) {
+                        const uint64_t so = (uint64_t)(s * ((2 * K8_B) >> 4));
+                        umma_f16(d, ah + so, bh + so, IDESC, 1u);
+                    }
+                    umma_commit(&empty_bar[st]);
+                    umma_commit(&tfull_bar[buf]);
+                }
+            }
+            __syncwarp();
+        } else {
+            // ================= epilogue: fp32 round-to-nearest accumulation of the stage partials =================
+            const int ew = warp - EPI_WARP0, q = ew & 3, hf = ew >> 2, row = 32 * q + lane;
+            const uint32_t taddr0 = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(hf * 64);
+            unsigned long long acc[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[j] = 0ull;
+#pragma unroll 1
+            for (int kc = 0; kc < n_kc; ++kc, ++cnt) {
+                const uint32_t buf = cnt % NBUF;
+                mbar_wait(&tfull_bar[buf], (cnt / NBUF) & 1);
+                tc_fence_after();
+                const float sc = ring[(cnt % RING) * TM + row];
+                const unsigned long long sc2 = pack2(sc, sc);
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    uint32_t v[16];
+                    TMEM_LD16(taddr0 + buf * TN + (uint32_t)(b * 16), v);
+                    TMEM_WAIT16(v);
+                    if (b == 3) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 16; j += 2)
+                        acc[b * 8 + (j >> 1)] = fma2(pack2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), sc2, acc[b * 8 + (j >> 1)]);
+                }
+            }
+            const int cell = ct * TM + row;
+            if (cell < n) {
+                // the two full-magnitude truncations of a stage's hi*hi MMAs: mean deficit 1.5 * 2^-25
+                constexpr double DEBIAS = 1.0 + 1.5 * 2.9802322387695312e-8;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    float a0, a1;
+                    unpack2(acc[j], a0, a1);
+                    const int c = cb * TN + hf * 64 + 2 * j;
+                    if (c < C) {
+                        const double off = __ldg(offset + c), v = (double)a0 * DEBIAS;
+                        z_out[(size_t)cell * C + c] = f32_flow ? (double)__fsub_rn((float)v, (float)off) : __dsub_rn(v, off);
+                    }
+                    if (c + 1 < C) {
+                        const double off = __ldg(offset + c + 1), v = (double)a1 * DEBIAS;
+                        z_out[(size_t)cell * C + c + 1] = f32_flow ? (double)__fsub_rn((float)v, (float)off) : __dsub_rn(v, off);
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == pcatc::MMA_WARP) tmem_dealloc(tmem_base, pcatc::NBUF * pcatc::TN);
+}
+
 // Exact re-evaluation of the decisions the fp16 x 3 kernel cannot sign with certainty.  Its error is a
 // few 2^-24 of the kernel sum (the z tile keeps 22 of the 24 significand bits of the float32 PCA scores,
 // and that rounding is common to all SVs of a row: measured 6e-5 at 20 000 SVs with sum(coef) = 2e4, 1e-6
@@ -520,6 +775,75 @@ int k_svm_tc(cia_ctx* h, const SvmModel& m, const double* z, int n, const int32_
                                                                      m.rho, 2e-4, 4e-7, dec, pred);
         CIA_LAUNCH_CHECK();
     }
+    *done = true;
+    return CIA_OK;
+}
+
+// Operand image of the PCA components for scaler_pca_tc_kernel (called from cia_load_scaler_pca): scaled by
+// 2^e_w, split hi + lo, as [component block of 128][stage of 32 features][hi | lo][feature / 8][128][8].
+int k_pca_tc_prepare(cia_ctx* h, ScalerPca& sp, const double* components /* [C][F] */) {
+    sp.tc_ok = false;
+    cudaFree(sp.tc_img); sp.tc_img = nullptr;
+    cudaFree(sp.tc_par); sp.tc_par = nullptr;
+    if (sp.F % pcatc::KC != 0) return CIA_OK;
+    // the kernel's fp32 scaler: float32 centre (sklearn fit on float32 features) and scale / 1/scale as fp32 pairs
+    if (sp.has_center && !sp.center_is_f32) return CIA_OK;
+    if (sp.has_scale && !sp.rscale_ok) return CIA_OK;
+    double mx = 0.0;
+    for (size_t i = 0; i < (size_t)sp.C * sp.F; ++i) {
+        if (!std::isfinite(components[i])) return CIA_OK;
+        mx = std::fmax(mx, std::fabs(components[i]));
+    }
+    const int ew = mx > 0.0 ? 13 - std::ilogb(mx) : 0;
+    if (ew < -20 || ew > 20) return CIA_OK;
+    const int ncb = (sp.C + pcatc::TN - 1) / pcatc::TN, n_kc = sp.F / pcatc::KC;
+    std::vector<__half> img((size_t)ncb * n_kc * 2 * (pcatc::KC / 8) * pcatc::TN * 8, __float2half_rn(0.f));
+    for (int c = 0; c < sp.C; ++c)
+        for (int f = 0; f < sp.F; ++f) {
+            const double v = std::ldexp(components[(size_t)c * sp.F + f], ew);
+            const __half hv = __double2half(v);
+            const int cbk = c / pcatc::TN, cr = c % pcatc::TN, kc = f / pcatc::KC, k8 = (f % pcatc::KC) / 8;
+            const size_t base = ((size_t)cbk * n_kc + kc) * 2 * (pcatc::KC / 8) * pcatc::TN * 8;
+            const size_t idx = ((size_t)k8 * pcatc::TN + cr) * 8 + (f % 8);
+            img[base + idx] = hv;
+            img[base + (size_t)(pcatc::KC / 8) * pcatc::TN * 8 + idx] = __double2half(v - (double)__half2float(hv));
+        }
+    CIA_CUDA(cudaMalloc(&sp.tc_img, img.size() * sizeof(__half)));
+    CIA_CUDA(cudaMemcpy(sp.tc_img, img.data(), img.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    {
+        std::vector<double> cen((size_t)sp.F, 0.0), sc((size_t)sp.F, 1.0);
+        if (sp.has_center) CIA_CUDA(cudaMemcpy(cen.data(), sp.center, sp.F * sizeof(double), cudaMemcpyDeviceToHost));
+        if (sp.has_scale) CIA_CUDA(cudaMemcpy(sc.data(), sp.scale, sp.F * sizeof(double), cudaMemcpyDeviceToHost));
+        std::vector<float> par((size_t)sp.F * 4);
+        for (int f = 0; f < sp.F; ++f) {
+            const float shi = (float)sc[f];
+            par[4 * f + 0] = (float)cen[f];
+            par[4 * f + 1] = (float)(1.0 / sc[f]);
+            par[4 * f + 2] = shi;
+            par[4 * f + 3] = (float)(sc[f] - (double)shi);
+            if (!std::isnormal(shi) || !std::isnormal(par[4 * f + 1])) { cudaFree(sp.tc_img); sp.tc_img = nullptr; return CIA_OK; }
+        }
+        CIA_CUDA(cudaMalloc(&sp.tc_par, par.size() * sizeof(float)));
+        CIA_CUDA(cudaMemcpy(sp.tc_par, par.data(), par.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    sp.tc_ew = ew;
+    sp.tc_ok = true;
+    return CIA_OK;
+}
+
+int k_pca_tc(cia_ctx* h, const float* features, int n, const int32_t* n_dev, double* z, bool* done, cudaStream_t s) {
+    using namespace pcatc;
+    const ScalerPca& sp = h->sp;
+    *done = false;
+    if (!sp.tc_ok) return CIA_OK;
+    if (first_use(h, (const void*)scaler_pca_tc_kernel))
+        CIA_CUDA(cudaFuncSetAttribute(scaler_pca_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_B));
+    const int n_ct = (n + TM - 1) / TM, ncb = (sp.C + TN - 1) / TN;
+    const int gx = std::min(n_ct, std::max(1, h->num_sms / ncb));
+    scaler_pca_tc_kernel<<<dim3(gx, ncb), NT, SMEM_B, s>>>(
+        features, n, n_dev, sp.F, sp.C, (const float4*)sp.tc_par, (const __half*)sp.tc_img,
+        std::ldexp(1.f, -sp.tc_ew), sp.offset, sp.f32_flow, z);
+    CIA_LAUNCH_CHECK();
     *done = true;
     return CIA_OK;
 }

@@ -108,3 +108,53 @@ def test_decisions_near_zero_are_recomputed_in_fp64(artifacts, golden_tiny):
     untouched = np.abs(dc_exact) > 1e-3
     assert np.array_equal(res[1][0][untouched], res[0][0][untouched])      # the refine pass leaves the rest alone
     assert np.abs(res[1][0] - dc_exact).max() <= 1e-5
+
+
+@pytest.mark.parametrize("n", [1, 130, 5000, 40000])
+def test_pca_tc_equals_dmma_projection(eng, golden_tiny, n):
+    """The tcgen05 projection (fp16 hi/lo x 3, stage partials added in fp32) against the fp64 DMMA one, which
+    is the exactly rounded float32 flow: differences of a few float32 ulps of the row scale at most, and the
+    scaler arithmetic (float32 subtraction, correctly rounded division) is the same code."""
+    f = _features(golden_tiny, n, seed=100 + n)
+    if n > 200:
+        f[7] *= 1e4          # an outlier row: its per-stage power of two differs from its neighbours'
+        f[8] *= 1e-4
+        f[9] = 0.0
+    feat = torch.from_numpy(f).to(eng.tdev)
+    z = {}
+    for k in (0, 1):
+        eng.set_option("pca_kernel", k)
+        z[k] = eng.svm_decision(feat, n, want_pca=True)[4][:n].cpu().numpy()
+        eng.check_status()
+    eng.set_option("pca_kernel", 1)
+    scale = np.abs(z[0]).max(axis=1, keepdims=True) + 1e-30
+    rel = np.abs(z[1] - z[0]) / scale
+    assert np.isfinite(z[1]).all()
+    assert rel.max() <= 2e-6, f"n={n}: max |dz| / row max {rel.max():.3e} (row {rel.max(axis=1).argmax()})"
+    assert np.median(rel) <= 1e-7
+
+
+def test_pca_tc_wide_projection_256_components(artifacts, golden_tiny):
+    """C = 256 components: two component blocks (blockIdx.y) and no scaler."""
+    from cell_image_analysis_b200.screening import Engine
+    rng = np.random.default_rng(4)
+    q, _ = np.linalg.qr(rng.standard_normal((2048, 256)))
+    comp = np.ascontiguousarray(q.T.astype(np.float32)).astype(np.float64)
+    arts = dict(artifacts)
+    arts["scaler_pca"] = dict(artifacts["scaler_pca"], C=256, center=None, scale=None, components=comp,
+                              offset=rng.standard_normal(256) * 0.1, f32_flow=True)
+    for k in ("svm_conservative", "svm_moderate"):
+        arts[k] = dict(sv=rng.standard_normal((300, 256)) * 3.0, coef=rng.uniform(0, 1, 300), gamma=1.0 / (256 * 9.0), rho=1.0)
+    e = Engine(device=0, precision=1)
+    e.load_artifacts(arts)
+    f = (rng.standard_normal((700, 2048)) * 3.0).astype(np.float32)
+    feat = torch.from_numpy(f).to(e.tdev)
+    z = {}
+    for k in (0, 1):
+        e.set_option("pca_kernel", k)
+        z[k] = e.svm_decision(feat, 700, want_pca=True)[4][:700].cpu().numpy()
+    e.close()
+    ref = (f.astype(np.float64) @ comp.T).astype(np.float32) - arts["scaler_pca"]["offset"].astype(np.float32)
+    assert np.abs(z[0] - ref).max() <= 1e-5
+    rel = np.abs(z[1] - z[0]) / (np.abs(z[0]).max(axis=1, keepdims=True))
+    assert rel.max() <= 1e-6, f"{rel.max():.3e}"

@@ -41,12 +41,14 @@ def case(tag, arts, feat_np, dets=None, n_ref=64):
     res = {}
     for k in (0, 1):
         eng.set_option("svm_kernel", k)
+        eng.set_option("pca_kernel", k)
         ms, (dc, dm, pc, pm, z) = timed(eng, feat, n)
         eng.check_status()
         res[k] = (ms, dc[:n].cpu().numpy(), dm[:n].cpu().numpy(), pc[:n].cpu().numpy(), pm[:n].cpu().numpy(), z[:n].cpu().numpy())
     d01 = max(np.abs(res[0][1] - res[1][1]).max(), np.abs(res[0][2] - res[1][2]).max())
     flips = int((res[0][3] != res[1][3]).sum() + (res[0][4] != res[1][4]).sum())
-    line = f"{tag}: n={n} dmma {res[0][0]:.3f} ms, tc {res[1][0]:.3f} ms ({res[0][0] / res[1][0]:.1f}x), max|tc-dmma| {d01:.3e}, sign flips {flips}"
+    dz = np.abs(res[0][5] - res[1][5]).max() / np.abs(res[0][5]).max()
+    line = f"{tag}: n={n} max|dz|/max|z| {dz:.2e}, dmma {res[0][0]:.3f} ms, tc {res[1][0]:.3f} ms ({res[0][0] / res[1][0]:.1f}x), max|tc-dmma| {d01:.3e}, sign flips {flips}"
     if dets is not None:
         zr = res[1][5][:n_ref]
         for i, det in enumerate(dets):
