@@ -3,7 +3,7 @@
 # usage (on the GPU box, via gpurun):  bash profiles/run_ncu.sh <tag> <kernel-regex> [bench args...]
 set -u
 TAG=$1; KRE=$2; shift 2
-CMD="python bench.py --steps 1 --warmup 1 --fields 32 --pool 16 --chunk 16 --no-cpu-baseline $*"
+CMD="python bench.py --steps 1 --warmup 1 --fields 32 --pool 16 --chunk 16 --no-cpu-baseline --no-svm-extras $*"
 mkdir -p gpurun_out
 $CMD > gpurun_out/plain_$TAG.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \
