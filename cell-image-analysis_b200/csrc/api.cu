@@ -395,9 +395,15 @@ static int screen_fields_impl(cia_handle h, const uint16_t* images, const int32_
     }
     if (rc) return rc;
     CIA_MARK(4);
-    if ((rc = k_svm_decision(h, feats, cells_cap, n_cells_dev, scores->dec_conservative,
-                             scores->dec_moderate, scores->pred_conservative, scores->pred_moderate,
-                             nullptr, s))) return rc;
+    {
+        // precision 0 is the exact anchor end to end: fp32 CUDA-core autoencoder AND the fp64 DMMA scoring kernels
+        const int sk = h->svm_kernel, pk = h->pca_kernel;
+        if (precision == 0) h->svm_kernel = h->pca_kernel = 0;
+        rc = k_svm_decision(h, feats, cells_cap, n_cells_dev, scores->dec_conservative, scores->dec_moderate,
+                            scores->pred_conservative, scores->pred_moderate, nullptr, s);
+        h->svm_kernel = sk; h->pca_kernel = pk;
+        if (rc) return rc;
+    }
     CIA_MARK(5);
     if (acc) {
         if ((rc = k_strain_accumulate(h, cells, cells_cap, n_cells_dev, scores, field_strain, acc, n_strains, s))) return rc;

@@ -46,7 +46,7 @@ struct SvmModel {
     void* tc_hi = nullptr;
     void* tc_lo = nullptr;
     float* tc_gcol = nullptr;
-    int tc_es = 0, tc_svt = 0;
+    int tc_es = 0, tc_svt = 0, tc_fx = 40;   // tc_fx: the row sums are 64-bit fixed point with 2^-tc_fx resolution
     bool tc_ok = false;
 };
 

@@ -123,14 +123,16 @@ __global__ void __launch_bounds__(svmtc::NT, 1)
 svm_rbf_tc_kernel(const double* __restrict__ z, int n_cells, const int32_t* __restrict__ n_dev, int D, int Dpad,
                   const __half* __restrict__ sv_hi, const __half* __restrict__ sv_lo,
                   const float* __restrict__ gcol, int n_svt, double fac_base, double gamma, int per_cta,
-                  int stages, double* __restrict__ partial, int pitch) {
+                  int stages, double fx_scale, long long* __restrict__ partial, int pitch,
+                  double* __restrict__ rowmul_out) {
     using namespace svmtc;
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], tfull_bar[NBUF], tempty_bar[NBUF];
     __shared__ uint32_t tmem_base_s;
     __shared__ float s_rowfac[TM], s_rowfac_lo[TM], s_nrow[TM];
     __shared__ int s_erow[TM];
-    __shared__ double s_rowmul[TM], s_red[4][TM];
+    __shared__ double s_rowmul[TM];
+    __shared__ long long s_red[4][TM];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n = dev_count(n_cells, n_dev);
@@ -291,7 +293,9 @@ svm_rbf_tc_kernel(const double* __restrict__ z, int n_cells, const int32_t* __re
             const unsigned long long rem2 = pack2(rem, rem);
             const bool slow = __any_sync(0xffffffffu, rem != 0.f);
             const uint32_t taddr0 = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(cq * 32);
-            double rowsum = 0.0;
+            // row sums in 64-bit FIXED POINT (2^-S, S from the model): integer addition is associative, so a cell's
+            // decision does not depend on how its SV tiles were cut over CTAs, i.e. on its position in the call
+            long long rowsum = 0;
             for (int t = t0; t < t0 + nt; ++t) {
                 // ---- z.s of this tile: the stage partials added in fp32 registers, round to nearest ----
                 float acc[32];
@@ -340,7 +344,7 @@ svm_rbf_tc_kernel(const double* __restrict__ z, int n_cells, const int32_t* __re
                         s0 += e0; s1 += e1; s2 += e2; s3 += e3;
                     }
                 }
-                rowsum += (double)((s0 + s1) + (s2 + s3));
+                rowsum += __double2ll_rn((double)((s0 + s1) + (s2 + s3)) * fx_scale);
             }
             s_red[cq][row] = rowsum;
             asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
@@ -349,7 +353,8 @@ svm_rbf_tc_kernel(const double* __restrict__ z, int n_cells, const int32_t* __re
                 if (cell < n) {
                     const int first_cta = (int)(((long long)ct * n_svt) / per_cta);
                     partial[(size_t)((int)blockIdx.x - first_cta) * pitch + cell] =
-                        ((s_red[0][row] + s_red[1][row]) + (s_red[2][row] + s_red[3][row])) * s_rowmul[row];
+                        (s_red[0][row] + s_red[1][row]) + (s_red[2][row] + s_red[3][row]);
+                    rowmul_out[cell] = s_rowmul[row];          // the same value from every CTA that shares the cell tile
                 }
             }
         }
@@ -362,17 +367,17 @@ svm_rbf_tc_kernel(const double* __restrict__ z, int n_cells, const int32_t* __re
 
 // dec = (partial sums of the CTAs that shared this cell tile, in CTA order) - rho
 __global__ void __launch_bounds__(256)
-svm_tc_finalize_kernel(const double* __restrict__ partial, int pitch, int n_svt, int per_cta, int n_cells,
-                       const int32_t* __restrict__ n_dev, double rho, double* __restrict__ dec,
-                       int8_t* __restrict__ pred) {
+svm_tc_finalize_kernel(const long long* __restrict__ partial, int pitch, int n_svt, int per_cta, int n_cells,
+                       const int32_t* __restrict__ n_dev, const double* __restrict__ rowmul, double fx_inv, double rho,
+                       double* __restrict__ dec, int8_t* __restrict__ pred) {
     const int n = dev_count(n_cells, n_dev);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const long long ct = i / svmtc::TM;
     const int first = (int)((ct * n_svt) / per_cta), last = (int)(((ct + 1) * n_svt - 1) / per_cta);
-    double s = 0.0;
-    for (int k = 0; k <= last - first; ++k) s += partial[(size_t)k * pitch + i];
-    s -= rho;
+    long long t = 0;
+    for (int k = 0; k <= last - first; ++k) t += partial[(size_t)k * pitch + i];
+    const double s = (double)t * fx_inv * rowmul[i] - rho;
     dec[i] = s;
     pred[i] = s > 0.0 ? 1 : -1;                    // svm.cpp:2841
 }
@@ -729,6 +734,10 @@ int k_svm_tc_prepare(cia_ctx* h, SvmModel& m, const double* sv, const double* co
     CIA_CUDA(cudaMemcpy(m.tc_hi, hi.data(), hi.size() * sizeof(__half), cudaMemcpyHostToDevice));
     CIA_CUDA(cudaMemcpy(m.tc_lo, lo.data(), lo.size() * sizeof(__half), cudaMemcpyHostToDevice));
     CIA_CUDA(cudaMemcpy(m.tc_gcol, g.data(), g.size() * sizeof(float), cudaMemcpyHostToDevice));
+    // fixed-point exponent of the row sums: sum_i coef_i K_i <= n_sv * max coef, kept below 2^61
+    double amax = 1.0;
+    for (int i = 0; i < m.n_sv; ++i) amax = std::fmax(amax, coef[i]);
+    m.tc_fx = std::max(0, std::min(50, 60 - (int)std::ceil(std::log2((double)n_svt * svmtc::TN * amax))));
     m.tc_es = es;
     m.tc_svt = n_svt;
     m.tc_ok = true;
@@ -758,16 +767,18 @@ int k_svm_tc(cia_ctx* h, const SvmModel& m, const double* z, int n, const int32_
     per_cta = std::max(per_cta, std::min(2, m.tc_svt));
     const int grid = (int)((W + per_cta - 1) / per_cta);
     const int slots = (m.tc_svt + per_cta - 1) / per_cta + 1;
-    int rc = ws_reserve(h, h->ws_svm, (size_t)slots * n * sizeof(double));
+    int rc = ws_reserve(h, h->ws_svm, (size_t)(slots + 1) * n * sizeof(double));
     if (rc) return rc;
-    double* partial = (double*)h->ws_svm.p;
+    long long* partial = (long long*)h->ws_svm.p;
+    double* rowmul = (double*)h->ws_svm.p + (size_t)slots * n;
     // mean deficit of the two full-magnitude round-toward-zero accumulations of a stage, in units of 2^-25
     static const double debias = [] { const char* e = getenv("CIA_SVM_DEBIAS"); return e ? atof(e) : 1.5; }();
     const double fac_base = std::ldexp(2.0 * m.gamma * LOG2E, -m.tc_es) * (1.0 + debias * 2.9802322387695312e-8);
     kern<<<grid, NT, smem_b, s>>>(z, n, n_dev, m.dim, m.dim_pad, (const __half*)m.tc_hi, (const __half*)m.tc_lo, m.tc_gcol, m.tc_svt, fac_base,
-                                  m.gamma, per_cta, stages, partial, n);
+                                  m.gamma, per_cta, stages, std::ldexp(1.0, m.tc_fx), partial, n, rowmul);
     CIA_LAUNCH_CHECK();
-    svm_tc_finalize_kernel<<<(n + 255) / 256, 256, 0, s>>>(partial, n, m.tc_svt, per_cta, n, n_dev, m.rho, dec, pred);
+    svm_tc_finalize_kernel<<<(n + 255) / 256, 256, 0, s>>>(partial, n, m.tc_svt, per_cta, n, n_dev, rowmul,
+                                                             std::ldexp(1.0, -m.tc_fx), m.rho, dec, pred);
     CIA_LAUNCH_CHECK();
     if (h->svm_refine) {
         int blocks = std::min((n + 255) / 256, h->num_sms * 4);

@@ -48,6 +48,7 @@ class Engine:
         self.h = h
         self.params = _lib.default_params()
         self.precision = precision
+        self._options = {}                        # cia_set_option values set through this object
         self.n_features = 2048
         self.n_components = None
 
@@ -77,6 +78,7 @@ class Engine:
 
     def set_option(self, name: str, value: float):
         self._check(self.lib.cia_set_option(self.h, name.encode(), float(value)))
+        self._options[name] = value
 
     @property
     def launch_count(self) -> int:
@@ -166,7 +168,23 @@ class Engine:
                                              _ptr(feat), prec, self._stream()))
         return mse, mae, feat
 
-    def svm_decision(self, feat: torch.Tensor, n: int, n_dev=None, want_pca: bool = False):
+    def svm_decision(self, feat: torch.Tensor, n: int, n_dev=None, want_pca: bool = False, precision=None):
+        """Scaler -> PCA -> both detectors.  ``precision`` 0 (the exact anchor, like ``cae_forward``'s) runs the
+        fp64 DMMA kernels whatever the ``svm_kernel`` / ``pca_kernel`` options say; anything else follows them
+        (default: the tcgen05 kernels)."""
+        prec = self.precision if precision is None else precision
+        if prec == 0:
+            saved = {k: self._options.get(k, 1) for k in ("svm_kernel", "pca_kernel")}
+            for k in saved:
+                self._check(self.lib.cia_set_option(self.h, k.encode(), 0.0))
+            try:
+                return self._svm_decision(feat, n, n_dev, want_pca)
+            finally:
+                for k, v in saved.items():
+                    self._check(self.lib.cia_set_option(self.h, k.encode(), float(v)))
+        return self._svm_decision(feat, n, n_dev, want_pca)
+
+    def _svm_decision(self, feat: torch.Tensor, n: int, n_dev=None, want_pca: bool = False):
         dc = torch.empty(max(n, 1), dtype=torch.float64, device=self.tdev)
         dm = torch.empty(max(n, 1), dtype=torch.float64, device=self.tdev)
         pc = torch.empty(max(n, 1), dtype=torch.int8, device=self.tdev)

@@ -87,7 +87,7 @@ def test_default_precision_on_held_out_weights(crops, seed, scale, nneg):
             for name, v in DEFAULT_DEBIAS:
                 eng.set_option(name, v if debias_on else 0.0)
             mse, mae, feat = eng.cae_forward(x, n, precision=precision)
-            dc, dm, pc, pm, _ = eng.svm_decision(feat, n)
+            dc, dm, pc, pm, _ = eng.svm_decision(feat, n, precision=precision)   # precision 0: fp64 scoring anchors too
             eng.check_status()
             return [t[:n].cpu().numpy() for t in (mse, feat, dc, dm, pc, pm)]
 

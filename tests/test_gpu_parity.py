@@ -160,20 +160,22 @@ def test_features_and_pca(screener, golden_tiny):
     f = feat[:n].cpu().numpy()
     ref = golden_tiny["features"]
     assert np.abs(f - ref).max() <= 1e-4 * max(1.0, np.abs(ref).max())
-    dc, dm, pc, pm, z = eng.svm_decision(feat, n, want_pca=True)
+    dc, dm, pc, pm, z = eng.svm_decision(feat, n, want_pca=True)      # precision-0 engine: the fp64 anchors
     z = z[:n].cpu().numpy()
     assert np.abs(z - golden_tiny["pca"]).max() <= 1e-3 * max(1.0, np.abs(golden_tiny["pca"]).max())
     # the SVM kernels themselves against real libsvm on the GPU's own PCA output: the fp64 DMMA anchor to
     # fp64 noise, the default tcgen05 kernel (fp16 x 3 cross term) well inside the 1e-4 gate, same signs
     for kernel, atol in ((0, 1e-9), (1, 1e-5)):
         eng.set_option("svm_kernel", kernel)
-        dc, dm, pc, pm, z2 = eng.svm_decision(feat, n, want_pca=True)
+        eng.set_option("pca_kernel", 0)
+        dc, dm, pc, pm, z2 = eng.svm_decision(feat, n, want_pca=True, precision=1)   # precision 1: the options decide
         assert np.array_equal(z2[:n].cpu().numpy(), z)
         for det, d_gpu, p_gpu in ((screener.detector_conservative, dc, pc), (screener.detector_moderate, dm, pm)):
             ref_dec = det.decision_function(z)
             np.testing.assert_allclose(d_gpu[:n].cpu().numpy(), ref_dec, rtol=0, atol=atol)
             assert np.array_equal(p_gpu[:n].cpu().numpy().astype(np.intp), det.predict(z))
     eng.set_option("svm_kernel", 1)
+    eng.set_option("pca_kernel", 1)
 
 
 def test_svm_scores_within_gate(screener, golden_tiny):

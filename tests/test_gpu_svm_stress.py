@@ -60,7 +60,7 @@ def test_config4_svm_20k_sv_256d(model_dir, artifacts, golden_config1, field_con
     eng.set_option("svm_kernel", kernel)
     n = 96
     feat = torch.from_numpy((rng.standard_normal((n, 2048)) * 3.0).astype(np.float32)).to(eng.tdev)
-    dc, dm, pc, pm, z = eng.svm_decision(feat, n, want_pca=True)
+    dc, dm, pc, pm, z = eng.svm_decision(feat, n, want_pca=True, precision=1)   # the options decide the kernels
     eng.check_status()
     z = z[:n].cpu().numpy()
     for det, d_gpu, p_gpu in ((dets[0], dc, pc), (dets[1], dm, pm)):
