@@ -108,7 +108,16 @@ int  cia_check_status(cia_handle h, void* stream);
  *   "cae_l1_debias", "cae_l2_debias", "cae_l3_debias"
  *                     compensation of tcgen05's round-toward-zero accumulation in the
  *                     split-precision encoder layers, in units of 2^-24 relative
- *                     (defaults 0.5 / 2.4 / 1.2, 0 = off) */
+ *                     (defaults 0.5 / 2.4 / 1.2, 0 = off)
+ *   "svm_kernel"      1 (default): tcgen05 GEMM-form RBF decision (csrc/score_tc.cu; |d dec| <= ~2e-5 vs
+ *                     libsvm at 20 000 SVs); 0: the fp64 DMMA kernel (equal to
+ *                     libsvm to 1e-9).  Models the tensor-core kernel does not serve (more than 256
+ *                     dimensions, negative dual coefficients) take the fp64 kernel by themselves.
+ *   "pca_kernel"      1 (default): tcgen05 RobustScaler + PCA projection; 0: the fp64 DMMA kernel
+ *   "svm_refine"      1 (default): decisions within the tensor-core kernel's error of zero are
+ *                     recomputed in fp64 (sign rule svm.cpp:2841 evaluated on exact values); 0: off
+ * A `precision` 0 call (cia_screen_fields*, cia_cae_forward) is the exact anchor end to end and uses the
+ * fp64 scoring kernels whatever these options say. */
 int  cia_set_option(cia_handle h, const char* name, double value);
 
 /* ---- artifacts (replaces load_trained_models, det:23-41) ----------------- */
