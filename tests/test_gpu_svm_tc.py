@@ -158,3 +158,55 @@ def test_pca_tc_wide_projection_256_components(artifacts, golden_tiny):
     assert np.abs(z[0] - ref).max() <= 1e-5
     rel = np.abs(z[1] - z[0]) / (np.abs(z[0]).max(axis=1, keepdims=True))
     assert rel.max() <= 1e-6, f"{rel.max():.3e}"
+
+
+def test_models_the_tensor_core_kernels_do_not_serve_take_the_fp64_kernels(artifacts, golden_tiny):
+    """Negative dual coefficients, more than 256 PCA dimensions, a feature count that is not a multiple of
+    32 and a float64 scaler centre are outside the tcgen05 kernels' contract: the fp64 DMMA kernels run
+    instead, silently and exactly (same bits as with the options set to 0)."""
+    from cell_image_analysis_b200.screening import Engine
+    rng = np.random.default_rng(8)
+    f = _features(golden_tiny, 500, seed=21)
+
+    def run(arts, feat, pca_kernels=(1, 0)):
+        e = Engine(device=0, precision=1)
+        e.load_artifacts(arts)
+        x = torch.from_numpy(feat).to(e.tdev)
+        out = {}
+        for k, pk in zip((1, 0), pca_kernels):
+            e.set_option("svm_kernel", k)
+            e.set_option("pca_kernel", pk)
+            dc, dm, pc, pm, z = e.svm_decision(x, len(feat), want_pca=True)
+            e.check_status()
+            out[k] = [t[:len(feat)].cpu().numpy() for t in (dc, dm, z)]
+        e.close()
+        return out
+
+    # (a) a negative dual coefficient in one detector: that detector goes to the fp64 kernel, the other stays
+    a = dict(artifacts)
+    cons = dict(artifacts["svm_conservative"])
+    coef = np.array(cons["coef"], dtype=np.float64).copy()
+    coef[3] = -abs(coef[3])
+    cons["coef"] = coef
+    a["svm_conservative"] = cons
+    o = run(a, f, pca_kernels=(0, 0))                          # same z in both runs
+    assert np.array_equal(o[1][0], o[0][0])                    # conservative: the fp64 kernel either way
+    assert not np.array_equal(o[1][1], o[0][1]) and np.abs(o[1][1] - o[0][1]).max() <= 1e-5   # moderate: tcgen05 vs fp64
+    # (b) float64 scaler centre: the projection takes the fp64 kernel, so z is bit-identical under both options
+    b = dict(artifacts)
+    sp = dict(artifacts["scaler_pca"])
+    sp["center"] = np.asarray(sp["center"], dtype=np.float64) + 1e-9
+    sp["center_is_f32"] = False
+    b["scaler_pca"] = sp
+    o = run(b, f)
+    assert np.array_equal(o[1][2], o[0][2])
+    # (c) 300 PCA dimensions (> 256): both stages on the fp64 kernels
+    q, _ = np.linalg.qr(rng.standard_normal((2048, 300)))
+    c = dict(artifacts)
+    c["scaler_pca"] = dict(artifacts["scaler_pca"], C=300, center=None, scale=None, components=np.ascontiguousarray(q.T),
+                           offset=np.zeros(300), f32_flow=True)
+    for k in ("svm_conservative", "svm_moderate"):
+        c[k] = dict(sv=rng.standard_normal((200, 300)) * 3.0, coef=rng.uniform(0, 1, 200), gamma=1.0 / (300 * 9.0), rho=1.0)
+    o = run(c, (rng.standard_normal((300, 2048)) * 3.0).astype(np.float32))
+    assert np.abs(o[1][2] - o[0][2]).max() <= 2e-6 * np.abs(o[0][2]).max()      # z: tcgen05 projection (3 column blocks)
+    assert np.abs(o[1][0] - o[0][0]).max() <= 1e-5                               # decisions: fp64 SVM on nearly equal z
