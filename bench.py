@@ -318,7 +318,7 @@ def run_native(args):
         rle_fraction = 1.0
     bs = BatchScreen(eng, H, W, max_label, chunk_fields=Fc, n_strains=n_strains,
                      label_transport=args.label_transport, host_threads=args.host_threads,
-                     rle_fraction=rle_fraction)
+                     rle_fraction=rle_fraction, host_buffers=args.host_buffers)
 
     def barrier():
         if world > 1:
@@ -538,6 +538,7 @@ def main():
     ap.add_argument("--cpu-fields", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-svm-extras", action="store_true")
+    ap.add_argument("--host-buffers", type=int, default=2, help="device chunk buffers of the host pass (A/B)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -26,7 +26,7 @@ class BatchScreen:
     def __init__(self, engine, H: int, W: int, max_label: int, chunk_fields: int = 16,
                  n_strains: int = 1, cells_per_field_cap: int | None = None,
                  label_transport: str = "rle", host_threads: int = 0, rle_fraction: float = 1.0,
-                 scan_runs: bool = True):
+                 scan_runs: bool = True, host_buffers: int = 2):
         """``label_transport``: "rle" run-length encodes the int32 label fields on the host
         cores (csrc/transport.cu) so that only the runs cross PCIe; "raw" copies them as is.
         ``rle_fraction`` < 1 sends only that share of the chunks as runs and the rest raw (several
@@ -44,7 +44,10 @@ class BatchScreen:
         self.cap = chunk_fields * (cells_per_field_cap or max_label)
         self.n_strains = n_strains
         d = engine.tdev
-        self.out = [engine.alloc_outputs(self.cap, chunk_fields) for _ in range(2)]
+        # device-side chunk buffers of the host pass (2 = double buffering; a third was measured and buys
+        # nothing: the pass is paced by the PCIe link, not by buffer turnover)
+        self.NB = max(2, int(host_buffers))
+        self.out = [engine.alloc_outputs(self.cap, chunk_fields) for _ in range(self.NB)]
         self.acc = torch.zeros((n_strains, 8), dtype=torch.float64, device=d)
         self.compute = torch.cuda.Stream(device=d)
         self.copy = torch.cuda.Stream(device=d)
@@ -92,18 +95,18 @@ class BatchScreen:
         d = self.eng.tdev
         if self._stage is None:
             self._stage = dict(
-                img=[torch.empty((self.Fc, self.H, self.W), dtype=torch.int16, device=d) for _ in range(2)],
-                lab=[torch.empty((self.Fc, self.H, self.W), dtype=torch.int32, device=d) for _ in range(2)],
-                ready=[torch.cuda.Event() for _ in range(2)],
-                done=[torch.cuda.Event() for _ in range(2)],
-                out_ready=[torch.cuda.Event() for _ in range(2)],
-                out_free=[torch.cuda.Event() for _ in range(2)])
+                img=[torch.empty((self.Fc, self.H, self.W), dtype=torch.int16, device=d) for _ in range(self.NB)],
+                lab=[torch.empty((self.Fc, self.H, self.W), dtype=torch.int32, device=d) for _ in range(self.NB)],
+                ready=[torch.cuda.Event() for _ in range(self.NB)],
+                done=[torch.cuda.Event() for _ in range(self.NB)],
+                out_ready=[torch.cuda.Event() for _ in range(self.NB)],
+                out_free=[torch.cuda.Event() for _ in range(self.NB)])
             if self.label_transport == "rle":
                 sw = self.eng.rle_slot_words(self.H, self.W)
                 self._stage.update(
-                    h_rle=[torch.empty((self.Fc, sw), dtype=torch.int32, pin_memory=True) for _ in range(2)],
-                    d_rle=[torch.empty((self.Fc, sw), dtype=torch.int32, device=d) for _ in range(2)],
-                    words=[np.zeros(self.Fc, np.uint32) for _ in range(2)])
+                    h_rle=[torch.empty((self.Fc, sw), dtype=torch.int32, pin_memory=True) for _ in range(self.NB)],
+                    d_rle=[torch.empty((self.Fc, sw), dtype=torch.int32, device=d) for _ in range(self.NB)],
+                    words=[np.zeros(self.Fc, np.uint32) for _ in range(self.NB)])
         if getattr(self, "_host_chunks", 0) < n_chunks:
             cap = self.cap
             pin = dict(pin_memory=True)
@@ -139,7 +142,7 @@ class BatchScreen:
         self.encode_seconds = 0.0          # host time spent inside the run-length encoder this pass
         n_rle = 0
         for i in range(n_chunks):
-            b = i & 1
+            b = i % self.NB
             p0 = (i * self.Fc) % P
             f = self.rle_fraction
             rle = self.label_transport == "rle" and int((i + 1) * f) > int(i * f)
