@@ -1,33 +1,39 @@
-// score_tc.cu -- K5 on the 5th-generation tensor cores: both one-class RBF SVM decision
-// functions in GEMM form, ||z - s||^2 = ||z||^2 + ||s||^2 - 2 z.s^T, with the z.s^T products of
-// a 128-cell x 128-SV tile as tcgen05.mma (fp16 operands split hi + lo, three MMAs per k-step,
-// fp32 accumulation in TMEM) and the exp / dual-coefficient reduction fused into the tile epilogue.
+// score_tc.cu -- K4 + K5 on the 5th-generation tensor cores (tcgen05, accumulators in TMEM):
+// RobustScaler -> PCA projection (scaler_pca_tc_kernel, further down) and both one-class RBF SVM
+// decision functions in GEMM form, ||z - s||^2 = ||z||^2 + ||s||^2 - 2 z.s^T, with the z.s^T products
+// of a 128-cell x 128-SV tile as tcgen05.mma (fp16 operands split hi + lo, three MMAs per k-step) and
+// the exp / dual-coefficient reduction fused into the tile epilogue (svm_rbf_tc_kernel).
 //
-// Replaces detector.predict + detector.decision_function (improved_detection.py:138-142; libsvm
-// k_function RBF, sklearn/svm/src/libsvm/svm.cpp:461-472, sum - rho and the sign rule :2832-2841).
-// The fp64 DMMA kernel in score.cu stays as the exact anchor (cia_set_option "svm_kernel" = 0).
+// Replaces scaler.transform / pca.transform (improved_detection.py:134-135) and detector.predict +
+// detector.decision_function (:138-142; libsvm k_function RBF, sklearn/svm/src/libsvm/svm.cpp:461-472,
+// sum - rho and the sign rule :2832-2841).  The fp64 DMMA kernels in score.cu stay as the exact anchors
+// (cia_set_option "svm_kernel" / "pca_kernel" = 0) and serve what these kernels do not (more than 256
+// dimensions, negative dual coefficients, float64 scaler centres, feature counts not divisible by 32).
 //
-// Why fp16 x 3 is accurate enough here: only the CROSS term z.s goes through
-// the tensor cores.  The PCA scores are centred, so gamma * z.s is O(1/sqrt(D)) while the two large
-// terms gamma||z||^2 and gamma||s||^2 are computed exactly in fp64 (per cell in the prologue, per SV
-// at load time).  Every row (cell) and the SV matrix are scaled by a power of two so that their
-// largest element sits in [2^13, 2^14): x = hi + lo carries 22 significant bits, the dropped lo*lo
-// term and the roundings are ~2^-22 of |z||s|, i.e. ~3e-8 in the exponent, random in sign over
-// the SVs.  What would be systematic is kept out of fp32: the per-cell term log2(e)*gamma||z||^2 is
-// split into an integer (added to the exponent) and a fraction that multiplies the finished row sum
-// in fp64; 2^t is a Cody-Waite reduction + degree-6 polynomial (max rel. error 1e-7, mean 4e-10,
-// no MUFU bias); row sums are fp32 over 32 terms, fp64 beyond.
+// Why fp16 x 3 is accurate enough for the SVM: only the CROSS term z.s goes
+// through the tensor cores; gamma||z||^2 (per cell, in the prologue) and gamma||s||^2 (per SV, at load
+// time) are exact fp64.  Every row (cell) and the SV matrix are scaled by a power of two so that their
+// largest element sits in [2^13, 2^14): x = hi + lo carries 22 significant bits, the dropped lo*lo term
+// is 2^-22 of |z||s|.  What would err systematically is kept out of fp32:
+//   * tcgen05 adds every MMA into its fp32 accumulator with round-toward-zero
+//     (profiles/umma_rounding_test.cu): a 16-k-step chain under-estimates z.s by ~6e-7 relative, always in
+//     the same direction for the near SVs that dominate a decision (measured: 3e-5 on the golden detectors).
+//     So a TMEM accumulator only ever holds ONE pipeline stage (32 dims: the four cross-term MMAs first, the
+//     two hi*hi MMAs last); the epilogue warps add the stage partials in fp32 registers with
+//     round-to-nearest while the other three TMEM stage buffers fill, and the mean deficit of the two
+//     remaining truncations (1.5 * 2^-25) rides on the row factor, which is an fp32 PAIR (a single fp32's
+//     own rounding would be an error of the same size, common to all pairs of a detector);
+//   * the per-cell term log2(e) * gamma||z||^2 is split into an integer (added to the exponent field as an
+//     integer) and a fraction that multiplies the finished row sum in fp64;
+//   * 2^t is a Cody-Waite reduction + degree-6 minimax polynomial in packed FFMA2 (max rel. error 1e-7,
+//     mean 4e-10; ex2.approx measured 1.3e-4 in the decision at 5 000 SVs: CIA_SVM_MUFU=1 keeps the A/B);
+//   * row sums: fp32 over 32 terms, then 64-bit fixed point -- integer addition is associative, so a cell's
+//     decision does not depend on how its SV tiles were cut over CTAs, i.e. on its position in the call;
+//   * decisions within the kernel's error of zero are recomputed in fp64 (svm_refine_kernel).
 //
 // Work distribution: the (cell tile, SV tile) pairs are one flat list cut into equal contiguous
 // ranges, one per CTA (one CTA per SM); a cell tile whose SV range spans several CTAs gets one
-// partial sum per CTA, added in CTA order by svm_tc_finalize_kernel (deterministic).
-// tcgen05 adds every MMA into its fp32 accumulator with round-toward-zero (profiles/umma_rounding_test.cu):
-// a 16-k-step chain under-estimates z.s by ~6e-7 relative, always in the same direction for the near SVs
-// that dominate a decision (measured: 3e-5 on the golden detectors).  So a TMEM accumulator only ever holds
-// ONE pipeline stage (32 dims: cross terms first, the two hi*hi k-steps last); the epilogue warps add the
-// stage partials in fp32 registers with round-to-nearest while the MMAs of the next stage fill the other
-// TMEM buffer, and the mean deficit of the two remaining truncations (1.5 * 2^-25) rides on the row factor,
-// which is carried as an fp32 pair (its own rounding would be an error of the same size, common to all pairs).
+// partial sum per CTA, added by svm_tc_finalize_kernel.
 //   warps 0..15 build the A operand (z tile: scale, split, K-major core matrices), then run the
 //               epilogue: TMEM quadrant = warp & 3, column quarter = warp >> 2
 //   warp 16     lane 0 streams the SV tiles (hi | lo images, 32 dims per stage) with cp.async.bulk
