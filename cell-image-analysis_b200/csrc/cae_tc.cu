@@ -17,14 +17,16 @@
 // fp32-grade encoder features: operands are split x = hi + lo (two fp16), weights scaled by
 // a power of two; three MMAs (hi*hi, hi*lo, lo*hi) accumulate into one fp32 TMEM tile.
 //
-// Default pass (precision 1), one launch per layer over up to 16576 cells:
-//   L1  1->32 @64  conv1_fp32_planar_kernel     CUDA cores, exact fp32 (FFMA2), writes hi/lo fp16
+// Default pass (precision 1), one launch per layer over up to cae_pass_cells (18944) cells:
+//   L1  1->32 @64  conv1_tc_split_kernel         K = 9 im2col rows built by byte permutes, 3 MMAs per phase, writes hi/lo fp16
+//                  (conv1_fp32_planar_kernel, exact fp32 on the CUDA cores: CIA_L1_KERNEL=0 and precision 2)
 //   L2 32->64 @32  conv_tc_acc2_kernel<..,32,3>  TMA-fed double-buffered half-cell blocks, 3 taps per flush
-//   L3 64->32 @16  conv_tc_acc_kernel<..,16,1>   row-pair tiles, register-staged, 1 tap per flush -> features
+//   L3 64->32 @16  conv_tc_acc_kernel<..,16,1>   row-pair tiles, N-stacked weights, register-staged, 1 tap per flush -> features
 //   L4 32->32 @8   conv_tc_kernel<EPI_PLAIN>     single pass, TMEM double-buffered
 //   L5 32->64 @16  conv_tc_kernel<EPI_PLAIN,UPSIN> up-sampling folded into the staging
 //   L6 64->32 @32  conv_tc_kernel<EPI_PHASE>     phase form at 16x16, N = 128
-//   L7 32->1  @64  conv_tc_kernel<EPI_FINAL>     phase form at 32x32 + sigmoid + MSE/MAE reduction
+//   L7 32->1  @64  final_tapsum_kernel           one tap, (phase, neighbour) pairs on N, shifted tap sum + sigmoid + MSE/MAE
+//                  (conv_tc_kernel<EPI_FINAL>, the nine-tap phase form: CIA_L7_KERNEL=0)
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
