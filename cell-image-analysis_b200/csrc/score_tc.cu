@@ -124,6 +124,15 @@ __device__ __forceinline__ void exp2x2(unsigned long long t, float tmin, float t
     r1f = __uint_as_float((uint32_t)(p >> 32) + ((uint32_t)(m >> 32) << 23) + nsh);
 }
 
+#ifdef CIA_SVM_TIMING
+__device__ unsigned long long g_svm_dbg[16];
+#define SDBG_T(var) const long long var = clock64()
+#define SDBG_ADD(acc, a, b) acc += (b) - (a)
+#else
+#define SDBG_T(var)
+#define SDBG_ADD(acc, a, b)
+#endif
+
 template <bool MUFU>
 __global__ void __launch_bounds__(svmtc::NT, 1)
 svm_rbf_tc_kernel(const double* __restrict__ z, int n_cells, const int32_t* __restrict__ n_dev, int D, int Dpad,
@@ -249,14 +258,21 @@ svm_rbf_tc_kernel(const double* __restrict__ z, int n_cells, const int32_t* __re
             // ================= MMA issuers =================
             if (lane == 0) {
                 const uint32_t me = (uint32_t)(warp - MMA_WARP);
+#ifdef CIA_SVM_TIMING
+                long long m_tempty = 0, m_full = 0, m_issue = 0;
+#endif
                 const uint64_t ah0 = make_smem_desc(a_addr, K8_B, 128), al0 = make_smem_desc(a_addr + a_half_b, K8_B, 128);
                 const uint64_t bh0 = make_smem_desc(st_addr, K8_B, 128), bl0 = make_smem_desc(st_addr + HALF_B, K8_B, 128);
                 for (int t = t0; t < t0 + nt; ++t) {
                     for (int kc = 0; kc < n_kc; ++kc, ++m_cnt) {
                         if ((m_cnt & 1) != me) continue;
                         const uint32_t buf = m_cnt & (NBUF - 1), st = m_cnt % (uint32_t)stages;
+                        SDBG_T(q0);
                         mbar_wait(&tempty_bar[buf], ((m_cnt / NBUF) & 1) ^ 1);   // the epilogue has drained this buffer
+                        SDBG_T(q1);
                         mbar_wait(&full_bar[st], (m_cnt / (uint32_t)stages) & 1);
+                        SDBG_T(q2);
+                        SDBG_ADD(m_tempty, q0, q1); SDBG_ADD(m_full, q1, q2);
                         tc_fence_after();
                         const uint32_t d = tmem_base + buf * TN;
                         const int ksn = min(KC / 16, (nk8 - kc * (KC / 8)) >> 1);
@@ -279,8 +295,16 @@ svm_rbf_tc_kernel(const double* __restrict__ z, int n_cells, const int32_t* __re
                             }
                         umma_commit(&empty_bar[st]);
                         umma_commit(&tfull_bar[buf]);
+                        SDBG_T(q3);
+                        SDBG_ADD(m_issue, q2, q3);
                     }
                 }
+#ifdef CIA_SVM_TIMING
+                if (me == 0) {
+                    atomicAdd(&g_svm_dbg[0], (unsigned long long)m_tempty); atomicAdd(&g_svm_dbg[1], (unsigned long long)m_full);
+                    atomicAdd(&g_svm_dbg[2], (unsigned long long)m_issue);
+                }
+#endif
             }
             __syncwarp();
         } else {
@@ -299,6 +323,9 @@ svm_rbf_tc_kernel(const double* __restrict__ z, int n_cells, const int32_t* __re
             const unsigned long long rem2 = pack2(rem, rem);
             const bool slow = __any_sync(0xffffffffu, rem != 0.f);
             const uint32_t taddr0 = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(cq * 32);
+#ifdef CIA_SVM_TIMING
+            long long e_wait = 0, e_flush = 0, e_exp = 0, e_tiles = 0;
+#endif
             // row sums in 64-bit FIXED POINT (2^-S, S from the model): integer addition is associative, so a cell's
             // decision does not depend on how its SV tiles were cut over CTAs, i.e. on its position in the call
             long long rowsum = 0;
@@ -310,7 +337,10 @@ svm_rbf_tc_kernel(const double* __restrict__ z, int n_cells, const int32_t* __re
 #pragma unroll 1
                 for (int kc = 0; kc < n_kc; ++kc, ++e_buf) {
                     const uint32_t buf = e_buf & (NBUF - 1);
+                    SDBG_T(w0);
                     mbar_wait(&tfull_bar[buf], (e_buf / NBUF) & 1);
+                    SDBG_T(w1);
+                    SDBG_ADD(e_wait, w0, w1);
                     tc_fence_after();
                     uint32_t v[32];
                     TMEM_LD32(taddr0 + buf * TN, v);
@@ -320,7 +350,10 @@ svm_rbf_tc_kernel(const double* __restrict__ z, int n_cells, const int32_t* __re
                     if (lane == 0) mbar_arrive(&tempty_bar[buf]);
 #pragma unroll
                     for (int j = 0; j < 32; j += 2) fadd2(acc[j], acc[j + 1], v[j], v[j + 1]);
+                    SDBG_T(w2);
+                    SDBG_ADD(e_flush, w1, w2);
                 }
+                SDBG_T(x0);
                 // ---- fused RBF + dual-coefficient reduction ----
                 // t = acc * (2 gamma log2e 2^-(e_row + e_s)) + (log2e * -gamma||s||^2 + log2 coef)  [+ n_row]
                 const float4* gc = reinterpret_cast<const float4*>(gcol + (size_t)t * TN + cq * 32);
@@ -351,7 +384,18 @@ svm_rbf_tc_kernel(const double* __restrict__ z, int n_cells, const int32_t* __re
                     }
                 }
                 rowsum += __double2ll_rn((double)((s0 + s1) + (s2 + s3)) * fx_scale);
+                SDBG_T(x1);
+                SDBG_ADD(e_exp, x0, x1);
+#ifdef CIA_SVM_TIMING
+                ++e_tiles;
+#endif
             }
+#ifdef CIA_SVM_TIMING
+            if (tid == 0) {
+                atomicAdd(&g_svm_dbg[4], (unsigned long long)e_wait); atomicAdd(&g_svm_dbg[5], (unsigned long long)e_flush);
+                atomicAdd(&g_svm_dbg[6], (unsigned long long)e_exp); atomicAdd(&g_svm_dbg[7], (unsigned long long)e_tiles);
+            }
+#endif
             s_red[cq][row] = rowsum;
             asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
             if (cq == 0) {
@@ -783,6 +827,19 @@ int k_svm_tc(cia_ctx* h, const SvmModel& m, const double* z, int n, const int32_
     kern<<<grid, NT, smem_b, s>>>(z, n, n_dev, m.dim, m.dim_pad, (const __half*)m.tc_hi, (const __half*)m.tc_lo, m.tc_gcol, m.tc_svt, fac_base,
                                   m.gamma, per_cta, stages, std::ldexp(1.0, m.tc_fx), partial, n, rowmul);
     CIA_LAUNCH_CHECK();
+#ifdef CIA_SVM_TIMING
+    if (getenv("CIA_SVM_DUMP")) {
+        unsigned long long d[16];
+        cudaStreamSynchronize(s);
+        cudaMemcpyFromSymbol(d, g_svm_dbg, sizeof(d));
+        const double u = d[7] ? (double)d[7] : 1.0;      // tiles seen by thread 0 of every CTA
+        fprintf(stderr, "svm_tc per tile (cycles): mma thread 0 {wait tmem-empty %.0f, wait smem-full %.0f, issue %.0f} x2 threads; "
+                        "epilogue warp 0 {wait tmem-full %.0f, flush %.0f, exp %.0f}; tiles %llu\n",
+                d[0] / u, d[1] / u, d[2] / u, d[4] / u, d[5] / u, d[6] / u, d[7]);
+        memset(d, 0, sizeof(d));
+        cudaMemcpyToSymbol(g_svm_dbg, d, sizeof(d));
+    }
+#endif
     svm_tc_finalize_kernel<<<(n + 255) / 256, 256, 0, s>>>(partial, n, m.tc_svt, per_cta, n, n_dev, rowmul,
                                                              std::ldexp(1.0, -m.tc_fx), m.rho, dec, pred);
     CIA_LAUNCH_CHECK();
