@@ -61,7 +61,8 @@ constexpr int K8_B = TN * 16;                // one 8-dim core-matrix column of 
 constexpr int HALF_B = (KC / 8) * K8_B;      // hi (or lo) part of a stage: 8 KB
 constexpr int STAGE_B = 2 * HALF_B;
 constexpr int MAX_STAGES = 8;
-constexpr int NBUF = 4;                      // TMEM stage accumulators (128 columns each)
+constexpr int NBUF = 4;                      // TMEM accumulators (128 columns each), one flush group each
+constexpr int FL = 2;                        // stages (of 32 dims) accumulated in TMEM between flushes
 constexpr int TMEM_COLS = NBUF * TN;
 constexpr int STATIC_SMEM_EST = 8 * 1024;    // barriers + per-row arrays below (host-side budget)
 constexpr double LOG2E = 1.4426950408889634074;
@@ -178,8 +179,8 @@ svm_rbf_tc_kernel(const double* __restrict__ z, int n_cells, const int32_t* __re
     constexpr uint32_t IDESC = make_idesc(TM, TN);
 
     uint32_t p_st = 0, p_ph = 0;                  // producer: stage, parity of its round
-    uint32_t m_cnt = 0;                           // MMA issuers: running stage count
-    uint32_t e_buf = 0;                           // epilogue
+    uint32_t m_st = 0, m_ph = 0, m_grp = 0;       // MMA issuers: stage ring position / parity, running flush-group count
+    uint32_t e_buf = 0;                           // epilogue: running flush-group count
 
     for (long long w = w0; w < w1;) {
         const int ct = (int)(w / n_svt), t0 = (int)(w - (long long)ct * n_svt);
@@ -243,7 +244,7 @@ svm_rbf_tc_kernel(const double* __restrict__ z, int n_cells, const int32_t* __re
             if (lane == 0) {
                 for (int t = t0; t < t0 + nt; ++t)
                     for (int kc = 0; kc < n_kc; ++kc) {
-                        mbar_wait(&empty_bar[p_st], p_ph ^ 1);
+                        mbar_wait_sleep(&empty_bar[p_st], p_ph ^ 1);
                         const int k8n = min(KC / 8, nk8 - kc * (KC / 8));
                         const uint32_t bytes = (uint32_t)k8n * K8_B;
                         const size_t off = ((size_t)t * nk8 + (size_t)kc * (KC / 8)) * (TN * 8);   // halves
@@ -255,8 +256,8 @@ svm_rbf_tc_kernel(const double* __restrict__ z, int n_cells, const int32_t* __re
             }
             __syncwarp();
         } else if (warp >= MMA_WARP) {
-            // ================= MMA issuers =================
-            if (lane == 0) {
+            // ================= MMA issuers (the whole warp runs the loop, one elected lane issues) =================
+            {
                 const uint32_t me = (uint32_t)(warp - MMA_WARP);
 #ifdef CIA_SVM_TIMING
                 long long m_tempty = 0, m_full = 0, m_issue = 0;
@@ -264,43 +265,68 @@ svm_rbf_tc_kernel(const double* __restrict__ z, int n_cells, const int32_t* __re
                 const uint64_t ah0 = make_smem_desc(a_addr, K8_B, 128), al0 = make_smem_desc(a_addr + a_half_b, K8_B, 128);
                 const uint64_t bh0 = make_smem_desc(st_addr, K8_B, 128), bl0 = make_smem_desc(st_addr + HALF_B, K8_B, 128);
                 for (int t = t0; t < t0 + nt; ++t) {
-                    for (int kc = 0; kc < n_kc; ++kc, ++m_cnt) {
-                        if ((m_cnt & 1) != me) continue;
-                        const uint32_t buf = m_cnt & (NBUF - 1), st = m_cnt % (uint32_t)stages;
+                    // a flush group = FL consecutive stages accumulated in one TMEM buffer; the two issuing threads
+                    // take alternate groups (m_st / m_ph: shared-memory stage and round parity of the group's first stage)
+                    for (int g0 = 0; g0 < n_kc; g0 += FL, ++m_grp) {
+                        const int gn = min(FL, n_kc - g0);
+                        const uint32_t st0 = m_st, ph0 = m_ph;
+                        m_st += (uint32_t)gn;
+                        if (m_st >= (uint32_t)stages) { m_st -= (uint32_t)stages; m_ph ^= 1; }
+                        if ((m_grp & 1) != me) continue;
+                        const uint32_t buf = m_grp & (NBUF - 1);
+                        uint32_t stv[FL];
                         SDBG_T(q0);
-                        mbar_wait(&tempty_bar[buf], ((m_cnt / NBUF) & 1) ^ 1);   // the epilogue has drained this buffer
+                        mbar_wait_sleep(&tempty_bar[buf], ((m_grp / NBUF) & 1) ^ 1);   // the epilogue has drained this buffer
                         SDBG_T(q1);
-                        mbar_wait(&full_bar[st], (m_cnt / (uint32_t)stages) & 1);
+#pragma unroll
+                        for (int u = 0; u < FL; ++u) {
+                            uint32_t st = st0 + (uint32_t)u, ph = ph0;
+                            if (st >= (uint32_t)stages) { st -= (uint32_t)stages; ph ^= 1; }
+                            stv[u] = st;
+                            if (u < gn) mbar_wait_sleep(&full_bar[st], ph);
+                        }
                         SDBG_T(q2);
                         SDBG_ADD(m_tempty, q0, q1); SDBG_ADD(m_full, q1, q2);
                         tc_fence_after();
+                        if (elect_one()) {
                         const uint32_t d = tmem_base + buf * TN;
-                        const int ksn = min(KC / 16, (nk8 - kc * (KC / 8)) >> 1);
-                        const uint64_t ao = (uint64_t)((uint32_t)(kc * (KC / 16)) * ((2 * K8_B) >> 4));
-                        const uint64_t bo = (uint64_t)(st * (STAGE_B >> 4));
-                        // cross terms (2^-11 of the product) first into the fresh accumulator, hi*hi last
+                        // all cross terms (2^-11 of the product) of the group first into the fresh accumulator, the
+                        // hi*hi k-steps last: only those are truncated at the sum's full magnitude
 #pragma unroll
                         for (int pass = 0; pass < 2; ++pass)
 #pragma unroll
-                            for (int s = 0; s < KC / 16; ++s) {
-                                if (s < ksn) {
-                                    const uint64_t so = (uint64_t)(s * ((2 * K8_B) >> 4));
-                                    if (pass == 0) {
-                                        umma_f16(d, ah0 + ao + so, bl0 + bo + so, IDESC, s == 0 ? 0u : 1u);
-                                        umma_f16(d, al0 + ao + so, bh0 + bo + so, IDESC, 1u);
-                                    } else {
-                                        umma_f16(d, ah0 + ao + so, bh0 + bo + so, IDESC, 1u);
+                            for (int u = 0; u < FL; ++u) {
+                                if (u < gn) {
+                                    const int kc = g0 + u;
+                                    const int ksn = min(KC / 16, (nk8 - kc * (KC / 8)) >> 1);
+                                    const uint64_t ao = (uint64_t)((uint32_t)(kc * (KC / 16)) * ((2 * K8_B) >> 4));
+                                    const uint64_t bo = (uint64_t)(stv[u] * (STAGE_B >> 4));
+#pragma unroll
+                                    for (int s = 0; s < KC / 16; ++s) {
+                                        if (s < ksn) {
+                                            const uint64_t so = (uint64_t)(s * ((2 * K8_B) >> 4));
+                                            if (pass == 0) {
+                                                umma_f16(d, ah0 + ao + so, bl0 + bo + so, IDESC, (u == 0 && s == 0) ? 0u : 1u);
+                                                umma_f16(d, al0 + ao + so, bh0 + bo + so, IDESC, 1u);
+                                            } else {
+                                                umma_f16(d, ah0 + ao + so, bh0 + bo + so, IDESC, 1u);
+                                            }
+                                        }
                                     }
                                 }
                             }
-                        umma_commit(&empty_bar[st]);
+#pragma unroll
+                        for (int u = 0; u < FL; ++u)
+                            if (u < gn) umma_commit(&empty_bar[stv[u]]);
                         umma_commit(&tfull_bar[buf]);
+                        }
+                        __syncwarp();
                         SDBG_T(q3);
                         SDBG_ADD(m_issue, q2, q3);
                     }
                 }
 #ifdef CIA_SVM_TIMING
-                if (me == 0) {
+                if (me == 0 && lane == 0) {
                     atomicAdd(&g_svm_dbg[0], (unsigned long long)m_tempty); atomicAdd(&g_svm_dbg[1], (unsigned long long)m_full);
                     atomicAdd(&g_svm_dbg[2], (unsigned long long)m_issue);
                 }
@@ -335,10 +361,10 @@ svm_rbf_tc_kernel(const double* __restrict__ z, int n_cells, const int32_t* __re
 #pragma unroll
                 for (int j = 0; j < 32; ++j) acc[j] = 0.f;
 #pragma unroll 1
-                for (int kc = 0; kc < n_kc; ++kc, ++e_buf) {
+                for (int g0 = 0; g0 < n_kc; g0 += FL, ++e_buf) {
                     const uint32_t buf = e_buf & (NBUF - 1);
                     SDBG_T(w0);
-                    mbar_wait(&tfull_bar[buf], (e_buf / NBUF) & 1);
+                    mbar_wait_sleep(&tfull_bar[buf], (e_buf / NBUF) & 1);
                     SDBG_T(w1);
                     SDBG_ADD(e_wait, w0, w1);
                     tc_fence_after();
@@ -571,7 +597,7 @@ scaler_pca_tc_kernel(const float* __restrict__ feat, int n_cells, const int32_t*
                 e = max(-100, min(100, e));
                 up[i] = __uint_as_float((uint32_t)(127 + e) << 23);
             }
-            mbar_wait(&empty_bar[st], ((c / STAGES) & 1) ^ 1);
+            mbar_wait_sleep(&empty_bar[st], ((c / STAGES) & 1) ^ 1);
             unsigned char* a_hi = smem + st * STAGE_B + ((ch >> 1) * TM) * 16 + (ch & 1) * 8;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -595,7 +621,7 @@ scaler_pca_tc_kernel(const float* __restrict__ feat, int n_cells, const int32_t*
             if (lane == 0) {
                 for (int kc = 0; kc < n_kc; ++kc, ++cnt) {
                     const uint32_t st = cnt % STAGES;
-                    mbar_wait(&empty_bar[st], ((cnt / STAGES) & 1) ^ 1);
+                    mbar_wait_sleep(&empty_bar[st], ((cnt / STAGES) & 1) ^ 1);
                     mbar_expect_tx(&full_bar[st], 2 * HALF_B);
                     bulk_load(s_addr + st * STAGE_B + 2 * HALF_B, comp_img + ((size_t)cb * n_kc + kc) * (2 * HALF_B / 2),
                               2 * HALF_B, &full_bar[st]);
@@ -610,8 +636,8 @@ scaler_pca_tc_kernel(const float* __restrict__ feat, int n_cells, const int32_t*
                 for (int kc = 0; kc < n_kc; ++kc, ++cnt) {
                     if ((cnt & 1) != me) continue;
                     const uint32_t st = cnt % STAGES, buf = cnt % NBUF;
-                    mbar_wait(&tempty_bar[buf], ((cnt / NBUF) & 1) ^ 1);
-                    mbar_wait(&full_bar[st], (cnt / STAGES) & 1);
+                    mbar_wait_sleep(&tempty_bar[buf], ((cnt / NBUF) & 1) ^ 1);
+                    mbar_wait_sleep(&full_bar[st], (cnt / STAGES) & 1);
                     tc_fence_after();
                     const uint32_t d = tmem_base + buf * TN;
                     const uint64_t ah = d0 + (uint64_t)((st * STAGE_B) >> 4), al = ah + (HALF_B >> 4);
@@ -642,7 +668,7 @@ scaler_pca_tc_kernel(const float* __restrict__ feat, int n_cells, const int32_t*
 #pragma unroll 1
             for (int kc = 0; kc < n_kc; ++kc, ++cnt) {
                 const uint32_t buf = cnt % NBUF;
-                mbar_wait(&tfull_bar[buf], (cnt / NBUF) & 1);
+                mbar_wait_sleep(&tfull_bar[buf], (cnt / NBUF) & 1);
                 tc_fence_after();
                 const float sc = ring[(cnt % RING) * TM + row];
                 const unsigned long long sc2 = pack2(sc, sc);
@@ -821,8 +847,10 @@ int k_svm_tc(cia_ctx* h, const SvmModel& m, const double* z, int n, const int32_
     if (rc) return rc;
     long long* partial = (long long*)h->ws_svm.p;
     double* rowmul = (double*)h->ws_svm.p + (size_t)slots * n;
-    // mean deficit of the two full-magnitude round-toward-zero accumulations of a stage, in units of 2^-25
-    static const double debias = [] { const char* e = getenv("CIA_SVM_DEBIAS"); return e ? atof(e) : 1.5; }();
+    // mean deficit of the full-magnitude round-toward-zero accumulations of a flush group, in units of 2^-25
+    // (a flush group is FL = 2 stages = four hi*hi k-steps whose running sum is truncated four times:
+    // (1/4 + 2/4 + 3/4 + 1) = 2.5 mean truncations of the group sum)
+    static const double debias = [] { const char* e = getenv("CIA_SVM_DEBIAS"); return e ? atof(e) : 2.5; }();
     const double fac_base = std::ldexp(2.0 * m.gamma * LOG2E, -m.tc_es) * (1.0 + debias * 2.9802322387695312e-8);
     kern<<<grid, NT, smem_b, s>>>(z, n, n_dev, m.dim, m.dim_pad, (const __half*)m.tc_hi, (const __half*)m.tc_lo, m.tc_gcol, m.tc_svt, fac_base,
                                   m.gamma, per_cta, stages, std::ldexp(1.0, m.tc_fx), partial, n, rowmul);

@@ -22,6 +22,30 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             : "=r"(done) : "r"(a), "r"(parity) : "memory");
     } while (!done);
 }
+// The same wait with a suspend-time hint: the thread sleeps in hardware until the phase completes (or the hint,
+// 10 ms, expires) instead of re-issuing try_wait + branch -- warps that wait for long (epilogue warps waiting for
+// MMAs, producers waiting for free stages) then leave the issue slots to the single MMA-issuing thread of their
+// scheduler (CUTLASS's ClusterBarrier::wait uses the same form).
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+    const uint32_t a = smem_u32(bar);
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}"
+        ::"r"(a), "r"(parity), "r"(0x989680u) : "memory");
+}
+// One lane of a converged warp (elect.sync).  Issue loops written as "whole warp runs the loop, the elected
+// lane executes the tcgen05 instruction" keep descriptors and addresses in uniform registers; an
+// `if (lane == 0) { loop }` makes them per-thread values that reach the instruction through R2UR + vote loops
+// (~20 instructions per MMA instead of ~6).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
