@@ -44,6 +44,37 @@ enum { EPI_POOL = 0, EPI_PLAIN = 2, EPI_FINAL = 3, EPI_PHASE = 4 };
 
 using namespace tcptx;
 
+// MMA issue loops of the accumulating encoder kernels (L2, L3): the whole warp runs the loop and one elected lane
+// executes the tcgen05 instructions, so that descriptors stay in uniform registers (tc_ptx.cuh, elect_one):
+// ~3 instead of ~20 instructions per MMA.  Measured (bench.py cae_layers, 486k cells): L2 52.4 -> 45.6 ms,
+// L3 23.4 -> 22.1 ms.  The single-pass kernels (L1, L4-L7) measured 2-5 % SLOWER in that form and keep
+// `if (lane == 0) { loop }` (ISSUE1_*).  -DCIA_LANE0_ISSUE restores the round-1 form everywhere for A/B runs.
+#ifdef CIA_LANE0_ISSUE
+#define ISSUE_WARP(cond) (lane == 0 && (cond))
+#define ISSUE_BEGIN {
+#define ISSUE_END }
+#else
+#define ISSUE_WARP(cond) (cond)
+#define ISSUE_BEGIN if (elect_one()) {
+#define ISSUE_END } __syncwarp();
+#endif
+// waits of the accumulating kernels: with the suspend-time hint a waiting warp sleeps in hardware instead of
+// re-issuing try_wait + branch next to the issuing warp of its scheduler (-DCIA_SPIN_WAIT: the plain loop)
+#ifdef CIA_SPIN_WAIT
+#define MBAR_WAIT mbar_wait
+#else
+#define MBAR_WAIT mbar_wait_sleep
+#endif
+#ifdef CIA_UNIFORM_ISSUE_ALL
+#define ISSUE1_WARP(cond) (cond)
+#define ISSUE1_BEGIN if (elect_one()) {
+#define ISSUE1_END } __syncwarp();
+#else
+#define ISSUE1_WARP(cond) (lane == 0 && (cond))
+#define ISSUE1_BEGIN {
+#define ISSUE1_END }
+#endif
+
 // Pooling layers: value of a pooled pixel from the max over its 2x2 window of the SIGN-FOLDED conv
 // accumulators (weight columns carry sign(bn scale), see k_cae_tc_prepare).  bias -> ReLU -> BN is
 // monotone in the conv output, so max-pool(f(c)) == f(max c) for a scale >= 0 and f(min c) otherwise;
@@ -243,8 +274,9 @@ conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_l
             // one extra warp issues for all tiles (an N = 128 MMA takes longer than the ~60 cycles a single
             // thread needs per issue; two issuing warps measured slower): the eight worker warps go straight
             // to their epilogue instead of two of them first spending the whole MMA time inside the issue loop
-            if (lane == 0 && warp == TCT / 32) {
+            if (ISSUE1_WARP(warp == TCT / 32)) {
                 tc_fence_after();
+                ISSUE1_BEGIN
                 const uint64_t ad0 = make_smem_desc(smem_u32(a_part[0]), C::CHUNK_B, C::SBO_A);
                 const uint64_t bd0 = make_smem_desc(smem_u32(w_part[0]), COUT * 16, 128);
 #pragma unroll
@@ -261,11 +293,13 @@ conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_l
                         }
                 }
                 umma_commit(&bar[tbuf]);
+                ISSUE1_END
             }
             return;
         }
-        if (lane == 0 && warp < NISS) {
+        if (ISSUE1_WARP(warp < NISS)) {
             tc_fence_after();
+            ISSUE1_BEGIN
             const int t = warp, py = t >> 1, px = t & 1;
             uint64_t dxo[3];          // tap-column offset in 16-byte units (pool: parity plane + half-column)
 #pragma unroll
@@ -291,6 +325,7 @@ conv_tc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_l
                 }
             }
             umma_commit(&bar[tbuf]);
+            ISSUE1_END
         }
     };
 
@@ -655,7 +690,7 @@ conv_tc_acc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
         // dependent uniform-register adds), more than the 45-48 cycles an M128 x N<=64 MMA takes;
         // four issuing warps, each owning the accumulator tile of one pooling phase, keep the
         // tensor pipe fed.  Each commits to the stage's full barrier (count 4).
-        if (lane == 0 && warp - ACC_EPI_WARPS < NT) {
+        if (ISSUE_WARP(warp - ACC_EPI_WARPS < NT)) {
             const int t = warp - ACC_EPI_WARPS, py = ROWPAIR ? 0 : t >> 1, px = t & 1;
             constexpr uint32_t SBO = ROWPAIR ? C::ROW_B : C::SBO_A;
             const uint64_t a_hi0 = make_smem_desc(smem_u32(a_part[0]) + py * C::ROW_B, C::CHUNK_B, SBO);
@@ -672,7 +707,7 @@ conv_tc_acc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
 #endif
             for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
                 DBG_T(m0);
-                mbar_wait(&ready_bar, uphase);
+                MBAR_WAIT(&ready_bar, uphase);
                 DBG_T(m1);
                 DBG_ADD(m_ready, m0, m1);
                 uphase ^= 1;
@@ -683,11 +718,12 @@ conv_tc_acc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
                 for (int grp = 0; grp < NGRP; ++grp) {
                     const uint32_t st = it & 1;
                     DBG_T(m2);
-                    mbar_wait(&empty_bar[st], ((it >> 1) & 1) ^ 1);
+                    MBAR_WAIT(&empty_bar[st], ((it >> 1) & 1) ^ 1);
                     DBG_T(m3);
                     DBG_ADD(m_empty, m2, m3);
                     tc_fence_after();
                     const uint32_t d = tmem_base + st * STAGE_COLS + (uint32_t)(t * TILE_COLS);
+                    ISSUE_BEGIN
                     if (STACK) {
                         // hi x [hi | lo] (N = 2*COUT, zero-initialising both column groups), then lo x hi into the cross group
 #pragma unroll
@@ -729,13 +765,14 @@ conv_tc_acc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
                         }
                     }
                     umma_commit(&full_bar[st]);
+                    ISSUE_END
                     DBG_T(m4);
                     DBG_ADD(m_issue, m3, m4);
                     ++it;
                 }
             }
 #ifdef CIA_ACC_TIMING
-            if (warp == ACC_EPI_WARPS) {
+            if (warp == ACC_EPI_WARPS && lane == 0) {
                 atomicAdd(&g_acc_dbg[8], (unsigned long long)m_ready);
                 atomicAdd(&g_acc_dbg[9], (unsigned long long)m_empty);
                 atomicAdd(&g_acc_dbg[10], (unsigned long long)m_issue);
@@ -781,7 +818,7 @@ conv_tc_acc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
             for (int grp = 0; grp < NGRP; ++grp) {
                 const uint32_t st = it & 1;
                 DBG_T(e2);
-                mbar_wait(&full_bar[st], (it >> 1) & 1);
+                MBAR_WAIT(&full_bar[st], (it >> 1) & 1);
                 DBG_T(e3);
                 DBG_ADD(e_full, e2, e3);
                 tc_fence_after();
@@ -985,7 +1022,7 @@ conv_tc_acc2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
 
     if (warp >= ACC_EPI_WARPS) {
         // ================= MMA issuers: one warp per phase tile =================
-        if (lane == 0 && warp - ACC_EPI_WARPS < NT) {
+        if (ISSUE_WARP(warp - ACC_EPI_WARPS < NT)) {
             const int t = warp - ACC_EPI_WARPS, py = ROWPAIR ? 0 : t >> 1, px = t & 1;
             const uint64_t b_hi0 = make_smem_desc(smem_u32(w_part[0]), COUT * 16, 128);
             const uint64_t b_lo0 = make_smem_desc(smem_u32(w_part[1]), COUT * 16, 128);
@@ -1003,7 +1040,7 @@ conv_tc_acc2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
                     const uint64_t a_hi0 = make_smem_desc(abase, C::PLANE_B, C::SBO_A);
                     const uint64_t a_lo0 = make_smem_desc(abase + C::REGION_B, C::PLANE_B, C::SBO_A);
                     DBG_T(m0);
-                    mbar_wait(&ready_bar[half], cphase);
+                    MBAR_WAIT(&ready_bar[half], cphase);
                     DBG_T(m1);
                     DBG_ADD(m_ready, m0, m1);
                     tc_fence_after();
@@ -1011,11 +1048,12 @@ conv_tc_acc2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
                     for (int grp = 0; grp < NGRP; ++grp) {
                         const uint32_t st = it & 1;
                         DBG_T(m2);
-                        mbar_wait(&empty_bar[st], ((it >> 1) & 1) ^ 1);
+                        MBAR_WAIT(&empty_bar[st], ((it >> 1) & 1) ^ 1);
                         DBG_T(m3);
                         DBG_ADD(m_empty, m2, m3);
                         tc_fence_after();
                         const uint32_t d = tmem_base + st * STAGE_COLS + (uint32_t)(t * COUT);
+                        ISSUE_BEGIN
                         // within a flush group: all cross terms (hi*lo, lo*hi; tiny) first, hi*hi last
 #pragma unroll
                         for (int pass = 0; pass < 3; ++pass) {
@@ -1036,6 +1074,7 @@ conv_tc_acc2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
                             }
                         }
                         umma_commit(&full_bar[st]);
+                        ISSUE_END
                         DBG_T(m4);
                         DBG_ADD(m_issue, m3, m4);
                         ++it;
@@ -1044,7 +1083,7 @@ conv_tc_acc2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
                 cphase ^= 1;
             }
 #ifdef CIA_ACC_TIMING
-            if (warp == ACC_EPI_WARPS) {
+            if (warp == ACC_EPI_WARPS && lane == 0) {
                 atomicAdd(&g_acc_dbg[8], (unsigned long long)m_ready);
                 atomicAdd(&g_acc_dbg[9], (unsigned long long)m_empty);
                 atomicAdd(&g_acc_dbg[10], (unsigned long long)m_issue);
@@ -1080,7 +1119,7 @@ conv_tc_acc2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
                 for (int grp = 0; grp < NGRP; ++grp) {
                     const uint32_t st = it & 1;
                     DBG_T(e2);
-                    mbar_wait(&full_bar[st], (it >> 1) & 1);
+                    MBAR_WAIT(&full_bar[st], (it >> 1) & 1);
                     DBG_T(e3);
                     DBG_ADD(e_full, e2, e3);
                     tc_fence_after();
@@ -1368,7 +1407,7 @@ conv1_tc_split_kernel(const float* __restrict__ crops, const uint4* __restrict__
         // ================= MMA issuer: one thread, 12 MMAs per unit =================
         // (the workers never run issue code: with the issue inside four of the worker warps the
         // other four waited for them at every block barrier)
-        if (lane == 0) {
+        if (ISSUE1_WARP(true)) {
             uint64_t d_ahi[4], d_alo[4], d_whi[2], d_wlo[2];
 #pragma unroll
             for (int ph = 0; ph < 4; ++ph) {
@@ -1385,6 +1424,7 @@ conv1_tc_split_kernel(const float* __restrict__ crops, const uint4* __restrict__
                 const uint32_t buf = it & 1;
                 mbar_wait(&afull_bar[buf], (it >> 1) & 1);      // A block written AND the TMEM stage drained
                 tc_fence_after();
+                ISSUE1_BEGIN
                 const uint64_t bo = (uint64_t)(buf * (A_BUF_B >> 4));
 #pragma unroll
                 for (int ph = 0; ph < 4; ++ph) {
@@ -1394,6 +1434,7 @@ conv1_tc_split_kernel(const float* __restrict__ crops, const uint4* __restrict__
                     umma_f16(d, d_ahi[ph] + bo, d_whi[ph & 1], IDESC, 1u);
                 }
                 umma_commit(&done_bar[buf]);
+                ISSUE1_END
             }
         }
     } else {
@@ -1567,11 +1608,12 @@ final_tapsum_kernel(const __half* __restrict__ a6, const uint4* __restrict__ w_i
     const uint32_t tmem_base = tmem_base_s;
 
     if (warp == EPI_WARPS) {
-        if (lane == 0) {
+        if (ISSUE1_WARP(true)) {
             constexpr uint32_t IDESC = make_idesc(128, 32);
             const uint64_t bd0 = make_smem_desc(smem_u32(w_s), 32 * 16, 128);
             const __half* src0 = a6 + (size_t)cell0 * (A_B / 2);
             // prologue: the first two cells' activations
+            ISSUE1_BEGIN
             for (int k = 0; k < 2; ++k) {
                 const int unit = (int)blockIdx.x + k * stride;
                 if (unit < n) {
@@ -1579,12 +1621,14 @@ final_tapsum_kernel(const __half* __restrict__ a6, const uint4* __restrict__ w_i
                     bulk_load(smem_u32(smem) + k * A_B, src0 + (size_t)unit * (A_B / 2), A_B, &a_full[k]);
                 }
             }
+            ISSUE1_END
             uint32_t it = 0;
             for (int unit = blockIdx.x; unit < n; unit += stride, ++it) {
                 const uint32_t st = it & 1, ph = (it >> 1) & 1;
                 mbar_wait(&a_full[st], ph);
                 mbar_wait(&d_empty[st], ph ^ 1);            // the epilogue of two cells ago has drained this stage
                 tc_fence_after();
+                ISSUE1_BEGIN
                 const uint64_t ad0 = make_smem_desc(smem_u32(smem) + st * A_B, 1024 * 16, 128);
 #pragma unroll
                 for (int t = 0; t < 8; ++t)
@@ -1594,11 +1638,14 @@ final_tapsum_kernel(const __half* __restrict__ a6, const uint4* __restrict__ w_i
                                  ad0 + (uint64_t)((t * 128 * 16 + 2 * ks * 1024 * 16) >> 4),
                                  bd0 + (uint64_t)((2 * ks * 32 * 16) >> 4), IDESC, ks);
                 umma_commit(&d_full[st]);
+                ISSUE1_END
                 // the MMAs have read the buffer: refill it with the cell after next
                 mbar_wait(&d_full[st], ph);
                 if (unit + 2 * stride < n) {
+                    ISSUE1_BEGIN
                     mbar_expect_tx(&a_full[st], A_B);
                     bulk_load(smem_u32(smem) + st * A_B, src0 + (size_t)(unit + 2 * stride) * (A_B / 2), A_B, &a_full[st]);
+                    ISSUE1_END
                 }
             }
         }
