@@ -454,8 +454,9 @@ def run_native(args):
                         "issued_tflops": l2_tf * split, "issued_frac": l2_tf * split / pk["tf_sust"],
                         "note": "achieved = algorithmic FLOPs (37.749 MFLOP per cell x cells per launch) / launch "
                                 "time; the kernel issues 3 fp16 MMAs per product for fp32-grade features "
-                                "(issued_*), and ncu shows its tensor-core pipe 90 % busy, bound by operand reads "
-                                "from shared memory at N = 64 (profiles/r1j_cae_full.txt); traffic per launch",
+                                "(issued_*: the algorithmic ceiling of this split is 1/3 of the issued rate), and ncu "
+                                "shows its tensor-core pipe > 90 % busy, bound by operand reads from shared memory at "
+                                "N = 64 (profiles/r2k_l2_full.txt); traffic per launch",
                         "share_of_step": l2_ms / (t_ms / args.steps)}
             layers = {f"L{i + 1}": {"ms_per_step": layer_ms[i] / args.steps,
                                     "tflops": LAYER_MFLOP[i] * 1e6 * cells_per_step_local / (layer_ms[i] / args.steps * 1e-3) / 1e12}
