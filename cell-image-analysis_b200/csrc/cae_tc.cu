@@ -1208,6 +1208,210 @@ conv_tc_acc2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
 }
 
 // ---------------------------------------------------------------------------------------
+// Layer 2 with N-STACKED weights (round 2; an A/B variant, CIA_L2_STACK=1 -- measured EQUAL to the kernel above:
+// 45.9 vs 45.1-45.9 ms per 486k cells, see the end of this comment).  conv_tc_acc2_kernel above sits on the tensor-core
+// pipe's operand-delivery limit (98.5 % busy, profiles/r2k_l2_full.txt): at N = 64 an M128 x K16 MMA costs the
+// 48 cycles of its 4 KB A + 2 KB B fetch, and the hi/lo split fetches the hi activations twice (x W_hi, x W_lo).
+// Here B is the stacked image [W_hi | W_lo] (N = 128, 64 cycles): hi x [W_hi | W_lo] puts the main product and the
+// hi*lo cross term into ADJACENT column groups [main | cross] with ONE A fetch, lo x W_hi (N = 64) adds the other
+// cross term: 112 instead of 144 pipe cycles per k-step.
+// What made the first attempt at this lose (profiles/r2_umma_microbench.txt: flushes doubled) is avoided by
+// keeping the two column groups apart in time:
+//   * the MAIN group is flushed every three taps as before (its hi*hi chain must stay short, see above); the first
+//     (tap, k-step) of a flush group is issued UN-stacked (hi x W_hi with accumulate = 0 zeroes the main group only),
+//   * the CROSS group -- 2^-11 of the sum, its truncations do not matter -- accumulates over all nine taps in TMEM
+//     and is read ONCE per tile.
+// TMEM: a tile is 128 columns, the four pooling-phase tiles of a half cell fill the 512; every tile has its own
+// full / empty barrier pair, so a tile's flush runs under the other three tiles' MMAs.
+//   warps 0..15: epilogue (quadrant = warp & 3, 16 of the 64 channels = warp >> 2), thread 0 issues the TMA refills
+//   warps 16-19: MMA issue, one warp per tile (whole warp runs the loop, elect.sync issues)
+// Measured (bench.py cae_layers, L2 ms per 486k cells; VAR = timing experiments of this kernel):
+//   stacked 45.9 | every k-step un-stacked (18 N = 64 MMAs per group) 49.5 | without the lo x W_hi MMAs 33.8 | kernel above 45.1
+// i.e. time = 13 ms + 2.0 ms per N = 64 MMA slot + 3.3 ms per N = 128 slot: in this accumulate pattern an N = 128 MMA costs
+// 1.64 N = 64 MMAs (79 cycles, not the 64 of the back-to-back microbenchmark), so stacking saves 12 % of the MMA part,
+// not 22 %, and 29 % of the kernel (flushes competing with the MMAs for TMEM, final epilogue) does not shrink with it.
+// A first version with two tiles in flight (pairs alternating) ran at 55.4 ms: an MMA waits for the previous one into
+// the same TMEM columns, the pipe needs four independent accumulate chains.
+// ---------------------------------------------------------------------------------------
+template <int G, int VAR = 0>     // VAR (timing experiments only): 1 = every k-step un-stacked, 2 = no lo x W_hi MMAs (wrong results)
+__global__ void __launch_bounds__(ACC_THREADS, 1)
+conv_tc_l2_stack_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
+                        const uint4* __restrict__ w_hi, const uint4* __restrict__ w_lo, float inv_scale, float invd,
+                        const float* __restrict__ bias, const float* __restrict__ bn_s,
+                        const float* __restrict__ bn_t, __half* __restrict__ out_hi, __half* __restrict__ out_lo,
+                        float* __restrict__ feat, int n_cells, const int32_t* __restrict__ n_dev, int cell0,
+                        int chunk_cells) {
+    constexpr int CIN = 32, COUT = 64, R = 32;
+    using C = Acc2Cfg<CIN, COUT, R>;
+    constexpr int NGRP = (9 + G - 1) / G;        // main-group flushes per tile
+    constexpr int CW = COUT / 4;                 // channels per epilogue warp
+    constexpr int TILE_COLS = 2 * COUT;          // [main | cross]
+    constexpr int WS_B = 2 * C::W_B;             // stacked image: [(tap, chunk)][hi rows 0..63 | lo rows 64..127][8 halves]
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ __align__(8) uint64_t full_bar[4], empty_bar[4], ready_bar[2];
+    __shared__ uint32_t tmem_base_s;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    unsigned char* const w_s = smem + C::HALVES * C::BUF_B;
+
+    int n = dev_count(n_cells, n_dev) - cell0;
+    if (n > chunk_cells) n = chunk_cells;
+    if (n <= 0) return;
+    const int n_units = n;
+
+    if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+    if (tid == 32) {
+        for (int t = 0; t < 4; ++t) { mbar_init(&full_bar[t], 1); mbar_init(&empty_bar[t], ACC_EPI_WARPS); }
+        mbar_init(&ready_bar[0], 1); mbar_init(&ready_bar[1], 1);
+        fence_barrier_init();
+    }
+    for (int i = tid; i < WS_B / 16; i += ACC_THREADS) {
+        const int tc = i / (2 * COUT), row = i - tc * (2 * COUT);
+        reinterpret_cast<uint4*>(w_s)[i] = row < COUT ? __ldg(w_hi + tc * COUT + row) : __ldg(w_lo + tc * COUT + row - COUT);
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    const uint32_t sbase = smem_u32(smem);
+    constexpr uint32_t IDESC64 = make_idesc(128, COUT), IDESC128 = make_idesc(128, 2 * COUT);
+
+    if (warp >= ACC_EPI_WARPS) {
+        // ================= MMA issuers: one warp per pooling-phase tile =================
+        // The four tiles are four independent accumulate chains (an MMA into a tile waits for the previous one into
+        // the same columns: with only two tiles in flight the pipe ran at half rate) with their own full / empty
+        // barriers: a tile's flush runs under the other three tiles' MMAs, no explicit stages.
+        if (warp - ACC_EPI_WARPS < 4) {
+            const int t = warp - ACC_EPI_WARPS, py = t >> 1, px = t & 1;
+            const uint64_t b_s0 = make_smem_desc(smem_u32(w_s), 2 * COUT * 16, 128);       // stacked (and, with N = 64, W_hi)
+            const uint64_t b_l0 = b_s0 + (uint64_t)((COUT * 16) >> 4);                     // W_lo rows
+            uint64_t dxo[3];
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) dxo[dx] = (uint64_t)((((px + dx) & 1) * C::PAR_B + ((px + dx) >> 1) * 16) >> 4);
+            const uint32_t d_main = tmem_base + (uint32_t)(t * TILE_COLS), d_cross = d_main + COUT;
+            uint32_t use = 0, cphase = 0;                    // use: running count of this tile's flush groups
+            for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+#pragma unroll 1
+                for (int half = 0; half < 2; ++half) {
+                    MBAR_WAIT(&ready_bar[half], cphase);
+                    tc_fence_after();
+                    const uint32_t abase = sbase + half * C::BUF_B + py * C::ROW_B;
+                    const uint64_t a_hi0 = make_smem_desc(abase, C::PLANE_B, C::SBO_A);
+                    const uint64_t a_lo0 = make_smem_desc(abase + C::REGION_B, C::PLANE_B, C::SBO_A);
+#pragma unroll
+                    for (int grp = 0; grp < NGRP; ++grp, ++use) {
+                        MBAR_WAIT(&empty_bar[t], (use & 1) ^ 1);
+                        tc_fence_after();
+                        ISSUE_BEGIN
+#pragma unroll
+                        for (int tg = 0; tg < G; ++tg) {
+                            const int tap = grp * G + tg;
+                            if (tap < 9) {
+                                const int dy = tap / 3, dx = tap % 3;
+#pragma unroll
+                                for (int s = 0; s < CIN / 16; ++s) {
+                                    const uint64_t ao = dxo[dx] + (uint64_t)((dy * C::ROW_B + 2 * s * C::PLANE_B) >> 4);
+                                    const uint64_t bo = (uint64_t)(((tap * C::NCH + 2 * s) * 2 * COUT * 16) >> 4);
+                                    if ((tg == 0 && s == 0) || VAR == 1) {
+                                        // un-stacked: zero the MAIN group only; the cross group starts with the tile
+                                        umma_f16(d_main, a_hi0 + ao, b_s0 + bo, IDESC64, (tg == 0 && s == 0) ? 0u : 1u);
+                                        umma_f16(d_cross, a_hi0 + ao, b_l0 + bo, IDESC64, (grp == 0 && tg == 0 && s == 0) ? 0u : 1u);
+                                    } else {
+                                        umma_f16(d_main, a_hi0 + ao, b_s0 + bo, IDESC128, 1u);     // [main | cross] += hi x [W_hi | W_lo]
+                                    }
+                                    if (VAR != 2) umma_f16(d_cross, a_lo0 + ao, b_s0 + bo, IDESC64, 1u);         // cross += lo x W_hi
+                                }
+                            }
+                        }
+                        umma_commit(&full_bar[t]);
+                        ISSUE_END
+                    }
+                }
+                cphase ^= 1;
+            }
+        }
+    } else {
+        // ================= copy issuer / accumulating epilogue =================
+        const int q = warp & 3, cq = warp >> 2;
+        const int r = 32 * q + lane;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(cq * CW);
+        uint32_t use = 0;
+        if (tid == 0 && (int)blockIdx.x < n_units) {
+            for (int hb = 0; hb < 2; ++hb)
+                tma_load_half_block<C>(&tm_hi, &tm_lo, sbase + hb * C::BUF_B, blockIdx.x, hb, &ready_bar[hb]);
+        }
+        for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+            const int cell = cell0 + unit;
+#pragma unroll 1
+            for (int sub = 0; sub < 2; ++sub) {
+                float acc[4][CW];
+#pragma unroll
+                for (int ph = 0; ph < 4; ++ph)
+#pragma unroll
+                    for (int k = 0; k < CW; ++k) acc[ph][k] = 0.f;
+#pragma unroll 1
+                for (int grp = 0; grp < NGRP; ++grp, ++use) {
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        MBAR_WAIT(&full_bar[t], use & 1);
+                        tc_fence_after();
+                        // the last MMAs reading this half's input block are done: refill it with the same half of the next cell
+                        if (grp == NGRP - 1 && t == 3 && tid == 0 && unit + (int)gridDim.x < n_units)
+                            tma_load_half_block<C>(&tm_hi, &tm_lo, sbase + sub * C::BUF_B, unit + (int)gridDim.x, sub,
+                                                   &ready_bar[sub]);
+                        // the tile's main group; on its last flush the cross group follows (once per tile)
+#pragma unroll
+                        for (int part = 0; part < 2; ++part) {
+                            if (part == 1 && grp != NGRP - 1) break;
+                            uint32_t v[CW / 8][8];
+#pragma unroll
+                            for (int k8 = 0; k8 < CW / 8; ++k8) TMEM_LD8(lane_addr + (uint32_t)(t * TILE_COLS + part * COUT + k8 * 8), v[k8]);
+#pragma unroll
+                            for (int k8 = 0; k8 < CW / 8; ++k8) TMEM_WAIT8(v[k8]);
+                            if (part == 1 || grp != NGRP - 1) {         // all TMEM reads of this tile's step are done
+                                tc_fence_before();
+                                __syncwarp();
+                                if (lane == 0) mbar_arrive(&empty_bar[t]);
+                            }
+#pragma unroll
+                            for (int k8 = 0; k8 < CW / 8; ++k8)
+#pragma unroll
+                                for (int k = 0; k < 8; k += 2) fadd2(acc[t][k8 * 8 + k], acc[t][k8 * 8 + k + 1], v[k8][k], v[k8][k + 1]);
+                        }
+                    }
+                }
+                // final epilogue from registers: bias -> ReLU -> BN -> 2x2 max -> hi/lo fp16 (+ fp32 tap)
+                constexpr int RO = R / 2;
+                const int Y = r >> 3, X = 8 * sub + (r & 7);
+#pragma unroll
+                for (int k8 = 0; k8 < CW / 8; ++k8) {
+                    const int c0 = cq * CW + k8 * 8;
+                    float o[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const float b = __ldg(bias + c0 + k), sc = __ldg(bn_s + c0 + k), sh = __ldg(bn_t + c0 + k);
+                        const float m = fmaxf(fmaxf(acc[0][k8 * 8 + k], acc[1][k8 * 8 + k]), fmaxf(acc[2][k8 * 8 + k], acc[3][k8 * 8 + k]));
+                        o[k] = pooled_act(m, inv_scale, invd, b, sc, sh);
+                    }
+                    const size_t off = ((((size_t)cell * (COUT / 8) + c0 / 8) * RO + Y) * RO + X) * 8;
+                    split_store8(o, out_hi + off, out_lo ? out_lo + off : nullptr);
+                    if (feat) {
+                        float4* f = reinterpret_cast<float4*>(feat + (size_t)cell * (RO * RO * COUT) +
+                                                             (size_t)(Y * RO + X) * COUT + c0);
+                        f[0] = make_float4(o[0], o[1], o[2], o[3]);
+                        f[1] = make_float4(o[4], o[5], o[6], o[7]);
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------------
 // Layer 1 (Cin = 1, K = 9)
 // ---------------------------------------------------------------------------------------
 // Layer 1 on the CUDA cores: with K = 9 the layer is epilogue-bound, not MMA-bound, and plain
@@ -1838,6 +2042,27 @@ int launch_tc_acc2(cia_ctx* h, const CaeWeights& w, int layer, const __half* in_
     return CIA_OK;
 }
 
+template <int G, int VAR = 0>
+int launch_l2_stack(cia_ctx* h, const CaeWeights& w, const __half* in_hi, const __half* in_lo, int buf_cells,
+                    __half* out_hi, __half* out_lo, float* feat, int n, const int32_t* n_dev, int cell0, int chunk,
+                    cudaStream_t s) {
+    using C = Acc2Cfg<32, 64, 32>;
+    auto kern = conv_tc_l2_stack_kernel<G, VAR>;
+    if (first_use(h, (const void*)kern))
+        CIA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_B));
+    CUtensorMap tm_hi, tm_lo;
+    int rc;
+    if ((rc = encode_act_map(h, &tm_hi, in_hi, C::NCH, C::R, buf_cells, C::BOX_X, C::FILL_ROWS))) return rc;
+    if ((rc = encode_act_map(h, &tm_lo, in_lo, C::NCH, C::R, buf_cells, C::BOX_X, C::FILL_ROWS))) return rc;
+    int grid = chunk;
+    if (grid > h->num_sms) grid = h->num_sms;
+    kern<<<grid, ACC_THREADS, C::SMEM_B, s>>>(tm_hi, tm_lo, (const uint4*)w.tc_w[1][0], (const uint4*)w.tc_w[1][1],
+                                              w.tc_inv_scale[1], w.tc_inv_scale[1] * acc_debias(h, 1), w.bias[1],
+                                              w.bn_scale[1], w.bn_shift[1], out_hi, out_lo, feat, n, n_dev, cell0, chunk);
+    CIA_LAUNCH_CHECK();
+    return CIA_OK;
+}
+
 // One B image: [(tap*NCH + chunk)*N + n][8] halves = w[tap][chunk*8 + j][n] * 2^sw, hi and lo parts.
 static void pack_image(const std::vector<float>& w /* [taps][cin][n] */, int taps, int cin, int N,
                        int n_real, int sw, std::vector<__half>& hi, std::vector<__half>& lo,
@@ -2076,7 +2301,12 @@ int k_cae_forward_tc(cia_ctx* h, const float* crops, int n, const int32_t* n_dev
             // was built and measured in round 2: 53.3 vs 51.5 ms -- its flushes double (main + cross column
             // groups) and the drain of a two-tile stage no longer hides under the other stage's MMAs
             static const int l2_g = [] { const char* e = getenv("CIA_L2_TAPS_PER_FLUSH"); return e ? atoi(e) : 3; }();
-            if (l2_g == 0) rc = launch_tc_acc<32, 64, 32, 1>(h, ae, 1, a1h, a1l, a2h, a2l, a2f, n, n_dev, c0, chunk, s);
+            // CIA_L2_STACK=1: the N-stacked kernel (conv_tc_l2_stack_kernel; 2 / 3: its timing experiments) for A/B runs
+            static const int l2_stack = [] { const char* e = getenv("CIA_L2_STACK"); return e ? atoi(e) : 0; }();
+            if (l2_stack == 2 && l2_g == 3) rc = launch_l2_stack<3, 1>(h, ae, A1h, A1l, CH, a2h, a2l, a2f, n, n_dev, c0, chunk, s);
+            else if (l2_stack == 3 && l2_g == 3) rc = launch_l2_stack<3, 2>(h, ae, A1h, A1l, CH, a2h, a2l, a2f, n, n_dev, c0, chunk, s);
+            else if (l2_stack && l2_g == 3) rc = launch_l2_stack<3>(h, ae, A1h, A1l, CH, a2h, a2l, a2f, n, n_dev, c0, chunk, s);
+            else if (l2_g == 0) rc = launch_tc_acc<32, 64, 32, 1>(h, ae, 1, a1h, a1l, a2h, a2l, a2f, n, n_dev, c0, chunk, s);
             else if (l2_g == 1) rc = launch_tc_acc2<32, 64, 32, 1>(h, ae, 1, A1h, A1l, CH, a2h, a2l, a2f, n, n_dev, c0, chunk, s);
             else if (l2_g == 9) rc = launch_tc_acc2<32, 64, 32, 9>(h, ae, 1, A1h, A1l, CH, a2h, a2l, a2f, n, n_dev, c0, chunk, s);
             else if (l2_g == 2) rc = launch_tc_acc2<32, 64, 32, 2>(h, ae, 1, A1h, A1l, CH, a2h, a2l, a2f, n, n_dev, c0, chunk, s);
