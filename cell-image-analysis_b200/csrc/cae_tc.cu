@@ -580,36 +580,6 @@ __device__ __forceinline__ void stage_pool_cell(const __half* __restrict__ in_hi
     }
 }
 
-// The same block through cp.async (LDGSTS): all of a thread's 16-byte copies are in flight at once and
-// land in shared memory without passing through registers -- ONE memory latency per cell instead of one
-// per batch of register-staged loads; the halo is zero-filled by copies of source size 0.
-template <class A, int R, int NT>
-__device__ __forceinline__ void stage_pool_cell_async(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo,
-                                                      unsigned char* a0, unsigned char* a1, int cell, int tid) {
-    constexpr int N_UNITS16 = A::NCH * A::FILL_ROWS * A::COLS;
-    constexpr int ITERS = (N_UNITS16 + NT - 1) / NT;
-    const uint32_t s0 = smem_u32(a0), s1 = smem_u32(a1);
-    const uint4* bh = reinterpret_cast<const uint4*>(in_hi) + (size_t)cell * A::NCH * R * R;
-    const uint4* bl = reinterpret_cast<const uint4*>(in_lo) + (size_t)cell * A::NCH * R * R;
-#pragma unroll
-    for (int i = 0; i < ITERS; ++i) {
-        const int idx = tid + i * NT;
-        if (idx < N_UNITS16) {
-            const int c = idx / (A::FILL_ROWS * A::COLS);
-            const int rem = idx - c * (A::FILL_ROWS * A::COLS);
-            const int ry = rem / A::COLS, rc = rem - ry * A::COLS;
-            const int y = ry - 1, x = rc - 1;
-            const uint32_t dst = (uint32_t)(((c * 2 + (rc & 1)) * A::FILL_ROWS + ry) * A::ROW_UNITS + (rc >> 1)) * 16u;
-            const bool in = y >= 0 && y < R && x >= 0 && x < R;
-            const size_t src = in ? ((size_t)c * R + y) * R + x : 0;
-            const uint32_t sz = in ? 16u : 0u;
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s0 + dst), "l"(bh + src), "r"(sz) : "memory");
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s1 + dst), "l"(bl + src), "r"(sz) : "memory");
-        }
-    }
-    asm volatile("cp.async.wait_all;" ::: "memory");
-}
-
 #ifdef CIA_ACC_TIMING
 __device__ unsigned long long g_acc_dbg[16];
 #define DBG_T(var) const long long var = clock64()
@@ -619,7 +589,7 @@ __device__ unsigned long long g_acc_dbg[16];
 #define DBG_ADD(acc, a, b)
 #endif
 
-template <int CIN, int COUT, int R, int G, bool ASYNC_STAGE = false>
+template <int CIN, int COUT, int R, int G>
 __global__ void __launch_bounds__(ACC_THREADS, 1)
 conv_tc_acc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo,
                    const uint4* __restrict__ w_hi, const uint4* __restrict__ w_lo, float inv_scale, float invd,
@@ -795,8 +765,7 @@ conv_tc_acc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
             // first cell is staged here, the others right after the previous cell's last flush (below;
             // R = 16 only -- the R = 32 instance holds 64 accumulators per thread at that point)
             if (!ROWPAIR || unit == (int)blockIdx.x) {
-                if (ASYNC_STAGE) stage_pool_cell_async<C, R, EPT>(in_hi, in_lo, a_part[0], a_part[1], cell, tid);
-                else stage_pool_cell<C, R, EPT, 6>(in_hi, in_lo, a_part[0], a_part[1], cell, tid);
+                stage_pool_cell<C, R, EPT, 6>(in_hi, in_lo, a_part[0], a_part[1], cell, tid);
                 fence_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&ready_bar);
@@ -868,8 +837,7 @@ conv_tc_acc_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
             // the cell's last MMAs have completed (its last full barrier): the input block is free, so the
             // next cell is staged NOW and its MMAs run under the final epilogue below
             if (ROWPAIR && sub == C::HALVES - 1 && unit + (int)gridDim.x < n_units) {
-                if (ASYNC_STAGE) stage_pool_cell_async<C, R, EPT>(in_hi, in_lo, a_part[0], a_part[1], cell + (int)gridDim.x, tid);
-                else stage_pool_cell<C, R, EPT, 6>(in_hi, in_lo, a_part[0], a_part[1], cell + (int)gridDim.x, tid);
+                stage_pool_cell<C, R, EPT, 6>(in_hi, in_lo, a_part[0], a_part[1], cell + (int)gridDim.x, tid);
                 fence_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&ready_bar);
@@ -1969,12 +1937,12 @@ static inline void acc_timing_dump(const char*, int, int, int, int, cudaStream_t
 // (cia_set_option "cae_l2_debias" / "cae_l3_debias", 0 = off; derivation in DESIGN.md section 5)
 static float acc_debias(const cia_ctx* h, int layer) { return h->cae_debias[layer == 1 ? 1 : 2] * 5.9604645e-8f; }
 
-template <int CIN, int COUT, int R, int G = 1, bool ASYNC_STAGE = false>
+template <int CIN, int COUT, int R, int G = 1>
 int launch_tc_acc(cia_ctx* h, const CaeWeights& w, int layer, const __half* in_hi, const __half* in_lo,
                   __half* out_hi, __half* out_lo, float* feat, int n, const int32_t* n_dev, int cell0,
                   int chunk, cudaStream_t s) {
     using C = AccCfg<CIN, COUT, R>;
-    auto kern = conv_tc_acc_kernel<CIN, COUT, R, G, ASYNC_STAGE>;
+    auto kern = conv_tc_acc_kernel<CIN, COUT, R, G>;
     if (first_use(h, (const void*)kern))
         CIA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_B));
     int grid = chunk;
@@ -2322,11 +2290,10 @@ int k_cae_forward_tc(cia_ctx* h, const float* crops, int n, const int32_t* n_dev
                 // the register-staged kernel (cae 75.6 vs 74.0 ms per 242k cells), which stays the default.
                 static const int l3_tma = [] { const char* e = getenv("CIA_L3_KERNEL"); return e ? atoi(e) : 0; }();
                 static const int l3_g = [] { const char* e = getenv("CIA_L3_TAPS_PER_FLUSH"); return e ? atoi(e) : 1; }();
-                // CIA_L3_ASYNC=1: the input block through cp.async (one memory latency per cell instead of two)
-                static const int l3_async = [] { const char* e = getenv("CIA_L3_ASYNC"); return e ? atoi(e) : 0; }();
+                // Measured and dropped in round 2: the input block through cp.async (27.3 vs 23.7 ms),
+                // four TMEM stages with the MMAs of two flush groups interleaved (23.8 vs 22.1 ms)
                 if (l3_tma) rc = launch_tc_acc2<64, 32, 16, 1>(h, ae, 2, A2h, A2l, CH, a3h, nullptr, feat, n, n_dev, c0, chunk, s);
                 else if (l3_g == 3) rc = launch_tc_acc<64, 32, 16, 3>(h, ae, 2, a2h, a2l, a3h, nullptr, feat, n, n_dev, c0, chunk, s);
-                else if (l3_async) rc = launch_tc_acc<64, 32, 16, 1, true>(h, ae, 2, a2h, a2l, a3h, nullptr, feat, n, n_dev, c0, chunk, s);
                 else rc = launch_tc_acc<64, 32, 16, 1>(h, ae, 2, a2h, a2l, a3h, nullptr, feat, n, n_dev, c0, chunk, s);
                 if (rc) return rc;
             }
