@@ -492,18 +492,6 @@ constexpr int PAR_F = 2048;                             // scaler constants of u
 constexpr int SMEM_B = STAGES * STAGE_B + RING * TM * 4 + PAR_F * 16;
 }  // namespace pcatc
 
-#define TMEM_LD16(taddr, v)                                                                               \
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "                                                \
-                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"                         \
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),     \
-                   "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), \
-                   "=r"(v[14]), "=r"(v[15]) : "r"(taddr))
-#define TMEM_WAIT16(v)                                                                                    \
-    asm volatile("tcgen05.wait::ld.sync.aligned;"                                                         \
-                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]),     \
-                   "+r"(v[7]), "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), \
-                   "+r"(v[14]), "+r"(v[15]) :: "memory")
-
 __global__ void __launch_bounds__(pcatc::NT, 1)
 scaler_pca_tc_kernel(const float* __restrict__ feat, int n_cells, const int32_t* __restrict__ n_dev, int F, int C,
                      const float4* __restrict__ par_g /* {center, RN(1/scale), scale hi, scale lo} per feature */,

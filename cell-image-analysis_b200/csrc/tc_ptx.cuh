@@ -80,6 +80,18 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                  : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), \
                    "+r"(v[7]) :: "memory")
 
+#define TMEM_LD16(taddr, v)                                                                               \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "                                                \
+                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"                         \
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),     \
+                   "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), \
+                   "=r"(v[14]), "=r"(v[15]) : "r"(taddr))
+#define TMEM_WAIT16(v)                                                                                    \
+    asm volatile("tcgen05.wait::ld.sync.aligned;"                                                         \
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]),     \
+                   "+r"(v[7]), "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), \
+                   "+r"(v[14]), "+r"(v[15]) :: "memory")
+
 // K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
 // canonical layout ((8,m),2):((16 B, SBO), LBO) in 16-byte units.
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
