@@ -617,8 +617,8 @@ scaler_pca_tc_kernel(const float* __restrict__ feat, int n_cells, const int32_t*
             }
             __syncwarp();
         } else if (warp >= MMA_WARP) {
-            // ================= MMA issuers (alternate stages) =================
-            if (lane == 0) {
+            // ================= MMA issuers (alternate stages; the whole warp runs the loop, one elected lane issues) =================
+            {
                 const uint32_t me = (uint32_t)(warp - MMA_WARP);
                 const uint64_t d0 = make_smem_desc(s_addr, K8_B, 128);
                 for (int kc = 0; kc < n_kc; ++kc, ++cnt) {
@@ -627,25 +627,27 @@ scaler_pca_tc_kernel(const float* __restrict__ feat, int n_cells, const int32_t*
                     mbar_wait_sleep(&tempty_bar[buf], ((cnt / NBUF) & 1) ^ 1);
                     mbar_wait_sleep(&full_bar[st], (cnt / STAGES) & 1);
                     tc_fence_after();
-                    const uint32_t d = tmem_base + buf * TN;
-                    const uint64_t ah = d0 + (uint64_t)((st * STAGE_B) >> 4), al = ah + (HALF_B >> 4);
-                    const uint64_t bh = ah + (2 * HALF_B >> 4), bl = ah + (3 * HALF_B >> 4);
+                    if (elect_one()) {
+                        const uint32_t d = tmem_base + buf * TN;
+                        const uint64_t ah = d0 + (uint64_t)((st * STAGE_B) >> 4), al = ah + (HALF_B >> 4);
+                        const uint64_t bh = ah + (2 * HALF_B >> 4), bl = ah + (3 * HALF_B >> 4);
 #pragma unroll
-                    for (int s = 0; s < KC / 16; ++s) {
-                        const uint64_t so = (uint64_t)(s * ((2 * K8_B) >> 4));
-                        umma_f16(d, ah + so, bl + so, IDESC, s == 0 ? 0u : 1u);
-                        umma_f16(d, al + so, bh + so, IDESC, 1u);
-                    }
+                        for (int s = 0; s < KC / 16; ++s) {
+                            const uint64_t so = (uint64_t)(s * ((2 * K8_B) >> 4));
+                            umma_f16(d, ah + so, bl + so, IDESC, s == 0 ? 0u : 1u);
+                            umma_f16(d, al + so, bh + so, IDESC, 1u);
+                        }
 #pragma unroll
-                    for (int s = 0; s < KC / 16; ++s) {
-                        const uint64_t so = (uint64_t)(s * ((2 * K8_B) >> 4));
-                        umma_f16(d, ah + so, bh + so, IDESC, 1u);
+                        for (int s = 0; s < KC / 16; ++s) {
+                            const uint64_t so = (uint64_t)(s * ((2 * K8_B) >> 4));
+                            umma_f16(d, ah + so, bh + so, IDESC, 1u);
+                        }
+                        umma_commit(&empty_bar[st]);
+                        umma_commit(&tfull_bar[buf]);
                     }
-                    umma_commit(&empty_bar[st]);
-                    umma_commit(&tfull_bar[buf]);
+                    __syncwarp();
                 }
             }
-            __syncwarp();
         } else {
             // ================= epilogue: fp32 round-to-nearest accumulation of the stage partials =================
             const int ew = warp - EPI_WARP0, q = ew & 3, hf = ew >> 2, row = 32 * q + lane;
