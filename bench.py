@@ -318,7 +318,8 @@ def run_native(args):
         rle_fraction = 1.0
     bs = BatchScreen(eng, H, W, max_label, chunk_fields=Fc, n_strains=n_strains,
                      label_transport=args.label_transport, host_threads=args.host_threads,
-                     rle_fraction=rle_fraction, host_buffers=args.host_buffers)
+                     rle_fraction=rle_fraction, host_buffers=args.host_buffers,
+                     image_transport="dense" if args.image_transport == "auto" else args.image_transport)
 
     def barrier():
         if world > 1:
@@ -478,7 +479,7 @@ def run_native(args):
                        "precision": args.precision, "l2_policy": "inputs larger than L2"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": float(ems.item()) / args.steps,
-                    "label_transport": args.label_transport, "rle_fraction": round(getattr(bs, "last_rle_share", bs.rle_fraction), 3),
+                    "label_transport": args.label_transport, "image_transport": bs.image_transport, "rle_fraction": round(getattr(bs, "last_rle_share", bs.rle_fraction), 3),
                     "host_threads": args.host_threads or (os.cpu_count() or 1),
                     "host": dict(host, encoder_gbs=float(enc_gbs.item()),
                                  host_dram_traffic_gbs=(4.0 + 2.0) * H * W * (e2e_value / (cells_per_step_local / NF)) / 1e9,
@@ -540,6 +541,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-svm-extras", action="store_true")
     ap.add_argument("--host-buffers", type=int, default=2, help="device chunk buffers of the host pass (A/B)")
+    ap.add_argument("--image-transport", default="auto", choices=["auto", "patches", "dense"],
+                    help="e2e pass: send whole images or only the bbox rectangles of the labelled regions "
+                         "(auto = dense: measured faster on this host at 1 and 2 GPUs, DESIGN.md section 6)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -89,6 +89,10 @@ SIGNATURES = {
     "cia_label_scan_rle": (_I, [_P, _P, C.c_size_t, _I, _I, _I, _I, _P, _P]),
     "cia_screen_fields_rle": (_I, [_P, _P, _P, C.c_size_t, _I, _I, _I, _I, C.POINTER(Params), _I, _P, _I, _P, _P,
                                    C.POINTER(Scores), _P, _P, _P, _P, _I, _P]),
+    "cia_rle_encode_pack_fields": (_I, [_P, _P, _I, _I, _I, _P, C.c_size_t, _P, _P, _I, _P, C.c_size_t, _P, _I]),
+    "cia_patch_upload": (_I, [_P, _P, _I, C.c_size_t, _P, _P, _P]),
+    "cia_screen_fields_rle_patches": (_I, [_P, _P, _P, C.c_size_t, _P, C.c_size_t, _I, _I, _I, _I, C.POINTER(Params), _I,
+                                           _P, _I, _P, _P, C.POINTER(Scores), _P, _P, _P, _P, _I, _P]),
     "cia_tiff_lzw_decode": (C.c_longlong, [_P, C.c_size_t, _P, C.c_size_t]),
     "cia_tiff_packbits_decode": (C.c_longlong, [_P, C.c_size_t, _P, C.c_size_t]),
     "cia_profile_begin": (_I, [_P, _I]),

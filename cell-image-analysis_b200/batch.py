@@ -26,14 +26,22 @@ class BatchScreen:
     def __init__(self, engine, H: int, W: int, max_label: int, chunk_fields: int = 16,
                  n_strains: int = 1, cells_per_field_cap: int | None = None,
                  label_transport: str = "rle", host_threads: int = 0, rle_fraction: float = 1.0,
-                 scan_runs: bool = True, host_buffers: int = 2):
+                 scan_runs: bool = True, host_buffers: int = 2, image_transport: str = "dense"):
         """``label_transport``: "rle" run-length encodes the int32 label fields on the host
         cores (csrc/transport.cu) so that only the runs cross PCIe; "raw" copies them as is.
         ``rle_fraction`` < 1 sends only that share of the chunks as runs and the rest raw (several
         ranks sharing the host cores: the encoder and the PCIe link then work side by side).
         ``scan_runs``: build the region table from the runs themselves (``cia_screen_fields_rle``);
         False expands them to the dense field first (``cia_rle_expand``)."""
-        assert label_transport in ("rle", "raw")
+        """``image_transport``: "dense" copies whole images; "patches" (with run-length labels scanned from the
+        runs) sends only the bbox rectangles of the labelled regions -- all the device ever reads of an image --
+        packed by the encoder threads and scattered into a dense device buffer after the region scan.  It cuts
+        the H2D bytes 5x (8.9 -> 1.65 GB per 1024 fields) but costs host time: on the benchmark host (16-24
+        vCPUs) the end-to-end rate is no better with it (one GPU: 172-186 vs 170 ms, two: 324-409 vs 276-289
+        ms per step), so "dense" is the default; it is the better choice where PCIe, not the host cores, is
+        the scarce resource."""
+        assert label_transport in ("rle", "raw") and image_transport in ("patches", "dense")
+        self.image_transport = image_transport
         self.label_transport, self.host_threads = label_transport, host_threads
         self.rle_fraction = 1.0 if label_transport == "rle" and rle_fraction >= 1.0 else \
             (0.0 if label_transport == "raw" else max(0.0, float(rle_fraction)))
@@ -107,6 +115,12 @@ class BatchScreen:
                     h_rle=[torch.empty((self.Fc, sw), dtype=torch.int32, pin_memory=True) for _ in range(self.NB)],
                     d_rle=[torch.empty((self.Fc, sw), dtype=torch.int32, device=d) for _ in range(self.NB)],
                     words=[np.zeros(self.Fc, np.uint32) for _ in range(self.NB)])
+                if self.image_transport == "patches" and self.scan_runs:
+                    cap_px = self.H * self.W // 2          # a field whose bbox rectangles exceed half its pixels goes densely
+                    self._stage.update(
+                        h_patch=[torch.empty((self.Fc, cap_px), dtype=torch.int16, pin_memory=True) for _ in range(self.NB)],
+                        d_patch=[torch.empty((self.Fc, cap_px), dtype=torch.int16, device=d) for _ in range(self.NB)],
+                        patch_px=[np.zeros(self.Fc, np.uint32) for _ in range(self.NB)])
         if getattr(self, "_host_chunks", 0) < n_chunks:
             cap = self.cap
             pin = dict(pin_memory=True)
@@ -146,28 +160,47 @@ class BatchScreen:
             p0 = (i * self.Fc) % P
             f = self.rle_fraction
             rle = self.label_transport == "rle" and int((i + 1) * f) > int(i * f)
-            with torch.cuda.stream(self.copy):
-                self.copy.wait_event(S["done"][b])
-                S["img"][b].copy_(images_pinned[p0:p0 + self.Fc], non_blocking=True)
+            use_patches = rle and "h_patch" in S
+            patches_ok = False
+            if not use_patches:
+                with torch.cuda.stream(self.copy):
+                    self.copy.wait_event(S["done"][b])
+                    S["img"][b].copy_(images_pinned[p0:p0 + self.Fc], non_blocking=True)
             if rle:
-                # the host encodes chunk i while its image copy and the device's work on chunk i-1
-                # are in flight; the slot buffer is reused only after its previous upload (chunk i-2)
+                # the host encodes chunk i while the device works on chunk i-1; the staging buffers are reused
+                # only after their previous upload (chunk i-NB)
                 S["ready"][b].synchronize()
                 t0 = time.perf_counter()
-                rle = eng.rle_encode(labels_pinned[p0:p0 + self.Fc], S["h_rle"][b], S["words"][b],
-                                     self.host_threads)
+                if use_patches:
+                    rle, patches_ok = eng.rle_encode_pack(labels_pinned[p0:p0 + self.Fc], images_pinned[p0:p0 + self.Fc],
+                                                          S["h_rle"][b], S["words"][b], self.max_label, S["h_patch"][b],
+                                                          S["patch_px"][b], self.host_threads)
+                else:
+                    rle = eng.rle_encode(labels_pinned[p0:p0 + self.Fc], S["h_rle"][b], S["words"][b],
+                                         self.host_threads)
                 self.encode_seconds += time.perf_counter() - t0
             with torch.cuda.stream(self.copy):
+                if use_patches:
+                    self.copy.wait_event(S["done"][b])
+                    if rle and patches_ok:
+                        eng.patch_upload(S["h_patch"][b], S["patch_px"][b], S["d_patch"][b])
+                        self.h2d_bytes += 2 * int(S["patch_px"][b].sum())
+                    else:
+                        patches_ok = False
+                        S["img"][b].copy_(images_pinned[p0:p0 + self.Fc], non_blocking=True)
+                        self.h2d_bytes += 2 * px
+                else:
+                    self.h2d_bytes += 2 * px
                 if rle:
                     n_rle += 1
                     if self.scan_runs:
                         eng.rle_upload(S["h_rle"][b], S["words"][b], S["d_rle"][b])
                     else:
                         eng.rle_upload_expand(S["h_rle"][b], S["words"][b], S["d_rle"][b], S["lab"][b])
-                    self.h2d_bytes += 2 * px + 4 * int(S["words"][b].sum())
+                    self.h2d_bytes += 4 * int(S["words"][b].sum())
                 else:
                     S["lab"][b].copy_(labels_pinned[p0:p0 + self.Fc], non_blocking=True)
-                    self.h2d_bytes += 6 * px
+                    self.h2d_bytes += 4 * px
                 S["ready"][b].record(self.copy)
             with torch.cuda.stream(self.compute):
                 self.compute.wait_event(S["ready"][b])
@@ -175,7 +208,8 @@ class BatchScreen:
                 o = self.out[b]
                 st = None if strain_of_visit is None else strain_of_visit[i * self.Fc:(i + 1) * self.Fc]
                 eng.screen_fields(S["img"][b], S["lab"][b], self.max_label, o, field_strain=st, acc=self.acc,
-                                  rle_slots=S["d_rle"][b] if rle and self.scan_runs else None)
+                                  rle_slots=S["d_rle"][b] if rle and self.scan_runs else None,
+                                  patches=S["d_patch"][b] if use_patches and patches_ok else None)
                 S["done"][b].record(self.compute)
                 S["out_ready"][b].record(self.compute)
             with torch.cuda.stream(self.d2h):

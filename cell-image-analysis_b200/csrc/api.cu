@@ -350,7 +350,7 @@ static int screen_fields_impl(cia_handle h, const uint16_t* images, const int32_
                       cia_cell* cells, int cells_cap, int32_t* n_cells_dev,
                       int32_t* field_counts_dev, const cia_scores* scores, float* crops32,
                       float* features, const int32_t* field_strain, double* acc, int n_strains,
-                      void* stream) {
+                      void* stream, const uint16_t* patches = nullptr, size_t patch_cap_px = 0) {
     if (!h) return bad_handle();
     if (!images || (!labels && !rle_slots) || !params || !cells || !n_cells_dev || !scores) {
         h->err = "cia_screen_fields: null pointer";
@@ -378,6 +378,9 @@ static int screen_fields_impl(cia_handle h, const uint16_t* images, const int32_
     if (labels) rc = k_label_scan(h, labels, n_fields, H, W, max_label, regions, s);
     else rc = k_label_scan_rle(h, rle_slots, slot_words, n_fields, H, W, max_label, regions, s);
     if (rc) return rc;
+    // patch transport: the bbox rectangles of the regions just found go back to their places in the dense image
+    if (patches && (rc = k_patch_scatter(h, patches, patch_cap_px, regions, n_fields, max_label, H, W,
+                                         const_cast<uint16_t*>(images), s))) return rc;
     CIA_MARK(1);
     if ((rc = k_filter(h, images, n_fields, H, W, max_label, regions, params, cells, cells_cap,
                        n_cells_dev, field_counts_dev, s))) return rc;
@@ -437,6 +440,18 @@ int cia_screen_fields_rle(cia_handle h, const uint16_t* images, const uint32_t* 
     return screen_fields_impl(h, images, nullptr, rle_slots, slot_words, n_fields, H, W, max_label, params,
                               precision, cells, cells_cap, n_cells_dev, field_counts_dev, scores, crops32,
                               features, field_strain, acc, n_strains, stream);
+}
+
+int cia_screen_fields_rle_patches(cia_handle h, uint16_t* images, const uint16_t* patches, size_t patch_cap_px,
+                                  const uint32_t* rle_slots, size_t slot_words, int n_fields, int H, int W,
+                                  int max_label, const cia_params* params, int precision, cia_cell* cells,
+                                  int cells_cap, int32_t* n_cells_dev, int32_t* field_counts_dev,
+                                  const cia_scores* scores, float* crops32, float* features,
+                                  const int32_t* field_strain, double* acc, int n_strains, void* stream) {
+    if (h && (!rle_slots || !patches || patch_cap_px == 0)) { h->err = "cia_screen_fields_rle_patches: null pointer"; return CIA_E_ARG; }
+    return screen_fields_impl(h, images, nullptr, rle_slots, slot_words, n_fields, H, W, max_label, params,
+                              precision, cells, cells_cap, n_cells_dev, field_counts_dev, scores, crops32,
+                              features, field_strain, acc, n_strains, stream, patches, patch_cap_px);
 }
 
 int cia_label_scan_rle(cia_handle h, const uint32_t* rle_slots, size_t slot_words, int n_fields, int H,

@@ -169,6 +169,8 @@ __device__ __forceinline__ T warp_sum(T v) {
 // stage-level forward declarations (one per .cu)
 int k_label_scan_rle(cia_ctx* h, const uint32_t* slots, size_t slot_words, int n_fields, int H, int W,
                      int max_label, cia_region* regions, cudaStream_t s);
+int k_patch_scatter(cia_ctx* h, const uint16_t* patches, size_t cap_px, const cia_region* regions, int n_fields,
+                    int max_label, int H, int W, uint16_t* images, cudaStream_t s);
 int k_label_scan(cia_ctx* h, const int32_t* labels, int n_fields, int H, int W, int max_label,
                  cia_region* regions, cudaStream_t s);
 int k_filter(cia_ctx* h, const uint16_t* images, int n_fields, int H, int W, int max_label,

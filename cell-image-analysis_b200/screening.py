@@ -211,6 +211,29 @@ class Engine:
             raise _lib.CiaError(rc, "cia_rle_encode_fields failed")
         return True
 
+    def rle_encode_pack(self, labels_host: torch.Tensor, images_host: torch.Tensor, slots_host: torch.Tensor,
+                        field_words: np.ndarray, label_cap: int, patches_host: torch.Tensor, patch_px: np.ndarray,
+                        threads: int = 0):
+        """``rle_encode`` + the patch transport of the image: the thread that encoded a field also packs the
+        bbox rectangles of its labels from ``images_host`` [F,H,W] (int16-viewed uint16) into ``patches_host``
+        [F, patch_cap_px].  Returns (labels_ok, patches_ok): False where a field did not fit its slot."""
+        F, H, W = labels_host.shape
+        rc = self.lib.cia_rle_encode_pack_fields(labels_host.data_ptr(), images_host.data_ptr(), F, H, W,
+                                                 slots_host.data_ptr(), slots_host.shape[1], field_words.ctypes.data,
+                                                 None, int(label_cap), patches_host.data_ptr(), patches_host.shape[1],
+                                                 patch_px.ctypes.data, threads)
+        if rc == _lib.CIA_E_CAPACITY:
+            return False, False
+        if rc != 0:
+            raise _lib.CiaError(rc, "cia_rle_encode_pack_fields failed")
+        return True, bool((patch_px != 0xFFFFFFFF).all())
+
+    def patch_upload(self, patches_host: torch.Tensor, patch_px: np.ndarray, patches_dev: torch.Tensor):
+        """Async: copy the used pixels of every field's patch slot."""
+        F, cap = patches_host.shape
+        self._check(self.lib.cia_patch_upload(self.h, patches_host.data_ptr(), F, cap, patch_px.ctypes.data,
+                                              patches_dev.data_ptr(), self._stream()))
+
     def rle_upload_expand(self, slots_host: torch.Tensor, field_words: np.ndarray, slots_dev: torch.Tensor,
                           labels_dev: torch.Tensor):
         """Async: copy the used words of every slot and expand to dense int32 labels [F,H,W]."""
@@ -261,14 +284,22 @@ class Engine:
 
     def screen_fields(self, images: torch.Tensor, labels: torch.Tensor, max_label: int, out: dict,
                       field_strain: torch.Tensor = None, acc: torch.Tensor = None, precision=None,
-                      rle_slots: torch.Tensor = None):
+                      rle_slots: torch.Tensor = None, patches: torch.Tensor = None):
         """Enqueue the whole path for device-resident fields (no host sync).  With ``rle_slots``
         ([F, slot_words] device words of the run-length transport) ``labels`` is ignored and the
-        region scan runs on the runs themselves."""
+        region scan runs on the runs themselves.  With ``patches`` as well ([F, patch_cap_px] device pixels of
+        the patch transport) ``images`` is a dense SCRATCH buffer the bbox rectangles are scattered into."""
         F, H, W = images.shape
         sc = self._scores(out)
         prec = self.precision if precision is None else precision
         ns = 0 if acc is None else acc.shape[0]
+        if rle_slots is not None and patches is not None:
+            self._check(self.lib.cia_screen_fields_rle_patches(
+                self.h, _ptr(images), _ptr(patches), patches.shape[1], _ptr(rle_slots), rle_slots.shape[1], F, H, W,
+                max_label, C.byref(self.params), prec, _ptr(out["cells"]), out["cap"], _ptr(out["counts"]),
+                C.c_void_p(out["counts"].data_ptr() + 4), C.byref(sc), _ptr(out["crops"]),
+                _ptr(out["features"]), _ptr(field_strain), _ptr(acc), ns, self._stream()))
+            return
         if rle_slots is not None:
             self._check(self.lib.cia_screen_fields_rle(
                 self.h, _ptr(images), _ptr(rle_slots), rle_slots.shape[1], F, H, W, max_label,

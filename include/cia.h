@@ -245,6 +245,30 @@ int cia_rle_upload(cia_handle h, const uint32_t* slots_host, int n_fields, size_
                    const uint32_t* field_words, uint32_t* slots_dev, void* stream);
 int cia_rle_expand(cia_handle h, const uint32_t* slots_dev, int n_fields, size_t slot_words,
                    int H, int W, int32_t* labels_dev, void* stream);
+/* ---- patch transport of the image (no reference counterpart: the implicit hand-over of `green_channel`,
+ * det:57-59, to the crop of det:88) ----
+ * The device reads the image only inside the bounding boxes of labelled regions, so only those rectangles
+ * cross PCIe (~1.2 of 8.4 MB per 2048^2 field with ~500 cells):
+ *   cia_rle_encode_pack_fields  cia_rle_encode_fields, and the thread that encoded a field also packs the bbox
+ *                        rectangles of its labels 1..label_cap (label ascending, rows contiguous) into
+ *                        patches_host[f * patch_cap_px ..]; patch_px[f] = pixels used, 0xFFFFFFFF if they do
+ *                        not fit (copy that chunk's images densely instead)
+ *   cia_patch_upload     one async copy per field of exactly the pixels used
+ *   cia_screen_fields_rle_patches  cia_screen_fields_rle whose `images` is a dense [n_fields, H, W] device
+ *                        SCRATCH buffer: after the region scan the rectangles are written to their bbox
+ *                        positions (pixels outside every bbox stay undefined; the path never reads them) */
+int cia_rle_encode_pack_fields(const int32_t* labels_host, const uint16_t* images_host, int n_fields, int H, int W,
+                               uint32_t* slots_host, size_t slot_words, uint32_t* field_words, int32_t* max_label,
+                               int label_cap, uint16_t* patches_host, size_t patch_cap_px, uint32_t* patch_px,
+                               int n_threads);
+int cia_patch_upload(cia_handle h, const uint16_t* patches_host, int n_fields, size_t patch_cap_px,
+                     const uint32_t* patch_px, uint16_t* patches_dev, void* stream);
+int cia_screen_fields_rle_patches(cia_handle h, uint16_t* images, const uint16_t* patches, size_t patch_cap_px,
+                                  const uint32_t* rle_slots, size_t slot_words, int n_fields, int H, int W,
+                                  int max_label, const cia_params* params, int precision, cia_cell* cells,
+                                  int cells_cap, int32_t* n_cells_dev, int32_t* field_counts_dev,
+                                  const cia_scores* scores, float* crops32, float* features,
+                                  const int32_t* field_strain, double* acc, int n_strains, void* stream);
 int cia_label_scan_rle(cia_handle h, const uint32_t* rle_slots, size_t slot_words, int n_fields,
                        int H, int W, int max_label, cia_region* regions, void* stream);
 int cia_screen_fields_rle(cia_handle h, const uint16_t* images, const uint32_t* rle_slots,

@@ -143,6 +143,53 @@ def test_rle_encoder_avx2_and_scalar_paths_agree_cpu():
     assert len(outs[0]) == 64 and outs[0] == outs[1]
 
 
+def _pack(lib, labs, imgs, label_cap, cap_px, threads=2):
+    F, H, W = labs.shape
+    sw = int(lib.cia_rle_slot_words(H, W))
+    slots = np.zeros((F, sw), np.uint32)
+    words = np.zeros(F, np.uint32)
+    patches = np.full((F, cap_px), 0xABCD, np.uint16)
+    px = np.zeros(F, np.uint32)
+    rc = lib.cia_rle_encode_pack_fields(labs.ctypes.data, imgs.ctypes.data, F, H, W, slots.ctypes.data, sw,
+                                        words.ctypes.data, None, label_cap, patches.ctypes.data, cap_px,
+                                        px.ctypes.data, threads)
+    return rc, slots, words, patches, px
+
+
+@pytest.mark.parametrize("shape", [(64, 64), (37, 101), (128, 1030)])
+def test_patch_pack_cpu(shape):
+    """The image's patch transport (host side): bbox rectangles of labels 1..label_cap, label ascending, rows
+    contiguous -- against scipy.ndimage.find_objects (what regionprops' bbox is, det:67); the runs are the same
+    words cia_rle_encode_fields writes."""
+    import scipy.ndimage as ndi
+    lib = _lib.load()
+    H, W = shape
+    labs = _fields(H, W)[:3].copy()
+    labs[2] %= 40                                                        # stripes: 40 labels whose bboxes span the field
+    labs[1, 3:9, 5:20] = -7                                              # negative labels are background
+    rng = np.random.default_rng(1)
+    imgs = rng.integers(0, 65536, labs.shape, dtype=np.uint16)
+    cap = int(labs.max())
+    rc, slots, words, patches, px = _pack(lib, labs, imgs, cap, 40 * H * W)
+    assert rc == 0
+    ref_rc, slots2, words2, _, _ = rc, *_pack(lib, labs, imgs, cap, 40 * H * W, threads=1)[1:3], None, None
+    assert np.array_equal(slots, slots2) and np.array_equal(words, words2)
+    for f in range(len(labs)):
+        want = [imgs[f][sl].ravel() for sl in ndi.find_objects(np.where(labs[f] > 0, labs[f], 0)) if sl is not None]
+        want = np.concatenate(want) if want else np.zeros(0, np.uint16)
+        assert int(px[f]) == len(want)
+        assert np.array_equal(patches[f, :len(want)], want)
+        assert (patches[f, len(want):] == 0xABCD).all()                  # nothing written past the used pixels
+    # a label cap below the largest label: the labels above it are left out (the device reports them)
+    rc, _, _, patches3, px3 = _pack(lib, labs[:1], imgs[:1], 5, 40 * H * W)
+    want = np.concatenate([imgs[0][sl].ravel() for sl in ndi.find_objects(np.where((labs[0] > 0) & (labs[0] <= 5), labs[0], 0))
+                           if sl is not None])
+    assert rc == 0 and int(px3[0]) == len(want) and np.array_equal(patches3[0, :len(want)], want)
+    # rectangles that do not fit the slot: flagged per field, the runs are still there
+    rc, _, words4, _, px4 = _pack(lib, labs, imgs, cap, 16)
+    assert rc == 0 and (words4 > 0).all() and px4[2] == 0xFFFFFFFF and px4[1] == 0      # field 1 has no positive label
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("shape", [(64, 64), (37, 101), (128, 1030), (512, 2048)])
 def test_rle_expand_gpu(shape):
@@ -218,15 +265,19 @@ def test_run_host_transport_variants_agree(model_dir):
     lab = torch.from_numpy(np.stack([f[1] for f in fields])).pin_memory()
     H, W = lab.shape[1:]
     res = []
-    for kw in (dict(label_transport="raw"), dict(label_transport="rle"),
-               dict(label_transport="rle", scan_runs=False), dict(label_transport="rle", rle_fraction=0.5)):
+    for kw in (dict(label_transport="raw"), dict(label_transport="rle"), dict(label_transport="rle", image_transport="patches"),
+               dict(label_transport="rle", scan_runs=False),
+               dict(label_transport="rle", rle_fraction=0.5),
+               dict(label_transport="rle", rle_fraction=0.5, image_transport="patches")):
         bs = BatchScreen(eng, H, W, int(lab.max()), chunk_fields=1, **kw)
         bs.run_host(g, lab, 6)
         bs.sync()
         eng.check_status()
         res.append(bs.collect_host())
         h2d = bs.host_bytes_per_pass(6)[0]
-        if kw.get("rle_fraction") == 0.5:      # three chunks raw, three as runs
+        if kw == dict(label_transport="rle", image_transport="patches"):    # bbox rectangles + runs only
+            assert h2d < 6 * H * W * 2
+        if kw.get("rle_fraction") == 0.5 and "image_transport" not in kw:      # three chunks raw, three as runs
             assert 3 * H * W * 6 + 3 * H * W * 2 < h2d < 3 * H * W * 6 + 3 * H * W * 3
             assert bs.last_rle_share == 0.5
     assert res[0]["n_cells"] > 0
@@ -290,3 +341,37 @@ def test_run_host_incompressible_labels_fall_back_to_raw(model_dir):
     assert a["n_cells"] == b["n_cells"]
     for k in ("cells", "mse", "dec_cons", "pred_mod", "field_counts"):
         assert np.array_equal(a[k], b[k]), k
+
+
+@pytest.mark.gpu
+def test_run_host_patch_transport_falls_back_when_rectangles_do_not_fit(model_dir):
+    """Two long diagonal regions: their bbox rectangles cover the whole field twice, more than a patch slot
+    (half a field) holds, so that chunk's images are copied densely; results equal the dense pass."""
+    import torch
+    from cell_image_analysis_b200.artifacts import load_model_dir
+    from cell_image_analysis_b200.batch import BatchScreen
+    from cell_image_analysis_b200.screening import Engine
+    from cell_image_analysis_b200.synth import make_fields
+    eng = Engine()
+    eng.load_artifacts(load_model_dir(model_dir))
+    fields = make_fields(range(4), "tiny")
+    g = np.stack([f[0] for f in fields])
+    lab = np.stack([f[1] for f in fields]).copy()
+    H, W = lab.shape[1:]
+    top = int(lab.max())
+    for k in range(min(H, W)):                       # two one-pixel diagonals with full-field bboxes in field 1
+        lab[1, k, k] = top + 1
+        lab[1, k, W - 1 - k] = top + 2
+    gp = torch.from_numpy(g.view(np.int16)).pin_memory()
+    lp = torch.from_numpy(lab).pin_memory()
+    res = {}
+    for mode in ("dense", "patches"):
+        bs = BatchScreen(eng, H, W, top + 2, chunk_fields=1, label_transport="rle", image_transport=mode)
+        bs.run_host(gp, lp, 4)
+        bs.sync()
+        res[mode] = (bs.collect_host(), bs.host_bytes_per_pass(4)[0])
+    (a, ha), (b, hb) = res["dense"], res["patches"]
+    assert a["n_cells"] == b["n_cells"] > 0
+    for k in ("cells", "mse", "mae", "dec_cons", "dec_mod", "pred_cons", "pred_mod", "field_counts"):
+        assert np.array_equal(a[k], b[k]), k
+    assert 2 * H * W < hb < ha                       # one field went densely, three as rectangles
