@@ -65,6 +65,9 @@ using namespace tcptx;
 #else
 #define MBAR_WAIT mbar_wait_sleep
 #endif
+#ifdef CIA_SLEEP_WAIT_ALL          // A/B: the single-pass kernels' waits with the suspend-time hint as well
+#define mbar_wait mbar_wait_sleep
+#endif
 #ifdef CIA_UNIFORM_ISSUE_ALL
 #define ISSUE1_WARP(cond) (cond)
 #define ISSUE1_BEGIN if (elect_one()) {
