@@ -100,6 +100,14 @@ SIGNATURES = {
     "cia_profile_layers": (_I, [_P, C.POINTER(C.c_double)]),
     "cia_debug_copy_workspace": (_I, [_P, _I, C.c_size_t, _P, C.c_size_t]),
     "cia_launch_count": (C.c_int64, [_P]),
+    # segmentation (csrc/segment.cu)
+    "cia_seg_load": (_I, [_P, _P, _I, C.POINTER(_P), C.POINTER(_P), _P, _P, _P]),
+    "cia_seg_normalize": (_I, [_P, _P, _I, _I, C.c_double, C.c_double, _P, _P, _P]),
+    "cia_seg_predict": (_I, [_P, _P, _I, _I, _P, _P, _P]),
+    "cia_seg_instances": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, C.c_double, C.c_double, _P, _P, _P]),
+    "cia_seg_details": (_I, [_P, _I, _P, _P, _P, _P]),
+    "cia_seg_layer_info": (_I, [_P, _I, _P]),
+    "cia_seg_debug_layer": (_I, [_P, _I, _P, _P, _P, _I, _I, _P, _P, _P, _P]),
 }
 
 _lib = None

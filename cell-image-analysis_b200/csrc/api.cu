@@ -108,6 +108,7 @@ int cia_destroy(cia_handle h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     free_cae(h->cae[0]); free_cae(h->cae[1]);
+    k_seg_free(h);
     cudaFree(h->sp.center); cudaFree(h->sp.scale); cudaFree(h->sp.rscale); cudaFree(h->sp.comp_t); cudaFree(h->sp.comp_pad); cudaFree(h->sp.offset); cudaFree(h->sp.tc_img); cudaFree(h->sp.tc_par);
     for (int i = 0; i < 2; ++i) { cudaFree(h->svm[i].sv_t); cudaFree(h->svm[i].coef); cudaFree(h->svm[i].sv_pad); cudaFree(h->svm[i].gsn);
                                   cudaFree(h->svm[i].tc_hi); cudaFree(h->svm[i].tc_lo); cudaFree(h->svm[i].tc_gcol); }
@@ -266,6 +267,49 @@ int cia_load_svm(cia_handle h, int which, int n_sv, int dim, const double* sv, c
     if ((rc = k_svm_tc_prepare(h, m, sv, coef))) return rc;
     m.loaded = true;
     return CIA_OK;
+}
+
+// ---- segmentation (segment.cu; improved_detection.py:44, 62-63) ----------------
+int cia_seg_load(cia_handle h, const cia_seg_config* cfg, int n_layers, const float* const* kernels,
+                 const float* const* biases, const int64_t* shapes, const double* ray_sin, const double* ray_cos) {
+    if (!h) return bad_handle();
+    if (!cfg || !kernels || !biases || !shapes || !ray_sin || !ray_cos || n_layers < 3) { h->err = "cia_seg_load: bad argument"; return CIA_E_ARG; }
+    for (int l = 0; l < n_layers; ++l)
+        if (!kernels[l] || !biases[l]) { h->err = "cia_seg_load: null layer"; return CIA_E_ARG; }
+    cudaSetDevice(h->device);
+    return k_seg_load(h, cfg, n_layers, kernels, biases, shapes, ray_sin, ray_cos);
+}
+int cia_seg_normalize(cia_handle h, const uint16_t* image, int H, int W, double pmin, double pmax, float* out,
+                      float* mi_ma, void* stream) {
+    if (!h) return bad_handle();
+    if (!image || !out || H <= 0 || W <= 0 || !(pmin >= 0 && pmin <= pmax && pmax <= 100)) { h->err = "cia_seg_normalize: bad argument"; return CIA_E_ARG; }
+    return k_seg_normalize(h, image, H, W, pmin, pmax, out, mi_ma, (cudaStream_t)stream);
+}
+int cia_seg_predict(cia_handle h, const float* image, int H, int W, float* prob, float* dist, void* stream) {
+    if (!h) return bad_handle();
+    if (!image) { h->err = "cia_seg_predict: null image"; return CIA_E_ARG; }
+    return k_seg_predict(h, image, H, W, prob, dist, (cudaStream_t)stream);
+}
+int cia_seg_instances(cia_handle h, const float* prob, const float* dist, int Hg, int Wg, int grid, int H, int W,
+                      double prob_thresh, double nms_thresh, int32_t* labels, int32_t* n_instances, void* stream) {
+    if (!h) return bad_handle();
+    if (!labels || Hg <= 0 || Wg <= 0 || grid <= 0 || H <= 0 || W <= 0) { h->err = "cia_seg_instances: bad argument"; return CIA_E_ARG; }
+    return k_seg_instances(h, prob, dist, Hg, Wg, grid, H, W, prob_thresh, nms_thresh, labels, n_instances, (cudaStream_t)stream);
+}
+int cia_seg_details(cia_handle h, int cap, int32_t* points, float* prob, float* coord, void* stream) {
+    if (!h) return bad_handle();
+    if (cap > 0 && (!points || !prob || !coord)) { h->err = "cia_seg_details: null pointer"; return CIA_E_ARG; }
+    return k_seg_details(h, cap, points, prob, coord, (cudaStream_t)stream);
+}
+int cia_seg_layer_info(cia_handle h, int layer, int32_t* info) {
+    if (!h) return bad_handle();
+    if (!info) { h->err = "cia_seg_layer_info: null pointer"; return CIA_E_ARG; }
+    return k_seg_layer_info(h, layer, info);
+}
+int cia_seg_debug_layer(cia_handle h, int layer, const void* src0, const void* src1, const float* image, int Ho, int Wo,
+                        void* out, float* prob, float* dist, void* stream) {
+    if (!h) return bad_handle();
+    return k_seg_debug_layer(h, layer, src0, src1, image, Ho, Wo, out, prob, dist, (cudaStream_t)stream);
 }
 
 // ---- stage wrappers ----------------------------------------------------------

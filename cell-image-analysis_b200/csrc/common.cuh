@@ -74,8 +74,11 @@ struct Workspace {
     size_t cap = 0;
 };
 
+struct SegModel;   // segment.cu
+
 struct cia_ctx {
     int device = 0;
+    SegModel* seg = nullptr;              // StarDist2D network + post-processing state (cia_seg_load)
     int num_sms = CIA_NUM_SMS_DEFAULT;
     int max_smem_optin = 227 * 1024;
     std::string err;
@@ -199,6 +202,18 @@ int k_pca_tc(cia_ctx* h, const float* features, int n, const int32_t* n_dev, dou
 int k_svm_tc_prepare(cia_ctx* h, SvmModel& m, const double* sv, const double* coef);
 int k_svm_tc(cia_ctx* h, const SvmModel& m, const double* z, int n, const int32_t* n_dev, double* dec,
              int8_t* pred, bool* done, cudaStream_t s);
+void k_seg_free(cia_ctx* h);
+int k_seg_load(cia_ctx* h, const cia_seg_config* cfg, int n_layers, const float* const* kernels,
+               const float* const* biases, const int64_t* shapes, const double* ray_sin, const double* ray_cos);
+int k_seg_normalize(cia_ctx* h, const uint16_t* img, int H, int W, double pmin, double pmax, float* out,
+                    float* mi_ma_out, cudaStream_t s);
+int k_seg_predict(cia_ctx* h, const float* img, int H, int W, float* prob_out, float* dist_out, cudaStream_t s);
+int k_seg_instances(cia_ctx* h, const float* prob, const float* dist, int Hg, int Wg, int grid, int H, int W,
+                    double prob_thresh, double nms_thresh, int32_t* labels, int32_t* n_inst_dev, cudaStream_t s);
+int k_seg_details(cia_ctx* h, int cap, int32_t* points, float* prob, float* coord, cudaStream_t s);
+int k_seg_layer_info(cia_ctx* h, int layer, int* info);
+int k_seg_debug_layer(cia_ctx* h, int layer, const void* src0, const void* src1, const float* img, int Ho, int Wo,
+                      void* out, float* prob, float* dist, cudaStream_t s);
 int k_strain_accumulate(cia_ctx* h, const cia_cell* cells, int n, const int32_t* n_dev,
                         const cia_scores* sc, const int32_t* field_strain, double* acc,
                         int n_strains, cudaStream_t s);

@@ -379,12 +379,21 @@ class ProductionMutantScreening:
     """
 
     def __init__(self, model_dir, segmenter=None, imread=None, device: int = 0,
-                 precision: int = PRECISION_TC):
+                 precision: int = PRECISION_TC, stardist_dir=None):
         self.model_dir = model_dir
         self.segmenter = segmenter
         self.imread = imread or _default_imread
         self.engine = Engine(device=device, precision=precision)
+        self.stardist_model = None
         self.load_trained_models()
+        if stardist_dir is not None and segmenter is None:
+            # det:44 on the GPU (csrc/segment.cu): a StarDist model folder instead of the download; the labels of
+            # det:62-63 stay on the device and feed the region scan without crossing PCIe
+            from .stardist import StarDist2D
+            self.stardist_model = StarDist2D(None, name=os.path.basename(os.path.normpath(stardist_dir)),
+                                             basedir=os.path.dirname(os.path.normpath(stardist_dir)) or ".",
+                                             engine=self.engine)
+            self.segmenter = lambda ch: self.stardist_model.segment_device(ch)[0]
 
     # det:23-46
     def load_trained_models(self):
@@ -439,14 +448,23 @@ class ProductionMutantScreening:
             raise UnsupportedImageError(
                 f"analysis channel dtype {green.dtype}: the CUDA path takes uint16 (16-bit TIFF fields) and "
                 "uint8 images; convert float / signed images before screening")
-        lab = np.ascontiguousarray(labels, dtype=np.int32)
-        if lab.shape != green.shape or lab.ndim != 2:
-            raise ValueError("labels and image must be 2-D arrays of the same shape")
-        max_label = int(lab.max()) if lab.size else 0
+        if isinstance(labels, torch.Tensor):          # device-resident labels (stardist.StarDist2D.segment_device)
+            lab = labels.to(device=eng.tdev, dtype=torch.int32).contiguous()
+            if tuple(lab.shape) != green.shape or lab.ndim != 2:
+                raise ValueError("labels and image must be 2-D arrays of the same shape")
+            max_label = int(lab.max().item()) if lab.numel() else 0
+            l = lab[None]
+        else:
+            lab = np.ascontiguousarray(labels, dtype=np.int32)
+            if lab.shape != green.shape or lab.ndim != 2:
+                raise ValueError("labels and image must be 2-D arrays of the same shape")
+            max_label = int(lab.max()) if lab.size else 0
+            l = None
         if max_label <= 0:
             return ([], [], None) if return_regions else ([], [])
         g = torch.from_numpy(green.view(np.int16)).to(eng.tdev)[None]   # uint16 bytes; only the pointer is used
-        l = torch.from_numpy(lab).to(eng.tdev)[None]
+        if l is None:
+            l = torch.from_numpy(lab).to(eng.tdev)[None]
         regions = eng.label_scan(l, max_label)
         cells, counts = eng.filter(g, regions, max_label)
         n = int(counts[0].item())

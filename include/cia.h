@@ -302,6 +302,59 @@ int cia_profile_layers(cia_handle h, double* layer_ms /* [7] */);
  * ws_id 5 holds the tensor-core path's fp16 activations (layout in cae_tc.cu). */
 int cia_debug_copy_workspace(cia_handle h, int ws_id, size_t offset, void* dst_host, size_t bytes);
 
+/* ---------------------------------------------------------------------------------------------
+ * Segmentation: the producer of the int32 label field.  Replaces
+ *   normalized_seg = normalize(seg_channel)                              improved_detection.py:62
+ *   labels, details = self.stardist_model.predict_instances(normalized_seg)   improved_detection.py:63
+ * (model construction improved_detection.py:44; the training twin CAE_improved_modeltrain.py:54-55).
+ * csbdeep / stardist are third-party packages absent from the reference tree; oracle/stardist.py and
+ * oracle/stardist_post.c restate them ("parity unpinned").  All image / map pointers are DEVICE
+ * pointers; weights, ray tables and the config are host pointers read during the call.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct cia_seg_config {   /* the fields of a StarDist2D config.json the network depends on */
+    int32_t n_channel_in;          /* 1 */
+    int32_t grid;                  /* 1, 2 or 4 (square grids) */
+    int32_t n_rays;                /* 32 */
+    int32_t unet_n_depth;
+    int32_t unet_n_filter_base;    /* multiple of 32 */
+    int32_t unet_n_conv_per_depth;
+    int32_t net_conv_after_unet;   /* channels of the `features` layer, multiple of 32 */
+    int32_t reserved;
+} cia_seg_config;
+
+/* StarDist2D.__init__ / _build (improved_detection.py:44): upload the 3x3 convolutions of the network in the
+ * order the model applies them (grid blocks, down levels, middle, up levels, `features`), then the 1x1 heads
+ * `prob` and `dist`: kernels[l] is HWIO float32 with shapes[4*l..4*l+3] = {kh, kw, cin, cout}.  ray_sin / ray_cos:
+ * float64 [n_rays] = sin / cos of np.linspace(0, 2 pi, n_rays, endpoint=False) (stardist ray_angles), passed in so
+ * that the polygon vertices equal the host library's bit for bit.  CIA_E_UNSUPPORTED / CIA_E_ARG (with
+ * cia_last_error) when the layers do not fit the configuration. */
+int cia_seg_load(cia_handle h, const cia_seg_config* cfg, int n_layers, const float* const* kernels,
+                 const float* const* biases, const int64_t* shapes, const double* ray_sin, const double* ray_cos);
+/* csbdeep.utils.normalize(x, pmin, pmax) of a uint16 field (improved_detection.py:62; defaults 3 / 99.8):
+ * np.percentile's linear interpolation from the exact histogram, then (x - mi) / (ma - mi + 1e-20) in float32.
+ * out: float32 [H][W]; mi_ma (may be NULL): float32 [2] on the device. */
+int cia_seg_normalize(cia_handle h, const uint16_t* image, int H, int W, double pmin, double pmax, float* out,
+                      float* mi_ma, void* stream);
+/* The network of predict_instances (improved_detection.py:63): normalized float32 field [H][W] -> prob
+ * float32 [H/grid][W/grid] and dist float32 [H/grid][W/grid][n_rays] (dist = max(1e-3, dist) as StarDist2D.predict).
+ * prob / dist may be NULL: the maps stay inside the handle for cia_seg_instances.  H, W must be multiples of
+ * grid * 2^depth (StarDist reflect-pads other sizes: CIA_E_UNSUPPORTED here). */
+int cia_seg_predict(cia_handle h, const float* image, int H, int W, float* prob, float* dist, void* stream);
+/* _instances_from_prediction: candidates prob > prob_thresh outside the 2-pixel border, sorted by
+ * probability, greedy polygon NMS (intersection / smaller area > nms_thresh suppresses), polygons_to_label.
+ * prob / dist NULL = the maps of the last cia_seg_predict.  labels: int32 [H][W]; n_instances (may be NULL): device int32. */
+int cia_seg_instances(cia_handle h, const float* prob, const float* dist, int Hg, int Wg, int grid, int H, int W,
+                      double prob_thresh, double nms_thresh, int32_t* labels, int32_t* n_instances, void* stream);
+/* `details` of the last cia_seg_instances for the first `cap` kept polygons, in label order:
+ * points int32 [cap][2] (y, x), prob float32 [cap], coord float32 [cap][2][n_rays]. */
+int cia_seg_details(cia_handle h, int cap, int32_t* points, float* prob, float* coord, void* stream);
+/* Test taps: the plan entry of a layer (info[6] = mode {-1 first, 0 direct, 1 pooled, 2 up ++ skip}, c0, c1, cout,
+ * log2 of the resolution divisor, number of 3x3 layers) and one layer run on caller-provided fp16 chunk-planar
+ * activations [C/8][H][W][8] (layer -2 = the heads). */
+int cia_seg_layer_info(cia_handle h, int layer, int32_t* info);
+int cia_seg_debug_layer(cia_handle h, int layer, const void* src0, const void* src1, const float* image, int Ho, int Wo,
+                        void* out, float* prob, float* dist, void* stream);
+
 /* Number of kernels this library has launched on the handle (bench's gpu_launches). */
 int64_t cia_launch_count(cia_handle h);
 

@@ -1,0 +1,203 @@
+"""GPU parity of the segmentation step (improved_detection.py:44, 62-63) against
+oracle/stardist.py + oracle/stardist_post.c ("parity unpinned": restated third-party algorithms).
+
+Gates: percentiles and normalized pixels bit-exact (integer order statistics, IEEE float32 ops); every
+convolution layer within fp16 rounding of a float32 convolution of the same fp16 operands; prob / dist of the
+whole network within 2e-2 of the float32 oracle and 1e-2 of its fp16-activation twin; NMS survivors and the
+rendered labels bit-exact against the oracle on the same (prob, dist)."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+pytestmark = pytest.mark.gpu
+
+CFG = dict(n_channel_in=1, grid=[2, 2], n_rays=32, unet_n_depth=3, unet_n_filter_base=32,
+           unet_n_conv_per_depth=2, net_conv_after_unet=128, unet_kernel_size=[3, 3], unet_pool=[2, 2],
+           unet_activation="relu", unet_last_activation="relu", unet_batch_norm=False)
+
+
+@pytest.fixture(scope="module")
+def model():
+    from cell_image_analysis_b200.stardist import StarDist2D
+    from oracle import stardist as sd
+    w = sd.random_model(CFG, seed=11)
+    m = StarDist2D.from_arrays(CFG, w, {"prob": 0.479071, "nms": 0.3})
+    m.oracle_weights = w
+    return m
+
+
+def planar(x):
+    """NCHW-less [C, H, W] float tensor -> fp16 chunk-planar [C/8][H][W][8]"""
+    Cc, H, W = x.shape
+    return x.half().view(Cc // 8, 8, H, W).permute(0, 2, 3, 1).contiguous()
+
+
+def unplanar(p):
+    P, H, W, _ = p.shape
+    return p.permute(0, 3, 1, 2).reshape(P * 8, H, W).float()
+
+
+def layer_check(m, layer, Ho, Wo, seed=0):
+    """max |gpu - ref| / max |ref| of one plan layer on random fp16 activations"""
+    import torch
+    import torch.nn.functional as F
+    eng = m.engine
+    info = (C.c_int32 * 6)()
+    eng._check(eng.lib.cia_seg_layer_info(eng.h, layer, info))
+    mode, c0, c1, cout, _shift, _n = list(info)
+    g = torch.Generator(device="cpu").manual_seed(seed + layer)
+    name = m.layer_order[layer]
+    k, b = m.oracle_weights[name]
+    kt = torch.from_numpy(np.ascontiguousarray(k.transpose(3, 2, 0, 1))).cuda()
+    bt = torch.from_numpy(b).cuda()
+    out = torch.zeros((cout // 8, Ho, Wo, 8), dtype=torch.float16, device="cuda")
+    if mode == -1:
+        img = torch.rand((Ho, Wo), generator=g).cuda()
+        ref = F.relu(F.conv2d(img[None, None], kt, bt, padding=1))[0]
+        eng._check(eng.lib.cia_seg_debug_layer(eng.h, layer, None, None, img.data_ptr(), Ho, Wo, out.data_ptr(), None,
+                                               None, eng._stream()))
+    else:
+        if mode == 0:
+            x0 = torch.randn((c0, Ho, Wo), generator=g).cuda().half().float()
+            xin, s0, s1 = x0, planar(x0), None
+        elif mode == 1:
+            x0 = torch.randn((c0, 2 * Ho, 2 * Wo), generator=g).cuda().half().float()
+            xin, s0, s1 = F.max_pool2d(x0[None], 2)[0], planar(x0), None
+        else:
+            x0 = torch.randn((c0, Ho // 2, Wo // 2), generator=g).cuda().half().float()
+            x1 = torch.randn((c1, Ho, Wo), generator=g).cuda().half().float()
+            xin = torch.cat([F.interpolate(x0[None], scale_factor=2, mode="nearest")[0], x1], 0)
+            s0, s1 = planar(x0), planar(x1)
+        ref = F.relu(F.conv2d(xin[None].double(), kt.half().double(), bt.double(), padding=1))[0].float()
+        eng._check(eng.lib.cia_seg_debug_layer(eng.h, layer, s0.data_ptr(), s1.data_ptr() if s1 is not None else None,
+                                               None, Ho, Wo, out.data_ptr(), None, None, eng._stream()))
+    torch.cuda.synchronize()
+    got = unplanar(out)
+    return float((got - ref).abs().max() / ref.abs().max())
+
+
+def test_normalize_bit_exact(model):
+    from cell_image_analysis_b200 import synth
+    from oracle import stardist as sd
+    H, W, n, lo, hi, lu = synth.FIELD_CONFIGS["tiny"]
+    for seed in (3, 4):
+        green, _ = synth.make_field(seed, H, W, n, lo, hi, lu)
+        got = model.normalize_device(green).cpu().numpy()
+        ref = sd.normalize(green)
+        assert np.array_equal(got, ref), np.abs(got - ref).max()
+    rng = np.random.default_rng(5)     # a flat histogram and an odd size: the interpolation weights matter
+    x = rng.integers(0, 65536, size=(301, 257)).astype(np.uint16)
+    assert np.array_equal(model.normalize_device(x, 1, 99.8).cpu().numpy(), sd.normalize(x, 1, 99.8))
+
+
+def test_every_layer_against_float32_conv(model):
+    n_layers = len(model.layer_order) - 2
+    for layer in range(n_layers):
+        # 48 x 40: edge tiles in both directions (tiles are 16 rows x 16 / 32 columns)
+        err = layer_check(model, layer, 48, 40)
+        print(f"layer {layer} {model.layer_order[layer]}: max rel err {err:.2e}")
+        assert err < 2e-3, (layer, model.layer_order[layer], err)
+
+
+def test_network_against_oracle(model):
+    from cell_image_analysis_b200 import synth
+    from oracle import stardist as sd
+    H, W, n, lo, hi, lu = synth.FIELD_CONFIGS["tiny"]
+    green, _ = synth.make_field(3, H, W, n, lo, hi, lu)
+    x = sd.normalize(green)
+    Hc, Wc = (H // 16) * 16, (W // 16) * 16
+    x = np.ascontiguousarray(x[:Hc, :Wc])
+    prob, dist = model.predict(x)
+    prob, dist = prob.cpu().numpy(), dist.cpu().numpy()
+    p32, d32 = sd.unet_forward(CFG, model.oracle_weights, x)
+    p16, d16 = sd.unet_forward(CFG, model.oracle_weights, x, half_activations=True)
+    e32 = (np.abs(prob - p32).max(), np.abs(dist - d32).max() / np.abs(d32).max())
+    e16 = (np.abs(prob - p16).max(), np.abs(dist - d16).max() / np.abs(d16).max())
+    print(f"prob/dist vs float32 oracle {e32[0]:.2e} {e32[1]:.2e}; vs fp16-activation twin {e16[0]:.2e} {e16[1]:.2e}")
+    assert e32[0] < 2e-2 and e32[1] < 2e-2, e32
+    assert e16[0] < 1e-2 and e16[1] < 1e-2, e16
+
+
+def _ellipse_field(H, W, n_side, seed):
+    rng = np.random.default_rng(seed)
+    pitch = min(H, W) / n_side
+    cells = []
+    for gy in range(n_side):
+        for gx in range(n_side):
+            a = rng.uniform(0.15, 0.42) * pitch
+            cells.append(((gy + 0.5) * pitch + rng.uniform(-4, 4), (gx + 0.5) * pitch + rng.uniform(-4, 4), a,
+                          a * rng.uniform(0.5, 1.0), rng.uniform(0, np.pi)))
+    return cells
+
+
+@pytest.mark.parametrize("H,W,n_side,seed", [(256, 320, 4, 0), (512, 512, 7, 1), (1024, 1024, 20, 2)])
+def test_instances_bit_exact(model, H, W, n_side, seed):
+    import torch
+    from oracle import stardist as sd
+    cells = _ellipse_field(H, W, n_side, seed)
+    prob, dist = sd.star_maps_from_ellipses(H, W, 2, cells)
+    rng = np.random.default_rng(seed)
+    prob = (prob * rng.uniform(0.9, 1.0, prob.shape)).astype(np.float32)       # break ties between pixels
+    dist = (dist * rng.uniform(0.97, 1.03, dist.shape)).astype(np.float32)     # ragged, overlapping polygons
+    ref, det = sd.instances_from_prediction(prob, dist, 2, (H, W), 0.4, 0.3)
+    labels, n = model.instances_from_prediction((H, W), torch.from_numpy(prob), torch.from_numpy(dist), 0.4, 0.3)
+    got = labels.cpu().numpy()
+    d = model.details(n)
+    assert n == len(det["prob"]) > 0, (n, len(det["prob"]))
+    assert np.array_equal(d["points"], det["points"])
+    assert np.array_equal(d["prob"], det["prob"])
+    assert np.array_equal(d["coord"], det["coord"])
+    assert np.array_equal(got, ref), int((got != ref).sum())
+    assert n >= 0.9 * len(cells)
+
+
+def test_instances_of_noise(model):
+    """dense random candidates (what an untrained network emits): thousands of overlapping polygons"""
+    import torch
+    from oracle import stardist as sd
+    rng = np.random.default_rng(7)
+    H = W = 256
+    prob = rng.uniform(0, 1, (H // 2, W // 2)).astype(np.float32)
+    dist = rng.uniform(2, 9, (H // 2, W // 2, 32)).astype(np.float32)
+    ref, det = sd.instances_from_prediction(prob, dist, 2, (H, W), 0.6, 0.3)
+    labels, n = model.instances_from_prediction((H, W), torch.from_numpy(prob), torch.from_numpy(dist), 0.6, 0.3)
+    assert n == len(det["prob"])
+    assert np.array_equal(labels.cpu().numpy(), ref)
+    # nothing above the threshold: an empty label image
+    labels, n = model.instances_from_prediction((H, W), torch.from_numpy(prob), torch.from_numpy(dist), 2.0, 0.3)
+    assert n == 0 and int(labels.max().item()) == 0
+
+
+def test_predict_instances_drop_in(model):
+    """the reference's two calls end to end, labels on the device feeding the region scan"""
+    from cell_image_analysis_b200 import synth
+    from oracle import stardist as sd
+    H, W, n, lo, hi, lu = synth.FIELD_CONFIGS["tiny"]
+    green, _ = synth.make_field(3, H, W, n, lo, hi, lu)
+    Hc, Wc = (H // 16) * 16, (W // 16) * 16
+    green = np.ascontiguousarray(green[:Hc, :Wc])
+    x = model.normalize_device(green)
+    labels, details = model.predict_instances(x.cpu().numpy())
+    assert labels.dtype == np.int32 and labels.shape == green.shape
+    assert set(details) >= {"points", "prob", "coord"}
+    # same (prob, dist) through the oracle's post-processing
+    prob, dist = model.predict(x)
+    ref, _ = sd.instances_from_prediction(prob.cpu().numpy(), dist.cpu().numpy(), 2, green.shape, 0.479071, 0.3)
+    assert np.array_equal(labels, ref)
+    dev_labels, n_inst = model.segment_device(green)
+    assert np.array_equal(dev_labels.cpu().numpy(), labels) and n_inst == labels.max()
+
+
+def test_reflect_padding_of_odd_sizes(model):
+    from oracle import stardist as sd
+    rng = np.random.default_rng(9)
+    x = rng.uniform(0, 1, (70, 90)).astype(np.float32)
+    prob, dist = model.predict(x)
+    xp = np.pad(x, ((0, 10), (0, 6)), mode="reflect")
+    p16, d16 = sd.unet_forward(CFG, model.oracle_weights, xp, half_activations=True)
+    assert prob.shape == (35, 45)
+    assert np.abs(prob.cpu().numpy() - p16[:35, :45]).max() < 1e-2
