@@ -81,7 +81,10 @@ namespace {
 // ---------------------------------------------------------------------------------------
 // csbdeep.utils.normalize: np.percentile (linear interpolation) of a uint16 image from its exact histogram
 // ---------------------------------------------------------------------------------------
+constexpr int SEG_HIST_COPIES = 16;   // copies of the histogram (by CTA): the background's few grey levels are hot addresses
+
 __global__ void seg_hist_kernel(const uint16_t* __restrict__ img, size_t n, uint32_t* __restrict__ hist) {
+    hist += (size_t)(blockIdx.x % SEG_HIST_COPIES) * 65536;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31;
     for (size_t i0 = (size_t)blockIdx.x * blockDim.x; i0 < n; i0 += stride) {     // warp-uniform trip count
@@ -91,6 +94,13 @@ __global__ void seg_hist_kernel(const uint16_t* __restrict__ img, size_t n, uint
         const unsigned peers = __match_any_sync(0xffffffffu, v);
         if (ok && lane == __ffs(peers) - 1) atomicAdd(hist + v, (uint32_t)__popc(peers));
     }
+}
+
+__global__ void seg_hist_reduce_kernel(uint32_t* __restrict__ hist) {      // copy 0 += copies 1..15
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t c = 0;
+    for (int cp = 0; cp < SEG_HIST_COPIES; ++cp) c += hist[(size_t)cp * 65536 + b];
+    hist[b] = c;
 }
 
 // numpy's percentile for the default method: virtual index n q + (1 + q (1 - 1 - 1)) - 1, the two neighbouring order
@@ -153,7 +163,7 @@ __global__ void seg_normalize_kernel(const uint16_t* __restrict__ img, size_t n,
 __global__ void __launch_bounds__(256) seg_first_kernel(const float* __restrict__ img, const float* __restrict__ w,
                                                         const float* __restrict__ bias, __half* __restrict__ out, int H,
                                                         int W, int cout) {
-    extern __shared__ float sw[];            // [9][cout] weights, [cout] bias
+    extern __shared__ __align__(16) float sw[];   // [9][cout] weights, [cout] bias
     for (int i = threadIdx.x; i < 10 * cout; i += blockDim.x) sw[i] = i < 9 * cout ? w[i] : bias[i - 9 * cout];
     __syncthreads();
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -165,15 +175,23 @@ __global__ void __launch_bounds__(256) seg_first_kernel(const float* __restrict_
         const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
         v[t] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(img + (size_t)yy * W + xx) : 0.f;
     }
+    const float4* sw4 = reinterpret_cast<const float4*>(sw);
     for (int cgp = 0; cgp < cout / 8; ++cgp) {
         __align__(16) __half o[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            float acc = sw[9 * cout + cgp * 8 + k];
-#pragma unroll
-            for (int t = 0; t < 9; ++t) acc = fmaf(v[t], sw[t * cout + cgp * 8 + k], acc);
-            o[k] = __float2half_rn(fmaxf(acc, 0.f));
+        float acc[8];
+        {
+            const float4 b0 = sw4[(9 * cout + cgp * 8) / 4], b1 = sw4[(9 * cout + cgp * 8) / 4 + 1];
+            acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w; acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
         }
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {                 // taps in order, one FMA each: the same sums as before
+            const float4 w0 = sw4[(t * cout + cgp * 8) / 4], w1 = sw4[(t * cout + cgp * 8) / 4 + 1];
+            acc[0] = fmaf(v[t], w0.x, acc[0]); acc[1] = fmaf(v[t], w0.y, acc[1]); acc[2] = fmaf(v[t], w0.z, acc[2]);
+            acc[3] = fmaf(v[t], w0.w, acc[3]); acc[4] = fmaf(v[t], w1.x, acc[4]); acc[5] = fmaf(v[t], w1.y, acc[5]);
+            acc[6] = fmaf(v[t], w1.z, acc[6]); acc[7] = fmaf(v[t], w1.w, acc[7]);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = __float2half_rn(fmaxf(acc[k], 0.f));
         *reinterpret_cast<uint4*>(out + (((size_t)cgp * H + y) * W + x) * 8) = *reinterpret_cast<const uint4*>(o);
     }
 }
@@ -467,6 +485,16 @@ __device__ double tri_tri_area(const double* sx, const double* sy, const double*
     mn1 = fmin(fmin(sy[0], sy[1]), sy[2]); mx1 = fmax(fmax(sy[0], sy[1]), sy[2]);
     mn2 = fmin(fmin(cy[0], cy[1]), cy[2]); mx2 = fmax(fmax(cy[0], cy[1]), cy[2]);
     if (mx1 < mn2 || mx2 < mn1) return 0.0;
+    // separating edge: all three vertices of one triangle strictly outside an edge of the other (both are
+    // counter-clockwise) -> exactly 0, the clipping below is only run on triangles that really overlap
+#pragma unroll
+    for (int e = 0; e < 3; ++e) {
+        const int e1 = e == 2 ? 0 : e + 1;
+        if (cross_rn(cx[e], cy[e], cx[e1], cy[e1], sx[0], sy[0]) < 0.0 && cross_rn(cx[e], cy[e], cx[e1], cy[e1], sx[1], sy[1]) < 0.0 &&
+            cross_rn(cx[e], cy[e], cx[e1], cy[e1], sx[2], sy[2]) < 0.0) return 0.0;
+        if (cross_rn(sx[e], sy[e], sx[e1], sy[e1], cx[0], cy[0]) < 0.0 && cross_rn(sx[e], sy[e], sx[e1], sy[e1], cx[1], cy[1]) < 0.0 &&
+            cross_rn(sx[e], sy[e], sx[e1], sy[e1], cx[2], cy[2]) < 0.0) return 0.0;
+    }
     double px[8], py[8], qx[8], qy[8];
     int n = 3;
     for (int k = 0; k < 3; ++k) { px[k] = sx[k]; py[k] = sy[k]; }
@@ -512,7 +540,8 @@ struct NmsArgs {
 };
 
 // polygons w (the winner) and i: intersection area over the smaller area.  One warp: lane a clips fan triangle a
-// of w against the 32 fan triangles of i; the lane sums are added in lane order (the oracle's order).
+// of w against the 32 fan triangles of i (starting at its own index); the lane sums are added in lane order
+// (the oracle's order).
 __device__ double seg_overlap_warp(const NmsArgs& a, int w, int i, float (*sp)[2][SEG_RAYS], int lane) {
     __syncwarp();
     sp[0][0][lane] = a.vy[(size_t)w * SEG_RAYS + lane]; sp[0][1][lane] = a.vx[(size_t)w * SEG_RAYS + lane];
@@ -534,7 +563,10 @@ __device__ double seg_overlap_warp(const NmsArgs& a, int w, int i, float (*sp)[2
     double sy[3] = {(double)a.pyx[2 * w], (double)sp[0][0][lane], (double)sp[0][0][l1]};
     const double cix = (double)a.pyx[2 * i + 1], ciy = (double)a.pyx[2 * i];
     double part = 0.0;
-    for (int b = 0; b < SEG_RAYS; ++b) {
+    for (int st = 0; st < SEG_RAYS; ++st) {
+        // fan triangle b = lane + st: for polygons of similar shape the lanes reach their overlapping pairs at
+        // the same steps, so a step in which no lane has work costs the separating-edge test only
+        const int b = (lane + st) & (SEG_RAYS - 1);
         const int b1 = (b + 1) & (SEG_RAYS - 1);
         double cx[3] = {cix, (double)sp[1][1][b], (double)sp[1][1][b1]};
         double cy[3] = {ciy, (double)sp[1][0][b], (double)sp[1][0][b1]};
@@ -663,6 +695,7 @@ __device__ __forceinline__ int seg_pnpoly(const float* vxs, const float* vys, do
     return r_cross & 1;
 }
 
+constexpr int SEG_RENDER_SPLIT = 16;   // warps that share one polygon's bounding box
 constexpr int SEG_EMPTY = 0x7F7F7F7F;   // cudaMemset(0x7F) background of the atomicMin target
 
 // polygons_to_label: polygons drawn in ascending probability, label = NMS output index + 1  ==  every pixel takes
@@ -674,7 +707,8 @@ __global__ void __launch_bounds__(256) seg_render_kernel(const float* __restrict
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, gwarps = (gridDim.x * blockDim.x) >> 5;
     const int nk = *n_kept;
-    for (int k = gwarp; k < nk; k += gwarps) {
+    for (int job = gwarp; job < nk * SEG_RENDER_SPLIT; job += gwarps) {
+        const int k = job / SEG_RENDER_SPLIT, part = job - k * SEG_RENDER_SPLIT;    // rows part, part + 16, ... of polygon k
         const int r = kept_rank[k];
         __syncwarp();
         const float yv = vy[(size_t)r * SEG_RAYS + lane], xv = vx[(size_t)r * SEG_RAYS + lane];
@@ -690,12 +724,12 @@ __global__ void __launch_bounds__(256) seg_render_kernel(const float* __restrict
         const int minr = (int)fmaxf(0.f, y0), maxr = min(H - 1, (int)ceilf(y1));
         const int minc = (int)fmaxf(0.f, x0), maxc = min(W - 1, (int)ceilf(x1));
         if (maxr < minr || maxc < minc) continue;
-        const int bw = maxc - minc + 1, tot = (maxr - minr + 1) * bw;
-        for (int p = lane; p < tot; p += 32) {
-            const int yy = minr + p / bw, xx = minc + p % bw;
-            if (seg_pnpoly(s_v[wib][1], s_v[wib][0], (double)xx, (double)yy))
-                atomicMin(labels + (size_t)yy * W + xx, k + 1);
-        }
+        const int bw = maxc - minc + 1;
+        for (int yy = minr + part; yy <= maxr; yy += SEG_RENDER_SPLIT)
+            for (int xx = minc + lane; xx <= maxc; xx += 32)
+                if (seg_pnpoly(s_v[wib][1], s_v[wib][0], (double)xx, (double)yy))
+                    atomicMin(labels + (size_t)yy * W + xx, k + 1);
+        (void)bw;
     }
 }
 
@@ -892,13 +926,15 @@ int k_seg_load(cia_ctx* h, const cia_seg_config* cfg, int n_layers, const float*
 int k_seg_normalize(cia_ctx* h, const uint16_t* img, int H, int W, double pmin, double pmax, float* out,
                     float* mi_ma_out, cudaStream_t s) {
     // scratch: 65536-bin histogram + the two percentiles
-    int rc = ws_reserve(h, h->ws_misc, 65536 * sizeof(uint32_t) + 64);
+    int rc = ws_reserve(h, h->ws_misc, (size_t)SEG_HIST_COPIES * 65536 * sizeof(uint32_t) + 64);
     if (rc) return rc;
     uint32_t* hist = (uint32_t*)h->ws_misc.p;
-    float* mima = mi_ma_out ? mi_ma_out : (float*)(hist + 65536);
+    float* mima = mi_ma_out ? mi_ma_out : (float*)(hist + (size_t)SEG_HIST_COPIES * 65536);
     const size_t n = (size_t)H * W;
-    CIA_CUDA(cudaMemsetAsync(hist, 0, 65536 * sizeof(uint32_t), s));
+    CIA_CUDA(cudaMemsetAsync(hist, 0, (size_t)SEG_HIST_COPIES * 65536 * sizeof(uint32_t), s));
     seg_hist_kernel<<<h->num_sms * 8, 256, 0, s>>>(img, n, hist);
+    CIA_LAUNCH_CHECK();
+    seg_hist_reduce_kernel<<<65536 / 256, 256, 0, s>>>(hist);
     CIA_LAUNCH_CHECK();
     seg_percentile_kernel<<<1, 1024, 0, s>>>(hist, n, pmin / 100.0, pmax / 100.0, mima);   // np.true_divide(q, 100)
     CIA_LAUNCH_CHECK();
@@ -1091,7 +1127,7 @@ int k_seg_instances(cia_ctx* h, const float* prob, const float* dist, int Hg, in
     h->launches++;
     seg_compact_kernel<<<(cap + 255) / 256, 256, 0, s>>>(flags, excl, cap, kept, small + 5);
     CIA_LAUNCH_CHECK();
-    seg_render_kernel<<<h->num_sms * 4, 256, 0, s>>>(vy, vx, kept, small + 5, H, W, labels);
+    seg_render_kernel<<<h->num_sms * 8, 256, 0, s>>>(vy, vx, kept, small + 5, H, W, labels);
     CIA_LAUNCH_CHECK();
     seg_finalize_kernel<<<h->num_sms * 8, 256, 0, s>>>(labels, (size_t)H * W);
     CIA_LAUNCH_CHECK();

@@ -53,6 +53,14 @@ static double tri_tri_area(const double* sx, const double* sy, const double* cx,
     mn1 = fmin(fmin(sy[0], sy[1]), sy[2]); mx1 = fmax(fmax(sy[0], sy[1]), sy[2]);
     mn2 = fmin(fmin(cy[0], cy[1]), cy[2]); mx2 = fmax(fmax(cy[0], cy[1]), cy[2]);
     if (mx1 < mn2 || mx2 < mn1) return 0.0;
+    /* separating edge (both triangles are counter-clockwise): exactly 0 */
+    for (int e = 0; e < 3; ++e) {
+        const int e1 = e == 2 ? 0 : e + 1;
+        if (cross_(cx[e], cy[e], cx[e1], cy[e1], sx[0], sy[0]) < 0.0 && cross_(cx[e], cy[e], cx[e1], cy[e1], sx[1], sy[1]) < 0.0 &&
+            cross_(cx[e], cy[e], cx[e1], cy[e1], sx[2], sy[2]) < 0.0) return 0.0;
+        if (cross_(sx[e], sy[e], sx[e1], sy[e1], cx[0], cy[0]) < 0.0 && cross_(sx[e], sy[e], sx[e1], sy[e1], cx[1], cy[1]) < 0.0 &&
+            cross_(sx[e], sy[e], sx[e1], sy[e1], cx[2], cy[2]) < 0.0) return 0.0;
+    }
     double px[8], py[8], qx[8], qy[8];
     int n = 3;
     for (int k = 0; k < 3; ++k) { px[k] = sx[k]; py[k] = sy[k]; }
@@ -99,7 +107,8 @@ double sd_overlap(const float* vy, const float* vx, const int32_t* pyx, const do
         const double sx[3] = {(double)pyx[2 * w + 1], (double)vx[w * NR + a], (double)vx[w * NR + a1]};
         const double sy[3] = {(double)pyx[2 * w], (double)vy[w * NR + a], (double)vy[w * NR + a1]};
         double part = 0.0;
-        for (int b = 0; b < NR; ++b) {
+        for (int st = 0; st < NR; ++st) {           /* the CUDA lane's order: b = a, a + 1, ... */
+            const int b = (a + st) % NR;
             const int b1 = (b + 1) % NR;
             const double cx[3] = {(double)pyx[2 * i + 1], (double)vx[i * NR + b], (double)vx[i * NR + b1]};
             const double cy[3] = {(double)pyx[2 * i], (double)vy[i * NR + b], (double)vy[i * NR + b1]};
