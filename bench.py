@@ -276,6 +276,88 @@ def svm_extras():
     return out
 
 
+def segmentation_extras(with_cpu: bool):
+    """The producer of the label field (csbdeep normalize + StarDist2D.predict_instances,
+    improved_detection.py:62-63) timed on one 2048 x 2048 field: percentile normalisation, the 2D_versatile_fluo
+    U-Net topology with synthetic weights (the pretrained weights are not available offline; the arithmetic does
+    not depend on their values), and candidates + polygon NMS + label rendering on the (prob, dist) maps a trained
+    network emits for a field of ~530 ellipses; then the same labels through the screening path."""
+    import torch
+    from cell_image_analysis_b200 import stardist as sdp, synth
+    from cell_image_analysis_b200.screening import Engine
+    pk = peaks()
+    H = W = 2048
+    cfg = sdp.CONFIG_2D_VERSATILE_FLUO
+    eng = Engine(device=0, precision=1)
+    m = sdp.StarDist2D.from_arrays(cfg, sdp.random_weights(cfg), {"prob": 0.479071, "nms": 0.3}, engine=eng)
+    green, _ = _gen_field(0)
+    g = torch.from_numpy(green.view(np.int16)).to(eng.tdev)
+    x = torch.empty((H, W), dtype=torch.float32, device=eng.tdev)
+    prob, dist = synth.star_maps_from_ellipses(H, W, 2, synth.ellipse_lattice(H, W, 23, 3))
+    pd, dd = torch.from_numpy(prob).to(eng.tdev), torch.from_numpy(dist).to(eng.tdev)
+    labels = torch.empty((H, W), dtype=torch.int32, device=eng.tdev)
+    n_inst = torch.zeros(1, dtype=torch.int32, device=eng.tdev)
+    st = eng._stream
+
+    def f_norm():
+        eng._check(eng.lib.cia_seg_normalize(eng.h, g.data_ptr(), H, W, 3.0, 99.8, x.data_ptr(), None, st()))
+
+    def f_net():
+        eng._check(eng.lib.cia_seg_predict(eng.h, x.data_ptr(), H, W, None, None, st()))
+
+    def f_inst():
+        eng._check(eng.lib.cia_seg_instances(eng.h, pd.data_ptr(), dd.data_ptr(), H // 2, W // 2, 2, H, W, 0.479071, 0.3,
+                                             labels.data_ptr(), n_inst.data_ptr(), st()))
+
+    def timed(fn, reps=5):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        best = 1e9
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1) / reps)
+        return best
+
+    t_norm, t_net, t_inst = timed(f_norm), timed(f_net), timed(f_inst)
+    l0 = eng.launch_count
+    f_norm(); f_net(); f_inst()
+    launches = eng.launch_count - l0
+    flops = sdp.network_flops(cfg, H, W)
+    total = t_norm + t_net + t_inst
+    out = {
+        "field": [H, W], "model": "2D_versatile_fluo topology (grid 2, depth 3, 32 filters, 128 features, 32 rays), synthetic weights",
+        "normalize_ms": t_norm, "unet_ms": t_net, "instances_ms": t_inst, "ms_per_field": total, "fields_per_s": 1e3 / total,
+        "unet_gflop": flops / 1e9, "unet_tflops": flops / (t_net * 1e-3) / 1e12,
+        "unet_frac_of_bf16_peak": flops / (t_net * 1e-3) / 1e12 / pk["tf_burst"],
+        "candidates": int((prob > np.float32(0.479071)).sum()), "instances": int(n_inst.item()),
+        "dtype": "f16 tensor core U-Net (fp32 accumulate), f64 polygon overlap",
+        "gpu_launches_per_field": int(launches),
+        "note": "CUDA events, best of 3 rounds of 5 calls per stage; one field per call",
+    }
+    if with_cpu:
+        # restated CPU path of the same step (oracle: torch-CPU float32 U-Net, C post-processing), one field
+        from oracle import stardist as sdo
+        t0 = time.perf_counter()
+        xn = sdo.normalize(green)
+        t1 = time.perf_counter()
+        sdo.unet_forward(cfg, sdp.random_weights(cfg), xn)
+        t2 = time.perf_counter()
+        ref, _ = sdo.instances_from_prediction(prob, dist, 2, (H, W), 0.479071, 0.3)
+        t3 = time.perf_counter()
+        out["cpu_port"] = {"normalize_ms": 1e3 * (t1 - t0), "unet_ms": 1e3 * (t2 - t1), "instances_ms": 1e3 * (t3 - t2),
+                           "cores": os.cpu_count(), "kind": "port",
+                           "labels_equal_gpu": bool(np.array_equal(ref, labels.cpu().numpy())),
+                           "sample": "one 2048 x 2048 field; the oracle's suppression is a plain O(kept x candidates) loop"}
+    eng.close()
+    return out
+
+
 # ---------------------------------------------------------------------------
 def run_native(args):
     import torch
@@ -510,6 +592,8 @@ def run_native(args):
         }
         if world == 1 and not args.no_svm_extras:
             line["extra"] = {"svm": svm_extras()}
+        if world == 1 and not args.no_seg_extras:
+            line.setdefault("extra", {})["segmentation"] = segmentation_extras(not args.no_cpu_baseline)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_inline(args.cpu_fields)
         print(json.dumps(line), flush=True)
@@ -540,6 +624,7 @@ def main():
     ap.add_argument("--cpu-fields", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-svm-extras", action="store_true")
+    ap.add_argument("--no-seg-extras", action="store_true")
     ap.add_argument("--host-buffers", type=int, default=2, help="device chunk buffers of the host pass (A/B)")
     ap.add_argument("--image-transport", default="auto", choices=["auto", "patches", "dense"],
                     help="e2e pass: send whole images or only the bbox rectangles of the labelled regions "

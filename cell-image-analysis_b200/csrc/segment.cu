@@ -476,25 +476,28 @@ __device__ __forceinline__ double cross_rn(double ax, double ay, double bx, doub
     return __dsub_rn(__dmul_rn(__dsub_rn(bx, ax), __dsub_rn(py, ay)), __dmul_rn(__dsub_rn(by, ay), __dsub_rn(px, ax)));
 }
 
-// area of the intersection of two counter-clockwise triangles (Sutherland-Hodgman, then the shoelace sum);
-// the same statements, in the same order, as oracle/stardist_post.c::tri_tri_area
-__device__ double tri_tri_area(const double* sx, const double* sy, const double* cx, const double* cy) {
+// Two counter-clockwise triangles: do their bounding boxes miss, or does an edge of one have all three vertices of
+// the other strictly outside?  (the same statements, in the same order, as oracle/stardist_post.c::tri_tri_area)
+__device__ __forceinline__ bool tri_separated(const double* sx, const double* sy, const double* cx, const double* cy) {
     double mn1 = fmin(fmin(sx[0], sx[1]), sx[2]), mx1 = fmax(fmax(sx[0], sx[1]), sx[2]);
     double mn2 = fmin(fmin(cx[0], cx[1]), cx[2]), mx2 = fmax(fmax(cx[0], cx[1]), cx[2]);
-    if (mx1 < mn2 || mx2 < mn1) return 0.0;
+    if (mx1 < mn2 || mx2 < mn1) return true;
     mn1 = fmin(fmin(sy[0], sy[1]), sy[2]); mx1 = fmax(fmax(sy[0], sy[1]), sy[2]);
     mn2 = fmin(fmin(cy[0], cy[1]), cy[2]); mx2 = fmax(fmax(cy[0], cy[1]), cy[2]);
-    if (mx1 < mn2 || mx2 < mn1) return 0.0;
-    // separating edge: all three vertices of one triangle strictly outside an edge of the other (both are
-    // counter-clockwise) -> exactly 0, the clipping below is only run on triangles that really overlap
+    if (mx1 < mn2 || mx2 < mn1) return true;
 #pragma unroll
     for (int e = 0; e < 3; ++e) {
         const int e1 = e == 2 ? 0 : e + 1;
         if (cross_rn(cx[e], cy[e], cx[e1], cy[e1], sx[0], sy[0]) < 0.0 && cross_rn(cx[e], cy[e], cx[e1], cy[e1], sx[1], sy[1]) < 0.0 &&
-            cross_rn(cx[e], cy[e], cx[e1], cy[e1], sx[2], sy[2]) < 0.0) return 0.0;
+            cross_rn(cx[e], cy[e], cx[e1], cy[e1], sx[2], sy[2]) < 0.0) return true;
         if (cross_rn(sx[e], sy[e], sx[e1], sy[e1], cx[0], cy[0]) < 0.0 && cross_rn(sx[e], sy[e], sx[e1], sy[e1], cx[1], cy[1]) < 0.0 &&
-            cross_rn(sx[e], sy[e], sx[e1], sy[e1], cx[2], cy[2]) < 0.0) return 0.0;
+            cross_rn(sx[e], sy[e], sx[e1], sy[e1], cx[2], cy[2]) < 0.0) return true;
     }
+    return false;
+}
+
+// area of the intersection of two triangles that are not separated: Sutherland-Hodgman, then the shoelace sum
+__device__ double tri_clip_area(const double* sx, const double* sy, const double* cx, const double* cy) {
     double px[8], py[8], qx[8], qy[8];
     int n = 3;
     for (int k = 0; k < 3; ++k) { px[k] = sx[k]; py[k] = sy[k]; }
@@ -526,14 +529,15 @@ __device__ double tri_tri_area(const double* sx, const double* sy, const double*
 }
 
 struct NmsArgs {
-    const float *vy, *vx, *rmax;
-    const int* pyx;
-    const double* area;
-    const unsigned long long* binkeys;
+    const float *vy, *vx;        // [rank][32]
+    const int* pyx;              // [rank][2]
+    const double* area;          // [rank]
+    const int* b_rank;           // candidates in BIN order (position k): rank,
+    const float4* b_yxr;         //   (y, x, rmax, -)
     const int* bin_start;
     const int* count;
     const unsigned* rmax_all;
-    int* state;          // 0 undecided, 2 suppressed, 4 + round: kept (winner of that round)
+    int* state;          // by bin position: 0 undecided, 2 suppressed, 4 + round: kept (winner of that round)
     int* cnt;            // [3] undecided counters of rounds r, r + 1, r + 2 (mod 3)
     int nbx, nby, cap;
     double thr;
@@ -559,18 +563,59 @@ __device__ double seg_overlap_warp(const NmsArgs& a, int w, int i, float (*sp)[2
     }
     if (y1 < u0 || u1 < y0 || x1 < v0 || v1 < x0) return 0.0;
     const int l1 = (lane + 1) & (SEG_RAYS - 1);
-    double sx[3] = {(double)a.pyx[2 * w + 1], (double)sp[0][1][lane], (double)sp[0][1][l1]};
-    double sy[3] = {(double)a.pyx[2 * w], (double)sp[0][0][lane], (double)sp[0][0][l1]};
+    const double cwx = (double)a.pyx[2 * w + 1], cwy = (double)a.pyx[2 * w];
     const double cix = (double)a.pyx[2 * i + 1], ciy = (double)a.pyx[2 * i];
+    // step 1: lane = fan triangle of w; bit st of `mask` = its pair with triangle (lane + st) of i needs clipping
+    unsigned mask = 0;
+    {
+        const double sx[3] = {cwx, (double)sp[0][1][lane], (double)sp[0][1][l1]};
+        const double sy[3] = {cwy, (double)sp[0][0][lane], (double)sp[0][0][l1]};
+        for (int st = 0; st < SEG_RAYS; ++st) {
+            const int b = (lane + st) & (SEG_RAYS - 1), b1 = (b + 1) & (SEG_RAYS - 1);
+            const double cx[3] = {cix, (double)sp[1][1][b], (double)sp[1][1][b1]};
+            const double cy[3] = {ciy, (double)sp[1][0][b], (double)sp[1][0][b1]};
+            if (!tri_separated(sx, sy, cx, cy)) mask |= 1u << st;
+        }
+    }
+    // step 2: the pairs of all lanes form one list (lane-major, ascending st), clipped 32 at a time with every lane
+    // busy; a lane then adds ITS pairs' areas in list order = the oracle's order (separated pairs contribute +0.0)
+    const int cnt = __popc(mask);
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const int off = incl - cnt, total = __shfl_sync(0xffffffffu, incl, 31);
     double part = 0.0;
-    for (int st = 0; st < SEG_RAYS; ++st) {
-        // fan triangle b = lane + st: for polygons of similar shape the lanes reach their overlapping pairs at
-        // the same steps, so a step in which no lane has work costs the separating-edge test only
-        const int b = (lane + st) & (SEG_RAYS - 1);
-        const int b1 = (b + 1) & (SEG_RAYS - 1);
-        double cx[3] = {cix, (double)sp[1][1][b], (double)sp[1][1][b1]};
-        double cy[3] = {ciy, (double)sp[1][0][b], (double)sp[1][0][b1]};
-        part = __dadd_rn(part, tri_tri_area(sx, sy, cx, cy));
+    for (int g0 = 0; g0 < total; g0 += 32) {
+        const int g = min(g0 + lane, total - 1);
+        int own = 0;                                     // largest lane whose first pair is at or before g
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+            const int oc = __shfl_sync(0xffffffffu, off, own + step);
+            if (oc <= g) own += step;
+        }
+        const int oo = __shfl_sync(0xffffffffu, off, own);
+        const unsigned om = __shfl_sync(0xffffffffu, mask, own);
+        const int st = (int)__fns(om, 0, g - oo + 1);   // the (g - oo + 1)-th set bit
+        double ar = 0.0;
+        if (g0 + lane < total) {
+            const int a1 = (own + 1) & (SEG_RAYS - 1);
+            const int b = (own + st) & (SEG_RAYS - 1), b1 = (b + 1) & (SEG_RAYS - 1);
+            const double sx[3] = {cwx, (double)sp[0][1][own], (double)sp[0][1][a1]};
+            const double sy[3] = {cwy, (double)sp[0][0][own], (double)sp[0][0][a1]};
+            const double cx[3] = {cix, (double)sp[1][1][b], (double)sp[1][1][b1]};
+            const double cy[3] = {ciy, (double)sp[1][0][b], (double)sp[1][0][b1]};
+            ar = tri_clip_area(sx, sy, cx, cy);
+        }
+        const int lo_g = max(off, g0), hi_g = min(off + cnt, g0 + 32);
+        const int mine = max(0, hi_g - lo_g);
+        const int most = __reduce_max_sync(0xffffffffu, mine);
+        for (int t = 0; t < most; ++t) {
+            const double v = __shfl_sync(0xffffffffu, ar, (lo_g + t - g0) & 31);
+            if (t < mine) part = __dadd_rn(part, v);
+        }
     }
     double inter = 0.0;
     for (int l = 0; l < 32; ++l) inter = __dadd_rn(inter, __shfl_sync(0xffffffffu, part, l));
@@ -579,6 +624,8 @@ __device__ double seg_overlap_warp(const NmsArgs& a, int w, int i, float (*sp)[2
 
 __device__ __forceinline__ int ld_volatile(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
 
+// A candidate's neighbours are the candidates of the bins its reach touches; a row of bins is one contiguous range
+// of bin positions, read 32 at a time (coalesced: rank, state, centre and radius all live in bin order).
 __global__ void __launch_bounds__(256) seg_nms_kernel(const NmsArgs a) {
     cg::grid_group grid = cg::this_grid();
     __shared__ float s_poly[8][2][2][SEG_RAYS];
@@ -592,78 +639,73 @@ __global__ void __launch_bounds__(256) seg_nms_kernel(const NmsArgs a) {
     for (int round = 0;; ++round) {
         const int mark = 4 + round;
         if (gtid == 0) a.cnt[(round + 1) % 3] = 0;
-        // ---- phase A: an undecided candidate none of whose better candidates in reach is still open wins ----
-        for (int i = gtid; i < n; i += gthreads) {
-            if (ld_volatile(a.state + i) != 0) continue;
-            const float cy = (float)a.pyx[2 * i], cx = (float)a.pyx[2 * i + 1], ri = a.rmax[i];
-            const float reach = ri + RM + 0.01f;
-            const int by0 = max(0, (int)floorf((cy - reach) * inv_bin)), by1 = min(a.nby - 1, (int)floorf((cy + reach) * inv_bin));
-            const int bx0 = max(0, (int)floorf((cx - reach) * inv_bin)), bx1 = min(a.nbx - 1, (int)floorf((cx + reach) * inv_bin));
-            bool blocked = false;
-            for (int by = by0; by <= by1 && !blocked; ++by)
-                for (int bx = bx0; bx <= bx1 && !blocked; ++bx) {
-                    const int b = by * a.nbx + bx;
-                    for (int k = a.bin_start[b]; k < a.bin_start[b + 1]; ++k) {
-                        const int j = (int)(a.binkeys[k] & 0xffffffffull);
-                        if (j >= i) continue;
-                        const int st = ld_volatile(a.state + j);
-                        if (st != 0 && st != mark) continue;
-                        const float dy = cy - (float)a.pyx[2 * j], dx = cx - (float)a.pyx[2 * j + 1];
-                        const float rr = ri + a.rmax[j] + 0.01f;
-                        if (dy * dy + dx * dx < rr * rr) { blocked = true; break; }
-                    }
-                }
-            if (!blocked) *reinterpret_cast<volatile int*>(a.state + i) = mark;
-        }
-        grid.sync();
-        // ---- phase B: the round's winners suppress their open neighbours (one warp per open candidate) ----
-        for (int i = gwarp; i < n; i += gwarps) {
-            if (ld_volatile(a.state + i) != 0) continue;            // warp-uniform
-            const float cy = (float)a.pyx[2 * i], cx = (float)a.pyx[2 * i + 1], ri = a.rmax[i];
-            const float reach = ri + RM + 0.01f;
-            const int by0 = max(0, (int)floorf((cy - reach) * inv_bin)), by1 = min(a.nby - 1, (int)floorf((cy + reach) * inv_bin));
-            const int bx0 = max(0, (int)floorf((cx - reach) * inv_bin)), bx1 = min(a.nbx - 1, (int)floorf((cx + reach) * inv_bin));
-            bool sup = false;
-            for (int by = by0; by <= by1 && !sup; ++by)
-                for (int bx = bx0; bx <= bx1 && !sup; ++bx) {
-                    const int b = by * a.nbx + bx;
-                    const int ke = a.bin_start[b + 1];
-                    for (int k0 = a.bin_start[b]; k0 < ke && !sup; k0 += 32) {
-                        const int k = k0 + lane;
+        for (int phase = 0; phase < 2; ++phase) {
+            // phase 0: an open candidate none of whose better candidates in reach is still open wins the round
+            // phase 1: the round's winners suppress their open neighbours by the exact overlap
+            for (int k = gwarp; k < n; k += gwarps) {
+                if (ld_volatile(a.state + k) != 0) continue;                 // warp-uniform
+                const int rank = a.b_rank[k];
+                const float4 me = a.b_yxr[k];
+                const float reach = me.z + RM + 0.01f;
+                const int by0 = max(0, (int)floorf((me.x - reach) * inv_bin)), by1 = min(a.nby - 1, (int)floorf((me.x + reach) * inv_bin));
+                const int bx0 = max(0, (int)floorf((me.y - reach) * inv_bin)), bx1 = min(a.nbx - 1, (int)floorf((me.y + reach) * inv_bin));
+                bool done = false;                                           // phase 0: blocked, phase 1: suppressed
+                for (int by = by0; by <= by1 && !done; ++by) {
+                    const int ke = a.bin_start[by * a.nbx + bx1 + 1];
+                    for (int k0 = a.bin_start[by * a.nbx + bx0]; k0 < ke && !done; k0 += 32) {
+                        const int kk = k0 + lane;
                         bool hit = false;
-                        int j = -1;
-                        if (k < ke) {
-                            j = (int)(a.binkeys[k] & 0xffffffffull);
-                            if (j < i && ld_volatile(a.state + j) == mark) {
-                                const float dy = cy - (float)a.pyx[2 * j], dx = cx - (float)a.pyx[2 * j + 1];
-                                const float rr = ri + a.rmax[j] + 0.01f;
-                                hit = dy * dy + dx * dx < rr * rr;
+                        int rj = -1;
+                        if (kk < ke) {
+                            rj = a.b_rank[kk];
+                            if (rj < rank) {
+                                const int st = ld_volatile(a.state + kk);
+                                if (phase == 0 ? (st == 0 || st == mark) : (st == mark)) {
+                                    const float4 o = a.b_yxr[kk];
+                                    const float dy = me.x - o.x, dx = me.y - o.y, rr = me.z + o.z + 0.01f;
+                                    hit = dy * dy + dx * dx < rr * rr;
+                                }
                             }
                         }
                         unsigned m = __ballot_sync(0xffffffffu, hit);
-                        while (m && !sup) {
+                        if (phase == 0) { done = m != 0; continue; }
+                        while (m && !done) {
                             const int src = __ffs(m) - 1;
                             m &= m - 1;
-                            const int w = __shfl_sync(0xffffffffu, j, src);
-                            sup = seg_overlap_warp(a, w, i, s_poly[wib], lane) > a.thr;
+                            const int w = __shfl_sync(0xffffffffu, rj, src);
+                            done = seg_overlap_warp(a, w, rank, s_poly[wib], lane) > a.thr;
                         }
                     }
                 }
-            if (lane == 0) {
-                if (sup) *reinterpret_cast<volatile int*>(a.state + i) = 2;
-                else atomicAdd(a.cnt + round % 3, 1);
+                if (lane == 0) {
+                    if (phase == 0) { if (!done) *reinterpret_cast<volatile int*>(a.state + k) = mark; }
+                    else if (done) *reinterpret_cast<volatile int*>(a.state + k) = 2;
+                    else atomicAdd(a.cnt + round % 3, 1);
+                }
             }
+            grid.sync();
         }
-        grid.sync();
         if (ld_volatile(a.cnt + round % 3) == 0) break;              // the same value for every thread
     }
 }
 
-__global__ void seg_flags_kernel(const int* __restrict__ state, const int* __restrict__ count, int cap,
-                                 int* __restrict__ flags) {
+// bin-order copies of what the suppression reads per neighbour
+__global__ void seg_binorder_kernel(const unsigned long long* __restrict__ binkeys, const int* __restrict__ count, int cap,
+                                    const int* __restrict__ pyx, const float* __restrict__ rmax, int* __restrict__ b_rank,
+                                    float4* __restrict__ b_yxr, int* __restrict__ pos) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= min(*count, cap)) return;
+    const int r = (int)(binkeys[k] & 0xffffffffull);
+    b_rank[k] = r;
+    b_yxr[k] = make_float4((float)pyx[2 * r], (float)pyx[2 * r + 1], rmax[r], 0.f);
+    pos[r] = k;
+}
+
+__global__ void seg_flags_kernel(const int* __restrict__ state, const int* __restrict__ pos, const int* __restrict__ count,
+                                 int cap, int* __restrict__ flags) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= cap) return;
-    flags[r] = (r < min(*count, cap) && state[r] >= 4) ? 1 : 0;
+    flags[r] = (r < min(*count, cap) && state[pos[r]] >= 4) ? 1 : 0;
 }
 
 __global__ void seg_compact_kernel(const int* __restrict__ flags, const int* __restrict__ excl, int cap,
@@ -1070,6 +1112,7 @@ int k_seg_instances(cia_ctx* h, const float* prob, const float* dist, int Hg, in
     const size_t o_area = take((size_t)cap * 8), o_state = take((size_t)cap * 4), o_flags = take((size_t)cap * 4);
     const size_t o_excl = take((size_t)cap * 4), o_kept = take((size_t)cap * 4);
     const size_t o_bins = take((size_t)(nbins + 1) * 4), o_small = take(64);
+    const size_t o_brank = take((size_t)cap * 4), o_byxr = take((size_t)cap * 16), o_pos = take((size_t)cap * 4);
     int rc = ws_reserve(h, m->post, o);
     if (rc) return rc;
     unsigned char* b = (unsigned char*)m->post.p;
@@ -1080,6 +1123,7 @@ int k_seg_instances(cia_ctx* h, const float* prob, const float* dist, int Hg, in
     double* area = (double*)(b + o_area);
     int* state = (int*)(b + o_state); int* flags = (int*)(b + o_flags); int* excl = (int*)(b + o_excl);
     int* kept = (int*)(b + o_kept); int* bins = (int*)(b + o_bins);
+    int* b_rank = (int*)(b + o_brank); float4* b_yxr = (float4*)(b + o_byxr); int* pos = (int*)(b + o_pos);
     int* small = (int*)(b + o_small);         // [0] count, [1] rmax bits, [2..4] nms counters, [5] n_kept
     m->last_cap = cap; m->vy = vy; m->vx = vx; m->pprob = pp; m->pyx = pyx; m->kept_rank = kept; m->n_kept = small + 5;
 
@@ -1107,9 +1151,11 @@ int k_seg_instances(cia_ctx* h, const float* prob, const float* dist, int Hg, in
     h->launches++;
     seg_bins_kernel<<<(nbins + 1 + 255) / 256, 256, 0, s>>>(bk1, small, cap, nbins, bins);
     CIA_LAUNCH_CHECK();
+    seg_binorder_kernel<<<(cap + 255) / 256, 256, 0, s>>>(bk1, small, cap, pyx, rm, b_rank, b_yxr, pos);
+    CIA_LAUNCH_CHECK();
     {
         NmsArgs a{};
-        a.vy = vy; a.vx = vx; a.rmax = rm; a.pyx = pyx; a.area = area; a.binkeys = bk1; a.bin_start = bins; a.count = small;
+        a.vy = vy; a.vx = vx; a.pyx = pyx; a.area = area; a.b_rank = b_rank; a.b_yxr = b_yxr; a.bin_start = bins; a.count = small;
         a.rmax_all = (const unsigned*)(small + 1); a.state = state; a.cnt = small + 2; a.nbx = nbx; a.nby = nby; a.cap = cap;
         a.thr = nms_thresh;
         int per_sm = 0;
@@ -1120,7 +1166,7 @@ int k_seg_instances(cia_ctx* h, const float* prob, const float* dist, int Hg, in
         CIA_CUDA(cudaLaunchCooperativeKernel((void*)seg_nms_kernel, dim3(h->num_sms * per_sm), dim3(256), args, 0, s));
         CIA_LAUNCH_CHECK();
     }
-    seg_flags_kernel<<<(cap + 255) / 256, 256, 0, s>>>(state, small, cap, flags);
+    seg_flags_kernel<<<(cap + 255) / 256, 256, 0, s>>>(state, pos, small, cap, flags);
     CIA_LAUNCH_CHECK();
     tmp_bytes = m->cubtmp.cap;
     CIA_CUDA(cub::DeviceScan::ExclusiveSum(m->cubtmp.p, tmp_bytes, flags, excl, cap, s));

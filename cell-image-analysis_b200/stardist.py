@@ -74,6 +74,79 @@ def load_weights_h5(path: str) -> dict:
     return {k: (v["kernel"], v["bias"]) for k, v in out.items() if "kernel" in v and "bias" in v}
 
 
+def layer_plan(config: dict):
+    """[(layer name, cin, cout, kernel side)] in application order: StarDist2D._build (grid blocks, `features`,
+    `prob`, `dist`) around csbdeep's unet_block (down levels, middle, up levels with skip concatenation)."""
+    grid, depth = int(config["grid"][0]), int(config["unet_n_depth"])
+    nconv, base = int(config["unet_n_conv_per_depth"]), int(config["unet_n_filter_base"])
+    plan, cin, k = [], int(config.get("n_channel_in", 1)), 0
+    pooled = 1
+    while pooled < grid:
+        for _ in range(nconv):
+            plan.append(("conv2d" if k == 0 else f"conv2d_{k}", cin, base, 3))
+            cin, k = base, k + 1
+        pooled *= 2
+    skips = []
+    for n in range(depth):
+        for i in range(nconv):
+            plan.append((f"down_level_{n}_no_{i}", cin, base << n, 3))
+            cin = base << n
+        skips.append(cin)
+    for i in range(nconv - 1):
+        plan.append((f"middle_{i}", cin, base << depth, 3))
+        cin = base << depth
+    plan.append((f"middle_{nconv}", cin, base << max(0, depth - 1), 3))
+    cin = base << max(0, depth - 1)
+    for n in reversed(range(depth)):
+        cin += skips[n]
+        for i in range(nconv - 1):
+            plan.append((f"up_level_{n}_no_{i}", cin, base << n, 3))
+            cin = base << n
+        plan.append((f"up_level_{n}_no_{nconv}", cin, base << max(0, n - 1), 3))
+        cin = base << max(0, n - 1)
+    after = int(config["net_conv_after_unet"])
+    return plan + [("features", cin, after, 3), ("prob", after, 1, 1), ("dist", after, int(config["n_rays"]), 1)]
+
+
+def network_flops(config: dict, H: int, W: int) -> float:
+    """multiply-adds x 2 of one forward pass over an H x W field"""
+    grid, depth, nconv = int(config["grid"][0]), int(config["unet_n_depth"]), int(config["unet_n_conv_per_depth"])
+    shifts, s = [], 0
+    pooled = 1
+    while pooled < grid:
+        shifts += [s] * nconv
+        s, pooled = s + 1, pooled * 2
+    for _ in range(depth):
+        shifts += [s] * nconv
+        s += 1
+    shifts += [s] * nconv
+    for _ in range(depth):
+        s -= 1
+        shifts += [s] * nconv
+    shifts += [s, s, s]
+    return float(sum(2.0 * k * k * ci * co * (H >> sh) * (W >> sh) for (_, ci, co, k), sh in zip(layer_plan(config), shifts)))
+
+
+def random_weights(config: dict, seed: int = 11) -> dict:
+    """Synthetic He-normal weights {layer: (kernel HWIO, bias)} (the pretrained models are not available offline):
+    the arithmetic and the memory traffic of the network do not depend on the weight values."""
+    rng = np.random.default_rng(seed)
+    out = {}
+    for name, cin, cout, k in layer_plan(config):
+        kern = (rng.standard_normal((k, k, cin, cout)) * np.sqrt(2.0 / (k * k * cin))).astype(np.float32)
+        bias = (rng.standard_normal(cout) * 0.05).astype(np.float32)
+        if name == "dist":
+            bias[:] = 6.0
+        out[name] = (kern, bias)
+    return out
+
+
+CONFIG_2D_VERSATILE_FLUO = dict(n_channel_in=1, grid=[2, 2], n_rays=32, unet_n_depth=3, unet_n_filter_base=32,
+                                unet_n_conv_per_depth=2, net_conv_after_unet=128, unet_kernel_size=[3, 3],
+                                unet_pool=[2, 2], unet_activation="relu", unet_last_activation="relu",
+                                unet_batch_norm=False)
+
+
 def ray_angles(n_rays=32):
     return np.linspace(0, 2 * np.pi, n_rays, endpoint=False)
 

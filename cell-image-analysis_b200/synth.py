@@ -15,7 +15,7 @@ from __future__ import annotations
 
 import numpy as np
 
-__all__ = ["make_field", "make_fields", "FIELD_CONFIGS"]
+__all__ = ["make_field", "make_fields", "FIELD_CONFIGS", "star_maps_from_ellipses", "ellipse_lattice"]
 
 # name -> (H, W, n_cells, a_lo, a_hi, log_uniform)
 FIELD_CONFIGS = {
@@ -84,3 +84,48 @@ def make_field(seed: int, H: int = 2048, W: int = 2048, n_cells: int = 520,
 def make_fields(seeds, config: str = "config1"):
     H, W, n, lo, hi, lu = FIELD_CONFIGS[config]
     return [make_field(int(s), H, W, n, lo, hi, lu) for s in seeds]
+
+
+# ---- segmentation inputs: what a trained StarDist network emits for a field of ellipses ----
+def star_maps_from_ellipses(H, W, grid, cells, n_rays=32):
+    """cells: [(cy, cx, a, b, theta)].  prob = 1 - normalized elliptical radius (object probability falling off
+    towards the boundary, as StarDist's edt_prob), dist = exact distance to the ellipse boundary along each ray."""
+    Hg, Wg = H // grid, W // grid
+    prob = np.zeros((Hg, Wg), np.float32)
+    dist = np.full((Hg, Wg, n_rays), 1e-3, np.float32)
+    phis = np.linspace(0, 2 * np.pi, n_rays, endpoint=False)
+    rs, rc = np.sin(phis), np.cos(phis)
+    for cy, cx, a, b, th in cells:
+        r = int(np.ceil(max(a, b))) + 1
+        y0, y1 = max(0, int((cy - r) // grid)), min(Hg, int((cy + r) // grid) + 2)
+        x0, x1 = max(0, int((cx - r) // grid)), min(Wg, int((cx + r) // grid) + 2)
+        yy, xx = np.mgrid[y0:y1, x0:x1]
+        dy, dx = yy * grid - cy, xx * grid - cx
+        c, s = np.cos(th), np.sin(th)
+        u, v = (dx * c + dy * s) / a, (-dx * s + dy * c) / b
+        rho = np.sqrt(u * u + v * v)
+        inside = rho < 1
+        # ray (sin, cos) in (y, x): solve |(p + t d)|_ellipse = 1
+        du = (rc[None, None] * c + rs[None, None] * s) / a
+        dv = (-rc[None, None] * s + rs[None, None] * c) / b
+        A = du * du + dv * dv
+        B = 2 * (u[..., None] * du + v[..., None] * dv)
+        Cc = (u * u + v * v - 1)[..., None]
+        t = (-B + np.sqrt(np.maximum(B * B - 4 * A * Cc, 0))) / (2 * A)
+        sub_p = prob[y0:y1, x0:x1]; sub_d = dist[y0:y1, x0:x1]
+        sub_p[inside] = (1 - rho[inside]).astype(np.float32)
+        sub_d[inside] = np.maximum(t[inside], 1e-3).astype(np.float32)
+    return prob, dist
+
+
+def ellipse_lattice(H, W, n_side, seed):
+    """[(cy, cx, a, b, theta)]: one ellipse per cell of an n_side x n_side jittered lattice, not touching."""
+    rng = np.random.default_rng(seed)
+    pitch = min(H, W) / n_side
+    cells = []
+    for gy in range(n_side):
+        for gx in range(n_side):
+            a = rng.uniform(0.15, 0.42) * pitch
+            cells.append(((gy + 0.5) * pitch + rng.uniform(-4, 4), (gx + 0.5) * pitch + rng.uniform(-4, 4), a,
+                          a * rng.uniform(0.5, 1.0), rng.uniform(0, np.pi)))
+    return cells

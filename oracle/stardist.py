@@ -208,35 +208,8 @@ def predict_instances(cfg, weights, x_normalized, prob_thresh, nms_thresh):
     return instances_from_prediction(prob, dist, int(cfg["grid"][0]), x_normalized.shape, prob_thresh, nms_thresh)
 
 
-# ---- synthetic (prob, dist) maps from ground-truth ellipses: what a trained network would emit ------------
-def star_maps_from_ellipses(H, W, grid, cells, n_rays=32):
-    """cells: [(cy, cx, a, b, theta)].  prob = 1 - normalized elliptical radius (object probability falling off
-    towards the boundary, as StarDist's edt_prob), dist = exact distance to the ellipse boundary along each ray."""
-    Hg, Wg = H // grid, W // grid
-    prob = np.zeros((Hg, Wg), np.float32)
-    dist = np.full((Hg, Wg, n_rays), 1e-3, np.float32)
-    rs, rc = ray_tables(n_rays)
-    for cy, cx, a, b, th in cells:
-        r = int(np.ceil(max(a, b))) + 1
-        y0, y1 = max(0, int((cy - r) // grid)), min(Hg, int((cy + r) // grid) + 2)
-        x0, x1 = max(0, int((cx - r) // grid)), min(Wg, int((cx + r) // grid) + 2)
-        yy, xx = np.mgrid[y0:y1, x0:x1]
-        dy, dx = yy * grid - cy, xx * grid - cx
-        c, s = np.cos(th), np.sin(th)
-        u, v = (dx * c + dy * s) / a, (-dx * s + dy * c) / b
-        rho = np.sqrt(u * u + v * v)
-        inside = rho < 1
-        # ray (sin, cos) in (y, x): solve |(p + t d)|_ellipse = 1
-        du = (rc[None, None] * c + rs[None, None] * s) / a
-        dv = (-rc[None, None] * s + rs[None, None] * c) / b
-        A = du * du + dv * dv
-        B = 2 * (u[..., None] * du + v[..., None] * dv)
-        Cc = (u * u + v * v - 1)[..., None]
-        t = (-B + np.sqrt(np.maximum(B * B - 4 * A * Cc, 0))) / (2 * A)
-        sub_p = prob[y0:y1, x0:x1]; sub_d = dist[y0:y1, x0:x1]
-        sub_p[inside] = (1 - rho[inside]).astype(np.float32)
-        sub_d[inside] = np.maximum(t[inside], 1e-3).astype(np.float32)
-    return prob, dist
+# synthetic (prob, dist) maps from ground-truth ellipses live with the other shared input generators
+from cell_image_analysis_b200.synth import star_maps_from_ellipses   # noqa: E402,F401
 
 
 # ---- a StarDist model folder (config.json, thresholds.json, weights_best.h5) for the loader tests -----------

@@ -123,15 +123,8 @@ def test_network_against_oracle(model):
 
 
 def _ellipse_field(H, W, n_side, seed):
-    rng = np.random.default_rng(seed)
-    pitch = min(H, W) / n_side
-    cells = []
-    for gy in range(n_side):
-        for gx in range(n_side):
-            a = rng.uniform(0.15, 0.42) * pitch
-            cells.append(((gy + 0.5) * pitch + rng.uniform(-4, 4), (gx + 0.5) * pitch + rng.uniform(-4, 4), a,
-                          a * rng.uniform(0.5, 1.0), rng.uniform(0, np.pi)))
-    return cells
+    from cell_image_analysis_b200 import synth
+    return synth.ellipse_lattice(H, W, n_side, seed)
 
 
 @pytest.mark.parametrize("H,W,n_side,seed", [(256, 320, 4, 0), (512, 512, 7, 1), (1024, 1024, 20, 2)])
