@@ -219,6 +219,9 @@ struct SegCfg {
     static constexpr int SMEM_B = A_B + W_B;
     static constexpr int TMEM_COLS = pow2_cols(TILES * N);
     static constexpr int NU = (SEG_KC / 8) * 18 * COLS;   // 16-byte units of one staged block
+    // CTAs that share an SM (512 TMEM columns, 227 KB of shared memory): their stage -> MMA -> epilogue chains interleave
+    static constexpr int CTAS_PER_SM = (512 / TMEM_COLS < (227 * 1024) / (SMEM_B + 2048) ? 512 / TMEM_COLS : (227 * 1024) / (SMEM_B + 2048)) > 3
+                                           ? 3 : (512 / TMEM_COLS < (227 * 1024) / (SMEM_B + 2048) ? 512 / TMEM_COLS : (227 * 1024) / (SMEM_B + 2048));
 };
 
 __device__ __forceinline__ uint4 hmax8(uint4 a, uint4 b) {
@@ -248,7 +251,7 @@ __device__ __forceinline__ uint4 seg_load(const SegConvArgs& a, int pl, int y, i
 
 // EPI 0: bias + ReLU -> fp16 chunk-planar;  EPI 1: heads (columns 0..31 dist = max(1e-3, .), column 32 prob = sigmoid)
 template <int N, int TILES, int EPI>
-__global__ void __launch_bounds__(256, 2) seg_conv_kernel(const SegConvArgs a) {
+__global__ void __launch_bounds__(256, SegCfg<N, TILES>::CTAS_PER_SM) seg_conv_kernel(const SegConvArgs a) {
     using C = SegCfg<N, TILES>;
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ __align__(8) uint64_t bar;
@@ -528,6 +531,9 @@ __device__ double tri_clip_area(const double* sx, const double* sy, const double
     return __dmul_rn(0.5, fabs(s));
 }
 
+#ifndef SEG_NMS_CTAS
+#define SEG_NMS_CTAS 4     // CTAs per SM of the suppression kernel (64 registers: latency-bound fp64 chains want warps)
+#endif
 struct NmsArgs {
     const float *vy, *vx;        // [rank][32]
     const int* pyx;              // [rank][2]
@@ -565,6 +571,29 @@ __device__ double seg_overlap_warp(const NmsArgs& a, int w, int i, float (*sp)[2
     const int l1 = (lane + 1) & (SEG_RAYS - 1);
     const double cwx = (double)a.pyx[2 * w + 1], cwy = (double)a.pyx[2 * w];
     const double cix = (double)a.pyx[2 * i + 1], ciy = (double)a.pyx[2 * i];
+    // step 0, a rigorous shortcut: every term of the fan sum is >= 0, so the sum over ANY subset of pairs is a lower
+    // bound of the intersection.  Candidates of the same nucleus (nearly all tests) overlap far above the threshold:
+    // the same-index pairs, then the neighbouring-index pairs, usually prove "suppressed" after one or three clipped
+    // batches instead of 1024 separation tests + the full list.  The exact sum is only needed near the threshold.
+    {
+        const double denom = __dadd_rn(fmin(a.area[w], a.area[i]), 1e-10);
+        const double need = a.thr * denom * (1.0 + 1e-9);
+        const double sx[3] = {cwx, (double)sp[0][1][lane], (double)sp[0][1][l1]};
+        const double sy[3] = {cwy, (double)sp[0][0][lane], (double)sp[0][0][l1]};
+        double lb = 0.0;
+#pragma unroll 1
+        for (int q = 0; q < 3; ++q) {
+            const int b = (lane + (q == 0 ? 0 : q == 1 ? 1 : SEG_RAYS - 1)) & (SEG_RAYS - 1), b1 = (b + 1) & (SEG_RAYS - 1);
+            const double cx[3] = {cix, (double)sp[1][1][b], (double)sp[1][1][b1]};
+            const double cy[3] = {ciy, (double)sp[1][0][b], (double)sp[1][0][b1]};
+            lb += tri_clip_area(sx, sy, cx, cy);
+            if (q == 1) continue;                        // test after the same-index pairs and after both neighbours
+            double tot = lb;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+            if (tot > need) return tot / denom;          // > thr: the full sum can only be larger
+        }
+    }
     // step 1: lane = fan triangle of w; bit st of `mask` = its pair with triangle (lane + st) of i needs clipping
     unsigned mask = 0;
     {
@@ -626,7 +655,7 @@ __device__ __forceinline__ int ld_volatile(const int* p) { return *reinterpret_c
 
 // A candidate's neighbours are the candidates of the bins its reach touches; a row of bins is one contiguous range
 // of bin positions, read 32 at a time (coalesced: rank, state, centre and radius all live in bin order).
-__global__ void __launch_bounds__(256) seg_nms_kernel(const NmsArgs a) {
+__global__ void __launch_bounds__(256, SEG_NMS_CTAS) seg_nms_kernel(const NmsArgs a) {
     cg::grid_group grid = cg::this_grid();
     __shared__ float s_poly[8][2][2][SEG_RAYS];
     const int n = min(*a.count, a.cap);
@@ -804,7 +833,7 @@ int launch_seg_conv(cia_ctx* h, const SegConvArgs& a, cudaStream_t s) {
         CIA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_B));
     const int tiles_x = (a.W + 8 * TILES - 1) / (8 * TILES), tiles_y = (a.H + 15) / 16;
     int grid = tiles_x * tiles_y * a.groups;
-    if (grid > 2 * h->num_sms) grid = 2 * h->num_sms;
+    if (grid > C::CTAS_PER_SM * h->num_sms) grid = C::CTAS_PER_SM * h->num_sms;
     kern<<<grid, 256, C::SMEM_B, s>>>(a);
     CIA_LAUNCH_CHECK();
     return CIA_OK;

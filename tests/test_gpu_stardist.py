@@ -194,3 +194,29 @@ def test_reflect_padding_of_odd_sizes(model):
     p16, d16 = sd.unet_forward(CFG, model.oracle_weights, xp, half_activations=True)
     assert prob.shape == (35, 45)
     assert np.abs(prob.cpu().numpy() - p16[:35, :45]).max() < 1e-2
+
+
+def test_screening_with_a_model_folder(tmp_path):
+    """ProductionMutantScreening(model_dir, stardist_dir=...): imread -> segmentation on the device -> region scan,
+    equal to handing the same labels over as a NumPy array (det:51-111)."""
+    from cell_image_analysis_b200 import synth
+    from cell_image_analysis_b200.screening import ProductionMutantScreening
+    from oracle import stardist as sd
+    w = sd.random_model(CFG, seed=11, dist_bias=14.0)          # polygons large enough for the area gate (>= 200 px)
+    folder = tmp_path / "sd_demo"
+    sd.write_model_folder(str(folder), CFG, w, prob_thresh=0.479071, nms_thresh=0.3)
+    H, W, n, lo, hi, lu = synth.FIELD_CONFIGS["tiny"]
+    green, _ = synth.make_field(3, H, W, n, lo, hi, lu)
+    golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "model_dir")
+    s = ProductionMutantScreening(golden, imread=lambda p: green, stardist_dir=str(folder))
+    m = s.stardist_model
+    assert m.layer_order == [p[0] for p in sd.layer_plan(CFG)] and m.thresholds["nms"] == 0.3
+    prob, _ = m.predict(m.normalize_device(green))
+    m.thresholds["prob"] = float(np.quantile(prob.cpu().numpy(), 0.7))     # an untrained network: pick a working threshold
+    cells, stats = s.extract_quality_cells("field_000.tif")
+    labels, _ = m.predict_instances(sd.normalize(green))
+    assert labels.max() > 0
+    cells2, stats2 = s.extract_quality_cells_from_labels(green, labels)
+    assert len(cells) == len(cells2) and stats == stats2
+    assert all(np.array_equal(a, b) for a, b in zip(cells, cells2))
+    print(f"{labels.max()} instances, {len(cells)} quality cells")
