@@ -175,23 +175,32 @@ __global__ void __launch_bounds__(256) seg_first_kernel(const float* __restrict_
         const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
         v[t] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(img + (size_t)yy * W + xx) : 0.f;
     }
-    const float4* sw4 = reinterpret_cast<const float4*>(sw);
+    // packed fp32x2 FMAs (sm_100): the pixel value in both lanes, two output channels per instruction (each lane
+    // an IEEE fma: the sums of the scalar loop), weights as 64-bit pairs straight from shared memory
+    unsigned long long v2[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) v2[t] = pack2(v[t], v[t]);
+    const ulonglong2* sw2 = reinterpret_cast<const ulonglong2*>(sw);
     for (int cgp = 0; cgp < cout / 8; ++cgp) {
         __align__(16) __half o[8];
-        float acc[8];
+        unsigned long long acc[4];
         {
-            const float4 b0 = sw4[(9 * cout + cgp * 8) / 4], b1 = sw4[(9 * cout + cgp * 8) / 4 + 1];
-            acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w; acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
+            const ulonglong2 b0 = sw2[(9 * cout + cgp * 8) / 4], b1 = sw2[(9 * cout + cgp * 8) / 4 + 1];
+            acc[0] = b0.x; acc[1] = b0.y; acc[2] = b1.x; acc[3] = b1.y;
         }
 #pragma unroll
-        for (int t = 0; t < 9; ++t) {                 // taps in order, one FMA each: the same sums as before
-            const float4 w0 = sw4[(t * cout + cgp * 8) / 4], w1 = sw4[(t * cout + cgp * 8) / 4 + 1];
-            acc[0] = fmaf(v[t], w0.x, acc[0]); acc[1] = fmaf(v[t], w0.y, acc[1]); acc[2] = fmaf(v[t], w0.z, acc[2]);
-            acc[3] = fmaf(v[t], w0.w, acc[3]); acc[4] = fmaf(v[t], w1.x, acc[4]); acc[5] = fmaf(v[t], w1.y, acc[5]);
-            acc[6] = fmaf(v[t], w1.z, acc[6]); acc[7] = fmaf(v[t], w1.w, acc[7]);
+        for (int t = 0; t < 9; ++t) {
+            const ulonglong2 w0 = sw2[(t * cout + cgp * 8) / 4], w1 = sw2[(t * cout + cgp * 8) / 4 + 1];
+            acc[0] = fma2(v2[t], w0.x, acc[0]); acc[1] = fma2(v2[t], w0.y, acc[1]);
+            acc[2] = fma2(v2[t], w1.x, acc[2]); acc[3] = fma2(v2[t], w1.y, acc[3]);
         }
 #pragma unroll
-        for (int k = 0; k < 8; ++k) o[k] = __float2half_rn(fmaxf(acc[k], 0.f));
+        for (int k = 0; k < 4; ++k) {
+            float lo, hi;
+            unpack2(acc[k], lo, hi);
+            o[2 * k] = __float2half_rn(fmaxf(lo, 0.f));
+            o[2 * k + 1] = __float2half_rn(fmaxf(hi, 0.f));
+        }
         *reinterpret_cast<uint4*>(out + (((size_t)cgp * H + y) * W + x) * 8) = *reinterpret_cast<const uint4*>(o);
     }
 }
@@ -220,8 +229,8 @@ struct SegCfg {
     static constexpr int TMEM_COLS = pow2_cols(TILES * N);
     static constexpr int NU = (SEG_KC / 8) * 18 * COLS;   // 16-byte units of one staged block
     // CTAs that share an SM (512 TMEM columns, 227 KB of shared memory): their stage -> MMA -> epilogue chains interleave
-    static constexpr int CTAS_PER_SM = (512 / TMEM_COLS < (227 * 1024) / (SMEM_B + 2048) ? 512 / TMEM_COLS : (227 * 1024) / (SMEM_B + 2048)) > 3
-                                           ? 3 : (512 / TMEM_COLS < (227 * 1024) / (SMEM_B + 2048) ? 512 / TMEM_COLS : (227 * 1024) / (SMEM_B + 2048));
+    static constexpr int BY_TMEM = 512 / TMEM_COLS, BY_SMEM = (227 * 1024) / (SMEM_B + 2048);
+    static constexpr int CTAS_PER_SM = (BY_TMEM < BY_SMEM ? BY_TMEM : BY_SMEM) > 4 ? 4 : (BY_TMEM < BY_SMEM ? BY_TMEM : BY_SMEM);
 };
 
 __device__ __forceinline__ uint4 hmax8(uint4 a, uint4 b) {
@@ -303,7 +312,9 @@ __global__ void __launch_bounds__(256, SegCfg<N, TILES>::CTAS_PER_SM) seg_conv_k
                         const int ry = rem / C::COLS, rc = rem - ry * C::COLS;
                         const int y = y0 + ry - 1, x = x0 + rc - 1;
                         d[j] = (uint32_t)idx * 16u;
-                        if (y >= 0 && y < a.H && x >= 0 && x < a.W) v[j] = seg_load(a, kc * (SEG_KC / 8) + c, y, x);
+                        // a one-tap layer (the heads) never reads the halo ring
+                        const bool halo = a.ntaps == 1 && (ry == 0 || ry == 17 || rc == 0 || rc == C::COLS - 1);
+                        if (!halo && y >= 0 && y < a.H && x >= 0 && x < a.W) v[j] = seg_load(a, kc * (SEG_KC / 8) + c, y, x);
                     }
                 }
 #pragma unroll
@@ -1078,7 +1089,7 @@ int k_seg_predict(cia_ctx* h, const float* img, int H, int W, float* prob_out, f
         a.w = (const uint4*)c.w_img; a.bias = c.bias;
         a.prob = m->prob_map; a.dist = m->dist_map;
         a.H = Hg; a.W = Wg; a.c0 = c.cin; a.c1 = 0; a.mode = 0; a.ntaps = 1; a.groups = 1; a.chunks = c.chunks;
-        rc = launch_seg_conv<48, 4, 1>(h, a, s);
+        rc = launch_seg_conv<48, 2, 1>(h, a, s);
         if (rc) return rc;
     }
     if (prob_out) CIA_CUDA(cudaMemcpyAsync(prob_out, m->prob_map, (size_t)Hg * Wg * sizeof(float), cudaMemcpyDeviceToDevice, s));
@@ -1097,7 +1108,7 @@ int k_seg_debug_layer(cia_ctx* h, int layer, const void* src0, const void* src1,
         SegConvArgs a{};
         a.src0 = (const __half*)src0; a.w = (const uint4*)c.w_img; a.bias = c.bias; a.prob = prob; a.dist = dist;
         a.H = Ho; a.W = Wo; a.c0 = c.cin; a.mode = 0; a.ntaps = 1; a.groups = 1; a.chunks = c.chunks;
-        return launch_seg_conv<48, 4, 1>(h, a, s);
+        return launch_seg_conv<48, 2, 1>(h, a, s);
     }
     if (layer < 0 || layer >= (int)m->ops.size()) { h->err = "segmentation: no such layer"; return CIA_E_ARG; }
     const SegOp& op = m->ops[layer];
