@@ -296,13 +296,15 @@ __global__ void __launch_bounds__(256, SegCfg<N, TILES>::CTAS_PER_SM) seg_conv_k
                 const uint4* wsrc = a.w + (size_t)(g * a.chunks + kc) * w_units;
                 for (int i = tid; i < w_units; i += 256) reinterpret_cast<uint4*>(sw)[i] = __ldg(wsrc + i);
             }
-            // input block: loads in batches of four independent requests per thread before any store
+            // input block: two batches of independent 16-byte requests per thread, all of a batch in flight before
+            // any store (a block costs two memory round trips)
+            constexpr int SB = ((C::NU + 255) / 256 + 1) / 2;
 #pragma unroll 1
-            for (int i0 = tid; i0 < C::NU; i0 += 4 * 256) {
-                uint4 v[4];
-                uint32_t d[4];
+            for (int i0 = tid; i0 < C::NU; i0 += SB * 256) {
+                uint4 v[SB];
+                uint32_t d[SB];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < SB; ++j) {
                     const int idx = i0 + j * 256;
                     d[j] = 0xFFFFFFFFu;
                     v[j] = make_uint4(0, 0, 0, 0);
@@ -318,7 +320,7 @@ __global__ void __launch_bounds__(256, SegCfg<N, TILES>::CTAS_PER_SM) seg_conv_k
                     }
                 }
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
+                for (int j = 0; j < SB; ++j)
                     if (d[j] != 0xFFFFFFFFu) *reinterpret_cast<uint4*>(sa + d[j]) = v[j];
             }
             fence_async_smem();

@@ -226,7 +226,10 @@ def screen_mutant_samples_sharded(screener, test_folders_dict, output_dir=None, 
                 seg, green = image[..., 2], image[..., 1]
             else:
                 seg = green = image
-            return np.ascontiguousarray(green), np.ascontiguousarray(screener._segment(seg), np.int32)
+            labels = screener._segment(seg)
+            if hasattr(labels, "cpu"):        # stardist_dir=...: the GPU segmentation returns a device tensor
+                labels = labels.cpu().numpy()
+            return np.ascontiguousarray(green), np.ascontiguousarray(labels, np.int32)
         except Exception as e:                                            # det:113-115: the file contributes no cells
             print(f"Error processing {files[i]}: {e}")
             return None

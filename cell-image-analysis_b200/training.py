@@ -69,7 +69,10 @@ class ImprovedAnomalyDetectionTraining:
                 seg_channel, green_channel = image[..., 2], image[..., 1]
             else:
                 seg_channel = green_channel = image
-            labels, _details = stardist_model.predict_instances(_normalize(seg_channel))   # train:54-55
+            if hasattr(stardist_model, "segment_device") and np.asarray(seg_channel).dtype in (np.uint8, np.uint16):
+                labels, _n = stardist_model.segment_device(seg_channel)      # train:54-55 on the GPU, labels stay there
+            else:
+                labels, _details = stardist_model.predict_instances(_normalize(seg_channel))   # train:54-55
             cells, stats = self._x.extract_quality_cells_from_labels(green_channel, labels)
             for s in stats:
                 s["file"] = os.path.basename(image_path)          # train:104

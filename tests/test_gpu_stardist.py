@@ -220,3 +220,25 @@ def test_screening_with_a_model_folder(tmp_path):
     assert len(cells) == len(cells2) and stats == stats2
     assert all(np.array_equal(a, b) for a, b in zip(cells, cells2))
     print(f"{labels.max()} instances, {len(cells)} quality cells")
+
+
+def test_training_twin_with_the_gpu_model(tmp_path):
+    """ImprovedAnomalyDetectionTraining.extract_quality_cells(image_path, stardist_model) (train:39-111) with the
+    GPU StarDist2D as ``stardist_model``: same cells as the NumPy-label route, 'file' and 'solidity' present."""
+    from cell_image_analysis_b200 import synth
+    from cell_image_analysis_b200.stardist import StarDist2D
+    from cell_image_analysis_b200.training import ImprovedAnomalyDetectionTraining
+    from oracle import stardist as sd
+    H, W, n, lo, hi, lu = synth.FIELD_CONFIGS["tiny"]
+    green, _ = synth.make_field(4, H, W, n, lo, hi, lu)
+    t = ImprovedAnomalyDetectionTraining(str(tmp_path), imread=lambda p: green)
+    m = StarDist2D.from_arrays(CFG, sd.random_model(CFG, seed=11, dist_bias=14.0), {"prob": 0.5, "nms": 0.3},
+                               engine=t.engine)
+    prob, _ = m.predict(m.normalize_device(green))
+    m.thresholds["prob"] = float(np.quantile(prob.cpu().numpy(), 0.7))
+    cells, stats = t.extract_quality_cells("a/b/field_7.tif", m)
+    labels, _ = m.predict_instances(sd.normalize(green))
+    cells2, stats2 = t._x.extract_quality_cells_from_labels(green, labels)
+    assert len(cells) == len(cells2) > 0
+    assert all(np.array_equal(a, b) for a, b in zip(cells, cells2))
+    assert all(s["file"] == "field_7.tif" and "solidity" in s for s in stats)
