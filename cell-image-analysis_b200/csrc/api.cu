@@ -84,6 +84,9 @@ int cia_set_option(cia_handle h, const char* name, double value) {
         h->pca_kernel = (int)value;
     } else if (n == "svm_refine") {
         h->svm_refine = value != 0;
+    } else if (n == "seg_conv_tma") {
+        // segmentation: 1 = single-chunk direct layers run the TMA-fed warp-specialised kernel, 0 = the staged kernel everywhere
+        h->seg_conv_tma = value != 0;
     } else {
         h->err = "cia_set_option: unknown option '" + n + "'";
         return CIA_E_ARG;

@@ -30,6 +30,7 @@
 
 #include <cooperative_groups.h>
 #include <cub/cub.cuh>
+#include <cuda.h>          // CUtensorMap (types only; the encoder is fetched through the runtime)
 #include <cuda_fp16.h>
 
 #include <cmath>
@@ -403,6 +404,137 @@ __global__ void __launch_bounds__(256, SegCfg<N, TILES>::CTAS_PER_SM) seg_conv_k
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------
+// The same convolution for layers that read their producer directly with Cin = 32 (one chunk, weights resident:
+// the two full-resolution layers, `features`, the second layer of a level): TMA-fed and warp-specialised.
+//   warp 8  : one lane issues a cp.async.bulk.tensor.4d box (8 halves, 8 TILES + 2 columns, 18 rows, 4 planes) per
+//             unit into a 3-stage ring; out-of-bounds coordinates zero-fill the halo ('same' padding for free)
+//   warp 9  : one elected lane issues the unit's 18 TILES MMAs into one of two TMEM accumulator sets and commits to the
+//             stage's `empty` barrier (the block is free) and the set's `full` barrier
+//   warps 0-7: epilogue of unit u (tcgen05.ld, bias, ReLU, fp16, 16-byte stores) under the MMAs of unit u + 1
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2,%3,%4,%5}], [%6];"
+        ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar)) : "memory");
+}
+
+template <int N, int TILES>
+struct SegTmaCfg {
+    using B = SegCfg<N, TILES>;
+    static constexpr int STAGES = 3;
+    static constexpr int A_STRIDE = (B::A_B + 1023) / 1024 * 1024;
+    static constexpr int SMEM_B = STAGES * A_STRIDE + B::W_B;
+    static constexpr int TMEM_COLS = pow2_cols(2 * TILES * N);
+    static constexpr int THREADS = 320;
+    static_assert(TMEM_COLS <= 512 && SMEM_B <= 225 * 1024, "does not fit");
+};
+
+template <int N, int TILES>
+__global__ void __launch_bounds__(320, 1) seg_conv_tma_kernel(const __grid_constant__ CUtensorMap tm, const uint4* __restrict__ w,
+                                                              const float* __restrict__ bias, __half* __restrict__ out,
+                                                              int H, int W) {
+    using C = SegCfg<N, TILES>;
+    using T = SegTmaCfg<N, TILES>;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ __align__(8) uint64_t full[T::STAGES], empty[T::STAGES], tfull[2], tempty[2];
+    __shared__ uint32_t tmem_base_s;
+    unsigned char* sw = smem + T::STAGES * T::A_STRIDE;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tiles_x = (W + 8 * TILES - 1) / (8 * TILES), tiles_y = (H + 15) / 16;
+    const int n_units = tiles_x * tiles_y;
+    if ((int)blockIdx.x >= n_units) return;
+
+    if (warp == 0) tmem_alloc(&tmem_base_s, T::TMEM_COLS);
+    if (tid == 32) {
+        for (int s = 0; s < T::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(&tfull[0], 1); mbar_init(&tfull[1], 1);
+        mbar_init(&tempty[0], 8); mbar_init(&tempty[1], 8);
+        fence_barrier_init();
+    }
+    for (int i = tid; i < C::W_B / 16; i += T::THREADS) reinterpret_cast<uint4*>(sw)[i] = __ldg(w + i);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    constexpr uint32_t IDESC = make_idesc(128, N);
+
+    if (warp == 8) {
+        if (lane == 0) {
+            int j = 0;
+            for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++j) {
+                const int s = j % T::STAGES;
+                mbar_wait(&empty[s], (uint32_t)(((j / T::STAGES) & 1) ^ 1));
+                const int ty = unit / tiles_x, tx = unit - ty * tiles_x;
+                mbar_expect_tx(&full[s], C::A_B);
+                tma_load_4d(smem_u32(smem + s * T::A_STRIDE), &tm, 0, 8 * TILES * tx - 1, 16 * ty - 1, 0, &full[s]);
+            }
+        }
+    } else if (warp == 9) {
+        int j = 0;
+        for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++j) {
+            const int s = j % T::STAGES, t = j & 1;
+            mbar_wait(&full[s], (uint32_t)((j / T::STAGES) & 1));
+            mbar_wait(&tempty[t], (uint32_t)(((j >> 1) & 1) ^ 1));
+            tc_fence_after();
+            if (elect_one()) {
+                const uint64_t ad0 = make_smem_desc(smem_u32(smem + s * T::A_STRIDE), C::PLANE_B, C::ROW_B);
+                const uint64_t bd0 = make_smem_desc(smem_u32(sw), N * 16, 128);
+                const uint32_t d0 = tmem_base + (uint32_t)(t * TILES * N);
+#pragma unroll
+                for (int tap = 0; tap < 9; ++tap) {
+                    const int dy = tap / 3, dx = tap % 3;
+#pragma unroll
+                    for (int ks = 0; ks < SEG_KC / 16; ++ks)
+#pragma unroll
+                        for (int tile = 0; tile < TILES; ++tile) {
+                            const uint64_t ad = ad0 + (uint64_t)((tile * 128 + dx * 16 + dy * C::ROW_B + 2 * ks * C::PLANE_B) >> 4);
+                            const uint64_t bd = bd0 + (uint64_t)(((tap * (SEG_KC / 8) + 2 * ks) * N * 16) >> 4);
+                            umma_f16(d0 + (uint32_t)(tile * N), ad, bd, IDESC, (tap == 0 && ks == 0) ? 0u : 1u);
+                        }
+                }
+                umma_commit(&empty[s]);
+                umma_commit(&tfull[t]);
+            }
+            __syncwarp();
+        }
+    } else {
+        const int q = warp & 3, half_sel = warp >> 2;
+        const int r = 32 * q + lane;
+        constexpr int SL = N / 8;
+        int j = 0;
+        for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++j) {
+            const int t = j & 1;
+            const int ty = unit / tiles_x, tx = unit - ty * tiles_x;
+            const int y = 16 * ty + (r >> 3), x0 = 8 * TILES * tx;
+            mbar_wait(&tfull[t], (uint32_t)((j >> 1) & 1));
+            tc_fence_after();
+            const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(t * TILES * N);
+#pragma unroll 1
+            for (int p = half_sel; p < TILES * SL; p += 2) {
+                const int tile = p / SL, sl = p - tile * SL;
+                const int x = x0 + 8 * tile + (r & 7);
+                uint32_t v[8];
+                TMEM_LD8(lane_addr + (uint32_t)(tile * N + sl * 8), v);
+                TMEM_WAIT8(v);
+                __align__(16) __half o[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    o[k] = __float2half_rn(fmaxf(__fadd_rn(__uint_as_float(v[k]), __ldg(bias + sl * 8 + k)), 0.f));
+                if (y < H && x < W)
+                    *reinterpret_cast<uint4*>(out + (((size_t)sl * H + y) * W + x) * 8) = *reinterpret_cast<const uint4*>(o);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[t]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, T::TMEM_COLS);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -860,6 +992,53 @@ int launch_seg_conv(cia_ctx* h, const SegConvArgs& a, cudaStream_t s) {
     return CIA_OK;
 }
 
+typedef CUresult (*SegTensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                         const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                         CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+template <int N, int TILES>
+int launch_seg_conv_tma(cia_ctx* h, const SegConvArgs& a, cudaStream_t s) {
+    using C = SegCfg<N, TILES>;
+    using T = SegTmaCfg<N, TILES>;
+    static SegTensorMapEncodeFn encode = [] {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess) fn = nullptr;
+        return (SegTensorMapEncodeFn)fn;
+    }();
+    if (!encode) { h->err = "cuTensorMapEncodeTiled is not available from this driver"; return CIA_E_UNSUPPORTED; }
+    // chunk-planar fp16 activations [4 planes][H][W][8]: dims (8, x, y, plane); out-of-bounds reads give zeros
+    CUtensorMap tm;
+    const cuuint64_t dims[4] = {8, (cuuint64_t)a.W, (cuuint64_t)a.H, 4};
+    const cuuint64_t strides[3] = {16, (cuuint64_t)16 * a.W, (cuuint64_t)16 * a.W * a.H};
+    const cuuint32_t box[4] = {8, (cuuint32_t)C::COLS, 18, 4};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    if (encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)a.src0, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+        h->err = "cuTensorMapEncodeTiled failed (segmentation activations)";
+        return CIA_E_CUDA;
+    }
+    auto kern = seg_conv_tma_kernel<N, TILES>;
+    if (first_use(h, (const void*)kern))
+        CIA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_B));
+    const int tiles_x = (a.W + 8 * TILES - 1) / (8 * TILES), tiles_y = (a.H + 15) / 16;
+    int grid = tiles_x * tiles_y;
+    if (grid > h->num_sms) grid = h->num_sms;
+    kern<<<grid, T::THREADS, T::SMEM_B, s>>>(tm, a.w, a.bias, a.out, a.H, a.W);
+    CIA_LAUNCH_CHECK();
+    return CIA_OK;
+}
+
+// one 3x3 layer of the plan: the TMA-fed kernel where the layer reads its producer directly with one 32-channel chunk
+int launch_seg_layer(cia_ctx* h, const SegConv& c, const SegConvArgs& a, cudaStream_t s) {
+    const bool tma = h->seg_conv_tma && a.mode == 0 && c.chunks == 1 && c.groups == 1 && ((size_t)a.src0 % 16) == 0;
+    if (tma && c.n_tile == 32) return launch_seg_conv_tma<32, 4>(h, a, s);
+    if (tma && c.n_tile == 128) return launch_seg_conv_tma<128, 2>(h, a, s);
+    if (c.n_tile == 128) return launch_seg_conv<128, 2, 0>(h, a, s);
+    if (c.n_tile == 64) return launch_seg_conv<64, 4, 0>(h, a, s);
+    return launch_seg_conv<32, 4, 0>(h, a, s);
+}
+
 int free_model(SegModel* m) {
     if (!m) return 0;
     for (auto& c : m->conv) { cudaFree(c.w_img); cudaFree(c.bias); cudaFree(c.w32); }
@@ -1078,9 +1257,7 @@ int k_seg_predict(cia_ctx* h, const float* img, int H, int W, float* prob_out, f
         a.src1 = op.src1 >= 0 ? (const __half*)(base + off[op.src1]) : nullptr;
         a.w = (const uint4*)c.w_img; a.bias = c.bias; a.out = out;
         a.H = Ho; a.W = Wo; a.c0 = op.c0; a.c1 = op.c1; a.mode = op.mode; a.ntaps = 9; a.groups = c.groups; a.chunks = c.chunks;
-        if (c.n_tile == 128) rc = launch_seg_conv<128, 2, 0>(h, a, s);
-        else if (c.n_tile == 64) rc = launch_seg_conv<64, 4, 0>(h, a, s);
-        else rc = launch_seg_conv<32, 4, 0>(h, a, s);
+        rc = launch_seg_layer(h, c, a, s);
         if (rc) return rc;
     }
     {
@@ -1124,9 +1301,7 @@ int k_seg_debug_layer(cia_ctx* h, int layer, const void* src0, const void* src1,
     SegConvArgs a{};
     a.src0 = (const __half*)src0; a.src1 = (const __half*)src1; a.w = (const uint4*)c.w_img; a.bias = c.bias; a.out = (__half*)out;
     a.H = Ho; a.W = Wo; a.c0 = op.c0; a.c1 = op.c1; a.mode = op.mode; a.ntaps = 9; a.groups = c.groups; a.chunks = c.chunks;
-    if (c.n_tile == 128) return launch_seg_conv<128, 2, 0>(h, a, s);
-    if (c.n_tile == 64) return launch_seg_conv<64, 4, 0>(h, a, s);
-    return launch_seg_conv<32, 4, 0>(h, a, s);
+    return launch_seg_layer(h, c, a, s);
 }
 
 int k_seg_layer_info(cia_ctx* h, int layer, int* info /* [6]: mode, c0, c1, cout, shift, n_layers */) {
