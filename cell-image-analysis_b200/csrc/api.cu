@@ -87,6 +87,11 @@ int cia_set_option(cia_handle h, const char* name, double value) {
     } else if (n == "seg_conv_tma") {
         // segmentation: 1 = single-chunk direct layers run the TMA-fed warp-specialised kernel, 0 = the staged kernel everywhere
         h->seg_conv_tma = value != 0;
+    } else if (n == "seg_conv_ws") {
+        // segmentation: the warp-specialised software-producer kernel: 1 = for the layers where it measured faster, 2 = every
+        // layer the TMA kernel does not take, 0 = the staged kernel
+        if (value != 0 && value != 1 && value != 2) { h->err = "cia_set_option: seg_conv_ws is 0 (off), 1 (where it pays) or 2 (every layer)"; return CIA_E_ARG; }
+        h->seg_conv_ws = (int)value;
     } else {
         h->err = "cia_set_option: unknown option '" + n + "'";
         return CIA_E_ARG;

@@ -538,6 +538,165 @@ __global__ void __launch_bounds__(320, 1) seg_conv_tma_kernel(const __grid_const
 }
 
 // ---------------------------------------------------------------------------------------
+// The general layer in the same warp-specialised form: the producer is SOFTWARE (eight warps run the staging of
+// seg_conv_kernel -- pooled, up-sampled + concatenated or direct inputs, any number of 32-channel chunks, each with
+// its weight block -- into a 2-3 stage ring and arrive on the stage's `full` barrier), one warp issues the MMAs of a
+// (unit, chunk) step as soon as its stage is full, eight warps run the epilogue of unit u under the MMAs of unit u + 1.
+// Staging, tensor math and epilogue of DIFFERENT units overlap inside one CTA instead of across co-resident CTAs.
+// ---------------------------------------------------------------------------------------
+template <int N, int TILES>
+struct SegWsCfg {
+    using B = SegCfg<N, TILES>;
+    static constexpr int STAGE_B = (B::A_B + B::W_B + 1023) / 1024 * 1024;
+    static constexpr int STAGES = (220 * 1024) / STAGE_B >= 3 ? 3 : 2;
+    static constexpr int SMEM_B = STAGES * STAGE_B;
+    static constexpr int TMEM_COLS = pow2_cols(2 * TILES * N);
+    static constexpr int PROD = 256;                       // producer threads (warps 8..15)
+    static constexpr int THREADS = 256 + PROD + 32;        // epilogue warps 0..7, producers, MMA warp 16
+    static_assert(TMEM_COLS <= 512 && SMEM_B <= 225 * 1024, "does not fit");
+};
+
+template <int N, int TILES>
+__global__ void __launch_bounds__(SegWsCfg<N, TILES>::THREADS, 1) seg_conv_ws_kernel(const SegConvArgs a) {
+    using C = SegCfg<N, TILES>;
+    using T = SegWsCfg<N, TILES>;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ __align__(8) uint64_t full[T::STAGES], empty[T::STAGES], tfull[2], tempty[2];
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tiles_x = (a.W + 8 * TILES - 1) / (8 * TILES), tiles_y = (a.H + 15) / 16;
+    const int per_group = tiles_x * tiles_y;
+    const int n_units = per_group * a.groups;
+    if ((int)blockIdx.x >= n_units) return;
+
+    if (warp == 0) tmem_alloc(&tmem_base_s, T::TMEM_COLS);
+    if (tid == 32) {
+        for (int s = 0; s < T::STAGES; ++s) { mbar_init(&full[s], T::PROD); mbar_init(&empty[s], 1); }
+        mbar_init(&tfull[0], 1); mbar_init(&tfull[1], 1);
+        mbar_init(&tempty[0], 8); mbar_init(&tempty[1], 8);
+        fence_barrier_init();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    constexpr uint32_t IDESC = make_idesc(128, N);
+    const int w_units = a.ntaps * (C::WT_B / 16);
+
+    if (warp >= 8 && warp < 16) {
+        // ---- producers ----
+        const int pt = tid - 256;
+        int step = 0;
+        for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+            const int g = unit / per_group, t2 = unit - g * per_group;
+            const int ty = t2 / tiles_x, tx = t2 - ty * tiles_x;
+            const int y0 = 16 * ty, x0 = 8 * TILES * tx;
+            for (int kc = 0; kc < a.chunks; ++kc, ++step) {
+                const int s = step % T::STAGES;
+                mbar_wait(&empty[s], (uint32_t)(((step / T::STAGES) & 1) ^ 1));
+                unsigned char* sa = smem + s * T::STAGE_B;
+                unsigned char* sw = sa + C::A_B;
+                const uint4* wsrc = a.w + (size_t)(g * a.chunks + kc) * w_units;
+                for (int i = pt; i < w_units; i += T::PROD) reinterpret_cast<uint4*>(sw)[i] = __ldg(wsrc + i);
+                constexpr int SB = ((C::NU + T::PROD - 1) / T::PROD + 1) / 2;
+#pragma unroll 1
+                for (int i0 = pt; i0 < C::NU; i0 += SB * T::PROD) {
+                    uint4 v[SB];
+                    uint32_t d[SB];
+#pragma unroll
+                    for (int j = 0; j < SB; ++j) {
+                        const int idx = i0 + j * T::PROD;
+                        d[j] = 0xFFFFFFFFu;
+                        v[j] = make_uint4(0, 0, 0, 0);
+                        if (idx < C::NU) {
+                            const int c = idx / (18 * C::COLS);
+                            const int rem = idx - c * (18 * C::COLS);
+                            const int ry = rem / C::COLS, rc = rem - ry * C::COLS;
+                            const int y = y0 + ry - 1, x = x0 + rc - 1;
+                            d[j] = (uint32_t)idx * 16u;
+                            if (y >= 0 && y < a.H && x >= 0 && x < a.W) v[j] = seg_load(a, kc * (SEG_KC / 8) + c, y, x);
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < SB; ++j)
+                        if (d[j] != 0xFFFFFFFFu) *reinterpret_cast<uint4*>(sa + d[j]) = v[j];
+                }
+                fence_async_smem();
+                mbar_arrive(&full[s]);
+            }
+        }
+    } else if (warp == 16) {
+        // ---- MMA issue ----
+        int step = 0, j = 0;
+        for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++j) {
+            const int t = j & 1;
+            for (int kc = 0; kc < a.chunks; ++kc, ++step) {
+                const int s = step % T::STAGES;
+                mbar_wait(&full[s], (uint32_t)((step / T::STAGES) & 1));
+                if (kc == 0) mbar_wait(&tempty[t], (uint32_t)(((j >> 1) & 1) ^ 1));
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t sa = smem_u32(smem + s * T::STAGE_B);
+                    const uint64_t ad0 = make_smem_desc(sa, C::PLANE_B, C::ROW_B);
+                    const uint64_t bd0 = make_smem_desc(sa + C::A_B, N * 16, 128);
+                    const uint32_t d0 = tmem_base + (uint32_t)(t * TILES * N);
+                    for (int tap = 0; tap < a.ntaps; ++tap) {
+                        const int dy = a.ntaps == 1 ? 1 : tap / 3, dx = a.ntaps == 1 ? 1 : tap % 3;
+#pragma unroll
+                        for (int ks = 0; ks < SEG_KC / 16; ++ks)
+#pragma unroll
+                            for (int tile = 0; tile < TILES; ++tile) {
+                                const uint64_t ad = ad0 + (uint64_t)((tile * 128 + dx * 16 + dy * C::ROW_B + 2 * ks * C::PLANE_B) >> 4);
+                                const uint64_t bd = bd0 + (uint64_t)(((tap * (SEG_KC / 8) + 2 * ks) * N * 16) >> 4);
+                                umma_f16(d0 + (uint32_t)(tile * N), ad, bd, IDESC, (kc == 0 && tap == 0 && ks == 0) ? 0u : 1u);
+                            }
+                    }
+                    umma_commit(&empty[s]);
+                    if (kc == a.chunks - 1) umma_commit(&tfull[t]);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp < 8) {
+        // ---- epilogue ----
+        const int q = warp & 3, half_sel = warp >> 2;
+        const int r = 32 * q + lane;
+        constexpr int SL = N / 8;
+        int j = 0;
+        for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++j) {
+            const int t = j & 1;
+            const int g = unit / per_group, t2 = unit - g * per_group;
+            const int ty = t2 / tiles_x, tx = t2 - ty * tiles_x;
+            const int y = 16 * ty + (r >> 3), x0 = 8 * TILES * tx;
+            mbar_wait(&tfull[t], (uint32_t)((j >> 1) & 1));
+            tc_fence_after();
+            const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(t * TILES * N);
+#pragma unroll 1
+            for (int p = half_sel; p < TILES * SL; p += 2) {
+                const int tile = p / SL, sl = p - tile * SL;
+                const int x = x0 + 8 * tile + (r & 7);
+                uint32_t v[8];
+                TMEM_LD8(lane_addr + (uint32_t)(tile * N + sl * 8), v);
+                TMEM_WAIT8(v);
+                const int c0 = g * N + sl * 8;
+                __align__(16) __half o[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    o[k] = __float2half_rn(fmaxf(__fadd_rn(__uint_as_float(v[k]), __ldg(a.bias + c0 + k)), 0.f));
+                if (y < a.H && x < a.W)
+                    *reinterpret_cast<uint4*>(a.out + (((size_t)(c0 >> 3) * a.H + y) * a.W + x) * 8) = *reinterpret_cast<const uint4*>(o);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[t]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, T::TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------
 // Instances from (prob, dist): candidates, polygons, bins, greedy NMS, rendering
 // ---------------------------------------------------------------------------------------
 // key: ascending sort = descending probability, ties: the larger flat index first (np.argsort(prob, stable)[::-1])
@@ -1029,11 +1188,35 @@ int launch_seg_conv_tma(cia_ctx* h, const SegConvArgs& a, cudaStream_t s) {
     return CIA_OK;
 }
 
+template <int N, int TILES>
+int launch_seg_conv_ws(cia_ctx* h, const SegConvArgs& a, cudaStream_t s) {
+    using T = SegWsCfg<N, TILES>;
+    auto kern = seg_conv_ws_kernel<N, TILES>;
+    if (first_use(h, (const void*)kern))
+        CIA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_B));
+    const int tiles_x = (a.W + 8 * TILES - 1) / (8 * TILES), tiles_y = (a.H + 15) / 16;
+    int grid = tiles_x * tiles_y * a.groups;
+    if (grid > h->num_sms) grid = h->num_sms;
+    kern<<<grid, T::THREADS, T::SMEM_B, s>>>(a);
+    CIA_LAUNCH_CHECK();
+    return CIA_OK;
+}
+
 // one 3x3 layer of the plan: the TMA-fed kernel where the layer reads its producer directly with one 32-channel chunk
 int launch_seg_layer(cia_ctx* h, const SegConv& c, const SegConvArgs& a, cudaStream_t s) {
     const bool tma = h->seg_conv_tma && a.mode == 0 && c.chunks == 1 && c.groups == 1 && ((size_t)a.src0 % 16) == 0;
     if (tma && c.n_tile == 32) return launch_seg_conv_tma<32, 4>(h, a, s);
     if (tma && c.n_tile == 128) return launch_seg_conv_tma<128, 2>(h, a, s);
+    // measured per layer on B200 (profiles/r2q_seg_launches.txt): the software producer pays for layers with two or more
+    // chunks and 64+ output channels per CTA (long MMA phases per step); short steps (N = 32) and pooled single- or
+    // double-chunk inputs are faster with three co-resident staged CTAs.  seg_conv_ws = 2 forces it everywhere (tests).
+    const bool ws = h->seg_conv_ws == 2 ||
+                    (h->seg_conv_ws == 1 && c.n_tile >= 64 && c.chunks >= 2 && !(a.mode == 1 && c.chunks == 2));
+    if (ws) {
+        if (c.n_tile == 128) return launch_seg_conv_ws<128, 2>(h, a, s);
+        if (c.n_tile == 64) return launch_seg_conv_ws<64, 4>(h, a, s);
+        return launch_seg_conv_ws<32, 4>(h, a, s);
+    }
     if (c.n_tile == 128) return launch_seg_conv<128, 2, 0>(h, a, s);
     if (c.n_tile == 64) return launch_seg_conv<64, 4, 0>(h, a, s);
     return launch_seg_conv<32, 4, 0>(h, a, s);

@@ -94,21 +94,24 @@ def test_normalize_bit_exact(model):
     assert np.array_equal(model.normalize_device(x, 1, 99.8).cpu().numpy(), sd.normalize(x, 1, 99.8))
 
 
-@pytest.mark.parametrize("tma", [1, 0])
-def test_every_layer_against_float32_conv(model, tma):
-    """tma = 1: layers that read their producer directly with Cin = 32 run the TMA-fed warp-specialised kernel
-    (the default); tma = 0: the staged kernel everywhere."""
+@pytest.mark.parametrize("tma,ws", [(1, 1), (0, 2), (0, 0)])
+def test_every_layer_against_float32_conv(model, tma, ws):
+    """(1, 1), the default: layers that read their producer directly with Cin = 32 run the TMA-fed kernel, the
+    warp-specialised software-producer kernel takes the layers where it measured faster; (0, 2): every layer through
+    the latter; (0, 0): the staged kernel everywhere."""
     n_layers = len(model.layer_order) - 2
     model.engine.set_option("seg_conv_tma", tma)
+    model.engine.set_option("seg_conv_ws", ws)
     try:
         for layer in range(n_layers):
             # 48 x 40: edge tiles in both directions (tiles are 16 rows x 16 / 32 columns); 80 x 112: several units per CTA
             for Ho, Wo in ((48, 40), (80, 112)):
                 err = layer_check(model, layer, Ho, Wo)
-                print(f"tma {tma} layer {layer} {model.layer_order[layer]} {Ho}x{Wo}: max rel err {err:.2e}")
+                print(f"tma {tma} ws {ws} layer {layer} {model.layer_order[layer]} {Ho}x{Wo}: max rel err {err:.2e}")
                 assert err < 2e-3, (layer, model.layer_order[layer], err)
     finally:
         model.engine.set_option("seg_conv_tma", 1)
+        model.engine.set_option("seg_conv_ws", 1)
 
 
 def test_network_against_oracle(model):
