@@ -887,6 +887,46 @@ __device__ double tri_clip_area(const double* sx, const double* sy, const double
     return __dmul_rn(0.5, fabs(s));
 }
 
+// The same clipping in float32 on coordinates relative to the winner's centre: only used for the LOWER BOUND of the
+// overlap (relative error ~1e-5 against a 1 % safety margin), never for a value that is compared exactly.
+__device__ float tri_clip_area_f32(const float* sx, const float* sy, const float* cx, const float* cy) {
+    float bx0[8], by0[8], bx1[8], by1[8];
+    int n = 3;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { bx0[k] = sx[k]; by0[k] = sy[k]; }
+#pragma unroll
+    for (int e = 0; e < 3; ++e) {
+        const float* px = (e & 1) ? bx1 : bx0;
+        const float* py = (e & 1) ? by1 : by0;
+        float* qx = (e & 1) ? bx0 : bx1;
+        float* qy = (e & 1) ? by0 : by1;
+        const float ax = cx[e], ay = cy[e], ex = cx[e == 2 ? 0 : e + 1] - ax, ey = cy[e == 2 ? 0 : e + 1] - ay;
+        int m = 0;
+        float dc = ex * (py[0] - ay) - ey * (px[0] - ax);
+        for (int k = 0; k < n; ++k) {
+            const int k1 = k + 1 == n ? 0 : k + 1;
+            const float dn = ex * (py[k1] - ay) - ey * (px[k1] - ax);
+            if (dc >= 0.f) { qx[m] = px[k]; qy[m] = py[k]; ++m; }
+            if ((dc >= 0.f) != (dn >= 0.f)) {
+                const float t = __fdividef(dc, dc - dn);
+                qx[m] = fmaf(t, px[k1] - px[k], px[k]);
+                qy[m] = fmaf(t, py[k1] - py[k], py[k]);
+                ++m;
+            }
+            dc = dn;
+        }
+        n = m;
+        if (n == 0) return 0.f;
+    }
+    // three clips: the result is in buffer 1
+    float s2 = 0.f;
+    for (int k = 0; k < n; ++k) {
+        const int k1 = k + 1 == n ? 0 : k + 1;
+        s2 += bx1[k] * by1[k1] - bx1[k1] * by1[k];
+    }
+    return 0.5f * fabsf(s2);
+}
+
 #ifndef SEG_NMS_CTAS
 #define SEG_NMS_CTAS 4     // CTAs per SM of the suppression kernel (64 registers: latency-bound fp64 chains want warps)
 #endif
@@ -933,22 +973,24 @@ __device__ double seg_overlap_warp(const NmsArgs& a, int w, int i, float (*sp)[2
     // batches (measured on ellipse fields: 80 % after three, all after five) instead of 1024 separation tests + the full list.  The exact sum is only needed near the threshold.
     {
         const double denom = __dadd_rn(fmin(a.area[w], a.area[i]), 1e-10);
-        const double need = a.thr * denom * (1.0 + 1e-9);
-        const double sx[3] = {cwx, (double)sp[0][1][lane], (double)sp[0][1][l1]};
-        const double sy[3] = {cwy, (double)sp[0][0][lane], (double)sp[0][0][l1]};
-        double lb = 0.0;
+        const float need = (float)(a.thr * denom * (1.0 + 1e-2));     // float32 clipping: 1 % covers its rounding many times over
+        const float ox = (float)a.pyx[2 * w + 1], oy = (float)a.pyx[2 * w];
+        const float sx[3] = {0.f, sp[0][1][lane] - ox, sp[0][1][l1] - ox};
+        const float sy[3] = {0.f, sp[0][0][lane] - oy, sp[0][0][l1] - oy};
+        const float fix = (float)a.pyx[2 * i + 1] - ox, fiy = (float)a.pyx[2 * i] - oy;
+        float lb = 0.f;
 #pragma unroll 1
         for (int q = 0; q < 5; ++q) {                    // index offsets 0, +1, -1, +2, -2
             const int b = (lane + (q == 0 ? 0 : q == 1 ? 1 : q == 2 ? SEG_RAYS - 1 : q == 3 ? 2 : SEG_RAYS - 2)) & (SEG_RAYS - 1);
             const int b1 = (b + 1) & (SEG_RAYS - 1);
-            const double cx[3] = {cix, (double)sp[1][1][b], (double)sp[1][1][b1]};
-            const double cy[3] = {ciy, (double)sp[1][0][b], (double)sp[1][0][b1]};
-            lb += tri_clip_area(sx, sy, cx, cy);
+            const float cx[3] = {fix, sp[1][1][b] - ox, sp[1][1][b1] - ox};
+            const float cy[3] = {fiy, sp[1][0][b] - oy, sp[1][0][b1] - oy};
+            lb += tri_clip_area_f32(sx, sy, cx, cy);
             if (q == 0 || q == 1 || q == 3) continue;    // test after both neighbours of each distance
-            double tot = lb;
+            float tot = lb;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-            if (tot > need) return tot / denom;          // > thr: the full sum can only be larger
+            if (tot > need) return (double)tot / denom;  // > thr: the full sum can only be larger
         }
     }
     // step 1: lane = fan triangle of w; bit st of `mask` = its pair with triangle (lane + st) of i needs clipping
