@@ -97,23 +97,26 @@ __global__ void seg_hist_kernel(const uint16_t* __restrict__ img, size_t n, uint
     }
 }
 
-__global__ void seg_hist_reduce_kernel(uint32_t* __restrict__ hist) {      // copy 0 += copies 1..15
+// copy 0 += copies 1..15; wsum[b / 32] = population of 32 consecutive bins (what the selection kernel scans)
+__global__ void seg_hist_reduce_kernel(uint32_t* __restrict__ hist, uint32_t* __restrict__ wsum) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t c = 0;
     for (int cp = 0; cp < SEG_HIST_COPIES; ++cp) c += hist[(size_t)cp * 65536 + b];
     hist[b] = c;
+    const uint32_t w = __reduce_add_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31) == 0) wsum[b >> 5] = w;
 }
 
 // numpy's percentile for the default method: virtual index n q + (1 + q (1 - 1 - 1)) - 1, the two neighbouring order
 // statistics a <= b and _lerp(a, b, t) = a + (b - a) t, or b - (b - a)(1 - t) where t >= 0.5 (numpy/lib/_function_base_impl.py)
-__global__ void __launch_bounds__(1024) seg_percentile_kernel(const uint32_t* __restrict__ hist, size_t n, double q_lo,
-                                                              double q_hi, float* __restrict__ mi_ma) {
+__global__ void __launch_bounds__(1024) seg_percentile_kernel(const uint32_t* __restrict__ hist, const uint32_t* __restrict__ wsum,
+                                                              size_t n, double q_lo, double q_hi, float* __restrict__ mi_ma) {
     typedef cub::BlockScan<unsigned long long, 1024> Scan;
     __shared__ typename Scan::TempStorage tmp;
     __shared__ unsigned s_val[4];
     const int t = threadIdx.x;
     unsigned long long local = 0;
-    for (int k = 0; k < 64; ++k) local += hist[t * 64 + k];
+    local = (unsigned long long)wsum[2 * t] + wsum[2 * t + 1];      // bins [64 t, 64 t + 64)
     unsigned long long before;
     Scan(tmp).ExclusiveSum(local, before);
     long long want[4];
@@ -781,7 +784,7 @@ __global__ void seg_polygons_kernel(const unsigned long long* __restrict__ keys,
                                     const double* __restrict__ rsin, const double* __restrict__ rcos, int H, int W,
                                     float* __restrict__ vy, float* __restrict__ vx, int* __restrict__ pyx,
                                     float* __restrict__ pprob, float* __restrict__ rmax, double* __restrict__ area,
-                                    unsigned long long* __restrict__ binkeys, unsigned* __restrict__ rmax_all) {
+                                    int* __restrict__ bin_of, int* __restrict__ bin_count, unsigned* __restrict__ rmax_all) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     const int n = min(*count, cap);
     if (r >= n) return;
@@ -814,21 +817,31 @@ __global__ void seg_polygons_kernel(const unsigned long long* __restrict__ keys,
     atomicMax(rmax_all, __float_as_uint(rm));            // rm >= 1e-3 > 0: the bit pattern orders like the value
     const int nbx = (W + SEG_BIN - 1) / SEG_BIN;
     const int bin = min(py / SEG_BIN, (H + SEG_BIN - 1) / SEG_BIN - 1) * nbx + min(px / SEG_BIN, nbx - 1);
-    binkeys[r] = ((unsigned long long)bin << 32) | (unsigned)r;
+    bin_of[r] = bin;
+    atomicAdd(bin_count + bin, 1);
 }
 
-__global__ void seg_bins_kernel(const unsigned long long* __restrict__ binkeys, const int* __restrict__ count, int cap,
-                                int nbins, int* __restrict__ bin_start) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b > nbins) return;
-    const int n = min(*count, cap);
-    const unsigned long long key = (unsigned long long)b << 32;
-    int lo = 0, hi = n;
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (binkeys[mid] < key) lo = mid + 1; else hi = mid;
+// counting sort of the candidates by bin: exclusive scan of the bin populations (one CTA), then seg_binorder_kernel
+// hands out positions with one atomic per candidate (the order INSIDE a bin is irrelevant to the suppression's result)
+__global__ void __launch_bounds__(1024) seg_bins_kernel(const int* __restrict__ bin_count, int nbins, int* __restrict__ bin_start,
+                                                        int* __restrict__ bin_cursor) {
+    typedef cub::BlockScan<int, 1024> Scan;
+    __shared__ typename Scan::TempStorage tmp;
+    __shared__ int carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int b0 = 0; b0 < nbins; b0 += 1024) {
+        const int b = b0 + threadIdx.x;
+        const int c = b < nbins ? bin_count[b] : 0;
+        int ex, total;
+        Scan(tmp).ExclusiveSum(c, ex, total);
+        const int carry = carry_s;
+        if (b < nbins) { bin_start[b] = carry + ex; bin_cursor[b] = carry + ex; }
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s = carry + total;
+        __syncthreads();
     }
-    bin_start[b] = lo;
+    if (threadIdx.x == 0) bin_start[nbins] = carry_s;
 }
 
 __device__ __forceinline__ double cross_rn(double ax, double ay, double bx, double by, double px, double py) {
@@ -1125,12 +1138,12 @@ __global__ void __launch_bounds__(256, SEG_NMS_CTAS) seg_nms_kernel(const NmsArg
 }
 
 // bin-order copies of what the suppression reads per neighbour
-__global__ void seg_binorder_kernel(const unsigned long long* __restrict__ binkeys, const int* __restrict__ count, int cap,
-                                    const int* __restrict__ pyx, const float* __restrict__ rmax, int* __restrict__ b_rank,
-                                    float4* __restrict__ b_yxr, int* __restrict__ pos) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= min(*count, cap)) return;
-    const int r = (int)(binkeys[k] & 0xffffffffull);
+__global__ void seg_binorder_kernel(const int* __restrict__ bin_of, int* __restrict__ bin_cursor, const int* __restrict__ count,
+                                    int cap, const int* __restrict__ pyx, const float* __restrict__ rmax,
+                                    int* __restrict__ b_rank, float4* __restrict__ b_yxr, int* __restrict__ pos) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= min(*count, cap)) return;
+    const int k = atomicAdd(bin_cursor + bin_of[r], 1);
     b_rank[k] = r;
     b_yxr[k] = make_float4((float)pyx[2 * r], (float)pyx[2 * r + 1], rmax[r], 0.f);
     pos[r] = k;
@@ -1474,17 +1487,18 @@ int k_seg_load(cia_ctx* h, const cia_seg_config* cfg, int n_layers, const float*
 int k_seg_normalize(cia_ctx* h, const uint16_t* img, int H, int W, double pmin, double pmax, float* out,
                     float* mi_ma_out, cudaStream_t s) {
     // scratch: 65536-bin histogram + the two percentiles
-    int rc = ws_reserve(h, h->ws_misc, (size_t)SEG_HIST_COPIES * 65536 * sizeof(uint32_t) + 64);
+    int rc = ws_reserve(h, h->ws_misc, (size_t)SEG_HIST_COPIES * 65536 * sizeof(uint32_t) + 2048 * sizeof(uint32_t) + 64);
     if (rc) return rc;
     uint32_t* hist = (uint32_t*)h->ws_misc.p;
-    float* mima = mi_ma_out ? mi_ma_out : (float*)(hist + (size_t)SEG_HIST_COPIES * 65536);
+    uint32_t* wsum = hist + (size_t)SEG_HIST_COPIES * 65536;
+    float* mima = mi_ma_out ? mi_ma_out : (float*)(wsum + 2048);
     const size_t n = (size_t)H * W;
     CIA_CUDA(cudaMemsetAsync(hist, 0, (size_t)SEG_HIST_COPIES * 65536 * sizeof(uint32_t), s));
     seg_hist_kernel<<<h->num_sms * 8, 256, 0, s>>>(img, n, hist);
     CIA_LAUNCH_CHECK();
-    seg_hist_reduce_kernel<<<65536 / 256, 256, 0, s>>>(hist);
+    seg_hist_reduce_kernel<<<65536 / 256, 256, 0, s>>>(hist, wsum);
     CIA_LAUNCH_CHECK();
-    seg_percentile_kernel<<<1, 1024, 0, s>>>(hist, n, pmin / 100.0, pmax / 100.0, mima);   // np.true_divide(q, 100)
+    seg_percentile_kernel<<<1, 1024, 0, s>>>(hist, wsum, n, pmin / 100.0, pmax / 100.0, mima);   // np.true_divide(q, 100)
     CIA_LAUNCH_CHECK();
     seg_normalize_kernel<<<h->num_sms * 8, 256, 0, s>>>(img, n, mima, 1e-20f, out);
     CIA_LAUNCH_CHECK();
@@ -1624,7 +1638,7 @@ int k_seg_instances(cia_ctx* h, const float* prob, const float* dist, int Hg, in
     size_t o = 0;
     auto take = [&](size_t bytes) { const size_t at = o; o += align_up(bytes, 256); return at; };
     const size_t o_keys0 = take((size_t)cap * 8), o_keys1 = take((size_t)cap * 8);
-    const size_t o_bk0 = take((size_t)cap * 8), o_bk1 = take((size_t)cap * 8);
+    const size_t o_binof = take((size_t)cap * 4), o_bcnt = take((size_t)(nbins + 1) * 4), o_bcur = take((size_t)(nbins + 1) * 4);
     const size_t o_vy = take((size_t)cap * SEG_RAYS * 4), o_vx = take((size_t)cap * SEG_RAYS * 4);
     const size_t o_pyx = take((size_t)cap * 8), o_pp = take((size_t)cap * 4), o_rm = take((size_t)cap * 4);
     const size_t o_area = take((size_t)cap * 8), o_state = take((size_t)cap * 4), o_flags = take((size_t)cap * 4);
@@ -1635,7 +1649,7 @@ int k_seg_instances(cia_ctx* h, const float* prob, const float* dist, int Hg, in
     if (rc) return rc;
     unsigned char* b = (unsigned char*)m->post.p;
     unsigned long long* keys0 = (unsigned long long*)(b + o_keys0); unsigned long long* keys1 = (unsigned long long*)(b + o_keys1);
-    unsigned long long* bk0 = (unsigned long long*)(b + o_bk0); unsigned long long* bk1 = (unsigned long long*)(b + o_bk1);
+    int* bin_of = (int*)(b + o_binof); int* bin_count = (int*)(b + o_bcnt); int* bin_cursor = (int*)(b + o_bcur);
     float* vy = (float*)(b + o_vy); float* vx = (float*)(b + o_vx);
     int* pyx = (int*)(b + o_pyx); float* pp = (float*)(b + o_pp); float* rm = (float*)(b + o_rm);
     double* area = (double*)(b + o_area);
@@ -1653,7 +1667,7 @@ int k_seg_instances(cia_ctx* h, const float* prob, const float* dist, int Hg, in
     size_t tmp_bytes = m->cubtmp.cap;
 
     CIA_CUDA(cudaMemsetAsync(keys0, 0xFF, (size_t)cap * 8, s));
-    CIA_CUDA(cudaMemsetAsync(bk0, 0xFF, (size_t)cap * 8, s));
+    CIA_CUDA(cudaMemsetAsync(bin_count, 0, (size_t)(nbins + 1) * 4, s));
     CIA_CUDA(cudaMemsetAsync(state, 0, (size_t)cap * 4, s));
     CIA_CUDA(cudaMemsetAsync(small, 0, 64, s));
     CIA_CUDA(cudaMemsetAsync(labels, 0x7F, (size_t)H * W * sizeof(int32_t), s));
@@ -1662,14 +1676,11 @@ int k_seg_instances(cia_ctx* h, const float* prob, const float* dist, int Hg, in
     CIA_CUDA(cub::DeviceRadixSort::SortKeys(m->cubtmp.p, tmp_bytes, keys0, keys1, cap, 0, 64, s));
     h->launches++;
     seg_polygons_kernel<<<(cap + 127) / 128, 128, 0, s>>>(keys1, small, cap, prob, dist, Wg, grid, m->ray_sin, m->ray_cos, H, W, vy, vx,
-                                                         pyx, pp, rm, area, bk0, (unsigned*)(small + 1));
+                                                         pyx, pp, rm, area, bin_of, bin_count, (unsigned*)(small + 1));
     CIA_LAUNCH_CHECK();
-    tmp_bytes = m->cubtmp.cap;
-    CIA_CUDA(cub::DeviceRadixSort::SortKeys(m->cubtmp.p, tmp_bytes, bk0, bk1, cap, 0, 64, s));
-    h->launches++;
-    seg_bins_kernel<<<(nbins + 1 + 255) / 256, 256, 0, s>>>(bk1, small, cap, nbins, bins);
+    seg_bins_kernel<<<1, 1024, 0, s>>>(bin_count, nbins, bins, bin_cursor);
     CIA_LAUNCH_CHECK();
-    seg_binorder_kernel<<<(cap + 255) / 256, 256, 0, s>>>(bk1, small, cap, pyx, rm, b_rank, b_yxr, pos);
+    seg_binorder_kernel<<<(cap + 255) / 256, 256, 0, s>>>(bin_of, bin_cursor, small, cap, pyx, rm, b_rank, b_yxr, pos);
     CIA_LAUNCH_CHECK();
     {
         NmsArgs a{};
