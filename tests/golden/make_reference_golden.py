@@ -26,6 +26,9 @@ Outputs (commit them; tests/test_reference_golden.py picks them up automatically
         weights as tests/golden/model_dir, plus copies of the four scikit-learn pickles
   tests/golden/reference_tiny_field.npz, reference_config1_seed0.npz
         crops, stats (incl. solidity), mse / mae, scores and predictions as the reference returns them
+  tests/golden/reference_stardist_model/, reference_stardist_tiny.npz   (only where stardist + csbdeep are installed)
+        a StarDist2D model folder written by the real package and its normalize / predict / predict_instances
+        outputs for the tiny field: pins oracle/stardist.py, oracle/stardist_post.c and csrc/segment.cu
   tests/golden/reference_versions.json   library versions of the generating environment
 """
 import argparse
@@ -92,6 +95,41 @@ def build_keras_models(weights):
     for layer, (gamma, beta, mean, var) in zip(bns, weights["bns"]):
         layer.set_weights([gamma, beta, mean, var])
     return autoencoder, encoder
+
+
+def stardist_golden(out, synth):
+    """Segmentation (det:44, 62-63) from the REAL csbdeep / stardist when they are installed: a StarDist2D model of
+    the 2D_versatile_fluo configuration with freshly initialised weights (the pretrained ones need a download) is
+    saved as a model folder, and ``normalize`` + ``predict`` + ``predict_instances`` of the seeded tiny field are
+    dumped.  tests/test_reference_golden.py then holds the oracle (oracle/stardist.py, stardist_post.c) and the CUDA
+    path to them -- including the one stated deviation of the restatement (Clipper's integer-snapped polygon
+    intersection): a mismatch there shows up as differing labels."""
+    try:
+        from csbdeep.utils import normalize
+        from stardist.models import Config2D, StarDist2D
+    except Exception as e:                                   # noqa: BLE001
+        print(f"stardist / csbdeep not importable ({type(e).__name__}): segmentation golden skipped")
+        return
+    if not hasattr(StarDist2D, "predict_instances") or not callable(normalize):
+        print("stardist / csbdeep are stubs: segmentation golden skipped")
+        return
+    conf = Config2D(n_rays=32, grid=(2, 2), n_channel_in=1)   # the published 2-D configuration
+    model = StarDist2D(conf, name="reference_stardist_model", basedir=out)
+    folder = os.path.join(out, "reference_stardist_model")
+    model.keras_model.save_weights(os.path.join(folder, "weights_best.h5"))
+    H, W, n, lo, hi, lu = synth.FIELD_CONFIGS["tiny"]
+    green, _ = synth.make_field(3, H, W, n, lo, hi, lu)
+    x = normalize(green)                                                        # det:62
+    prob, dist = model.predict(x)
+    thr = float(np.quantile(prob, 0.7))                       # an untrained network: a threshold that yields objects
+    with open(os.path.join(folder, "thresholds.json"), "w") as f:
+        json.dump({"prob": thr, "nms": 0.3}, f)
+    labels, details = model.predict_instances(x, prob_thresh=thr, nms_thresh=0.3)   # det:63
+    np.savez_compressed(os.path.join(out, "reference_stardist_tiny.npz"), normalized=x, prob=prob, dist=dist,
+                        labels=labels.astype(np.int32), points=np.asarray(details["points"]),
+                        prob_kept=np.asarray(details["prob"]), coord=np.asarray(details["coord"]),
+                        prob_thresh=np.array(thr), nms_thresh=np.array(0.3))
+    print("stardist tiny:", int(labels.max()), "instances")
 
 
 def main():
@@ -168,8 +206,10 @@ def main():
     print("config 1 seed 0:", len(cells), "cells; anomaly rates",
           s["conservative_anomaly_rate"], s["moderate_anomaly_rate"])
 
+    stardist_golden(args.out, synth)
+
     versions = {}
-    for mod in ("numpy", "scipy", "skimage", "tensorflow", "keras", "sklearn"):
+    for mod in ("numpy", "scipy", "skimage", "tensorflow", "keras", "sklearn", "stardist", "csbdeep"):
         try:
             versions[mod] = importlib.import_module(mod).__version__
         except Exception as e:                      # noqa: BLE001

@@ -118,3 +118,56 @@ def test_cuda_path_against_reference_golden(case, precision, model_dir):
     green, labels = _field(case)
     cells, stats = s.extract_quality_cells_from_labels(green, labels)
     _check(ref, cells, stats, s.compute_anomaly_scores(cells))
+
+
+# ---- segmentation (det:44, 62-63): golden from the real csbdeep / stardist, when the recipe could make it ----
+SD_NPZ = os.path.join(GOLDEN, "reference_stardist_tiny.npz")
+SD_DIR = os.path.join(GOLDEN, "reference_stardist_model")
+needs_sd = pytest.mark.skipif(not (os.path.exists(SD_NPZ) and os.path.isdir(SD_DIR)),
+                              reason="parity unpinned: tests/golden/reference_stardist_tiny.npz has not been generated "
+                                     "(run tests/golden/make_reference_golden.py where stardist + csbdeep are installed)")
+
+
+def _sd_case():
+    import json
+    from cell_image_analysis_b200 import synth
+    from cell_image_analysis_b200.stardist import load_weights_h5
+    ref = np.load(SD_NPZ)
+    with open(os.path.join(SD_DIR, "config.json")) as f:
+        cfg = json.load(f)
+    H, W, n, lo, hi, lu = synth.FIELD_CONFIGS["tiny"]
+    green, _ = synth.make_field(3, H, W, n, lo, hi, lu)
+    return ref, cfg, load_weights_h5(os.path.join(SD_DIR, "weights_best.h5")), green
+
+
+@needs_sd
+def test_stardist_oracle_against_reference_golden():
+    from oracle import stardist as sd
+    ref, cfg, weights, green = _sd_case()
+    assert np.array_equal(sd.normalize(green), ref["normalized"])
+    prob, dist = sd.unet_forward(cfg, weights, ref["normalized"])
+    assert np.abs(prob - ref["prob"]).max() <= 1e-4 and np.abs(dist - ref["dist"]).max() <= 1e-3 * np.abs(ref["dist"]).max()
+    labels, det = sd.instances_from_prediction(ref["prob"], ref["dist"], int(cfg["grid"][0]), green.shape,
+                                               float(ref["prob_thresh"]), float(ref["nms_thresh"]))
+    assert np.array_equal(det["points"], ref["points"]), "kept set differs (Clipper's integer-snapped intersection?)"
+    assert np.array_equal(labels, ref["labels"])
+
+
+@needs_sd
+@pytest.mark.gpu
+def test_stardist_cuda_path_against_reference_golden():
+    from cell_image_analysis_b200.stardist import StarDist2D
+    ref, cfg, _weights, green = _sd_case()
+    m = StarDist2D(None, name="reference_stardist_model", basedir=GOLDEN)
+    assert np.array_equal(m.normalize_device(green).cpu().numpy(), ref["normalized"])
+    prob, dist = m.predict(ref["normalized"])
+    assert np.abs(prob.cpu().numpy() - ref["prob"]).max() <= 2e-2
+    labels, n = m.instances_from_prediction(green.shape, torch_from(ref["prob"]), torch_from(ref["dist"]),
+                                            float(ref["prob_thresh"]), float(ref["nms_thresh"]))
+    assert np.array_equal(labels.cpu().numpy(), ref["labels"])
+
+
+def torch_from(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a))
+
