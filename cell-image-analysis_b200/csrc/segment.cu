@@ -546,6 +546,134 @@ __global__ void __launch_bounds__(320, 1) seg_conv_tma_kernel(const __grid_const
 }
 
 // ---------------------------------------------------------------------------------------
+// The 1x1 heads (`prob`, `dist`) in the TMA-fed form: one box per unit brings ALL `features` channels of a 16 x 16
+// pixel tile (no halo for one tap), the unit is Cin / 16 k-steps x 2 tiles of N = 48 MMAs, the epilogue writes
+// dist = max(1e-3, .) and prob = sigmoid(.) in fp32.  The layer is bandwidth bound (268 MB in, 138 MB out).
+// ---------------------------------------------------------------------------------------
+template <int CIN>
+struct SegHeadsCfg {
+    static constexpr int N = 48, TILES = 2, PLANES = CIN / 8;
+    static constexpr int ROW_B = 16 * 16, PLANE_B = 16 * ROW_B;        // 16 x 16 pixels, 16 bytes each
+    static constexpr int A_B = PLANES * PLANE_B;
+    static constexpr int W_B = PLANES * N * 16;
+    static constexpr int STAGES = (215 * 1024 - W_B) / A_B >= 3 ? 3 : 2;
+    static constexpr int SMEM_B = STAGES * A_B + W_B;
+    static constexpr int TMEM_COLS = 256;                               // two sets of 2 x 48 columns
+    static constexpr int SET_COLS = 128;
+    static constexpr int THREADS = 320;
+    static_assert(SMEM_B <= 225 * 1024 && A_B % 1024 == 0, "does not fit");
+};
+
+template <int CIN>
+__global__ void __launch_bounds__(320, 1) seg_heads_tma_kernel(const __grid_constant__ CUtensorMap tm, const uint4* __restrict__ w,
+                                                               const float* __restrict__ bias, float* __restrict__ prob,
+                                                               float* __restrict__ dist, int H, int W) {
+    using T = SegHeadsCfg<CIN>;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ __align__(8) uint64_t full[T::STAGES], empty[T::STAGES], tfull[2], tempty[2];
+    __shared__ uint32_t tmem_base_s;
+    unsigned char* sw = smem + T::STAGES * T::A_B;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tiles_x = (W + 15) / 16, tiles_y = (H + 15) / 16;
+    const int n_units = tiles_x * tiles_y;
+    if ((int)blockIdx.x >= n_units) return;
+
+    if (warp == 0) tmem_alloc(&tmem_base_s, T::TMEM_COLS);
+    if (tid == 32) {
+        for (int s = 0; s < T::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(&tfull[0], 1); mbar_init(&tfull[1], 1);
+        mbar_init(&tempty[0], 8); mbar_init(&tempty[1], 8);
+        fence_barrier_init();
+    }
+    for (int i = tid; i < T::W_B / 16; i += T::THREADS) reinterpret_cast<uint4*>(sw)[i] = __ldg(w + i);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    constexpr uint32_t IDESC = make_idesc(128, T::N);
+
+    if (warp == 8) {
+        if (lane == 0) {
+            int j = 0;
+            for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++j) {
+                const int s = j % T::STAGES;
+                mbar_wait(&empty[s], (uint32_t)(((j / T::STAGES) & 1) ^ 1));
+                const int ty = unit / tiles_x, tx = unit - ty * tiles_x;
+                mbar_expect_tx(&full[s], T::A_B);
+                tma_load_4d(smem_u32(smem + s * T::A_B), &tm, 0, 16 * tx, 16 * ty, 0, &full[s]);
+            }
+        }
+    } else if (warp == 9) {
+        int j = 0;
+        for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++j) {
+            const int s = j % T::STAGES, t = j & 1;
+            mbar_wait(&full[s], (uint32_t)((j / T::STAGES) & 1));
+            mbar_wait(&tempty[t], (uint32_t)(((j >> 1) & 1) ^ 1));
+            tc_fence_after();
+            if (elect_one()) {
+                const uint64_t ad0 = make_smem_desc(smem_u32(smem + s * T::A_B), T::PLANE_B, T::ROW_B);
+                const uint64_t bd0 = make_smem_desc(smem_u32(sw), T::N * 16, 128);
+                const uint32_t d0 = tmem_base + (uint32_t)(t * T::SET_COLS);
+#pragma unroll
+                for (int ks = 0; ks < CIN / 16; ++ks)
+#pragma unroll
+                    for (int tile = 0; tile < T::TILES; ++tile) {
+                        const uint64_t ad = ad0 + (uint64_t)((tile * 128 + 2 * ks * T::PLANE_B) >> 4);
+                        const uint64_t bd = bd0 + (uint64_t)((2 * ks * T::N * 16) >> 4);
+                        umma_f16(d0 + (uint32_t)(tile * T::N), ad, bd, IDESC, ks == 0 ? 0u : 1u);
+                    }
+                umma_commit(&empty[s]);
+                umma_commit(&tfull[t]);
+            }
+            __syncwarp();
+        }
+    } else {
+        const int q = warp & 3, half_sel = warp >> 2;
+        const int r = 32 * q + lane;
+        constexpr int SL = SEG_RAYS / 8 + 1;
+        int j = 0;
+        for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++j) {
+            const int t = j & 1;
+            const int ty = unit / tiles_x, tx = unit - ty * tiles_x;
+            const int y = 16 * ty + (r >> 3), x0 = 16 * tx;
+            mbar_wait(&tfull[t], (uint32_t)((j >> 1) & 1));
+            tc_fence_after();
+            const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(t * T::SET_COLS);
+#pragma unroll 1
+            for (int p = half_sel; p < T::TILES * SL; p += 2) {
+                const int tile = p / SL, sl = p - tile * SL;
+                const int x = x0 + 8 * tile + (r & 7);
+                uint32_t v[8];
+                TMEM_LD8(lane_addr + (uint32_t)(tile * T::N + sl * 8), v);
+                TMEM_WAIT8(v);
+                if (y < H && x < W) {
+                    const size_t px = (size_t)y * W + x;
+                    if (sl < SEG_RAYS / 8) {
+                        float o[8];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)
+                            o[k] = fmaxf(1e-3f, __fadd_rn(__uint_as_float(v[k]), __ldg(bias + sl * 8 + k)));
+                        float4* dd = reinterpret_cast<float4*>(dist + px * SEG_RAYS + sl * 8);
+                        dd[0] = make_float4(o[0], o[1], o[2], o[3]);
+                        dd[1] = make_float4(o[4], o[5], o[6], o[7]);
+                    } else {
+                        const float z = __fadd_rn(__uint_as_float(v[0]), __ldg(bias + SEG_RAYS));
+                        prob[px] = 1.f / (1.f + expf(-z));
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[t]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, T::TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------
 // The general layer in the same warp-specialised form: the producer is SOFTWARE (eight warps run the staging of
 // seg_conv_kernel -- pooled, up-sampled + concatenated or direct inputs, any number of 32-channel chunks, each with
 // its weight block -- into a 2-3 stage ring and arrive on the stage's `full` barrier), one warp issues the MMAs of a
@@ -1309,6 +1437,42 @@ int launch_seg_conv_ws(cia_ctx* h, const SegConvArgs& a, cudaStream_t s) {
     return CIA_OK;
 }
 
+// heads over a CIN = 128 `features` map: weights as one linear image [plane][48][8] (the chunks of the staged layout
+// are consecutive planes, so the same upload serves both kernels)
+int launch_seg_heads_tma(cia_ctx* h, const SegConvArgs& a, cudaStream_t s) {
+    using T = SegHeadsCfg<128>;
+    static SegTensorMapEncodeFn encode = [] {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess) fn = nullptr;
+        return (SegTensorMapEncodeFn)fn;
+    }();
+    if (!encode) { h->err = "cuTensorMapEncodeTiled is not available from this driver"; return CIA_E_UNSUPPORTED; }
+    CUtensorMap tm;
+    const cuuint64_t dims[4] = {8, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)T::PLANES};
+    const cuuint64_t strides[3] = {16, (cuuint64_t)16 * a.W, (cuuint64_t)16 * a.W * a.H};
+    const cuuint32_t box[4] = {8, 16, 16, (cuuint32_t)T::PLANES};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    if (encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)a.src0, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+        h->err = "cuTensorMapEncodeTiled failed (segmentation features)";
+        return CIA_E_CUDA;
+    }
+    auto kern = seg_heads_tma_kernel<128>;
+    if (first_use(h, (const void*)kern))
+        CIA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_B));
+    int grid = ((a.W + 15) / 16) * ((a.H + 15) / 16);
+    if (grid > h->num_sms) grid = h->num_sms;
+    kern<<<grid, T::THREADS, T::SMEM_B, s>>>(tm, a.w, a.bias, a.prob, a.dist, a.H, a.W);
+    CIA_LAUNCH_CHECK();
+    return CIA_OK;
+}
+
+int launch_seg_heads(cia_ctx* h, const SegConv& c, const SegConvArgs& a, cudaStream_t s) {
+    if (h->seg_conv_tma && c.cin == 128 && ((size_t)a.src0 % 16) == 0) return launch_seg_heads_tma(h, a, s);
+    return launch_seg_conv<48, 2, 1>(h, a, s);
+}
+
 // one 3x3 layer of the plan: the TMA-fed kernel where the layer reads its producer directly with one 32-channel chunk
 int launch_seg_layer(cia_ctx* h, const SegConv& c, const SegConvArgs& a, cudaStream_t s) {
     const bool tma = h->seg_conv_tma && a.mode == 0 && c.chunks == 1 && c.groups == 1 && ((size_t)a.src0 % 16) == 0;
@@ -1575,7 +1739,7 @@ int k_seg_predict(cia_ctx* h, const float* img, int H, int W, float* prob_out, f
         a.w = (const uint4*)c.w_img; a.bias = c.bias;
         a.prob = m->prob_map; a.dist = m->dist_map;
         a.H = Hg; a.W = Wg; a.c0 = c.cin; a.c1 = 0; a.mode = 0; a.ntaps = 1; a.groups = 1; a.chunks = c.chunks;
-        rc = launch_seg_conv<48, 2, 1>(h, a, s);
+        rc = launch_seg_heads(h, c, a, s);
         if (rc) return rc;
     }
     if (prob_out) CIA_CUDA(cudaMemcpyAsync(prob_out, m->prob_map, (size_t)Hg * Wg * sizeof(float), cudaMemcpyDeviceToDevice, s));
@@ -1594,7 +1758,7 @@ int k_seg_debug_layer(cia_ctx* h, int layer, const void* src0, const void* src1,
         SegConvArgs a{};
         a.src0 = (const __half*)src0; a.w = (const uint4*)c.w_img; a.bias = c.bias; a.prob = prob; a.dist = dist;
         a.H = Ho; a.W = Wo; a.c0 = c.cin; a.mode = 0; a.ntaps = 1; a.groups = 1; a.chunks = c.chunks;
-        return launch_seg_conv<48, 2, 1>(h, a, s);
+        return launch_seg_heads(h, c, a, s);
     }
     if (layer < 0 || layer >= (int)m->ops.size()) { h->err = "segmentation: no such layer"; return CIA_E_ARG; }
     const SegOp& op = m->ops[layer];
