@@ -284,6 +284,7 @@ def segmentation_extras(with_cpu: bool):
     network emits for a field of ~530 ellipses; then the same labels through the screening path."""
     import torch
     from cell_image_analysis_b200 import stardist as sdp, synth
+    from cell_image_analysis_b200.artifacts import load_model_dir
     from cell_image_analysis_b200.screening import Engine
     pk = peaks()
     H = W = 2048
@@ -330,6 +331,28 @@ def segmentation_extras(with_cpu: bool):
     launches = eng.launch_count - l0
     flops = sdp.network_flops(cfg, H, W)
     total = t_norm + t_net + t_inst
+    # the whole chain of det:51-153 for one field with nothing but the uint16 image given: normalize, U-Net,
+    # instances (on the star maps of THIS field's true labels: what a trained network emits; the synthetic-weight
+    # network's own maps are computed and discarded), region scan, gates, crops, autoencoder, SVMs
+    _, truth = _gen_field(0)
+    pt, dt = synth.star_maps_from_labels(truth, 2)
+    ptd, dtd = torch.from_numpy(pt).to(eng.tdev), torch.from_numpy(dt).to(eng.tdev)
+    eng.load_artifacts(load_model_dir(MODEL_DIR))
+    out = eng.alloc_outputs(4096, 1)
+    img3 = g.view(1, H, W)
+
+    def f_chain():
+        f_norm()
+        f_net()
+        eng._check(eng.lib.cia_seg_instances(eng.h, ptd.data_ptr(), dtd.data_ptr(), H // 2, W // 2, 2, H, W, 0.479071, 0.3,
+                                             labels.data_ptr(), n_inst.data_ptr(), st()))
+        eng.screen_fields(img3, labels.view(1, H, W), 1024, out)
+
+    t_chain = timed(f_chain)
+    eng.check_status()
+    chain_cells = int(out["counts"][0].item())
+    chain_inst = int(n_inst.item())
+    f_inst()
     out = {
         "field": [H, W], "model": "2D_versatile_fluo topology (grid 2, depth 3, 32 filters, 128 features, 32 rays), synthetic weights",
         "normalize_ms": t_norm, "unet_ms": t_net, "instances_ms": t_inst, "ms_per_field": total, "fields_per_s": 1e3 / total,
@@ -338,6 +361,10 @@ def segmentation_extras(with_cpu: bool):
         "candidates": int((prob > np.float32(0.479071)).sum()), "instances": int(n_inst.item()),
         "dtype": "f16 tensor core U-Net (fp32 accumulate), f64 polygon overlap",
         "gpu_launches_per_field": int(launches),
+        "chain": {"what": "uint16 image -> normalize -> U-Net -> instances -> region scan -> gates -> crops -> autoencoder -> SVMs, "
+                          "one field per call, labels never leave the device",
+                  "ms_per_field": t_chain, "fields_per_s": 1e3 / t_chain, "instances": chain_inst, "scored_cells": chain_cells,
+                  "cells_per_s": chain_cells * 1e3 / t_chain},
         "note": "CUDA events, best of 3 rounds of 5 calls per stage; one field per call",
     }
     if with_cpu:

@@ -275,8 +275,9 @@ class StarDist2D:
         hg, wg = -(-H // self.grid), -(-W // self.grid)
         return prob[:hg, :wg].contiguous(), dist[:hg, :wg].contiguous()
 
-    def instances_from_prediction(self, img_shape, prob, dist, prob_thresh=None, nms_thresh=None):
-        """prob / dist cuda tensors -> (labels int32 cuda tensor [H, W], n_instances)."""
+    def instances_from_prediction(self, img_shape, prob, dist, prob_thresh=None, nms_thresh=None, sync=True):
+        """prob / dist cuda tensors -> (labels int32 cuda tensor [H, W], n_instances).  ``sync=False`` returns the
+        count as a one-element cuda tensor instead of reading it back (a stream-ordered pipeline stage)."""
         eng = self.engine
         pt = self.thresholds["prob"] if prob_thresh is None else prob_thresh
         nt = self.thresholds["nms"] if nms_thresh is None else nms_thresh
@@ -288,7 +289,7 @@ class StarDist2D:
         n = torch.zeros(1, dtype=torch.int32, device=eng.tdev)
         eng._check(eng.lib.cia_seg_instances(eng.h, _ptr(prob), _ptr(dist), Hg, Wg, self.grid, H, W, float(pt),
                                              float(nt), _ptr(labels), _ptr(n), eng._stream()))
-        return labels, int(n.item())
+        return labels, (int(n.item()) if sync else n)
 
     def details(self, n):
         eng = self.engine

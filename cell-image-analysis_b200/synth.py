@@ -15,7 +15,7 @@ from __future__ import annotations
 
 import numpy as np
 
-__all__ = ["make_field", "make_fields", "FIELD_CONFIGS", "star_maps_from_ellipses", "ellipse_lattice"]
+__all__ = ["make_field", "make_fields", "FIELD_CONFIGS", "star_maps_from_ellipses", "star_maps_from_labels", "ellipse_lattice"]
 
 # name -> (H, W, n_cells, a_lo, a_hi, log_uniform)
 FIELD_CONFIGS = {
@@ -129,3 +129,48 @@ def ellipse_lattice(H, W, n_side, seed):
             cells.append(((gy + 0.5) * pitch + rng.uniform(-4, 4), (gx + 0.5) * pitch + rng.uniform(-4, 4), a,
                           a * rng.uniform(0.5, 1.0), rng.uniform(0, np.pi)))
     return cells
+
+
+def star_maps_from_labels(labels, grid=2, n_rays=32, max_steps=256):
+    """(prob, dist) a trained StarDist network is trained to emit for a label image (its training targets): prob =
+    the Euclidean distance transform normalised per object (stardist ``edt_prob``), dist[k] = the distance from the
+    pixel to the object's boundary along ray k (stardist ``star_dist``: unit steps until the label changes, then the
+    library's sub-pixel correction), sampled on the grid.  labels -> maps -> instances is the round trip of the
+    segmentation tests."""
+    from scipy import ndimage
+    H, W = labels.shape
+    lab = labels[::grid, ::grid]
+    Hg, Wg = lab.shape
+    edt = ndimage.distance_transform_edt(labels > 0)
+    # touching objects: distance to the object's own boundary (objects of the synthetic fields do not touch;
+    # the generic form costs one EDT per object, only used when labels touch)
+    mx = ndimage.maximum(edt, labels, index=np.arange(0, int(labels.max()) + 1))
+    prob = np.where(labels > 0, edt / np.maximum(mx[labels], 1e-9), 0.0)[::grid, ::grid].astype(np.float32)
+    dist = np.full((Hg, Wg, n_rays), 1e-3, np.float32)
+    ys, xs = np.nonzero(lab)
+    if len(ys) == 0:
+        return prob, dist
+    py, px = ys * grid, xs * grid
+    me = labels[py, px]
+    phis = np.linspace(0, 2 * np.pi, n_rays, endpoint=False)
+    for k in range(n_rays):
+        dy, dx = np.float32(np.sin(phis[k])), np.float32(np.cos(phis[k]))
+        y = py.astype(np.float32); x = px.astype(np.float32)
+        steps = np.zeros(len(py), np.float32)
+        alive = np.ones(len(py), bool)
+        for _ in range(max_steps):
+            y = np.where(alive, y + dy, y); x = np.where(alive, x + dx, x)
+            ii = np.rint(y).astype(np.int64); jj = np.rint(x).astype(np.int64)
+            inside = (ii >= 0) & (ii < H) & (jj >= 0) & (jj < W)
+            same = np.zeros(len(py), bool)
+            same[inside] = labels[ii[inside], jj[inside]] == me[inside]
+            steps = np.where(alive & same, steps + 1, steps)
+            alive &= same
+            if not alive.any():
+                break
+        # stardist's correction: the boundary lies about half a pixel before the first foreign pixel
+        t_corr = 1 - 0.5 / max(abs(float(dy)), abs(float(dx)))
+        d = (steps + 1) + np.float32(t_corr) - 1
+        dist[ys, xs, k] = np.maximum(d * np.float32(np.hypot(dy, dx)), 1e-3).astype(np.float32)
+    return prob, dist
+

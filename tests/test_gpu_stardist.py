@@ -268,3 +268,32 @@ def test_fused_first_layer_is_bit_identical(model):
     finally:
         eng.set_option("seg_fuse_first", 0)
     assert np.array_equal(p0.cpu().numpy(), p1.cpu().numpy()) and np.array_equal(d0.cpu().numpy(), d1.cpu().numpy())
+
+
+def test_round_trip_through_the_screen(model):
+    """true labels -> star maps -> GPU instances -> region scan, gates, crops, scores: the objects come back (labels
+    bit-equal to the oracle's instances, IoU > 0.9 with the truth) and the screen keeps the same cells as it does on
+    the true labels."""
+    import torch
+    from cell_image_analysis_b200 import synth
+    from cell_image_analysis_b200.screening import ProductionMutantScreening
+    from oracle import stardist as sd
+    H, W, n, lo, hi, lu = synth.FIELD_CONFIGS["tiny"]
+    green, truth = synth.make_field(3, H, W, n, lo, hi, lu)
+    prob, dist = synth.star_maps_from_labels(truth, 2)
+    labels, n_inst = model.instances_from_prediction((H, W), torch.from_numpy(prob), torch.from_numpy(dist), 0.479071, 0.3)
+    ref, _ = sd.instances_from_prediction(prob, dist, 2, (H, W), 0.479071, 0.3)
+    got = labels.cpu().numpy()
+    assert np.array_equal(got, ref) and n_inst == len(np.unique(truth)) - 1
+    for i in np.unique(truth)[1:]:
+        m = truth == i
+        k = np.bincount(got[m]).argmax()
+        assert k > 0 and (m & (got == k)).sum() / (m | (got == k)).sum() > 0.9
+    golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "model_dir")
+    s = ProductionMutantScreening(golden, segmenter=lambda ch: None)
+    cells_t, stats_t = s.extract_quality_cells_from_labels(green, truth)
+    cells_g, stats_g = s.extract_quality_cells_from_labels(green, labels.to(s.engine.tdev))     # device-resident labels
+    assert len(cells_g) == len(cells_t) > 0
+    a_t = sorted(st["area"] for st in stats_t); a_g = sorted(st["area"] for st in stats_g)
+    assert np.allclose(a_t, a_g, rtol=0.12)          # polygons of 32 rays against the true ellipses
+

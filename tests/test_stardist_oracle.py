@@ -171,3 +171,20 @@ def test_model_folder_round_trip(tmp_path):
     assert np.array_equal(np.sin(prod.ray_angles(32)), rs) and np.array_equal(np.cos(prod.ray_angles(32)), rc)
     with pytest.raises(FileNotFoundError):
         prod.StarDist2D.from_pretrained("2D_versatile_fluo", engine=object())
+
+
+def test_round_trip_labels_to_star_maps_to_instances():
+    """labels -> (prob, dist) as StarDist's training targets define them -> instances: every object comes back once,
+    with its shape (the size-independent property of the segmentation's post-processing)."""
+    from cell_image_analysis_b200 import synth
+    H, W, n, lo, hi, lu = synth.FIELD_CONFIGS["tiny"]
+    _, truth = synth.make_field(3, H, W, n, lo, hi, lu)
+    prob, dist = synth.star_maps_from_labels(truth, 2)
+    labels, det = sd.instances_from_prediction(prob, dist, 2, truth.shape, 0.479071, 0.3)
+    ids = np.unique(truth)[1:]
+    assert labels.max() == len(ids) == len(det["prob"])
+    for i in ids:
+        m = truth == i
+        k = np.bincount(labels[m]).argmax()
+        assert k > 0 and (m & (labels == k)).sum() / (m | (labels == k)).sum() > 0.9
+
