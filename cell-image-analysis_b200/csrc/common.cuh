@@ -112,7 +112,9 @@ struct cia_ctx {
     int pca_kernel = 1;        // "pca_kernel": 1 = tcgen05 projection (score_tc.cu), 0 = fp64 DMMA anchor
     int seg_fuse_first = 0;    // "seg_fuse_first": the Cin = 1 layer evaluated inside the second layer's producer warps
                                // (bit-identical; measured SLOWER: 336 us against 110 + 128 us for the two launches, the eight
-                               // producer warps become the bottleneck -- kept as an option, off by default)
+                               // producer warps become the bottleneck; the same evaluation inside the staged kernel, by all
+                               // threads of three CTAs per SM, measured 295 us and was removed again: the layer's 288 FMAs per
+                               // pixel cost what they cost wherever they run -- kept as an option, off by default)
     int seg_conv_ws = 1;       // "seg_conv_ws": warp-specialised software-producer kernel for the other layers (0: staged kernel)
     int seg_conv_tma = 1;      // "seg_conv_tma": segment.cu's TMA-fed convolution kernel for Cin = 32 direct layers (0: staged kernel)
     int svm_refine = 1;        // "svm_refine": decisions within the tensor-core kernel's error of 0 are recomputed in fp64

@@ -17,6 +17,9 @@ from cell_image_analysis_b200 import synth             # noqa: E402
 H = W = int(os.environ.get("SEG_SIDE", "2048"))
 w = sd.random_model(T.CFG, seed=11)
 m = StarDist2D.from_arrays(T.CFG, w, {"prob": 0.479071, "nms": 0.3})
+for opt in ("seg_fuse_first", "seg_conv_tma", "seg_conv_ws"):      # A/B runs: SEG_FUSE_FIRST=1 etc.
+    if os.environ.get(opt.upper()):
+        m.engine.set_option(opt, float(os.environ[opt.upper()]))
 green, _ = synth.make_field(0, 2048, 2048, *synth.FIELD_CONFIGS["config1"][2:])
 green = np.ascontiguousarray(green[:H, :W])
 cells = T._ellipse_field(H, W, max(2, int(23 * H / 2048)), 3)
