@@ -163,49 +163,62 @@ __global__ void seg_normalize_kernel(const uint16_t* __restrict__ img, size_t n,
 // ---------------------------------------------------------------------------------------
 // U-Net
 // ---------------------------------------------------------------------------------------
-// First layer, Cin = 1 (K = 9: no tensor-core shape): one thread per pixel, fp32 FMAs, fp16 chunk-planar output.
+// First layer, Cin = 1 (K = 9: no tensor-core shape): one thread per PAIR of horizontally adjacent pixels (W is even:
+// field sides are multiples of 16), packed fp32x2 FMAs (the pixel value in both lanes, two output channels per
+// instruction, each lane an IEEE fma: bias first, taps in order), every 128-bit weight read from shared memory serves
+// both pixels, fp16 chunk-planar output.
 __global__ void __launch_bounds__(256) seg_first_kernel(const float* __restrict__ img, const float* __restrict__ w,
                                                         const float* __restrict__ bias, __half* __restrict__ out, int H,
                                                         int W, int cout) {
     extern __shared__ __align__(16) float sw[];   // [9][cout] weights, [cout] bias
     for (int i = threadIdx.x; i < 10 * cout; i += blockDim.x) sw[i] = i < 9 * cout ? w[i] : bias[i - 9 * cout];
     __syncthreads();
+    const int Wp = (W + 1) >> 1;
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (size_t)H * W) return;
-    const int y = (int)(idx / W), x = (int)(idx - (size_t)y * W);
-    float v[9];
+    if (idx >= (size_t)H * Wp) return;
+    const int y = (int)(idx / Wp), x = 2 * (int)(idx - (size_t)y * Wp);
+    const bool two = x + 1 < W;
+    float win[3][4];                               // rows y-1..y+1, columns x-1..x+2
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int yy = y + r - 1, xx = x + c - 1;
+            win[r][c] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(img + (size_t)yy * W + xx) : 0.f;
+        }
+    unsigned long long va[9], vb[9];
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
-        const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
-        v[t] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(img + (size_t)yy * W + xx) : 0.f;
+        va[t] = pack2(win[t / 3][t % 3], win[t / 3][t % 3]);
+        vb[t] = pack2(win[t / 3][t % 3 + 1], win[t / 3][t % 3 + 1]);
     }
-    // packed fp32x2 FMAs (sm_100): the pixel value in both lanes, two output channels per instruction (each lane
-    // an IEEE fma: the sums of the scalar loop), weights as 64-bit pairs straight from shared memory
-    unsigned long long v2[9];
-#pragma unroll
-    for (int t = 0; t < 9; ++t) v2[t] = pack2(v[t], v[t]);
     const ulonglong2* sw2 = reinterpret_cast<const ulonglong2*>(sw);
     for (int cgp = 0; cgp < cout / 8; ++cgp) {
-        __align__(16) __half o[8];
-        unsigned long long acc[4];
+        unsigned long long aa[4], ab[4];
         {
             const ulonglong2 b0 = sw2[(9 * cout + cgp * 8) / 4], b1 = sw2[(9 * cout + cgp * 8) / 4 + 1];
-            acc[0] = b0.x; acc[1] = b0.y; acc[2] = b1.x; acc[3] = b1.y;
+            aa[0] = ab[0] = b0.x; aa[1] = ab[1] = b0.y; aa[2] = ab[2] = b1.x; aa[3] = ab[3] = b1.y;
         }
 #pragma unroll
         for (int t = 0; t < 9; ++t) {
             const ulonglong2 w0 = sw2[(t * cout + cgp * 8) / 4], w1 = sw2[(t * cout + cgp * 8) / 4 + 1];
-            acc[0] = fma2(v2[t], w0.x, acc[0]); acc[1] = fma2(v2[t], w0.y, acc[1]);
-            acc[2] = fma2(v2[t], w1.x, acc[2]); acc[3] = fma2(v2[t], w1.y, acc[3]);
+            aa[0] = fma2(va[t], w0.x, aa[0]); aa[1] = fma2(va[t], w0.y, aa[1]);
+            aa[2] = fma2(va[t], w1.x, aa[2]); aa[3] = fma2(va[t], w1.y, aa[3]);
+            ab[0] = fma2(vb[t], w0.x, ab[0]); ab[1] = fma2(vb[t], w0.y, ab[1]);
+            ab[2] = fma2(vb[t], w1.x, ab[2]); ab[3] = fma2(vb[t], w1.y, ab[3]);
         }
+        __align__(16) __half oa[8], ob[8];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             float lo, hi;
-            unpack2(acc[k], lo, hi);
-            o[2 * k] = __float2half_rn(fmaxf(lo, 0.f));
-            o[2 * k + 1] = __float2half_rn(fmaxf(hi, 0.f));
+            unpack2(aa[k], lo, hi);
+            oa[2 * k] = __float2half_rn(fmaxf(lo, 0.f)); oa[2 * k + 1] = __float2half_rn(fmaxf(hi, 0.f));
+            unpack2(ab[k], lo, hi);
+            ob[2 * k] = __float2half_rn(fmaxf(lo, 0.f)); ob[2 * k + 1] = __float2half_rn(fmaxf(hi, 0.f));
         }
-        *reinterpret_cast<uint4*>(out + (((size_t)cgp * H + y) * W + x) * 8) = *reinterpret_cast<const uint4*>(o);
+        __half* dst = out + (((size_t)cgp * H + y) * W + x) * 8;
+        *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(oa);
+        if (two) *reinterpret_cast<uint4*>(dst + 8) = *reinterpret_cast<const uint4*>(ob);
     }
 }
 
@@ -1718,7 +1731,7 @@ int k_seg_predict(cia_ctx* h, const float* img, int H, int W, float* prob_out, f
             continue;
         }
         if (op.mode == -1) {
-            const size_t n = (size_t)Ho * Wo;
+            const size_t n = (size_t)Ho * ((Wo + 1) / 2);
             seg_first_kernel<<<(unsigned)((n + 255) / 256), 256, 10 * c.cout * sizeof(float), s>>>(img, c.w32, c.bias, out, Ho, Wo, c.cout);
             CIA_LAUNCH_CHECK();
             continue;
@@ -1764,7 +1777,7 @@ int k_seg_debug_layer(cia_ctx* h, int layer, const void* src0, const void* src1,
     const SegOp& op = m->ops[layer];
     const SegConv& c = m->conv[layer];
     if (op.mode == -1) {
-        const size_t n = (size_t)Ho * Wo;
+        const size_t n = (size_t)Ho * ((Wo + 1) / 2);
         seg_first_kernel<<<(unsigned)((n + 255) / 256), 256, 10 * c.cout * sizeof(float), s>>>(img, c.w32, c.bias, (__half*)out, Ho, Wo, c.cout);
         CIA_LAUNCH_CHECK();
         return CIA_OK;
