@@ -11,20 +11,28 @@
 // U-Net (csbdeep unet_block behind StarDist2D._build): every 3x3 convolution except the first (Cin = 1) is a
 // tcgen05 implicit GEMM over fp16 activations in chunk-planar order [C/8][y][x][8] (16 bytes = one pixel's 8
 // channels = one row of a K-major UMMA core matrix, the layout of cae_tc.cu).  A unit is a 16-row x 8*TILES-column
-// output tile: its zero-padded (18 x 8*TILES+2) input block of 32 channels is staged in shared memory ONCE per
+// output tile: its zero-padded (18 x 8*TILES+2) input block of 32 channels sits in shared memory ONCE per
 // 32-channel chunk and serves all nine taps through shifted descriptor start addresses (no im2col); max-pooling
-// and "nearest up-sampling + concatenate with the skip" are folded into that staging, so neither is a kernel or a
-// trip through HBM.  Accumulators (TILES x N fp32 columns) live in TMEM; two CTAs per SM overlap one CTA's staging
-// / epilogue with the other's MMAs.  The 1x1 heads (prob: sigmoid, dist: linear, floor 1e-3) are one more
-// launch of the same kernel with a single tap and N = 48.
+// and "nearest up-sampling + concatenate with the skip" are folded into the staging, so neither is a kernel or a
+// trip through HBM.  Accumulators (TILES x N fp32 columns) live in TMEM.  Three forms of the same arithmetic,
+// chosen per layer (launch_seg_layer):
+//   seg_conv_tma_kernel  Cin = 32 layers that read their producer directly: a cp.async.bulk.tensor box per unit into a
+//                        3-stage ring (out-of-bounds zero fill = the padding), producer / MMA / epilogue warps, two
+//                        TMEM accumulator sets: the epilogue of unit u runs under the MMAs of unit u + 1
+//   seg_conv_ws_kernel   the same pipeline with eight SOFTWARE producer warps (pooled / up-sampled + concatenated /
+//                        multi-chunk inputs with their weight blocks): layers with long MMA phases per step
+//   seg_conv_kernel      stage -> MMA -> epilogue in sequence, up to four CTAs per SM interleaving: the rest
+// The 1x1 heads (prob: sigmoid, dist: linear, floor 1e-3) are seg_heads_tma_kernel (all feature channels of a
+// 16 x 16 tile per box, N = 48).
 //
 // Post-processing: candidates (prob > threshold, 2-pixel border excluded) are sorted by probability (cub radix
-// sort), binned on a 32-px lattice, and suppressed greedily IN PARALLEL with the sequential algorithm's exact
-// result: a candidate becomes a winner once every better candidate whose bounding circle reaches it is decided;
-// the winners of a round then suppress their undecided neighbours by the exact polygon overlap (intersection /
-// smaller area > threshold; the intersection of two star-convex polygons as the sum over their triangle fans'
-// pairwise clipped areas, fp64, one warp per pair).  One cooperative kernel runs all rounds.  Kept polygons are
-// rendered with skimage.draw.polygon's point-in-polygon rule, the better polygon winning a pixel (atomicMin).
+// sort), binned on a 32-px lattice (counting sort), and suppressed greedily IN PARALLEL with the sequential algorithm's
+// exact result: a candidate becomes a winner once every better candidate whose bounding circle reaches it is decided;
+// the winners of a round then suppress their undecided neighbours by the polygon overlap (intersection / smaller
+// area > threshold; the intersection of two star-convex polygons as the sum over their triangle fans' pairwise
+// clipped areas: a float32 partial sum as a rigorous lower bound first, the exact fp64 sum where that does not
+// decide, one warp per pair).  One cooperative kernel runs all rounds.  Kept polygons are rendered with
+// skimage.draw.polygon's point-in-polygon rule, the better polygon winning a pixel (atomicMin).
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
