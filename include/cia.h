@@ -116,6 +116,12 @@ int  cia_check_status(cia_handle h, void* stream);
  *   "pca_kernel"      1 (default): tcgen05 RobustScaler + PCA projection; 0: the fp64 DMMA kernel
  *   "svm_refine"      1 (default): decisions within the tensor-core kernel's error of zero are
  *                     recomputed in fp64 (sign rule svm.cpp:2841 evaluated on exact values); 0: off
+ *   "seg_conv_tma"    segmentation (csrc/segment.cu): 1 (default) the Cin = 32 direct layers and the heads run the
+ *                     TMA-fed warp-specialised kernels; 0: the staged kernel everywhere (same arithmetic)
+ *   "seg_conv_ws"     1 (default): the software-producer warp-specialised kernel for the layers where it measured
+ *                     faster; 2: for every layer the TMA kernel does not take; 0: off
+ *   "seg_fuse_first"  1: the Cin = 1 layer evaluated inside the second layer's producer warps (bit-identical,
+ *                     measured slower); 0 (default): two launches
  * A `precision` 0 call (cia_screen_fields*, cia_cae_forward) is the exact anchor end to end and uses the
  * fp64 scoring kernels whatever these options say. */
 int  cia_set_option(cia_handle h, const char* name, double value);
