@@ -903,32 +903,32 @@ __global__ void __launch_bounds__(SegWsCfg<N, TILES>::THREADS, 1) seg_conv_ws_ke
 // ---------------------------------------------------------------------------------------
 // Instances from (prob, dist): candidates, polygons, bins, greedy NMS, rendering
 // ---------------------------------------------------------------------------------------
-// key: ascending sort = descending probability, ties: the larger flat index first (np.argsort(prob, stable)[::-1])
-__global__ void seg_candidates_kernel(const float* __restrict__ prob, int Hg, int Wg, float thr, int border,
-                                      unsigned long long* __restrict__ keys, int* __restrict__ count, int cap) {
+// Candidates in descending probability, ties: the larger flat index first (np.argsort(prob, stable)[::-1]):
+// flags -> exclusive scan -> compaction in DESCENDING index order -> stable radix sort of the inverted probability
+// bits (32-bit keys, the index as the value: half the passes of a 64-bit key sort)
+__global__ void seg_cand_flags_kernel(const float* __restrict__ prob, int Hg, int Wg, float thr, int border,
+                                      int* __restrict__ flags) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    bool ok = false;
-    float p = 0.f;
-    if (idx < Hg * Wg) {
-        const int i = idx / Wg, j = idx - i * Wg;
-        p = prob[idx];
-        ok = p > thr && i >= border && i < Hg - border && j >= border && j < Wg - border;
-    }
-    const unsigned m = __ballot_sync(0xffffffffu, ok);
-    if (!m) return;
-    const int lane = threadIdx.x & 31;
-    int base = 0;
-    if (lane == __ffs(m) - 1) base = atomicAdd(count, __popc(m));
-    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-    if (ok) {
-        const int pos = base + __popc(m & ((1u << lane) - 1u));
-        if (pos < cap)
-            keys[pos] = ((unsigned long long)(~__float_as_uint(p)) << 32) | (unsigned long long)(~(unsigned)idx);
+    if (idx >= Hg * Wg) return;
+    const int i = idx / Wg, j = idx - i * Wg;
+    flags[idx] = (prob[idx] > thr && i >= border && i < Hg - border && j >= border && j < Wg - border) ? 1 : 0;
+}
+
+__global__ void seg_cand_scatter_kernel(const float* __restrict__ prob, const int* __restrict__ flags, const int* __restrict__ excl,
+                                        int cap, unsigned* __restrict__ keys, unsigned* __restrict__ vals, int* __restrict__ count) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= cap) return;
+    const int total = excl[cap - 1] + flags[cap - 1];
+    if (idx == 0) *count = total;
+    if (flags[idx]) {
+        const int pos = total - 1 - excl[idx];
+        keys[pos] = ~__float_as_uint(prob[idx]);
+        vals[pos] = (unsigned)idx;
     }
 }
 
 // dist_to_coord: coord = (dist * [sin, cos]).astype(float32); coord += points  (float32 += int: added in fp64, stored fp32)
-__global__ void seg_polygons_kernel(const unsigned long long* __restrict__ keys, const int* __restrict__ count, int cap,
+__global__ void seg_polygons_kernel(const unsigned* __restrict__ sorted_idx, const int* __restrict__ count, int cap,
                                     const float* __restrict__ prob, const float* __restrict__ dist, int Wg, int grid,
                                     const double* __restrict__ rsin, const double* __restrict__ rcos, int H, int W,
                                     float* __restrict__ vy, float* __restrict__ vx, int* __restrict__ pyx,
@@ -937,7 +937,7 @@ __global__ void seg_polygons_kernel(const unsigned long long* __restrict__ keys,
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     const int n = min(*count, cap);
     if (r >= n) return;
-    const unsigned idx = ~(unsigned)(keys[r] & 0xffffffffull);
+    const unsigned idx = sorted_idx[r];
     const int i = (int)(idx / (unsigned)Wg), j = (int)(idx - (unsigned)i * Wg);
     const int py = i * grid, px = j * grid;
     const float* d = dist + (size_t)idx * SEG_RAYS;
@@ -1822,7 +1822,7 @@ int k_seg_instances(cia_ctx* h, const float* prob, const float* dist, int Hg, in
     // workspace carve-up
     size_t o = 0;
     auto take = [&](size_t bytes) { const size_t at = o; o += align_up(bytes, 256); return at; };
-    const size_t o_keys0 = take((size_t)cap * 8), o_keys1 = take((size_t)cap * 8);
+    const size_t o_keys0 = take((size_t)cap * 4), o_keys1 = take((size_t)cap * 4), o_vals0 = take((size_t)cap * 4), o_vals1 = take((size_t)cap * 4);
     const size_t o_binof = take((size_t)cap * 4), o_bcnt = take((size_t)(nbins + 1) * 4), o_bcur = take((size_t)(nbins + 1) * 4);
     const size_t o_vy = take((size_t)cap * SEG_RAYS * 4), o_vx = take((size_t)cap * SEG_RAYS * 4);
     const size_t o_pyx = take((size_t)cap * 8), o_pp = take((size_t)cap * 4), o_rm = take((size_t)cap * 4);
@@ -1833,7 +1833,8 @@ int k_seg_instances(cia_ctx* h, const float* prob, const float* dist, int Hg, in
     int rc = ws_reserve(h, m->post, o);
     if (rc) return rc;
     unsigned char* b = (unsigned char*)m->post.p;
-    unsigned long long* keys0 = (unsigned long long*)(b + o_keys0); unsigned long long* keys1 = (unsigned long long*)(b + o_keys1);
+    unsigned* keys0 = (unsigned*)(b + o_keys0); unsigned* keys1 = (unsigned*)(b + o_keys1);
+    unsigned* vals0 = (unsigned*)(b + o_vals0); unsigned* vals1 = (unsigned*)(b + o_vals1);
     int* bin_of = (int*)(b + o_binof); int* bin_count = (int*)(b + o_bcnt); int* bin_cursor = (int*)(b + o_bcur);
     float* vy = (float*)(b + o_vy); float* vx = (float*)(b + o_vx);
     int* pyx = (int*)(b + o_pyx); float* pp = (float*)(b + o_pp); float* rm = (float*)(b + o_rm);
@@ -1845,22 +1846,28 @@ int k_seg_instances(cia_ctx* h, const float* prob, const float* dist, int Hg, in
     m->last_cap = cap; m->vy = vy; m->vx = vx; m->pprob = pp; m->pyx = pyx; m->kept_rank = kept; m->n_kept = small + 5;
 
     size_t tmp_sort = 0, tmp_scan = 0;
-    cub::DeviceRadixSort::SortKeys(nullptr, tmp_sort, keys0, keys1, cap, 0, 64, s);
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, keys0, keys1, vals0, vals1, cap, 0, 32, s);
     cub::DeviceScan::ExclusiveSum(nullptr, tmp_scan, flags, excl, cap, s);
     rc = ws_reserve(h, m->cubtmp, std::max(tmp_sort, tmp_scan));
     if (rc) return rc;
     size_t tmp_bytes = m->cubtmp.cap;
 
-    CIA_CUDA(cudaMemsetAsync(keys0, 0xFF, (size_t)cap * 8, s));
+    CIA_CUDA(cudaMemsetAsync(keys0, 0xFF, (size_t)cap * 4, s));
     CIA_CUDA(cudaMemsetAsync(bin_count, 0, (size_t)(nbins + 1) * 4, s));
     CIA_CUDA(cudaMemsetAsync(state, 0, (size_t)cap * 4, s));
     CIA_CUDA(cudaMemsetAsync(small, 0, 64, s));
     CIA_CUDA(cudaMemsetAsync(labels, 0x7F, (size_t)H * W * sizeof(int32_t), s));
-    seg_candidates_kernel<<<(cap + 255) / 256, 256, 0, s>>>(prob, Hg, Wg, (float)prob_thresh, 2, keys0, small, cap);
+    seg_cand_flags_kernel<<<(cap + 255) / 256, 256, 0, s>>>(prob, Hg, Wg, (float)prob_thresh, 2, flags);
     CIA_LAUNCH_CHECK();
-    CIA_CUDA(cub::DeviceRadixSort::SortKeys(m->cubtmp.p, tmp_bytes, keys0, keys1, cap, 0, 64, s));
+    tmp_bytes = m->cubtmp.cap;
+    CIA_CUDA(cub::DeviceScan::ExclusiveSum(m->cubtmp.p, tmp_bytes, flags, excl, cap, s));
     h->launches++;
-    seg_polygons_kernel<<<(cap + 127) / 128, 128, 0, s>>>(keys1, small, cap, prob, dist, Wg, grid, m->ray_sin, m->ray_cos, H, W, vy, vx,
+    seg_cand_scatter_kernel<<<(cap + 255) / 256, 256, 0, s>>>(prob, flags, excl, cap, keys0, vals0, small);
+    CIA_LAUNCH_CHECK();
+    tmp_bytes = m->cubtmp.cap;
+    CIA_CUDA(cub::DeviceRadixSort::SortPairs(m->cubtmp.p, tmp_bytes, keys0, keys1, vals0, vals1, cap, 0, 32, s));
+    h->launches++;
+    seg_polygons_kernel<<<(cap + 127) / 128, 128, 0, s>>>(vals1, small, cap, prob, dist, Wg, grid, m->ray_sin, m->ray_cos, H, W, vy, vx,
                                                          pyx, pp, rm, area, bin_of, bin_count, (unsigned*)(small + 1));
     CIA_LAUNCH_CHECK();
     seg_bins_kernel<<<1, 1024, 0, s>>>(bin_count, nbins, bins, bin_cursor);
