@@ -1340,8 +1340,9 @@ constexpr int SEG_EMPTY = 0x7F7F7F7F;   // cudaMemset(0x7F) background of the at
 // polygons_to_label: polygons drawn in ascending probability, label = NMS output index + 1  ==  every pixel takes
 // the smallest index among the polygons that cover it
 __global__ void __launch_bounds__(256) seg_render_kernel(const float* __restrict__ vy, const float* __restrict__ vx,
-                                                         const int* __restrict__ kept_rank, const int* __restrict__ n_kept,
-                                                         int H, int W, int32_t* __restrict__ labels) {
+                                                         const int* __restrict__ pyx, const int* __restrict__ kept_rank,
+                                                         const int* __restrict__ n_kept, int H, int W,
+                                                         int32_t* __restrict__ labels) {
     __shared__ float s_v[8][2][SEG_RAYS];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, gwarps = (gridDim.x * blockDim.x) >> 5;
@@ -1359,15 +1360,30 @@ __global__ void __launch_bounds__(256) seg_render_kernel(const float* __restrict
             y0 = fminf(y0, __shfl_xor_sync(0xffffffffu, y0, o)); y1 = fmaxf(y1, __shfl_xor_sync(0xffffffffu, y1, o));
             x0 = fminf(x0, __shfl_xor_sync(0xffffffffu, x0, o)); x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, o));
         }
+        // pixels within the fan's inscribed circle are inside, pixels beyond its largest vertex distance outside,
+        // whatever the crossing test would say (margins of 0.1 % and 0.01 px: nothing near the boundary is decided here)
+        const float cyf = (float)pyx[2 * r], cxf = (float)pyx[2 * r + 1];
+        float d2 = (yv - cyf) * (yv - cyf) + (xv - cxf) * (xv - cxf), d2min = d2, d2max = d2;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            d2min = fminf(d2min, __shfl_xor_sync(0xffffffffu, d2min, o));
+            d2max = fmaxf(d2max, __shfl_xor_sync(0xffffffffu, d2max, o));
+        }
+        const float rin = fmaxf(sqrtf(d2min) * 0.9942f - 0.01f, 0.f);     // cos(pi / 32) = 0.99518: the chords' distance
+        const float rout = sqrtf(d2max) * 1.001f + 0.01f;
+        const float rin2 = rin * rin, rout2 = rout * rout;
         // minr = int(max(0, r.min())), maxr = min(shape[0] - 1, int(ceil(r.max())))
         const int minr = (int)fmaxf(0.f, y0), maxr = min(H - 1, (int)ceilf(y1));
         const int minc = (int)fmaxf(0.f, x0), maxc = min(W - 1, (int)ceilf(x1));
         if (maxr < minr || maxc < minc) continue;
         const int bw = maxc - minc + 1;
         for (int yy = minr + part; yy <= maxr; yy += SEG_RENDER_SPLIT)
-            for (int xx = minc + lane; xx <= maxc; xx += 32)
-                if (seg_pnpoly(s_v[wib][1], s_v[wib][0], (double)xx, (double)yy))
+            for (int xx = minc + lane; xx <= maxc; xx += 32) {
+                const float q2 = ((float)yy - cyf) * ((float)yy - cyf) + ((float)xx - cxf) * ((float)xx - cxf);
+                if (q2 > rout2) continue;
+                if (q2 < rin2 || seg_pnpoly(s_v[wib][1], s_v[wib][0], (double)xx, (double)yy))
                     atomicMin(labels + (size_t)yy * W + xx, k + 1);
+            }
         (void)bw;
     }
 }
@@ -1894,7 +1910,7 @@ int k_seg_instances(cia_ctx* h, const float* prob, const float* dist, int Hg, in
     h->launches++;
     seg_compact_kernel<<<(cap + 255) / 256, 256, 0, s>>>(flags, excl, cap, kept, small + 5);
     CIA_LAUNCH_CHECK();
-    seg_render_kernel<<<h->num_sms * 8, 256, 0, s>>>(vy, vx, kept, small + 5, H, W, labels);
+    seg_render_kernel<<<h->num_sms * 8, 256, 0, s>>>(vy, vx, pyx, kept, small + 5, H, W, labels);
     CIA_LAUNCH_CHECK();
     seg_finalize_kernel<<<h->num_sms * 8, 256, 0, s>>>(labels, (size_t)H * W);
     CIA_LAUNCH_CHECK();
