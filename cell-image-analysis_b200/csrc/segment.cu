@@ -1115,17 +1115,6 @@ __device__ double seg_overlap_warp(const NmsArgs& a, int w, int i, float (*sp)[2
     sp[0][0][lane] = a.vy[(size_t)w * SEG_RAYS + lane]; sp[0][1][lane] = a.vx[(size_t)w * SEG_RAYS + lane];
     sp[1][0][lane] = a.vy[(size_t)i * SEG_RAYS + lane]; sp[1][1][lane] = a.vx[(size_t)i * SEG_RAYS + lane];
     __syncwarp();
-    // bounding boxes (the vertices' extent, as the oracle)
-    float y0 = sp[0][0][lane], y1 = y0, x0 = sp[0][1][lane], x1 = x0;
-    float u0 = sp[1][0][lane], u1 = u0, v0 = sp[1][1][lane], v1 = v0;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        y0 = fminf(y0, __shfl_xor_sync(0xffffffffu, y0, o)); y1 = fmaxf(y1, __shfl_xor_sync(0xffffffffu, y1, o));
-        x0 = fminf(x0, __shfl_xor_sync(0xffffffffu, x0, o)); x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, o));
-        u0 = fminf(u0, __shfl_xor_sync(0xffffffffu, u0, o)); u1 = fmaxf(u1, __shfl_xor_sync(0xffffffffu, u1, o));
-        v0 = fminf(v0, __shfl_xor_sync(0xffffffffu, v0, o)); v1 = fmaxf(v1, __shfl_xor_sync(0xffffffffu, v1, o));
-    }
-    if (y1 < u0 || u1 < y0 || x1 < v0 || v1 < x0) return 0.0;
     const int l1 = (lane + 1) & (SEG_RAYS - 1);
     const double cwx = (double)a.pyx[2 * w + 1], cwy = (double)a.pyx[2 * w];
     const double cix = (double)a.pyx[2 * i + 1], ciy = (double)a.pyx[2 * i];
@@ -1155,6 +1144,17 @@ __device__ double seg_overlap_warp(const NmsArgs& a, int w, int i, float (*sp)[2
             if (tot > need) return (double)tot / denom;  // > thr: the full sum can only be larger
         }
     }
+    // bounding boxes (the vertices' extent, as the oracle): only reached by pairs the lower bound did not decide
+    float y0 = sp[0][0][lane], y1 = y0, x0 = sp[0][1][lane], x1 = x0;
+    float u0 = sp[1][0][lane], u1 = u0, v0 = sp[1][1][lane], v1 = v0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        y0 = fminf(y0, __shfl_xor_sync(0xffffffffu, y0, o)); y1 = fmaxf(y1, __shfl_xor_sync(0xffffffffu, y1, o));
+        x0 = fminf(x0, __shfl_xor_sync(0xffffffffu, x0, o)); x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, o));
+        u0 = fminf(u0, __shfl_xor_sync(0xffffffffu, u0, o)); u1 = fmaxf(u1, __shfl_xor_sync(0xffffffffu, u1, o));
+        v0 = fminf(v0, __shfl_xor_sync(0xffffffffu, v0, o)); v1 = fmaxf(v1, __shfl_xor_sync(0xffffffffu, v1, o));
+    }
+    if (y1 < u0 || u1 < y0 || x1 < v0 || v1 < x0) return 0.0;
     // step 1: lane = fan triangle of w; bit st of `mask` = its pair with triangle (lane + st) of i needs clipping
     unsigned mask = 0;
     {
@@ -1515,7 +1515,7 @@ int launch_seg_layer(cia_ctx* h, const SegConv& c, const SegConvArgs& a, cudaStr
     const bool tma = h->seg_conv_tma && a.mode == 0 && c.chunks == 1 && c.groups == 1 && ((size_t)a.src0 % 16) == 0;
     if (tma && c.n_tile == 32) return launch_seg_conv_tma<32, 4>(h, a, s);
     if (tma && c.n_tile == 128) return launch_seg_conv_tma<128, 2>(h, a, s);
-    // measured per layer on B200 (profiles/r2r_seg_launches.txt): the software producer pays for layers with two or more
+    // measured per layer on B200 (profiles/r2t_seg_launches.txt): the software producer pays for layers with two or more
     // chunks and 64+ output channels per CTA (long MMA phases per step); short steps (N = 32) and pooled single- or
     // double-chunk inputs are faster with three co-resident staged CTAs.  seg_conv_ws = 2 forces it everywhere (tests).
     const bool ws = h->seg_conv_ws == 2 ||
