@@ -297,3 +297,49 @@ def test_round_trip_through_the_screen(model):
     a_t = sorted(st["area"] for st in stats_t); a_g = sorted(st["area"] for st in stats_g)
     assert np.allclose(a_t, a_g, rtol=0.12)          # polygons of 32 rays against the true ellipses
 
+
+
+@pytest.mark.parametrize("H,W", [(16, 16), (16, 48), (64, 16), (32, 272)])
+def test_small_and_oblong_fields(model, H, W):
+    """fields smaller than one tile of a level (the coarsest maps are 1 x 1 ... 2 x 17 pixels; TMA boxes larger than the
+    tensor) and strongly oblong ones, against the fp16-activation twin of the oracle; instances on their maps bit-equal"""
+    from oracle import stardist as sd
+    rng = np.random.default_rng(H * 1000 + W)
+    x = rng.uniform(-0.2, 1.5, (H, W)).astype(np.float32)
+    prob, dist = model.predict(x)
+    p16, d16 = sd.unet_forward(CFG, model.oracle_weights, x, half_activations=True)
+    assert prob.shape == p16.shape and dist.shape == d16.shape
+    assert np.abs(prob.cpu().numpy() - p16).max() < 1e-2
+    assert np.abs(dist.cpu().numpy() - d16).max() < 1e-2 * np.abs(d16).max()
+    thr = float(np.quantile(p16, 0.6))
+    labels, n = model.instances_from_prediction((H, W), prob, dist, thr, 0.3)
+    ref, det = sd.instances_from_prediction(prob.cpu().numpy(), dist.cpu().numpy(), 2, (H, W), thr, 0.3)
+    assert n == len(det["prob"]) and np.array_equal(labels.cpu().numpy(), ref)
+
+
+def test_normalize_uint8_and_constant_fields(model):
+    from oracle import stardist as sd
+    rng = np.random.default_rng(21)
+    x8 = rng.integers(0, 256, (96, 80)).astype(np.uint8)
+    assert np.array_equal(model.normalize_device(x8).cpu().numpy(), sd.normalize(x8))
+    flat = np.full((64, 64), 1234, np.uint16)                # ma == mi: division by eps, as csbdeep does
+    got, ref = model.normalize_device(flat).cpu().numpy(), sd.normalize(flat)
+    assert np.array_equal(got, ref)
+    with pytest.raises(TypeError):
+        model.normalize_device(rng.uniform(0, 1, (32, 32)).astype(np.float32))
+
+
+def test_large_radii_keep_the_suppression_exact(model):
+    """one candidate with a huge radius makes every candidate a neighbour of every other (reach = r + r_max): slow path,
+    same result"""
+    import torch
+    from oracle import stardist as sd
+    rng = np.random.default_rng(33)
+    H = W = 128
+    prob = rng.uniform(0, 1, (H // 2, W // 2)).astype(np.float32)
+    dist = rng.uniform(1.5, 6, (H // 2, W // 2, 32)).astype(np.float32)
+    dist[20, 20] = 90.0
+    prob[20, 20] = 0.95
+    ref, det = sd.instances_from_prediction(prob, dist, 2, (H, W), 0.7, 0.3)
+    labels, n = model.instances_from_prediction((H, W), torch.from_numpy(prob), torch.from_numpy(dist), 0.7, 0.3)
+    assert n == len(det["prob"]) and np.array_equal(labels.cpu().numpy(), ref)
