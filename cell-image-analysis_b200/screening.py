@@ -564,6 +564,60 @@ class ProductionMutantScreening:
         from .distributed import screen_mutant_samples_sharded
         return screen_mutant_samples_sharded(self, test_folders_dict, output_dir, chunk_fields)
 
+    def screen_images(self, images, cells_cap_per_field: int = 4096, prob_thresh=None, nms_thresh=None):
+        """det:51-153 for a batch of single-channel uint16 fields with NOTHING but the images given: per field
+        normalize -> U-Net -> instances (csrc/segment.cu) -> region scan -> gates -> crops -> autoencoder -> SVMs, all
+        enqueued on one stream (the labels never leave the device, no host synchronisation inside the loop; one at
+        the end).  Needs ``stardist_dir=`` (or ``self.stardist_model``).  Returns per-cell arrays in (field, ascending
+        label) order: ``field``, ``label``, ``reconstruction_mse`` / ``_mae``, ``conservative_scores`` /
+        ``moderate_scores`` (negated decisions, det:149-150), ``*_predictions``, and ``n_instances`` per field."""
+        m = self.stardist_model
+        if m is None:
+            raise RuntimeError("screen_images needs the GPU segmentation: construct with stardist_dir=<model folder>")
+        eng = self.engine
+        imgs = np.ascontiguousarray(images)
+        if imgs.dtype != np.uint16 or imgs.ndim != 3:
+            raise UnsupportedImageError(f"screen_images takes uint16 [F, H, W] fields, got {imgs.dtype} {imgs.shape}")
+        F, H, W = imgs.shape
+        cap = int(cells_cap_per_field)
+        dev = torch.from_numpy(imgs.view(np.int16)).to(eng.tdev)
+        outs = [eng.alloc_outputs(cap, 1) for _ in range(F)]
+        n_inst = torch.zeros(F, dtype=torch.int32, device=eng.tdev)
+        x = torch.empty((H, W), dtype=torch.float32, device=eng.tdev)
+        pt = m.thresholds["prob"] if prob_thresh is None else prob_thresh
+        nt = m.thresholds["nms"] if nms_thresh is None else nms_thresh
+        labels = torch.empty((H, W), dtype=torch.int32, device=eng.tdev)
+        padded = (-H % m.div_by, -W % m.div_by) != (0, 0)
+        for f in range(F):
+            eng._check(eng.lib.cia_seg_normalize(eng.h, _ptr(dev[f]), H, W, 3.0, 99.8, _ptr(x), C.c_void_p(0), eng._stream()))
+            if padded:                       # StarDist's reflect padding (host-side mirror of the device tensor ops)
+                prob, dist = m.predict(x)
+                lab, cnt = m.instances_from_prediction((H, W), prob, dist, pt, nt, sync=False)
+                labels.copy_(lab)
+                n_inst[f:f + 1].copy_(cnt)
+            else:
+                eng._check(eng.lib.cia_seg_predict(eng.h, _ptr(x), H, W, C.c_void_p(0), C.c_void_p(0), eng._stream()))
+                eng._check(eng.lib.cia_seg_instances(eng.h, C.c_void_p(0), C.c_void_p(0), H // m.grid, W // m.grid, m.grid,
+                                                     H, W, float(pt), float(nt), _ptr(labels), _ptr(n_inst[f:f + 1]),
+                                                     eng._stream()))
+            eng.screen_fields(dev[f:f + 1], labels.view(1, H, W), cap, outs[f])
+        eng.check_status()                   # synchronises; raises on capacity / label overflow
+        cols = {k: [] for k in ("field", "label", "mse", "mae", "dec_cons", "dec_mod", "pred_cons", "pred_mod")}
+        for f, o in enumerate(outs):
+            n = int(o["counts"][0].item())
+            rec = o["cells"][:n].cpu().numpy().view(_lib.CELL_DTYPE).reshape(-1)
+            cols["field"].append(np.full(n, f, np.int64))
+            cols["label"].append(rec["label"].astype(np.int64))
+            for k in ("mse", "mae", "dec_cons", "dec_mod", "pred_cons", "pred_mod"):
+                cols[k].append(o[k][:n].cpu().numpy())
+        cat = {k: np.concatenate(v) if v else np.zeros(0) for k, v in cols.items()}
+        return {"field": cat["field"], "label": cat["label"],
+                "reconstruction_mse": cat["mse"], "reconstruction_mae": cat["mae"],
+                "conservative_scores": -cat["dec_cons"], "moderate_scores": -cat["dec_mod"],      # det:149-150
+                "conservative_predictions": cat["pred_cons"].astype(np.intp),
+                "moderate_predictions": cat["pred_mod"].astype(np.intp),
+                "n_instances": n_inst.cpu().numpy()}
+
     def screen_fields_sharded(self, fields, field_strain, n_strains: int, chunk_fields: int = 16):
         """``fields``: sequence of (green uint16 [H,W], labels int32 [H,W]) of one size, ``field_strain``
         their strain ids.  Every rank scores fields[rank::world]; returns the all-reduced per-strain

@@ -343,3 +343,37 @@ def test_large_radii_keep_the_suppression_exact(model):
     ref, det = sd.instances_from_prediction(prob, dist, 2, (H, W), 0.7, 0.3)
     labels, n = model.instances_from_prediction((H, W), torch.from_numpy(prob), torch.from_numpy(dist), 0.7, 0.3)
     assert n == len(det["prob"]) and np.array_equal(labels.cpu().numpy(), ref)
+
+
+def test_screen_images_equals_the_per_field_calls(tmp_path):
+    """ProductionMutantScreening.screen_images (segmentation + screen, stream-ordered, labels on the device) against
+    extract_quality_cells + compute_anomaly_scores field by field"""
+    from cell_image_analysis_b200 import synth
+    from cell_image_analysis_b200.screening import ProductionMutantScreening
+    from oracle import stardist as sd
+    w = sd.random_model(CFG, seed=11, dist_bias=14.0)
+    folder = tmp_path / "sd_demo"
+    sd.write_model_folder(str(folder), CFG, w, prob_thresh=0.479071, nms_thresh=0.3)
+    H, W, n, lo, hi, lu = synth.FIELD_CONFIGS["tiny"]
+    fields = np.stack([synth.make_field(s_, H, W, n, lo, hi, lu)[0] for s_ in (3, 4, 5)])
+    golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "model_dir")
+    current = {}
+    s = ProductionMutantScreening(golden, imread=lambda p: current["img"], stardist_dir=str(folder))
+    m = s.stardist_model
+    prob, _ = m.predict(m.normalize_device(fields[0]))
+    m.thresholds["prob"] = float(np.quantile(prob.cpu().numpy(), 0.7))
+    res = s.screen_images(fields)
+    assert len(res["n_instances"]) == 3 and res["n_instances"].min() > 0
+    k = 0
+    for f in range(3):
+        current["img"] = fields[f]
+        cells, stats = s.extract_quality_cells(f"field_{f}.tif")
+        sel = res["field"] == f
+        assert sel.sum() == len(cells)
+        if len(cells):
+            r = s.compute_anomaly_scores(cells)
+            assert np.allclose(res["reconstruction_mse"][sel], r["reconstruction_mse"], rtol=1e-5)
+            assert np.array_equal(res["conservative_predictions"][sel], r["conservative_predictions"])
+            assert np.abs(res["moderate_scores"][sel] - r["moderate_scores"]).max() < 1e-6
+        k += len(cells)
+    assert k == len(res["field"]) > 0
