@@ -33,6 +33,19 @@ def test_native_line_carries_the_contract_keys():
     assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
 
 
+def test_final_line_carries_the_segmentation_extras():
+    """the last bench line of the round: the contract keys plus extra.segmentation"""
+    d = _line("r2t_bench_default.json")
+    assert BASE_KEYS <= set(d), BASE_KEYS - set(d)
+    sg = d["extra"]["segmentation"]
+    assert abs(sg["ms_per_field"] - (sg["normalize_ms"] + sg["unet_ms"] + sg["instances_ms"])) < 1e-6
+    assert sg["instances"] > 0 and sg["candidates"] > sg["instances"] and sg["gpu_launches_per_field"] > 0
+    assert abs(sg["unet_tflops"] - sg["unet_gflop"] / sg["unet_ms"]) < 1e-6 * sg["unet_tflops"] + 1e-9
+    assert sg["cpu_port"]["kind"] == "port" and sg["cpu_port"]["labels_equal_gpu"] is True
+    ch = sg["chain"]
+    assert ch["scored_cells"] > 0 and abs(ch["cells_per_s"] - ch["scored_cells"] * 1e3 / ch["ms_per_field"]) < 1e-3
+
+
 def test_reference_line():
     d = _line("r2k_bench_reference.json")
     assert d["impl"] == "reference" and d["unit"] == "cells/s" and d["cpu_baseline"]["value"] == d["value"]
