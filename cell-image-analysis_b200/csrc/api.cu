@@ -87,6 +87,8 @@ int cia_set_option(cia_handle h, const char* name, double value) {
     } else if (n == "seg_conv_tma") {
         // segmentation: 1 = single-chunk direct layers run the TMA-fed warp-specialised kernel, 0 = the staged kernel everywhere
         h->seg_conv_tma = value != 0;
+    } else if (n == "seg_pool_out") {
+        h->seg_pool_out = value != 0;
     } else if (n == "seg_fuse_first") {
         h->seg_fuse_first = value != 0;
     } else if (n == "seg_conv_ws") {

@@ -115,6 +115,7 @@ struct cia_ctx {
                                // producer warps become the bottleneck; the same evaluation inside the staged kernel, by all
                                // threads of three CTAs per SM, measured 295 us and was removed again: the layer's 288 FMAs per
                                // pixel cost what they cost wherever they run -- kept as an option, off by default)
+    int seg_pool_out = 1;      // "seg_pool_out": TMA-fed layers also write the max-pooled copy the next layer reads (0: it pools itself)
     int seg_conv_ws = 1;       // "seg_conv_ws": warp-specialised software-producer kernel for the other layers (0: staged kernel)
     int seg_conv_tma = 1;      // "seg_conv_tma": segment.cu's TMA-fed convolution kernel for Cin = 32 direct layers (0: staged kernel)
     int svm_refine = 1;        // "svm_refine": decisions within the tensor-core kernel's error of 0 are recomputed in fp64

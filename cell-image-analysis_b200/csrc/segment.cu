@@ -64,6 +64,8 @@ struct SegOp {
     int src0, src1, dst;         // activation buffer ids
     int c0, c1;                  // channels of src0 / src1
     int shift;                   // output resolution = field >> shift
+    int pool_dst;                // >= 0: buffer for the 2x2 max-pooled copy of the output (the next layer pools this one)
+    int full_needed;             // the full-resolution output is read as well (a skip connection)
 };
 
 }  // namespace
@@ -245,6 +247,8 @@ struct SegConvArgs {
     const float* img;
     const float* w1;
     const float* b1;
+    // seg_conv_tma_kernel: POOL 1 / 2 also writes (only writes) MaxPooling2D((2, 2)) of the output for the next layer
+    __half* out_pool;
 };
 
 template <int N, int TILES>
@@ -461,10 +465,13 @@ struct SegTmaCfg {
     static_assert(TMEM_COLS <= 512 && SMEM_B <= 225 * 1024, "does not fit");
 };
 
-template <int N, int TILES>
+// POOL 0: the layer's output; 1: only its 2x2 max-pooled copy (the full-resolution map is read by nobody else: it never
+// exists in HBM); 2: both (a skip connection).  The four pool partners of a pixel are lanes l, l ^ 1 (column), l ^ 8 (row)
+// of one warp; max of the rounded halves = rounding of the max, so the consumer sees what pooling the stored map gives.
+template <int N, int TILES, int POOL>
 __global__ void __launch_bounds__(320, 1) seg_conv_tma_kernel(const __grid_constant__ CUtensorMap tm, const uint4* __restrict__ w,
                                                               const float* __restrict__ bias, __half* __restrict__ out,
-                                                              int H, int W) {
+                                                              __half* __restrict__ out_pool, int H, int W) {
     using C = SegCfg<N, TILES>;
     using T = SegTmaCfg<N, TILES>;
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -553,8 +560,19 @@ __global__ void __launch_bounds__(320, 1) seg_conv_tma_kernel(const __grid_const
 #pragma unroll
                 for (int k = 0; k < 8; ++k)
                     o[k] = __float2half_rn(fmaxf(__fadd_rn(__uint_as_float(v[k]), __ldg(bias + sl * 8 + k)), 0.f));
-                if (y < H && x < W)
+                if (POOL != 1 && y < H && x < W)
                     *reinterpret_cast<uint4*>(out + (((size_t)sl * H + y) * W + x) * 8) = *reinterpret_cast<const uint4*>(o);
+                if (POOL != 0) {
+                    uint4 u = *reinterpret_cast<const uint4*>(o), p1;
+                    p1.x = __shfl_xor_sync(0xffffffffu, u.x, 1); p1.y = __shfl_xor_sync(0xffffffffu, u.y, 1);
+                    p1.z = __shfl_xor_sync(0xffffffffu, u.z, 1); p1.w = __shfl_xor_sync(0xffffffffu, u.w, 1);
+                    u = hmax8(u, p1);
+                    p1.x = __shfl_xor_sync(0xffffffffu, u.x, 8); p1.y = __shfl_xor_sync(0xffffffffu, u.y, 8);
+                    p1.z = __shfl_xor_sync(0xffffffffu, u.z, 8); p1.w = __shfl_xor_sync(0xffffffffu, u.w, 8);
+                    u = hmax8(u, p1);
+                    if (((r & 1) | ((r >> 3) & 1)) == 0 && y < H && x < W)
+                        *reinterpret_cast<uint4*>(out_pool + (((size_t)sl * (H >> 1) + (y >> 1)) * (W >> 1) + (x >> 1)) * 8) = u;
+                }
             }
             tc_fence_before();
             __syncwarp();
@@ -1427,7 +1445,7 @@ typedef CUresult (*SegTensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuui
                                          const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                          CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-template <int N, int TILES>
+template <int N, int TILES, int POOL = 0>
 int launch_seg_conv_tma(cia_ctx* h, const SegConvArgs& a, cudaStream_t s) {
     using C = SegCfg<N, TILES>;
     using T = SegTmaCfg<N, TILES>;
@@ -1449,13 +1467,13 @@ int launch_seg_conv_tma(cia_ctx* h, const SegConvArgs& a, cudaStream_t s) {
         h->err = "cuTensorMapEncodeTiled failed (segmentation activations)";
         return CIA_E_CUDA;
     }
-    auto kern = seg_conv_tma_kernel<N, TILES>;
+    auto kern = seg_conv_tma_kernel<N, TILES, POOL>;
     if (first_use(h, (const void*)kern))
         CIA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_B));
     const int tiles_x = (a.W + 8 * TILES - 1) / (8 * TILES), tiles_y = (a.H + 15) / 16;
     int grid = tiles_x * tiles_y;
     if (grid > h->num_sms) grid = h->num_sms;
-    kern<<<grid, T::THREADS, T::SMEM_B, s>>>(tm, a.w, a.bias, a.out, a.H, a.W);
+    kern<<<grid, T::THREADS, T::SMEM_B, s>>>(tm, a.w, a.bias, a.out, a.out_pool, a.H, a.W);
     CIA_LAUNCH_CHECK();
     return CIA_OK;
 }
@@ -1510,10 +1528,22 @@ int launch_seg_heads(cia_ctx* h, const SegConv& c, const SegConvArgs& a, cudaStr
     return launch_seg_conv<48, 2, 1>(h, a, s);
 }
 
+// does this layer run in the TMA-fed kernel (and can therefore hand a pooled copy of its output to the next layer)?
+bool seg_tma_eligible(const cia_ctx* h, const SegConv& c, int mode) {
+    return h->seg_conv_tma && mode == 0 && c.chunks == 1 && c.groups == 1;
+}
+
 // one 3x3 layer of the plan: the TMA-fed kernel where the layer reads its producer directly with one 32-channel chunk
 int launch_seg_layer(cia_ctx* h, const SegConv& c, const SegConvArgs& a, cudaStream_t s) {
     const bool tma = h->seg_conv_tma && a.mode == 0 && c.chunks == 1 && c.groups == 1 && ((size_t)a.src0 % 16) == 0;
+    if (tma && a.out_pool && (a.H & 1) == 0 && (a.W & 1) == 0) {       // pooled copy for the next layer (see seg_tma_eligible)
+        const bool both = a.out != nullptr;
+        if (c.n_tile == 32) return both ? launch_seg_conv_tma<32, 4, 2>(h, a, s) : launch_seg_conv_tma<32, 4, 1>(h, a, s);
+        if (c.n_tile == 64) return both ? launch_seg_conv_tma<64, 4, 2>(h, a, s) : launch_seg_conv_tma<64, 4, 1>(h, a, s);
+        return both ? launch_seg_conv_tma<128, 2, 2>(h, a, s) : launch_seg_conv_tma<128, 2, 1>(h, a, s);
+    }
     if (tma && c.n_tile == 32) return launch_seg_conv_tma<32, 4>(h, a, s);
+    if (tma && c.n_tile == 64) return launch_seg_conv_tma<64, 4>(h, a, s);
     if (tma && c.n_tile == 128) return launch_seg_conv_tma<128, 2>(h, a, s);
     // measured per layer on B200 (profiles/r2t_seg_launches.txt): the software producer pays for layers with two or more
     // chunks and 64+ output channels per CTA (long MMA phases per step); short steps (N = 32) and pooled single- or
@@ -1578,6 +1608,7 @@ int k_seg_load(cia_ctx* h, const cia_seg_config* cfg, int n_layers, const float*
         else if (up_low >= 0) { op.mode = 2; op.src0 = up_low; op.src1 = up_skip; op.c0 = up_low_ch; op.c1 = up_skip_ch; up_low = -1; }
         else { op.mode = pend_pool ? 1 : 0; op.src0 = cur; op.src1 = -1; op.c0 = cur_ch; op.c1 = 0; }
         pend_pool = false;
+        op.pool_dst = -1; op.full_needed = 1;
         op.dst = new_buf(cout, shift);
         cur = op.dst; cur_ch = cout;
         plan_cout.push_back(cout);
@@ -1602,6 +1633,16 @@ int k_seg_load(cia_ctx* h, const cia_seg_config* cfg, int n_layers, const float*
         emit(m->base << std::max(0, n - 1));
     }
     emit(m->after);
+    // a layer whose output is max-pooled by the next one gets a buffer for the pooled copy (written by the producer's
+    // epilogue when it runs in the TMA-fed kernel); the full-resolution map is only needed where something else reads it
+    for (size_t l = 0; l + 1 < m->ops.size(); ++l) {
+        if (m->ops[l + 1].mode != 1 || m->ops[l + 1].src0 != m->ops[l].dst) continue;
+        m->ops[l].pool_dst = new_buf(m->buf_ch[m->ops[l].dst], m->ops[l].shift + 1);
+        bool other_reader = false;
+        for (size_t k = l + 2; k < m->ops.size(); ++k)
+            other_reader |= m->ops[k].src0 == m->ops[l].dst || m->ops[k].src1 == m->ops[l].dst;
+        m->ops[l].full_needed = other_reader ? 1 : 0;
+    }
     const int n_body = (int)plan_cout.size();
     if (n_layers != n_body + 2) {
         h->err = "segmentation: expected " + std::to_string(n_body + 2) + " conv layers, got " + std::to_string(n_layers);
@@ -1737,6 +1778,7 @@ int k_seg_predict(cia_ctx* h, const float* img, int H, int W, float* prob_out, f
     // directly: no 2 x 268 MB round trip of the full-resolution 32-channel map through HBM, one launch less
     const bool fuse_first = h->seg_fuse_first && m->ops.size() >= 2 && m->ops[0].mode == -1 && m->ops[1].mode == 0 &&
                             m->ops[1].src0 == m->ops[0].dst && m->conv[0].cout % SEG_KC == 0 && m->conv[0].cout <= 128;
+    std::vector<char> pooled_by_producer(m->ops.size(), 0);
     for (size_t l = 0; l < m->ops.size(); ++l) {
         const SegOp& op = m->ops[l];
         const SegConv& c = m->conv[l];
@@ -1765,6 +1807,17 @@ int k_seg_predict(cia_ctx* h, const float* img, int H, int W, float* prob_out, f
         a.src1 = op.src1 >= 0 ? (const __half*)(base + off[op.src1]) : nullptr;
         a.w = (const uint4*)c.w_img; a.bias = c.bias; a.out = out;
         a.H = Ho; a.W = Wo; a.c0 = op.c0; a.c1 = op.c1; a.mode = op.mode; a.ntaps = 9; a.groups = c.groups; a.chunks = c.chunks;
+        // pooled input already written by the producer's epilogue: read it directly (a Cin = 32 layer then runs TMA-fed too)
+        if (op.mode == 1 && l > 0 && pooled_by_producer[l - 1]) {
+            a.mode = 0;
+            a.src0 = (const __half*)(base + off[m->ops[l - 1].pool_dst]);
+        }
+        // and this layer's own pooled copy, when the next layer pools it and this one runs in the TMA-fed kernel
+        pooled_by_producer[l] = h->seg_pool_out && op.pool_dst >= 0 && seg_tma_eligible(h, c, a.mode) && !(Ho & 1) && !(Wo & 1);
+        if (pooled_by_producer[l]) {
+            a.out_pool = (__half*)(base + off[op.pool_dst]);
+            if (!op.full_needed) a.out = nullptr;
+        }
         rc = launch_seg_layer(h, c, a, s);
         if (rc) return rc;
     }

@@ -377,3 +377,18 @@ def test_screen_images_equals_the_per_field_calls(tmp_path):
             assert np.abs(res["moderate_scores"][sel] - r["moderate_scores"]).max() < 1e-6
         k += len(cells)
     assert k == len(res["field"]) > 0
+
+
+def test_pooled_outputs_are_bit_identical(model):
+    """seg_pool_out (default): TMA-fed layers write the max-pooled copy the next layer reads (the full-resolution map of
+    the second layer then never exists in HBM); the maps equal those of consumer-side pooling bit for bit"""
+    rng = np.random.default_rng(14)
+    x = rng.uniform(-0.2, 1.6, (176, 240)).astype(np.float32)
+    eng = model.engine
+    p1, d1 = model.predict(x)
+    eng.set_option("seg_pool_out", 0)
+    try:
+        p0, d0 = model.predict(x)
+    finally:
+        eng.set_option("seg_pool_out", 1)
+    assert np.array_equal(p0.cpu().numpy(), p1.cpu().numpy()) and np.array_equal(d0.cpu().numpy(), d1.cpu().numpy())
