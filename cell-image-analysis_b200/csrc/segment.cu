@@ -1545,7 +1545,7 @@ int launch_seg_layer(cia_ctx* h, const SegConv& c, const SegConvArgs& a, cudaStr
     if (tma && c.n_tile == 32) return launch_seg_conv_tma<32, 4>(h, a, s);
     if (tma && c.n_tile == 64) return launch_seg_conv_tma<64, 4>(h, a, s);
     if (tma && c.n_tile == 128) return launch_seg_conv_tma<128, 2>(h, a, s);
-    // measured per layer on B200 (profiles/r2t_seg_launches.txt): the software producer pays for layers with two or more
+    // measured per layer on B200 (profiles/r2u_seg_launches.txt): the software producer pays for layers with two or more
     // chunks and 64+ output channels per CTA (long MMA phases per step); short steps (N = 32) and pooled single- or
     // double-chunk inputs are faster with three co-resident staged CTAs.  seg_conv_ws = 2 forces it everywhere (tests).
     const bool ws = h->seg_conv_ws == 2 ||

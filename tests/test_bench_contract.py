@@ -35,7 +35,7 @@ def test_native_line_carries_the_contract_keys():
 
 def test_final_line_carries_the_segmentation_extras():
     """the last bench line of the round: the contract keys plus extra.segmentation"""
-    d = _line("r2t_bench_default.json")
+    d = _line("r2u_bench_default.json")
     assert BASE_KEYS <= set(d), BASE_KEYS - set(d)
     sg = d["extra"]["segmentation"]
     assert abs(sg["ms_per_field"] - (sg["normalize_ms"] + sg["unet_ms"] + sg["instances_ms"])) < 1e-6
