@@ -392,3 +392,32 @@ def test_pooled_outputs_are_bit_identical(model):
     finally:
         eng.set_option("seg_pool_out", 1)
     assert np.array_equal(p0.cpu().numpy(), p1.cpu().numpy()) and np.array_equal(d0.cpu().numpy(), d1.cpu().numpy())
+
+
+@pytest.mark.parametrize("cfg_kw", [
+    dict(grid=[1, 1], unet_n_depth=2, unet_n_filter_base=32, unet_n_conv_per_depth=2, net_conv_after_unet=64),
+    dict(grid=[4, 4], unet_n_depth=1, unet_n_filter_base=32, unet_n_conv_per_depth=1, net_conv_after_unet=32),
+    dict(grid=[2, 2], unet_n_depth=2, unet_n_filter_base=64, unet_n_conv_per_depth=3, net_conv_after_unet=128),
+])
+def test_other_stardist_configurations(cfg_kw):
+    """the plan builder follows StarDist2D._build / unet_block for other grids, depths, filter counts and convolutions per
+    level (first layer inside the U-Net for grid 1, a single convolution per level, three per level, 64-channel heads)"""
+    from cell_image_analysis_b200.stardist import StarDist2D, layer_plan
+    from oracle import stardist as sd
+    cfg = dict(CFG, **cfg_kw)
+    w = sd.random_model(cfg, seed=5)
+    assert layer_plan(cfg) == sd.layer_plan(cfg)
+    m = StarDist2D.from_arrays(cfg, w, {"prob": 0.5, "nms": 0.3})
+    assert m.layer_order == [p[0] for p in sd.layer_plan(cfg)]
+    g = int(cfg["grid"][0])
+    rng = np.random.default_rng(3)
+    x = rng.uniform(-0.2, 1.5, (64, 96)).astype(np.float32)
+    prob, dist = m.predict(x)
+    p16, d16 = sd.unet_forward(cfg, w, x, half_activations=True)
+    assert prob.shape == (64 // g, 96 // g) == p16.shape
+    assert np.abs(prob.cpu().numpy() - p16).max() < 1e-2
+    assert np.abs(dist.cpu().numpy() - d16).max() < 1e-2 * np.abs(d16).max()
+    thr = float(np.quantile(p16, 0.6))
+    labels, n = m.instances_from_prediction((64, 96), prob, dist, thr, 0.3)
+    ref, det = sd.instances_from_prediction(prob.cpu().numpy(), dist.cpu().numpy(), g, (64, 96), thr, 0.3)
+    assert n == len(det["prob"]) and np.array_equal(labels.cpu().numpy(), ref)
