@@ -188,3 +188,29 @@ def test_round_trip_labels_to_star_maps_to_instances():
         k = np.bincount(labels[m]).argmax()
         assert k > 0 and (m & (labels == k)).sum() / (m | (labels == k)).sum() > 0.9
 
+
+
+def test_weights_reader_takes_both_keras_layouts(tmp_path):
+    """legacy H5 weights (/<layer>/<layer>/kernel:0) and the Keras-3 ``*.weights.h5`` layout (/layers/<layer>/vars/0|1)"""
+    from cell_image_analysis_b200 import stardist as prod
+    from oracle.h5write import write_h5
+    w = sd.random_model(CFG, seed=6)
+    tree = {"layers": {name: {"vars": {"0": k, "1": b}} for name, (k, b) in w.items()}}
+    path = tmp_path / "model.weights.h5"
+    path.write_bytes(write_h5(tree))
+    got = prod.load_weights_h5(str(path))
+    assert set(got) == set(w)
+    assert all(np.array_equal(got[k][0], w[k][0]) and np.array_equal(got[k][1], w[k][1]) for k in w)
+
+
+def test_c_abi_segmentation_entry_points_reject_a_null_handle():
+    """no GPU needed: every cia_seg_* call returns CIA_E_ARG (-2) on a null handle instead of touching the device"""
+    from cell_image_analysis_b200 import _lib
+    lib = _lib.load()
+    assert lib.cia_seg_load(None, None, 0, None, None, None, None, None) == -2
+    assert lib.cia_seg_normalize(None, None, 16, 16, 3.0, 99.8, None, None, None) == -2
+    assert lib.cia_seg_predict(None, None, 16, 16, None, None, None) == -2
+    assert lib.cia_seg_instances(None, None, None, 8, 8, 2, 16, 16, 0.5, 0.3, None, None, None) == -2
+    assert lib.cia_seg_details(None, 0, None, None, None, None) == -2
+    assert lib.cia_seg_layer_info(None, 0, None) == -2
+    assert lib.cia_seg_debug_layer(None, 0, None, None, None, 16, 16, None, None, None, None) == -2
