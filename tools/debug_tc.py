@@ -1,7 +1,7 @@
 """GPU debugging aid (not a pytest module): layer-by-layer comparison of the tensor-core
 CAE path against the oracle, through the cia_debug_copy_workspace tap.
 
-    python tests/debug_tc.py [precision]      # on the B200 box
+    python tools/debug_tc.py [precision]      # on the B200 box
 """
 import ctypes as C
 import os
