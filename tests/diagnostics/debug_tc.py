@@ -1,7 +1,7 @@
 """GPU debugging aid (not a pytest module): layer-by-layer comparison of the tensor-core
 CAE path against the oracle, through the cia_debug_copy_workspace tap.
 
-    python tools/debug_tc.py [precision]      # on the B200 box
+    python tests/diagnostics/debug_tc.py [precision]      # on the B200 box
 """
 import ctypes as C
 import os
@@ -11,7 +11,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 from cell_image_analysis_b200.screening import ProductionMutantScreening  # noqa: E402

@@ -1,8 +1,8 @@
 """Diagnostic (GPU box): decision / feature error of every CAE precision mode against the oracle
-on held-out synthetic autoencoders.  Usage: python tools/heldout_probe.py [modes...]"""
+on held-out synthetic autoencoders.  Usage: python tests/diagnostics/heldout_probe.py [modes...]"""
 import os, sys
 import numpy as np, torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from helpers import artifacts_from, fit_detectors, synth_cae_weights
 from oracle import scoring as oscoring

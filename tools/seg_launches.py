@@ -1,4 +1,4 @@
-"""ncu launch list (csv of `--metrics gpu__time_duration.sum`) of tools/seg_once.py -> the committed text summary:
+"""ncu launch list (csv of `--metrics gpu__time_duration.sum`) of tests/diagnostics/seg_once.py -> the committed text summary:
   python tools/seg_launches.py gpurun_out/seg_launches_<tag>.csv > profiles/<tag>_seg_launches.txt
 Prints the LAST of the passes the script made (one 2048 x 2048 field: normalize, U-Net, instances)."""
 import csv
@@ -11,7 +11,7 @@ out = [(r[ki], float(r[vi].replace(",", "")), r[gi], r[bi]) for r in rows[1:]]
 first = [i for i, o in enumerate(out) if "seg_hist_kernel" in o[0]]
 out = out[first[-1]:] if first else out
 tot = sum(v for _, v, _, _ in out)
-print("# ncu --metrics gpu__time_duration.sum --clock-control none, python tools/seg_once.py (last pass):")
+print("# ncu --metrics gpu__time_duration.sum --clock-control none, python tests/diagnostics/seg_once.py (last pass):")
 print("# one 2048 x 2048 field: normalize, U-Net (2D_versatile_fluo topology), instances (58 050 candidates -> 529 labels)")
 groups = {"normalize": 0.0, "unet": 0.0, "instances": 0.0}
 for name, v, g, b in out:
