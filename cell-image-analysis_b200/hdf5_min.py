@@ -32,7 +32,10 @@ class H5FormatError(ValueError):
 class H5File:
     def __init__(self, data: bytes):
         self.b = memoryview(data)
-        self._parse_superblock()
+        try:
+            self._parse_superblock()
+        except IndexError as e:
+            raise H5FormatError("truncated HDF5 superblock") from e
 
     # ---- primitives -------------------------------------------------------
     def _u(self, off, n):
@@ -86,6 +89,7 @@ class H5File:
             p += szn
             chunks = [(p, chunk0)]
             track_order = bool(flags & 0x04)
+            visited = 0
             while chunks:
                 s, n = chunks.pop(0)
                 e = s + n
@@ -100,6 +104,9 @@ class H5File:
                         co, cl = self._u(s, 8) + self.base_addr, self._u(s + 8, 8)
                         if bytes(b[co:co + 4]) != b"OCHK":
                             raise H5FormatError("bad OCHK")
+                        visited += 1
+                        if visited > 4096:
+                            raise H5FormatError("object header continuation chain does not end")
                         chunks.append((co + 4, cl - 8))
                     elif mtype != 0:
                         out.append((mtype, mflags, s, msize))
@@ -326,5 +333,12 @@ class H5File:
                 return
             for name, child in self.links(addr).items():
                 rec(child, f"{path}/{name}" if path else name)
-        rec(self.root_header, "")
+        try:
+            rec(self.root_header, "")
+        except H5FormatError:
+            raise
+        except (IndexError, ValueError, TypeError, KeyError, OverflowError, RecursionError, MemoryError,
+                UnicodeDecodeError, struct.error) as e:
+            # a corrupted address / size / name: callers (artifacts.py) report H5FormatError with the file name
+            raise H5FormatError(f"malformed HDF5 structure: {type(e).__name__}: {e}") from e
         return out

@@ -231,7 +231,12 @@ def read_tiff(path: str) -> np.ndarray:
     pages, seen = [], set()
     while ifd and ifd not in seen and ifd < len(buf):
         seen.add(ifd)
-        page, ifd = _read_page(buf, bo, big, ifd)
+        try:
+            page, ifd = _read_page(buf, bo, big, ifd)
+        except TiffError:
+            raise
+        except (struct.error, TypeError, IndexError, ValueError, OverflowError, MemoryError) as e:
+            raise TiffError(f"malformed TIFF directory: {type(e).__name__}: {e}") from e   # corrupted tag values
         if pages and (page.shape != pages[0].shape or page.dtype != pages[0].dtype):
             break                                   # thumbnails / pyramids: keep the first series, like tifffile
         pages.append(page)
