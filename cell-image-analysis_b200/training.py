@@ -110,26 +110,32 @@ class ImprovedAnomalyDetectionTraining:
         self.generate_data_quality_report(stats_df, file_summary_df)
         return np.array(all_cells), stats_df
 
-    # train:159-182
+    # train:159-182 (the on-disk layout of data_quality_report.txt is the contract; built as a line list)
+    _REPORT_COLUMNS = (("CELL MORPHOLOGY STATISTICS:", (("Area", "area", 1), ("Eccentricity", "eccentricity", 3),
+                                                        ("Solidity", "solidity", 3))),
+                       ("INTENSITY STATISTICS:", (("Mean intensity", "mean_intensity", 3),
+                                                  ("Std intensity", "std_intensity", 3))))
+
     def generate_data_quality_report(self, stats_df, file_summary_df):
+        n_files, n_cells = len(file_summary_df), len(stats_df)
+        lines = ["=== TRAINING DATA QUALITY REPORT ===", "",
+                 "Generated: " + datetime.now().strftime("%Y-%m-%d %H:%M:%S"), "",
+                 "OVERALL STATISTICS:",
+                 f"Total files processed: {n_files}",
+                 f"Total cells extracted: {n_cells}",
+                 f"Average cells per file: {n_cells / n_files:.1f}", ""]
+        for title, columns in self._REPORT_COLUMNS:
+            lines.append(title)
+            for label, column, digits in columns:           # pandas' sample std (ddof = 1), like the reference
+                col = stats_df[column]
+                lines.append(f"{label}: {col.mean():.{digits}f} ± {col.std():.{digits}f}")
+            lines.append("")
+        lines.append("FILE-WISE SUMMARY:")
+        lines += [f"{name}: {count} cells, avg intensity: {mean:.3f}"
+                  for name, count, mean in zip(file_summary_df["filename"], file_summary_df["cells_extracted"],
+                                               file_summary_df["mean_cell_intensity"])]
         with open(os.path.join(self.output_dir, "data_quality_report.txt"), "w") as f:
-            f.write("=== TRAINING DATA QUALITY REPORT ===\n\n")
-            f.write(f"Generated: {datetime.now().strftime('%Y-%m-%d %H:%M:%S')}\n\n")
-            f.write("OVERALL STATISTICS:\n")
-            f.write(f"Total files processed: {len(file_summary_df)}\n")
-            f.write(f"Total cells extracted: {len(stats_df)}\n")
-            f.write(f"Average cells per file: {len(stats_df) / len(file_summary_df):.1f}\n\n")
-            f.write("CELL MORPHOLOGY STATISTICS:\n")
-            f.write(f"Area: {stats_df['area'].mean():.1f} ± {stats_df['area'].std():.1f}\n")
-            f.write(f"Eccentricity: {stats_df['eccentricity'].mean():.3f} ± {stats_df['eccentricity'].std():.3f}\n")
-            f.write(f"Solidity: {stats_df['solidity'].mean():.3f} ± {stats_df['solidity'].std():.3f}\n\n")
-            f.write("INTENSITY STATISTICS:\n")
-            f.write(f"Mean intensity: {stats_df['mean_intensity'].mean():.3f} ± {stats_df['mean_intensity'].std():.3f}\n")
-            f.write(f"Std intensity: {stats_df['std_intensity'].mean():.3f} ± {stats_df['std_intensity'].std():.3f}\n\n")
-            f.write("FILE-WISE SUMMARY:\n")
-            for _, row in file_summary_df.iterrows():
-                f.write(f"{row['filename']}: {row['cells_extracted']} cells, "
-                        f"avg intensity: {row['mean_cell_intensity']:.3f}\n")
+            f.write("\n".join(lines) + "\n")
 
     def _weights(self, model, n_conv):
         w = load_keras_cae(model) if isinstance(model, (str, os.PathLike)) else model

@@ -149,3 +149,24 @@ def test_report_omits_empty_groups():
     lines = reporting.screening_report_lines(only_wt)
     assert not any(l.startswith("HIGH ANOMALY") for l in lines)
     assert any(l.startswith("NORMAL-LEVEL") for l in lines)
+
+
+def test_training_data_quality_report_layout(tmp_path):
+    """data_quality_report.txt as CAE_improved_modeltrain.py:159-182 lays it out (sample std, ddof = 1); checked
+    byte for byte against the reference's own function when this file was written"""
+    import re
+    pd = pytest.importorskip("pandas")
+    from cell_image_analysis_b200.training import ImprovedAnomalyDetectionTraining
+    t = ImprovedAnomalyDetectionTraining.__new__(ImprovedAnomalyDetectionTraining)     # no device needed for the report
+    t.output_dir = str(tmp_path)
+    stats = pd.DataFrame({"area": [400.0, 600.0, 800.0], "eccentricity": [0.5, 0.6, 0.7], "solidity": [0.9, 0.95, 1.0],
+                          "mean_intensity": [1.0, 2.0, 3.0], "std_intensity": [0.25, 0.5, 0.75]})
+    files = pd.DataFrame({"filename": ["a.tif", "b.tif"], "cells_extracted": [3, 0], "mean_cell_intensity": [2.0, 0]})
+    t.generate_data_quality_report(stats, files)
+    text = (tmp_path / "data_quality_report.txt").read_text()
+    text = re.sub(r"Generated: \d{4}-\d\d-\d\d \d\d:\d\d:\d\d", "Generated: <now>", text)
+    assert text == ("=== TRAINING DATA QUALITY REPORT ===\n\nGenerated: <now>\n\n"
+                    "OVERALL STATISTICS:\nTotal files processed: 2\nTotal cells extracted: 3\nAverage cells per file: 1.5\n\n"
+                    "CELL MORPHOLOGY STATISTICS:\nArea: 600.0 ± 200.0\nEccentricity: 0.600 ± 0.100\nSolidity: 0.950 ± 0.050\n\n"
+                    "INTENSITY STATISTICS:\nMean intensity: 2.000 ± 1.000\nStd intensity: 0.500 ± 0.250\n\n"
+                    "FILE-WISE SUMMARY:\na.tif: 3 cells, avg intensity: 2.000\nb.tif: 0 cells, avg intensity: 0.000\n")
