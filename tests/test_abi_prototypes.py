@@ -98,3 +98,29 @@ def test_every_struct_layout_matches_the_ctypes_classes():
             off = (off + size - 1) // size * size + size
         align = max(s for _, (_, s) in hdr)
         assert (off + align - 1) // align * align == C.sizeof(cls), cname
+
+
+def test_every_entry_point_answers_a_null_handle_and_null_buffers_with_an_error_code():
+    """error behaviour at the boundary: CIA_E_ARG (-2) for a null handle on every handle-taking entry point, and the
+    host-only functions refuse null buffers -- nothing dereferences, nothing needs a GPU"""
+    lib = _lib.load()
+    raw = open(os.path.join(ROOT, "include", "cia.h")).read()
+    swept = 0
+    for name, (res, args) in _lib.SIGNATURES.items():
+        if not re.search(rf"\b{name}\s*\(\s*cia_handle\s+h\b", raw):
+            continue
+        vals = [0.0 if a in (C.c_double, C.c_float) else 0 if _kind_ctypes(a)[0] == "i" else None for a in args]
+        r = getattr(lib, name)(*vals)
+        swept += 1
+        if name == "cia_last_error":
+            assert r == b"null handle"
+        elif name == "cia_launch_count":
+            assert r == 0
+        else:
+            assert r == _lib.CIA_E_ARG, (name, r)
+    assert swept >= 35
+    assert lib.cia_rle_encode_fields(None, 1, 8, 8, None, 0, None, None, 1) == _lib.CIA_E_ARG
+    assert lib.cia_rle_encode_pack_fields(None, None, 1, 8, 8, None, 0, None, None, 4, None, 0, None, 1) == _lib.CIA_E_ARG
+    assert lib.cia_tiff_lzw_decode(None, 0, None, 0) == -1 and lib.cia_tiff_packbits_decode(None, 0, None, 0) == -1
+    assert lib.cia_host_read_probe(None, 1 << 20, 1, 1) == 0.0
+    assert lib.cia_create(0, None) == _lib.CIA_E_ARG
