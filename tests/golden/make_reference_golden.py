@@ -140,9 +140,15 @@ def main():
 
     _stub_missing(["stardist.models", "csbdeep.utils"])
     sys.path.insert(0, args.reference)
-    import matplotlib
-    matplotlib.use("Agg")
-    ref = importlib.import_module("improved_detection")          # the unmodified reference module
+    try:
+        import matplotlib
+        matplotlib.use("Agg")
+        ref = importlib.import_module("improved_detection")      # the unmodified reference module
+    except ImportError as e:
+        sys.exit(f"make_reference_golden: {e}.\nThis recipe runs the reference's own code: it needs the reference's "
+                 "imports (scikit-image, tensorflow / keras, tifffile, matplotlib, seaborn, pandas, scikit-learn; "
+                 "stardist / csbdeep are optional) and a checkout at --reference. Nothing was written; the tests "
+                 "keep reporting 'parity unpinned' for the stages that depend on these files.")
 
     from helpers import synth_cae_weights
     from cell_image_analysis_b200 import synth
