@@ -113,7 +113,6 @@ _REF = {}
 
 
 def _ref_init(threads):
-    import pickle
     import torch
     torch.set_num_threads(threads)
     from cell_image_analysis_b200.artifacts import load_model_dir

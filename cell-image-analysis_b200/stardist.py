@@ -23,7 +23,6 @@ import re
 import numpy as np
 import torch
 
-from . import _lib
 from .hdf5_min import H5File
 
 
